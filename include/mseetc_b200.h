@@ -1,0 +1,122 @@
+/* mseetc_b200 -- C ABI of the B200-native batched multiple-shooting OCP solver.
+ *
+ * Drop-in boundary for the NLP build-and-solve of dkouzoup/ms-eetc:
+ *   - mseetc_create       replaces what casadiSolver.__init__ hands to ca.nlpsol (mseetc/ocp.py:288-290):
+ *                         the problem *structure* (flags fixed by train/options, ocp.py:101-102,184,216).
+ *   - mseetc_solve_batch  replaces self.solver(lbx=,ubx=,lbg=,ubg=,x0=) (mseetc/ocp.py:359) for a whole batch
+ *                         of instances; it returns, per instance, what ocp.py:360-362 reads back:
+ *                         zOpt, f, return_status, iter_count.
+ *   - mseetc_eval_interval  kernel-level parity hook for TrainIntegrator.solve (mseetc/train.py:347-364).
+ *
+ * Plain pointers and sizes only.  Every `*_dev` pointer is a CUDA device pointer owned by the caller
+ * (torch tensors in the Python shim); the library never allocates or frees per call.  Calls on one handle
+ * must be serialised by the caller.  Work is enqueued on `stream`; mseetc_solve_batch synchronises the
+ * stream before returning (it polls a device-side completion counter).
+ *
+ * Return value: 0 ok, <0 usage error, >0 cudaError_t.  mseetc_last_error() gives the message.
+ * Per-instance solver outcomes are *never* an error return: see status_out.
+ */
+#ifndef MSEETC_B200_H
+#define MSEETC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSEETC_B200_VERSION 100
+
+/* per-instance parameter planes: params_dev[field * n_instances + instance], specific units (ocp.py:96-116) */
+enum mseetc_param {
+    MSEETC_P_SR0 = 0,   /* r0/(mass*rho)                      train.py:181 */
+    MSEETC_P_SR1,       /* r1/(mass*rho)                      train.py:182 */
+    MSEETC_P_SR2,       /* r2/(mass*rho)                      train.py:183 */
+    MSEETC_P_FEL_LO,    /* forceMin/M or 0 (no regen brake)   ocp.py:107,175 */
+    MSEETC_P_FEL_UP,    /* forceMax/M                         ocp.py:106,176 */
+    MSEETC_P_FPB_LO,    /* forceMinPn/M                       ocp.py:108,175 */
+    MSEETC_P_POW_LO,    /* -|lowerBound|                      ocp.py:187,192 */
+    MSEETC_P_POW_UP,    /* |upperBound|                       ocp.py:186,191 */
+    MSEETC_P_ACC_LO,    /* accMin                             ocp.py:114 */
+    MSEETC_P_ACC_UP,    /* accMax                             ocp.py:113 */
+    MSEETC_P_LOSS_TR,   /* (1-etaT)/etaT  (static map)        train.py:204 */
+    MSEETC_P_LOSS_RG,   /* (1-etaR)                           train.py:204 */
+    MSEETC_P_BMIN,      /* minimumVelocity^2                  ocp.py:271 */
+    MSEETC_P_OBJ_SCALE, /* scalingFactorObjective             ocp.py:276-284 */
+    MSEETC_P_T_END,     /* terminalTime                       ocp.py:353 */
+    MSEETC_P_T_START,   /* initialTime                        ocp.py:347 */
+    MSEETC_P_B_START,   /* clipped v0^2                       ocp.py:343,348 */
+    MSEETC_P_B_END,     /* clipped vN^2                       ocp.py:344,349 */
+    MSEETC_P_MASS,      /* mass*rho (informational)           ocp.py:97 */
+    MSEETC_PARAM_COUNT
+};
+
+/* per-instance status_out codes; the Python shim maps them to IPOPT's return_status strings (ocp.py:362) */
+enum mseetc_status {
+    MSEETC_SOLVE_SUCCEEDED = 0,
+    MSEETC_MAXIMUM_ITERATIONS_EXCEEDED = 1,
+    MSEETC_RESTORATION_FAILED = 2,
+    MSEETC_ERROR_IN_STEP_COMPUTATION = 3,
+    MSEETC_INFEASIBLE_PROBLEM_DETECTED = 4,
+    MSEETC_INVALID_NUMBER_DETECTED = 5
+};
+
+typedef struct mseetc_problem {
+    int32_t n_intervals_max;    /* largest numIntervals in any batch solved with this handle (ocp.py:88) */
+    int32_t with_pn_brake;      /* train.forceMinPn != 0                 ocp.py:102 */
+    int32_t with_power_rows;    /* powerMax or powerMin present          ocp.py:184 */
+    int32_t energy_optimal;     /* opts.energyOptimal                    ocp.py:146,216 */
+    int32_t loss_kind;          /* 0 none / 1 static efficiencies (train.py:204) / 2 dynamic map (efficiency.py) */
+    int32_t num_steps;          /* OptionsRK.numSteps                    train.py:463 */
+    int32_t num_approx_steps;   /* OptionsRK.numApproxSteps              train.py:465 */
+    int32_t max_iterations;     /* opts.maxIterations -> ipopt max_iter  ocp.py:290 */
+    double tol;                 /* IPOPT tol (default 1e-8) */
+    double mu_init;             /* IPOPT mu_init (default 0.1) */
+} mseetc_problem;
+
+typedef struct mseetc_solver* mseetc_handle;
+
+int mseetc_version(void);
+const char* mseetc_last_error(void);
+
+int mseetc_create(const mseetc_problem* problem, mseetc_handle* out);
+int mseetc_destroy(mseetc_handle h);
+
+/* bytes of device workspace needed to solve `n_instances` at once */
+size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);
+
+/* Solve a batch.
+ *   params_dev        [MSEETC_PARAM_COUNT * n_instances] planes (see enum mseetc_param)
+ *   n_intervals_dev   [n_instances]  numIntervals of each instance (<= n_intervals_max)
+ *   track_of_inst_dev [n_instances]  index of the track table an instance runs on
+ *   track_offset_dev  [n_tracks+1]   interval offsets (CSR) into ds/c0; node arrays use offset+track index
+ *   ds_dev, c0_dev    [sum N_j]      interval length; g*grad/rho + curvRes/rho   (ocp.py:125, train.py:252-254)
+ *   bmax_dev          [sum (N_j+1)]  min(limit_i, vmax, limit_{i-1})^2 at the nodes (ocp.py:266-272)
+ * outputs (device, caller-owned; each may be NULL except status_out):
+ *   z_out_dev    [n_instances * (n_intervals_max*(3+nu)+2)]  reference variable order (ocp.py:166-181,248-249)
+ *   lam_g_out_dev[n_instances * n_intervals_max*rows]        multipliers of g in reference row order
+ *   obj_out_dev, kkt_out_dev [n_instances]; iters_out_dev, status_out_dev [n_instances]
+ */
+int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
+                       const double* params_dev, const int32_t* n_intervals_dev,
+                       const int32_t* track_of_inst_dev, const int32_t* track_offset_dev,
+                       const double* ds_dev, const double* c0_dev, const double* bmax_dev,
+                       double* z_out_dev, double* lam_g_out_dev, double* obj_out_dev, double* kkt_out_dev,
+                       int32_t* iters_out_dev, int32_t* status_out_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
+
+/* number of solver ticks (lock-step rounds) and kernel launches of the last mseetc_solve_batch on h */
+int mseetc_last_ticks(mseetc_handle h);
+int mseetc_last_launches(mseetc_handle h);
+
+/* One shooting interval for n points (train.py:347-364): tau = t1 - t0 and b1, with first and second
+ * sensitivities w.r.t. (b0, F).  in_dev planes [7*n]: b0, F, ds, c0, sr0, sr1, sr2; out_dev planes [12*n]:
+ * tau, dtau/db, dtau/dF, d2tau/dbb, d2tau/dbF, d2tau/dFF, then the same six for b1. */
+int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx_steps,
+                         const double* in_dev, double* out_dev, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

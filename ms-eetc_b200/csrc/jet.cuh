@@ -1,0 +1,66 @@
+// Second-order forward-mode jets in two variables (value, gradient, symmetric Hessian).
+// Used by the shooting-interval device functions to get exact first and second sensitivities of
+// the RK4 step (replaces CasADi's AD of train.py:294-344 inside IPOPT callbacks, ocp.py:290).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MS_HD __host__ __device__ __forceinline__
+#else
+#define MS_HD inline
+#endif
+
+namespace mseetc {
+
+// variables: x0 (= b at interval start), x1 (= total specific force F)
+struct Jet2 {
+    double v, g0, g1, h00, h01, h11;
+};
+
+MS_HD Jet2 jconst(double c) { return Jet2{c, 0, 0, 0, 0, 0}; }
+MS_HD Jet2 jvar0(double x) { return Jet2{x, 1, 0, 0, 0, 0}; }
+MS_HD Jet2 jvar1(double x) { return Jet2{x, 0, 1, 0, 0, 0}; }
+
+MS_HD Jet2 operator+(const Jet2& a, const Jet2& b) {
+    return Jet2{a.v + b.v, a.g0 + b.g0, a.g1 + b.g1, a.h00 + b.h00, a.h01 + b.h01, a.h11 + b.h11};
+}
+MS_HD Jet2 operator-(const Jet2& a, const Jet2& b) {
+    return Jet2{a.v - b.v, a.g0 - b.g0, a.g1 - b.g1, a.h00 - b.h00, a.h01 - b.h01, a.h11 - b.h11};
+}
+MS_HD Jet2 operator+(const Jet2& a, double c) { Jet2 r = a; r.v += c; return r; }
+MS_HD Jet2 operator-(const Jet2& a, double c) { Jet2 r = a; r.v -= c; return r; }
+MS_HD Jet2 operator*(double c, const Jet2& a) {
+    return Jet2{c * a.v, c * a.g0, c * a.g1, c * a.h00, c * a.h01, c * a.h11};
+}
+MS_HD Jet2 operator*(const Jet2& a, const Jet2& b) {
+    Jet2 r;
+    r.v = a.v * b.v;
+    r.g0 = a.g0 * b.v + a.v * b.g0;
+    r.g1 = a.g1 * b.v + a.v * b.g1;
+    r.h00 = a.h00 * b.v + 2.0 * a.g0 * b.g0 + a.v * b.h00;
+    r.h01 = a.h01 * b.v + a.g0 * b.g1 + a.g1 * b.g0 + a.v * b.h01;
+    r.h11 = a.h11 * b.v + 2.0 * a.g1 * b.g1 + a.v * b.h11;
+    return r;
+}
+// f(a) for scalar f with derivatives f1, f2 at a.v
+MS_HD Jet2 jchain(const Jet2& a, double f0, double f1, double f2) {
+    Jet2 r;
+    r.v = f0;
+    r.g0 = f1 * a.g0;
+    r.g1 = f1 * a.g1;
+    r.h00 = f1 * a.h00 + f2 * a.g0 * a.g0;
+    r.h01 = f1 * a.h01 + f2 * a.g0 * a.g1;
+    r.h11 = f1 * a.h11 + f2 * a.g1 * a.g1;
+    return r;
+}
+MS_HD Jet2 jsqrt(const Jet2& a) {
+    double s = sqrt(a.v);
+    double f1 = 0.5 / s;
+    return jchain(a, s, f1, -0.5 * f1 / a.v);
+}
+MS_HD Jet2 jrecip(const Jet2& a) {
+    double r = 1.0 / a.v;
+    return jchain(a, r, -r * r, 2.0 * r * r * r);
+}
+
+}  // namespace mseetc

@@ -28,7 +28,7 @@ class Result(dict):
 
 
 def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scaling=True, verbose=False,
-          soc=True):
+          soc=True, ls_mult=True, relax=1e-8):
     t_start = time.perf_counter()
     n_all, m_all = len(x0), len(lbg)
     fixed = lbz == ubz                                   # fixed_variable_treatment = make_parameter
@@ -56,7 +56,6 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
     xL, xU = lbz[free].copy(), ubz[free].copy()
     dL, dU = (lbg * sg)[inr], (ubg * sg)[inr]
     cE = (lbg * sg)[eqr]
-    relax = 1e-8
     xL = np.where(np.isfinite(xL), xL - relax * np.maximum(1, np.abs(xL)), xL)
     xU = np.where(np.isfinite(xU), xU + relax * np.maximum(1, np.abs(xU)), xU)
     dL = np.where(np.isfinite(dL), dL - relax * np.maximum(1, np.abs(dL)), dL)
@@ -107,6 +106,8 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
     # least-square multiplier estimate (constr_mult_init_max = 1000)
     yc = np.zeros(mE); yd = np.zeros(mI)
     try:
+        if not ls_mult:
+            raise ValueError
         A = sp.bmat([[sp.identity(n + mI), sp.bmat([[Jc.T, Jd.T], [None, -sp.identity(mI)]])],
                      [sp.bmat([[Jc, None], [Jd, -sp.identity(mI)]]), None]], format='csc')
         rhs = -np.concatenate([gf - zL + zU, -vL + vU, np.zeros(mE + mI)])
@@ -238,7 +239,7 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
         accepted = False
         nls = 0
         soc_used = False
-        while alpha >= a_min * a_max or nls == 0:
+        while alpha >= a_min or nls == 0:
             xt, wt = x + alpha * dx, w + alpha * dw
             ct, dt = evalg(xt)
             ft = evalf(xt)

@@ -1,0 +1,79 @@
+// TEST HARNESS ONLY -- not part of the product, never loaded by the ms-eetc_b200 package.
+//
+// Compiles the solver's host/device headers (ms-eetc_b200/csrc/*.cuh) with g++ and runs the identical
+// lock-step tick sequence with plain loops in place of CUDA thread grids, so that the algorithmic logic
+// (interval sensitivities, stage-QP condensation, Riccati recursion, filter line search) can be unit-tested
+// against the oracle on a machine without a GPU.  The C-ABI library (libmseetc_b200.so) contains no such
+// path: it launches CUDA kernels or fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../ms-eetc_b200/csrc/io.cuh"
+
+using namespace mseetc;
+
+extern "C" {
+
+struct hostsim_problem {
+    int32_t n_intervals_max, with_pn_brake, with_power_rows, energy_optimal, loss_kind, num_steps, num_approx_steps,
+        max_iterations;
+    double tol, mu_init;
+};
+
+int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* params, const int32_t* nint,
+                        const int32_t* trk_of, const int32_t* trk_off, const double* ds, const double* c0,
+                        const double* bmax, double* z_out, double* lam_out, double* obj, double* kkt, int32_t* iters,
+                        int32_t* status, int32_t verbose_inst, int32_t* ticks_out) {
+    Config g;
+    memset(&g, 0, sizeof g);
+    g.S = pad_slots(n);
+    g.NK = pr->n_intervals_max + 1;
+    g.nInst = n;
+    g.withPn = pr->with_pn_brake; g.withPower = pr->with_power_rows; g.energy = pr->energy_optimal;
+    g.lossKind = pr->loss_kind; g.numSteps = pr->num_steps; g.numApprox = pr->num_approx_steps;
+    g.maxIter = pr->max_iterations; g.tol = pr->tol; g.muInit = pr->mu_init;
+    WsPlan plan = plan_workspace(g.S, g.NK);
+    std::vector<char> buf(plan.total, 0);
+    Ctx c;
+    c.cfg = g;
+    c.ws = (double*)(buf.data() + plan.off_ws);
+    c.par = (double*)(buf.data() + plan.off_par);
+    c.sd = (double*)(buf.data() + plan.off_sd);
+    c.si = (int*)(buf.data() + plan.off_si);
+    c.done = (int*)(buf.data() + plan.off_done);
+    BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, z_out, lam_out, obj, kkt, iters, status};
+    for (int s = 0; s < g.S; ++s) inst_setup(c, io, s);
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_init(c, k, s);
+    int tick = 0;
+    const int maxTicks = 20 * pr->max_iterations + 50;
+    auto report = [&](const char* tag) {
+        int s = verbose_inst;
+        if (s < 0 || s >= n) return;
+        printf("%s tick %3d it %3d ph %d f=%.10e th=%.3e dinf=%.2e pinf=%.2e mu=%.1e a=%.3e az=%.3e kkt=%.2e nls=%d nreg=%d\n", tag,
+               tick, c.I(SI_ITERS, s), c.I(SI_PHASE, s), c.D(SD_FOBJ, s), c.D(SD_THETA, s), c.D(SD_DINF, s), c.D(SD_PINF, s),
+               c.D(SD_MU, s), c.D(SD_ALPHA, s), c.D(SD_ALPHA_Z, s), c.D(SD_KKT, s), c.I(SI_NLS, s), c.I(SI_NREG, s));
+    };
+    for (;;) {
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_eval(c, k, s);
+        for (int s = 0; s < g.S; ++s) inst_step(c, s);
+        report("step ");
+        if (*c.done >= n || tick >= maxTicks) break;
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_trial(c, k, s);
+        for (int s = 0; s < g.S; ++s) inst_decide(c, s);
+        ++tick;
+        if (*c.done >= n) break;
+    }
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_extract(c, io, k, s);
+    if (ticks_out) *ticks_out = tick;
+    return 0;
+}
+
+int hostsim_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out) {
+    for (int i = 0; i < n; ++i) eval_interval_point(i, n, num_steps, num_approx, in, out);
+    return 0;
+}
+
+}  // extern "C"
