@@ -1,0 +1,197 @@
+// CUDA kernels (sm_100a) and the C ABI of include/mseetc_b200.h.
+//
+// Kernel roles (one lock-step "tick" = trial -> decide -> eval -> step):
+//   k_cells<OP>  one thread per (interval k, instance): coalesced SoA streaming, HBM-bound
+//   k_insts<OP>  one thread per instance: sequential sweeps over k (Riccati), loads coalesced across the warp
+// No tensor cores: the per-interval blocks are 3x3 / 6x6 FP64 and there is no dense contraction.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mseetc_b200.h"
+#include "io.cuh"
+
+using namespace mseetc;
+
+static_assert((int)MSEETC_PARAM_COUNT == (int)PAR_N, "parameter plane enum out of sync");
+static_assert((int)MSEETC_P_MASS == (int)P_MASS, "parameter plane enum out of sync");
+
+namespace {
+
+thread_local std::string g_err;
+
+enum Op { OP_SETUP = 0, OP_INIT, OP_TRIAL, OP_DECIDE, OP_EVAL, OP_STEP, OP_EXTRACT };
+
+template <int OP>
+__global__ void __launch_bounds__(128) k_cells(Ctx c, BatchIO io) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)(idx % c.cfg.S);
+    const int k = (int)(idx / c.cfg.S);
+    if (k >= c.cfg.NK) return;
+    if (OP == OP_SETUP) cell_setup(c, io, k, s);
+    if (OP == OP_INIT) cell_init(c, k, s);
+    if (OP == OP_TRIAL) cell_trial(c, k, s);
+    if (OP == OP_EVAL) cell_eval(c, k, s);
+    if (OP == OP_EXTRACT) cell_extract(c, io, k, s);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(64) k_insts(Ctx c, BatchIO io) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.cfg.S) return;
+    if (OP == OP_SETUP) inst_setup(c, io, s);
+    if (OP == OP_DECIDE) inst_decide(c, s);
+    if (OP == OP_STEP) inst_step(c, s);
+}
+
+__global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    eval_interval_point(i, n, numSteps, numApprox, in, out);
+}
+
+}  // namespace
+
+struct mseetc_solver {
+    mseetc_problem prob;
+    int* done_host;     // pinned
+    int last_ticks;
+    int last_launches;
+};
+
+extern "C" {
+
+int mseetc_version(void) { return MSEETC_B200_VERSION; }
+const char* mseetc_last_error(void) { return g_err.c_str(); }
+
+static int fail(int code, const char* msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+
+int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
+    if (!p || !out) return fail(-1, "mseetc_create: null argument");
+    if (p->n_intervals_max < 2) return fail(-2, "mseetc_create: n_intervals_max must be >= 2");
+    if (p->num_steps < 1 || p->num_approx_steps < 0) return fail(-3, "mseetc_create: bad RK options");
+    if (p->loss_kind < 0 || p->loss_kind > 1) return fail(-4, "mseetc_create: loss_kind not supported by this build");
+    if (p->max_iterations < 1 || !(p->tol > 0.0) || !(p->mu_init > 0.0)) return fail(-5, "mseetc_create: bad IP options");
+    mseetc_solver* h = new (std::nothrow) mseetc_solver;
+    if (!h) return fail(-6, "mseetc_create: out of host memory");
+    h->prob = *p;
+    h->last_ticks = 0;
+    h->last_launches = 0;
+    cudaError_t e = cudaHostAlloc((void**)&h->done_host, sizeof(int), cudaHostAllocDefault);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
+    *out = h;
+    return 0;
+}
+
+int mseetc_destroy(mseetc_handle h) {
+    if (!h) return 0;
+    cudaFreeHost(h->done_host);
+    delete h;
+    return 0;
+}
+
+size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n) {
+    if (!h || n < 1) return 0;
+    return plan_workspace(pad_slots(n), h->prob.n_intervals_max + 1).total;
+}
+
+int mseetc_last_ticks(mseetc_handle h) { return h ? h->last_ticks : -1; }
+int mseetc_last_launches(mseetc_handle h) { return h ? h->last_launches : -1; }
+
+int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const int32_t* nint, const int32_t* trk_of,
+                       const int32_t* trk_off, const double* ds, const double* c0, const double* bmax, double* z_out,
+                       double* lam_out, double* obj, double* kkt, int32_t* iters, int32_t* status, void* workspace,
+                       size_t ws_bytes, void* cuda_stream) {
+    if (!h) return fail(-1, "mseetc_solve_batch: null handle");
+    if (n < 1) return fail(-2, "mseetc_solve_batch: n_instances must be >= 1");
+    if (!params || !nint || !trk_of || !trk_off || !ds || !c0 || !bmax || !status || !workspace)
+        return fail(-3, "mseetc_solve_batch: null device pointer");
+    const mseetc_problem& p = h->prob;
+    Config g;
+    memset(&g, 0, sizeof g);
+    g.S = pad_slots(n);
+    g.NK = p.n_intervals_max + 1;
+    g.nInst = n;
+    g.withPn = p.with_pn_brake; g.withPower = p.with_power_rows; g.energy = p.energy_optimal; g.lossKind = p.loss_kind;
+    g.numSteps = p.num_steps; g.numApprox = p.num_approx_steps; g.maxIter = p.max_iterations;
+    g.tol = p.tol; g.muInit = p.mu_init;
+    WsPlan plan = plan_workspace(g.S, g.NK);
+    if (ws_bytes < plan.total) return fail(-4, "mseetc_solve_batch: workspace too small (see mseetc_workspace_bytes)");
+    if (((uintptr_t)workspace & 255) != 0) return fail(-5, "mseetc_solve_batch: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    char* base = (char*)workspace;
+    Ctx c;
+    c.cfg = g;
+    c.ws = (double*)(base + plan.off_ws);
+    c.par = (double*)(base + plan.off_par);
+    c.sd = (double*)(base + plan.off_sd);
+    c.si = (int*)(base + plan.off_si);
+    c.done = (int*)(base + plan.off_done);
+    BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, z_out, lam_out, obj, kkt, iters, status};
+
+    const size_t cellThreads = (size_t)g.NK * g.S;
+    const unsigned cgrid = (unsigned)((cellThreads + 127) / 128);
+    const int ib = (g.S >= 148 * 64 * 2) ? 64 : 32;
+    const unsigned igrid = (unsigned)((g.S + ib - 1) / ib);
+    int launches = 0;
+    cudaError_t e;
+    e = cudaMemsetAsync(c.done, 0, 256, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    e = cudaMemsetAsync(c.si, 0, sizeof(int) * (size_t)SI_N * g.S, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    k_insts<OP_SETUP><<<igrid, ib, 0, st>>>(c, io);
+    k_cells<OP_SETUP><<<cgrid, 128, 0, st>>>(c, io);
+    k_cells<OP_INIT><<<cgrid, 128, 0, st>>>(c, io);
+    launches += 3;
+    const int maxTicks = 3 * p.max_iterations + 100;
+    int tick = 0;
+    for (;;) {
+        k_cells<OP_EVAL><<<cgrid, 128, 0, st>>>(c, io);
+        k_insts<OP_STEP><<<igrid, ib, 0, st>>>(c, io);
+        launches += 2;
+        if (tick >= maxTicks) break;
+        if (tick >= 16 && (tick & 3) == 0) {
+            e = cudaMemcpyAsync(h->done_host, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(done)");
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
+            if (*h->done_host >= n) break;
+        }
+        k_cells<OP_TRIAL><<<cgrid, 128, 0, st>>>(c, io);
+        k_insts<OP_DECIDE><<<igrid, ib, 0, st>>>(c, io);
+        launches += 2;
+        ++tick;
+    }
+    k_cells<OP_EXTRACT><<<cgrid, 128, 0, st>>>(c, io);
+    launches += 1;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
+    h->last_ticks = tick;
+    h->last_launches = launches;
+    return 0;
+}
+
+int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out, void* cuda_stream) {
+    if (n < 1 || !in || !out) return fail(-1, "mseetc_eval_interval: bad argument");
+    if (num_steps < 1 || num_approx < 0) return fail(-2, "mseetc_eval_interval: bad RK options");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_eval_interval launch");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "k_eval_interval");
+    return 0;
+}
+
+}  // extern "C"

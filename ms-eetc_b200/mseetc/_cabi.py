@@ -1,0 +1,142 @@
+"""ctypes binding of libmseetc_b200.so (include/mseetc_b200.h).
+
+torch is used only to own device buffers and the CUDA stream; every call crosses the C ABI with raw
+pointers.  There is no CPU fallback: without the shared library or without a CUDA device every entry point
+raises RuntimeError.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmseetc_b200.so')
+
+PARAMS = ['SR0', 'SR1', 'SR2', 'FEL_LO', 'FEL_UP', 'FPB_LO', 'POW_LO', 'POW_UP', 'ACC_LO', 'ACC_UP', 'LOSS_TR', 'LOSS_RG',
+          'BMIN', 'OBJ_SCALE', 'T_END', 'T_START', 'B_START', 'B_END', 'MASS']
+PARAM_INDEX = {name: i for i, name in enumerate(PARAMS)}
+
+STATUS_STRINGS = {   # IPOPT's return_status vocabulary (what stats['Solver status'] holds in the reference, ocp.py:362)
+    0: 'Solve_Succeeded',
+    1: 'Maximum_Iterations_Exceeded',
+    2: 'Restoration_Failed',
+    3: 'Error_In_Step_Computation',
+    4: 'Infeasible_Problem_Detected',
+    5: 'Invalid_Number_Detected',
+}
+
+
+class Problem(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('n_intervals_max', 'with_pn_brake', 'with_power_rows', 'energy_optimal',
+                                               'loss_kind', 'num_steps', 'num_approx_steps', 'max_iterations')] + \
+               [('tol', ctypes.c_double), ('mu_init', ctypes.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    "Load the shared library (built by __graft_entry__.build()); loud failure if it is missing."
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libmseetc_b200.so not found at {} -- build it with `python __graft_entry__.py` "
+                           "(nvcc, sm_100a); there is no CPU fallback".format(LIB_PATH))
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_size_t
+    L.mseetc_version.restype = ctypes.c_int
+    L.mseetc_last_error.restype = ctypes.c_char_p
+    L.mseetc_create.argtypes = [ctypes.POINTER(Problem), ctypes.POINTER(vp)]
+    L.mseetc_destroy.argtypes = [vp]
+    L.mseetc_workspace_bytes.argtypes = [vp, i32]
+    L.mseetc_workspace_bytes.restype = sz
+    L.mseetc_solve_batch.argtypes = [vp, i32] + [vp] * 13 + [vp, sz, vp]
+    L.mseetc_last_ticks.argtypes = [vp]
+    L.mseetc_last_launches.argtypes = [vp]
+    L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("{} failed ({}): {}".format(what, rc, lib().mseetc_last_error().decode()))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Handle:
+    "Owns one mseetc_handle plus the device workspace (a torch uint8 tensor, re-used across solves)."
+
+    def __init__(self, n_intervals_max, with_pn, with_power, energy, loss_kind, num_steps, num_approx, max_iter,
+                 tol=1e-8, mu_init=0.1):
+        self.problem = Problem(int(n_intervals_max), int(with_pn), int(with_power), int(energy), int(loss_kind),
+                               int(num_steps), int(num_approx), int(max_iter), float(tol), float(mu_init))
+        self._h = ctypes.c_void_p(0)
+        _check(lib().mseetc_create(ctypes.byref(self.problem), ctypes.byref(self._h)), 'mseetc_create')
+        self._ws = None
+        self.nu = 1 + int(with_pn)
+        self.rows = (2 if with_power else 0) + 3 + (2 if energy else 0)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().mseetc_destroy(self._h)
+                self._h = ctypes.c_void_p(0)
+        except Exception:
+            pass
+
+    def workspace(self, n, device):
+        torch = _torch_cuda()
+        need = lib().mseetc_workspace_bytes(self._h, int(n))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws, need
+
+    def solve_device(self, params, nint, trk_of, trk_off, ds, c0, bmax, want_z=True, want_lam=False):
+        """All arguments are torch CUDA tensors (float64 / int32).  Returns dict of device tensors."""
+        torch = _torch_cuda()
+        n = int(nint.numel())
+        dev = params.device
+        Nmax = self.problem.n_intervals_max
+        stp = 3 + self.nu
+        out = dict(
+            z=torch.zeros((n, Nmax * stp + 2), dtype=torch.float64, device=dev) if want_z else None,
+            lam=torch.zeros((n, Nmax * self.rows), dtype=torch.float64, device=dev) if want_lam else None,
+            obj=torch.empty(n, dtype=torch.float64, device=dev),
+            kkt=torch.empty(n, dtype=torch.float64, device=dev),
+            iters=torch.empty(n, dtype=torch.int32, device=dev),
+            status=torch.empty(n, dtype=torch.int32, device=dev),
+        )
+        ws, need = self.workspace(n, dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib().mseetc_solve_batch(self._h, n, _ptr(params), _ptr(nint), _ptr(trk_of), _ptr(trk_off), _ptr(ds), _ptr(c0),
+                                      _ptr(bmax), _ptr(out['z']), _ptr(out['lam']), _ptr(out['obj']), _ptr(out['kkt']),
+                                      _ptr(out['iters']), _ptr(out['status']), _ptr(ws), need, ctypes.c_void_p(stream))
+        _check(rc, 'mseetc_solve_batch')
+        out['ticks'] = lib().mseetc_last_ticks(self._h)
+        out['launches'] = lib().mseetc_last_launches(self._h)
+        return out
+
+
+def eval_interval(inp, num_steps, num_approx):
+    """inp: numpy [7, n] planes (b0, F, ds, c0, sr0, sr1, sr2) -> numpy [12, n] (tau jets, b1 jets)."""
+    torch = _torch_cuda()
+    inp = np.ascontiguousarray(inp, dtype=np.float64)
+    n = inp.shape[1]
+    d_in = torch.from_numpy(inp).cuda()
+    d_out = torch.empty((12, n), dtype=torch.float64, device=d_in.device)
+    stream = torch.cuda.current_stream().cuda_stream
+    _check(lib().mseetc_eval_interval(n, int(num_steps), int(num_approx), _ptr(d_in), _ptr(d_out), ctypes.c_void_p(stream)),
+           'mseetc_eval_interval')
+    return d_out.cpu().numpy()

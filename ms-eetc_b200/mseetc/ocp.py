@@ -1,0 +1,288 @@
+"""Drop-in replacement of ``mseetc.ocp``: same ``OptionsCasadiSolver`` / ``casadiSolver`` construction and
+``solve()`` call surface (reference ocp.py:12-74, :77-307, :310-409), but the NLP is never built symbolically
+and never handed to IPOPT: construction turns train + track + options into per-interval SoA tables and scalar
+parameter planes, and ``solve`` / ``solve_batch`` run the batched interior-point / Riccati kernels of
+``libmseetc_b200.so`` on the GPU through the C ABI.
+
+Additive API (no reference analogue): ``casadiSolver.solve_batch`` solves many instances that share this
+solver's track and options (trip-time sweeps, parameter Monte Carlo) in one device call.
+"""
+import time as _time
+
+import numpy as np
+import pandas as pd
+
+from mseetc.train import *  # noqa: F401,F403  (the reference re-exports the train module the same way)
+from mseetc.train import OptionsRK, OptionsIRK, OptionsCVODES
+from mseetc.track import computeDiscretizationPoints
+from mseetc.utils import Options, postProcessDataFrame
+from mseetc import _cabi
+
+_ACC_INF = 10   # stand-in for an absent force / acceleration limit (reference ocp.py:104)
+
+
+class OptionsCasadiSolver(Options):
+
+    def __init__(self, paramsDict):
+        self.numIntervals = 100          # shooting intervals (piecewise constant controls)
+        self.maxIterations = 1e3         # interior-point iteration limit
+        self.energyOptimal = True        # False: minimum time
+        self.minimumVelocity = 1         # lower bound on speed [m/s]
+        self.integrationMethod = 'RK'    # 'RK', 'IRK' or 'CVODES'
+        self.integrationOptions = {}     # options of the chosen method
+        self.integrateLosses = False     # False: mid-point rule for the losses of an interval
+        super().__init__(paramsDict)
+
+    def overwriteDefaults(self, paramsDict):
+        super().overwriteDefaults(paramsDict)
+        nested = paramsDict.get('integrationOptions', {})
+        kinds = {'RK': OptionsRK, 'IRK': OptionsIRK, 'CVODES': OptionsCVODES}
+        if self.integrationMethod in kinds:
+            self.integrationOptions = kinds[self.integrationMethod](nested)
+
+    def checkValues(self):
+        self.checkPositiveInteger(self.numIntervals, 'Number of intervals', allowZero=False)
+        self.checkPositiveInteger(self.maxIterations, 'Maximum number of iterations', allowZero=False)
+        if not isinstance(self.energyOptimal, bool):
+            raise ValueError("'energyOptimal' flag must be a boolean!")
+        if type(self.minimumVelocity) not in {int, float} or self.minimumVelocity <= 0:
+            raise ValueError("Minimum velocity should be a strictly positive number!")
+        if self.integrationMethod not in {'RK', 'IRK', 'CVODES'}:
+            raise ValueError("Unknown integration method!")
+        if not isinstance(self.integrateLosses, bool):
+            raise ValueError("'integrateLosses' flag must be a boolean!")
+
+
+def classify_losses(train):
+    """Recognise the loss model of a train: ('none'|'static', cT, cR) with
+    PLtr/v = cT*f and PLrgb/v = -cR*f (reference train.py:204 + utils.py:197-220).
+
+    Arbitrary Python callables cannot run on the device; the shipped families are recognised by probing."""
+    if not hasattr(train, 'powerLosses'):
+        if hasattr(train, 'etaTraction') and hasattr(train, 'etaRgBrake'):
+            return 'static', (1 - train.etaTraction) / train.etaTraction, 1 - train.etaRgBrake
+        raise ValueError("Power losses function of train must by either explicitly or implicitly defined!")
+    fun = train.powerLosses
+    kind = getattr(fun, 'mseetc_kind', None)
+    if kind is not None:
+        raise NotImplementedError("loss model '{}' is not available in this build of the device library".format(kind))
+    fmax = train.forceMax if train.forceMax is not None else _ACC_INF * train.mass * train.rho
+    F, V = np.meshgrid(np.array([0.05, 0.3, 0.9]) * fmax, np.array([2.0, 15.0, 33.0]))
+    one = np.ones_like(F)
+    pos = np.asarray(fun(F, V), dtype=float) * one / (F * V)       # = (1-etaT)/etaT for the static family
+    neg = np.asarray(fun(-F, V), dtype=float) * one / (F * V)      # = (1-etaR)
+    zero = np.asarray(fun(0.0 * F, V), dtype=float) * one
+    cT, cR = float(pos.flat[0]), float(neg.flat[0])
+    ok = np.allclose(pos, cT, rtol=1e-12, atol=1e-15) and np.allclose(neg, cR, rtol=1e-12, atol=1e-15) and np.all(zero == 0)
+    if not ok:
+        raise NotImplementedError("train.powerLosses is not one of the loss families available on the device "
+                                  "(none / constant efficiencies)")
+    return ('none' if cT == 0 and cR == 0 else 'static'), cT, cR
+
+
+def _curve_res(kappa, g):
+    k = np.abs(kappa)
+    return np.where(k <= 1 / 300, g * 0.5 * k / (1 - 30 * k), g * 0.65 * k / (1 - 55 * k))
+
+
+class casadiSolver():
+    "Solver object with the reference's name and interface; the numerics run on the GPU."
+
+    def __init__(self, train, track, optsDict={}):
+        track.checkFields()
+        train.checkFields()
+        opts = OptionsCasadiSolver(optsDict)
+        if opts.integrationMethod != 'RK':
+            raise NotImplementedError("integrationMethod '{}' is not implemented on the device (only 'RK')".format(opts.integrationMethod))
+        if opts.integrateLosses:
+            raise NotImplementedError("integrateLosses=True is not implemented on the device")
+
+        self.train = train
+        self.opts = opts
+        self.numIntervals = int(opts.numIntervals)
+        self.velocityMin = opts.minimumVelocity
+        self.energyOptimal = opts.energyOptimal
+        self.totalMass = train.mass * train.rho
+        self.withRgBrake = train.forceMin != 0
+        self.withPnBrake = train.forceMinPn != 0
+        self.withPower = train.powerMax is not None or train.powerMin is not None
+        self.trackLength = track.length
+        if opts.energyOptimal:
+            self.scalingFactorObjective = 3.6 / (1e-6 * self.totalMass)           # objective in kWh
+        else:
+            self.scalingFactorObjective = track.length / train.velocityMax        # fastest conceivable trip
+
+        self.points = computeDiscretizationPoints(track, self.numIntervals)
+        self.steps = np.diff(self.points.index)
+        self._lossKind, _, _ = classify_losses(train) if opts.energyOptimal else ('none', 0.0, 0.0)
+        # snapshot of everything the kernels need; train attributes are read NOW (callers mutate them afterwards)
+        self._base = self._train_scalars(train)
+        self._handle = None
+        self._dev = {}
+
+    # ------------------------------------------------------------------ packing
+    @staticmethod
+    def _train_scalars(train):
+        keys = ('mass', 'rho', 'g', 'velocityMax', 'forceMax', 'forceMin', 'forceMinPn', 'powerMax', 'powerMin', 'accMax',
+                'accMin', 'r0', 'r1', 'r2')
+        d = {k: getattr(train, k) for k in keys}
+        return d
+
+    def _planes(self, n, T, t0, v0, vN, overrides, lossT, lossR):
+        "Parameter planes [PARAM_COUNT, n] in specific units (reference ocp.py:96-116,343-355)."
+        b = dict(self._base)
+        get = lambda k: np.broadcast_to(np.asarray(overrides[k], dtype=float), (n,)) if k in overrides else b[k]
+        mass, rho = get('mass'), get('rho')
+        M = mass * rho
+        vmax = get('velocityMax')
+        opt = lambda k, dflt: (get(k) / M) if (k in overrides or b[k] is not None) else dflt
+        fMax = opt('forceMax', _ACC_INF)
+        fMin = opt('forceMin', -_ACC_INF) if self.withRgBrake else 0.0
+        fMinPn = opt('forceMinPn', -_ACC_INF) if self.withPnBrake else -1.0
+        hasPmax = 'powerMax' in overrides or b['powerMax'] is not None
+        hasPmin = 'powerMin' in overrides or b['powerMin'] is not None
+        if self.withPower:
+            up = get('powerMax') / M if hasPmax else fMax * vmax
+            lo = 0.0 if not self.withRgBrake else (get('powerMin') / M if hasPmin else fMin * vmax)
+            pUp, pLo = np.abs(up), -np.abs(lo)
+        else:
+            pUp, pLo = 1.0, -1.0
+        accMax = np.minimum(_ACC_INF, get('accMax')) if ('accMax' in overrides or b['accMax'] is not None) else _ACC_INF
+        accMin = np.maximum(-_ACC_INF, -np.abs(get('accMin'))) if ('accMin' in overrides or b['accMin'] is not None) else -_ACC_INF
+        scale = 3.6 / (1e-6 * M) if self.energyOptimal else self.trackLength / vmax
+        lim0 = self.points['Speed limit [m/s]'].values[0]
+        limN = self.points['Speed limit [m/s]'].values[-1]
+        v0c = np.minimum(np.maximum(v0, self.velocityMin), lim0)
+        vNc = np.minimum(np.maximum(vN, self.velocityMin), limN)
+        P = np.empty((len(_cabi.PARAMS), n))
+        rows = dict(SR0=get('r0') / M, SR1=get('r1') / M, SR2=get('r2') / M, FEL_LO=fMin, FEL_UP=fMax, FPB_LO=fMinPn,
+                    POW_LO=pLo, POW_UP=pUp, ACC_LO=accMin, ACC_UP=accMax, LOSS_TR=lossT, LOSS_RG=lossR,
+                    BMIN=float(self.velocityMin) ** 2, OBJ_SCALE=scale, T_END=T, T_START=t0, B_START=v0c ** 2, B_END=vNc ** 2, MASS=M)
+        for name, val in rows.items():
+            P[_cabi.PARAM_INDEX[name]] = val
+        return P, M
+
+    def _tables(self, rho, g, vmax):
+        "Per-interval tables ds, c0 and node table bmax for one (rho, g, vmax)."
+        pts = self.points
+        N = self.numIntervals
+        grad = pts['Gradient [permil]'].values[:N] / 1e3
+        curv = pts['Curvature [1/m]'].values[:N]
+        lim = pts['Speed limit [m/s]'].values
+        c0 = g * grad / rho + _curve_res(curv, g) / rho                          # reference train.py:252-254
+        bmax = np.ones(N + 1)
+        bmax[1:N] = np.minimum(np.minimum(lim[1:N], vmax), lim[0:N - 1]) ** 2    # reference ocp.py:266-269
+        return np.asarray(self.steps, dtype=float), c0, bmax
+
+    def _ensure_handle(self):
+        if self._handle is None:
+            io = self.opts.integrationOptions
+            self._handle = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
+                                        {'none': 0, 'static': 1}[self._lossKind], io.numSteps, io.numApproxSteps,
+                                        int(self.opts.maxIterations))
+        return self._handle
+
+    # ------------------------------------------------------------------ batched solve (additive API)
+    def solve_batch(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None,
+                    want_multipliers=False, device=None):
+        """Solve n instances that share this solver's track, options and problem structure.
+
+        terminalTime / initialTime / terminalVelocity / initialVelocity: scalars or arrays of length n.
+        overrides: optional dict of per-instance train attributes (arrays of length n), any of
+        mass, rho, r0, r1, r2, forceMax, forceMin, forceMinPn, powerMax, powerMin, accMax, accMin, velocityMax,
+        etaTraction, etaRgBrake.
+        Returns a dict of numpy arrays: z [n, nz] (reference variable order), cost, kkt, iters, status,
+        plus timing; nothing is post-processed."""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        overrides = dict(overrides or {})
+        arrs = [np.atleast_1d(np.asarray(a, dtype=float)) for a in (terminalTime, initialTime, terminalVelocity, initialVelocity)]
+        n = max([len(a) for a in arrs] + [len(np.atleast_1d(v)) for v in overrides.values()])
+        T, t0, vN, v0 = [np.broadcast_to(a, (n,)) for a in arrs]
+        etaT = np.asarray(overrides.pop('etaTraction', getattr(self.train, 'etaTraction', 1.0)), dtype=float)
+        etaR = np.asarray(overrides.pop('etaRgBrake', getattr(self.train, 'etaRgBrake', 1.0)), dtype=float)
+        if not self.energyOptimal:
+            lossT, lossR = 0.0, 0.0
+        elif hasattr(self.train, 'powerLosses'):
+            _, lossT, lossR = classify_losses(self.train)
+        else:
+            lossT, lossR = (1 - etaT) / etaT, 1 - etaR
+        P, M = self._planes(n, T, t0, v0, vN, overrides, lossT, lossR)
+        dev = torch.device(device if device is not None else 'cuda')
+        t_begin = _time.perf_counter()
+        # ---- track tables: shared unless rho / g / velocityMax vary per instance
+        per_inst_track = any(k in overrides for k in ('rho', 'velocityMax'))
+        N = self.numIntervals
+        if per_inst_track:
+            rho = np.broadcast_to(np.asarray(overrides.get('rho', self._base['rho']), dtype=float), (n,))
+            vmx = np.broadcast_to(np.asarray(overrides.get('velocityMax', self._base['velocityMax']), dtype=float), (n,))
+            tabs = [self._tables(rho[i], self._base['g'], vmx[i]) for i in range(n)]
+            ds = np.concatenate([t[0] for t in tabs]); c0 = np.concatenate([t[1] for t in tabs]); bmax = np.concatenate([t[2] for t in tabs])
+            trk_of = np.arange(n, dtype=np.int32)
+            trk_off = (np.arange(n + 1) * N).astype(np.int32)
+        else:
+            ds, c0, bmax = self._tables(self._base['rho'], self._base['g'], self._base['velocityMax'])
+            trk_of = np.zeros(n, dtype=np.int32)
+            trk_off = np.array([0, N], dtype=np.int32)
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt, non_blocking=False)
+        h = self._ensure_handle()
+        out = h.solve_device(up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
+                             up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64),
+                             want_z=True, want_lam=want_multipliers)
+        res = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
+        res['wall'] = _time.perf_counter() - t_begin
+        scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
+        # reference ocp.py:361: cost in kWh (energy) or s (time)
+        res['cost'] = ((1e-6 / 3.6) * M if self.energyOptimal else 1.0) * res['obj'] * scale
+        res['totalMass'] = M
+        return res
+
+    # ------------------------------------------------------------------ reference call surface
+    def solve(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1):
+        if not isinstance(initialTime, (int, float)) or initialTime < 0:
+            raise ValueError("Initial time must be a positive number, not {}!".format(initialTime))
+        if not isinstance(terminalTime, (int, float)) or terminalTime <= 0:
+            raise ValueError("Terminal time must be a strictly positive number, not {}!".format(terminalTime))
+        res = self.solve_batch(terminalTime, initialTime, terminalVelocity, initialVelocity)
+        status = int(res['status'][0])
+        stats = {'Solver status': _cabi.STATUS_STRINGS.get(status, 'Internal_Error'), 'IP iterations': int(res['iters'][0]),
+                 'CPU time [s]': res['wall'], 'Cost': float(res['cost'][0])}
+        if status != 0:
+            print("Solver failed with status '{}'".format(stats['Solver status']))
+            return None, stats
+        print("Solver converged in {:4d} iterations.".format(stats['IP iterations']))
+        df = self.table_from_z(res['z'][0])
+        df = postProcessDataFrame(df, self.points, self.train)
+        return df, stats
+
+    def table_from_z(self, z):
+        "De-interleave one solution vector into the reference's raw table (reference ocp.py:376-405)."
+        N = self.numIntervals
+        stp = 4 + int(self.withPnBrake)
+        body = np.asarray(z[:N * stp]).reshape(N, stp)
+        tail = z[N * stp:N * stp + 2]
+        nanrow = lambda col: np.append(col, np.nan)
+        o = 1 + int(self.withPnBrake)
+        t = np.append(body[:, o + 1], tail[0])
+        b = np.append(body[:, o + 2], tail[1])
+        df = pd.DataFrame({'Time [s]': t, 'Position [m]': self.points.index.values}).set_index('Time [s]')
+        df['Velocity [m/s]'] = np.sqrt(b)
+        df['Force (el) [N]'] = nanrow(body[:, 0]) * self.totalMass
+        df['Force (pnb) [N]'] = nanrow(body[:, 1]) * self.totalMass if self.withPnBrake else np.zeros(N + 1)
+        df['Slacks'] = nanrow(body[:, o]) * self.totalMass
+        return df
+
+
+if __name__ == '__main__':
+    from mseetc.train import Train
+    from mseetc.track import Track
+
+    train = Train(config={'id': 'NL_Intercity_VIRM6', 'max deceleration': None, 'max acceleration': {'unit': 'm/s^2', 'value': 0.45}})
+    track = Track(config={'id': '00_var_speed_limit_100'})
+    solver = casadiSolver(train, track, {'numIntervals': 200, 'integrationMethod': 'RK', 'integrationOptions': {'numApproxSteps': 1}})
+    df, stats = solver.solve(1541)
+    if df is not None:
+        print("Objective value = {:.2f} {}".format(stats['Cost'], 'kWh' if solver.opts.energyOptimal else 's'))
+    else:
+        print("Solver failed!")

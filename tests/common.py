@@ -1,0 +1,68 @@
+"""Shared problem builders for the tests (oracle side and product side from the same JSON fixtures)."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'ms-eetc_b200')
+TRAIN_JSON = os.path.join(PKG, 'trains', 'NL_Intercity_VIRM6.json')
+FLAT_JSON = os.path.join(PKG, 'tracks', '00_var_speed_limit_100.json')
+SWISS_JSON = os.path.join(PKG, 'tracks', 'CH_StGallen_Wil.json')
+RK = dict(numSteps=1, numApproxSteps=1)
+
+
+def oracle_nlp(train, track, N, energy=True, vmin=1.0, **rk):
+    from oracle.problem import discretization_points
+    from oracle.nlp import ReferenceNLP
+    pos, g, v, c = discretization_points(track, N)
+    o = dict(RK); o.update(rk); o.update(energyOptimal=energy, minimumVelocity=vmin)
+    return ReferenceNLP(train, pos, g, v, c, track.length, o)
+
+
+def oracle_solve(nlp, T, t0=0.0, v0=1.0, vN=1.0, **kw):
+    from oracle import ipm
+    lbz, ubz, lbg, ubg = nlp.bounds(T, t0, v0, vN)
+    return ipm.solve(nlp, nlp.x0(T, t0), lbz, ubz, lbg, ubg, **kw)
+
+
+def virm6(**mut):
+    from oracle.problem import load_train
+    t = load_train(TRAIN_JSON)
+    for k, v in mut.items():
+        setattr(t, k, v)
+    return t
+
+
+def fig5_train():
+    "VIRM6 after the side effects of totalLossesFunction (reference efficiency.py:64-71), pn brake off."
+    t = virm6(forceMinPn=0)
+    t.powerMax = t.forceMax * (((55 - 20) / 150) * 140 + 20) / 3.6
+    t.powerMin = -t.powerMax
+    t.forceMin = -t.forceMax
+    t.velocityMax = 160 / 3.6
+    return t
+
+
+def fig10_train():
+    "reference simulations/figure10.py:14-22"
+    t = virm6(forceMinPn=0)
+    t.forceMin = -t.forceMax
+    t.powerMax = 3129277
+    t.powerMin = -t.powerMax
+    t.losses = ('static', 0.73, 0.73)
+    return t
+
+
+def active_set(nlp, z, T, t0=0.0, v0=1.0, vN=1.0, rtol=1e-6):
+    """Active variable bounds and rows at z.  Returns (active, ambiguous) boolean vectors over
+    [lower z, upper z, lower g, upper g]; 'ambiguous' marks slacks within a decade of the threshold."""
+    lbz, ubz, lbg, ubg = nlp.bounds(T, t0, v0, vN)
+    g = nlp.g(z)
+    slack = np.concatenate([z - lbz, ubz - z, g - lbg, ubg - g])
+    bound = np.concatenate([lbz, ubz, lbg, ubg])
+    scale = np.maximum(1.0, np.abs(np.where(np.isfinite(bound), bound, 1.0)))
+    thr = rtol * scale
+    with np.errstate(invalid='ignore'):
+        active = slack <= thr
+        ambiguous = (slack > thr / 10) & (slack < thr * 10)
+    return active, ambiguous

@@ -1,0 +1,224 @@
+"""Host layer (Train / Track / options / table) -- CPU only.  Includes the pure-Python assertions of the
+reference's testClothoidApproximation (unitTests/curvatureResistance/curvatureResistance.py:204-286)."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from common import FLAT_JSON, SWISS_JSON, TRAIN_JSON, ROOT
+
+
+def test_train_fields_match_oracle_restatement():
+    from mseetc.train import Train
+    from oracle.problem import load_train
+    a = Train(config={'id': 'NL_Intercity_VIRM6'})
+    b = load_train(TRAIN_JSON)
+    for k in ('mass', 'rho', 'velocityMax', 'forceMax', 'forceMin', 'forceMinPn', 'powerMax', 'powerMin', 'accMax', 'accMin',
+              'r0', 'r1', 'r2', 'etaTraction', 'etaRgBrake', 'g'):
+        assert getattr(a, k) == getattr(b, k), k
+    M = a.mass * a.rho
+    assert abs(M - 414460) < 1e-6 and abs(a.forceMax / M - 0.516093) < 1e-6      # SURVEY 8(a2) probed values
+    assert abs(a.r0 / M - 1.41244e-2) < 1e-7 and abs(a.r2 / M - 3.12696e-5) < 1e-10
+
+
+def test_train_overrides_and_errors():
+    from mseetc.train import Train
+    cfg = {'id': 'NL_Intercity_VIRM6', 'max deceleration': None, 'max acceleration': {'unit': 'm/s^2', 'value': 0.45}}
+    t = Train(config=cfg)
+    assert t.accMin is None and t.accMax == 0.45
+    assert 'id' not in cfg                      # consumed, like the reference (train.py:42)
+    with pytest.raises(ValueError):
+        Train(config={'id': 'NL_Intercity_VIRM6', 'nonsense': {'unit': 'm', 'value': 1}})
+    with pytest.raises(ValueError):
+        Train(config={'id': 'NL_Intercity_VIRM6', 'mass': 5})
+    with pytest.raises(ValueError):
+        Train(config='NL_Intercity_VIRM6')
+    t = Train(config={'id': 'NL_Intercity_VIRM6'})
+    t.forceMin = 0
+    t.forceMinPn = 0
+    with pytest.raises(ValueError):
+        t.checkFields()
+
+
+def test_grid_matches_oracle_and_survey_facts():
+    from mseetc.track import Track, computeDiscretizationPoints
+    from oracle.problem import load_track, discretization_points
+    for name, path in (('00_var_speed_limit_100', FLAT_JSON), ('CH_StGallen_Wil', SWISS_JSON)):
+        tk = Track(config={'id': name})
+        pts = computeDiscretizationPoints(tk, 300)
+        pos, g, v, c = discretization_points(load_track(path), 300)
+        assert len(pts) == 301
+        assert np.array_equal(pts.index.values, pos)
+        assert np.array_equal(pts['Gradient [permil]'].values, g)
+        assert np.array_equal(pts['Speed limit [m/s]'].values, v)
+        assert np.array_equal(pts['Curvature [1/m]'].values, c)
+    ds = np.diff(pts.index.values)
+    assert abs(ds.min() - 0.0713) < 1e-3 and abs(ds.max() - 217.32) < 1e-2
+    assert len(tk.mergeDataFrames()) == 165
+    with pytest.raises(ValueError):
+        computeDiscretizationPoints(tk, 100)     # fewer intervals than track sections
+
+
+def test_crop_and_reverse():
+    from mseetc.track import Track
+    tk = Track(config={'id': '00_var_speed_limit_100'})
+    tk.updateLimits(positionEnd=8500)
+    assert tk.length == 8500 and list(tk.speedLimits.index) == [0.0]
+    tk = Track(config={'id': 'CH_StGallen_Wil'})
+    L = tk.length
+    g0 = tk.gradients.copy()
+    tk.reverse().reverse()
+    assert np.allclose(tk.gradients.index.values, g0.index.values) and np.allclose(tk.gradients.values, g0.values)
+    assert abs(tk.length - L) < 1e-12
+    with pytest.raises(ValueError):
+        tk.updateLimits(positionStart=-1)
+
+
+def test_clothoid_approximation_reference_assertions():
+    from mseetc.track import Track
+    track = Track(config={'id': '00_var_speed_limit_100'})
+    t = copy.deepcopy(track)
+    r0, rf = 1000, 500
+    k0, kf = 1 / r0, 1 / rf
+    t.importCurvatureTuples(tuples=[[0.0, r0, rf]])
+    assert t.curvatures['Curvature [1/m]'].to_dict() == {0.0: (k0 + kf) / 2}
+    t.importCurvatureTuples(tuples=[[0.0, r0, rf]], clothoidSamplingInterval=t.length + 1)
+    assert t.curvatures['Curvature [1/m]'].to_dict() == {0.0: (k0 + kf) / 2}
+    ds = t.length / 4
+    t.importCurvatureTuples(tuples=[[0.0, r0, rf]], clothoidSamplingInterval=ds)
+    alpha = t.length / (kf - k0)
+    k1 = (k0 + (k0 + ds * 1 / alpha)) / 2
+    k2 = ((k0 + ds * 1 / alpha) + (k0 + ds * 2 / alpha)) / 2
+    k3 = ((k0 + ds * 2 / alpha) + (k0 + ds * 3 / alpha)) / 2
+    k4 = ((k0 + ds * 3 / alpha) + kf) / 2
+    assert t.curvatures['Curvature [1/m]'].to_dict() == {0.0: k1, ds: k2, 2 * ds: k3, 3 * ds: k4}
+    ds = t.length / 4 + 1
+    t.importCurvatureTuples(tuples=[[0.0, r0, rf]], clothoidSamplingInterval=ds)
+    k1 = (k0 + (k0 + ds * 1 / alpha)) / 2
+    k2 = ((k0 + ds * 1 / alpha) + (k0 + ds * 2 / alpha)) / 2
+    k3 = ((k0 + ds * 2 / alpha) + kf) / 2
+    assert t.curvatures['Curvature [1/m]'].to_dict() == {0.0: k1, ds: k2, 2 * ds: k3}
+    t.importCurvatureTuples(tuples=[[0.0, r0, "infinity"]])
+    assert t.curvatures['Curvature [1/m]'].to_dict() == {0.0: k0 / 2}
+    with pytest.raises(ValueError):
+        t.importCurvatureTuples(tuples=[[0.0, r0, rf]], clothoidSamplingInterval=-1)
+    with pytest.raises(ValueError):
+        t.importCurvatureTuples(tuples=[[0.0, 0.0, rf]])
+    with pytest.raises(ValueError):
+        t.importCurvatureTuples(tuples=[[500, r0, rf], [500, rf, 1 + rf]])
+    with pytest.raises(ValueError):
+        t.importCurvatureTuples(tuples=[[-1, r0, rf]])
+
+
+def test_options_validation():
+    from mseetc.ocp import OptionsCasadiSolver
+    import json
+    with open(os.path.join(ROOT, 'ms-eetc_b200', 'simulations', 'config.json')) as fh:
+        cfg = json.load(fh)
+    o = OptionsCasadiSolver(cfg)
+    assert o.numIntervals == 300 and o.maxIterations == 500 and o.energyOptimal is True and o.minimumVelocity == 1
+    assert o.integrationOptions.numSteps == 1 and o.integrationOptions.numApproxSteps == 1 and o.integrationOptions.order == 4
+    d = o.toDict()
+    assert d['integrationOptions'] == {'numApproxSteps': 1, 'numSteps': 1, 'order': 4}
+    for bad in ({'nonexistent': 1}, {'numIntervals': 0}, {'numIntervals': 2.5}, {'energyOptimal': 1}, {'minimumVelocity': 0},
+                {'integrationMethod': 'LINEAR'}, {'integrateLosses': 'yes'}, {'integrationOptions': {'order': 3}},
+                {'integrationOptions': {'numSteps': 0}}, {'integrationOptions': {'bogus': 0}}):
+        with pytest.raises(ValueError):
+            OptionsCasadiSolver(bad)
+
+
+def test_solver_construction_and_argument_errors_without_gpu():
+    "Construction (grid, scalars) needs no device; bad boundary times raise before the ABI is crossed."
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    s = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), Track(config={'id': '00_var_speed_limit_100'}),
+                     {'numIntervals': 300, 'integrationOptions': {'numApproxSteps': 1}})
+    assert len(s.points) == 301 and len(s.steps) == 300 and s.withPnBrake and s.withRgBrake and s.numIntervals == 300
+    assert abs(s.totalMass - 414460) < 1e-6 and abs(s.scalingFactorObjective - 3.6 / (1e-6 * 414460)) < 1e-9
+    with pytest.raises(ValueError):
+        s.solve(-5)
+    with pytest.raises(ValueError):
+        s.solve(100, initialTime=-1)
+    with pytest.raises(ValueError):
+        s.solve('abc')
+    with pytest.raises(ValueError):
+        casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), Track(config={'id': 'CH_StGallen_Wil'}), {'numIntervals': 100})
+
+
+def test_parameter_planes_match_oracle():
+    "The planes handed to the C ABI equal the oracle's independently derived specific-unit scalars."
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from mseetc import _cabi
+    from common import virm6, oracle_nlp
+    from oracle.problem import load_track
+    import harness
+    s = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), Track(config={'id': 'CH_StGallen_Wil'}),
+                     {'numIntervals': 300, 'integrationOptions': {'numApproxSteps': 1}})
+    P, M = s._planes(1, np.array([1242.0]), np.array([0.0]), np.array([1.0]), np.array([1.0]), {}, 0.125 / 0.875, 0.3)
+    nlp = oracle_nlp(virm6(), load_track(SWISS_JSON), 300)
+    p, ds, c0, bmax = harness.pack_instance(nlp, 1242.0)
+    assert np.allclose(P[:, 0], p, rtol=1e-14, atol=0)
+    d2, c2, b2 = s._tables(s._base['rho'], s._base['g'], s._base['velocityMax'])
+    assert np.array_equal(d2, ds) and np.allclose(c2, c0, rtol=1e-15) and np.array_equal(b2, bmax)
+
+
+def test_cabi_library_exports_every_declared_symbol(built_lib):
+    "No compute calls without a GPU: only that the library loads and exports what include/mseetc_b200.h declares."
+    lib = ctypes.CDLL(built_lib)
+    header = open(os.path.join(ROOT, 'include', 'mseetc_b200.h')).read()
+    names = set(re.findall(r'\b(mseetc_[a-z_]+)\s*\(', header))
+    assert {'mseetc_create', 'mseetc_destroy', 'mseetc_solve_batch', 'mseetc_workspace_bytes', 'mseetc_eval_interval',
+            'mseetc_last_error', 'mseetc_version'} <= names
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.mseetc_version.restype = ctypes.c_int
+    assert lib.mseetc_version() == 100
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    s = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), Track(config={'id': '00_var_speed_limit_100'}),
+                     {'numIntervals': 50, 'integrationOptions': {'numApproxSteps': 1}})
+    with pytest.raises(RuntimeError):
+        s.solve(1541)
+
+
+def test_postprocess_table_columns():
+    "Column set / order of the returned table (reference ocp.py:401-405, utils.py:230-334)."
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from mseetc.utils import postProcessDataFrame
+    from common import virm6, oracle_nlp, oracle_solve
+    from oracle.problem import load_track
+    N = 60
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    s = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), {'numIntervals': N, 'integrationOptions': {'numApproxSteps': 1}})
+    nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), N)
+    r = oracle_solve(nlp, 1541.0)
+    assert r.success
+    df = postProcessDataFrame(s.table_from_z(r.x), s.points, train)
+    assert df.index.name == 'Time [s]'
+    assert list(df.columns) == ['Position [m]', 'Velocity [m/s]', 'Force (el) [N]', 'Force (pnb) [N]', 'Slacks', 'Speed limit [m/s]',
+                                'Gradient [permil]', 'Curvature [1/m]', 'Force (acc) [N]', 'Force (rgb) [N]', 'Force [N]',
+                                'Max. Power [kW]', 'Min. Power [kW]', 'Losses [kWh]', 'Energy [kWh]', 'Energy (pnb) [kWh]',
+                                'Energy (kin) [kWh]', 'Acceleration [m/s^2]', 'Position - cvodes [m]', 'Velocity - cvodes [m/s]',
+                                'Error position [m]', 'Error velocity [m/s]']
+    assert np.isnan(df['Force (el) [N]'].values[-1]) and np.isnan(df['Slacks'].values[-1])
+    # at the optimum the epigraph rows are active: sum(Energy) = J - smoothing penalty
+    u = nlp.unpack(r.x)
+    pen = 1e-3 * np.sum(np.diff(u['Fel']) ** 2) / nlp.scale
+    assert abs(df['Energy [kWh]'].sum() - (r.f - pen)) / r.f < 1e-6
+    # the re-simulated trajectory stays close to the RK4 multiple-shooting one
+    assert df['Error velocity [m/s]'].max() < 0.5

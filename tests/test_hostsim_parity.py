@@ -1,0 +1,131 @@
+"""The solver's host/device headers, compiled with g++ (tests/hostsim), against the oracle -- CPU only.
+
+This exercises exactly the arithmetic the CUDA kernels run (interval sensitivities, stage-QP condensation,
+Riccati recursion, filter line search) on a machine without a GPU.  It is a test harness, not a product path."""
+import numpy as np
+import pytest
+
+import harness
+from common import FLAT_JSON, SWISS_JSON, fig5_train, fig10_train, oracle_nlp, oracle_solve, virm6
+
+
+@pytest.fixture(scope='module')
+def lib():
+    return harness.build()
+
+
+def test_interval_sensitivities_match_sympy(lib):
+    "Hand-written forward-mode jets of the RK4 / ERK4+ step vs sympy derivatives of the reference formulas."
+    from oracle.nlp import _stage_functions
+    rng = np.random.default_rng(3)
+    n = 200
+    b0 = rng.uniform(1.0, 1600.0, n); F = rng.uniform(-0.6, 0.5, n); ds = rng.uniform(0.05, 400.0, n)
+    F = np.maximum(F, (2.0 - b0) / (2 * ds) + 0.3)                 # keep every RK stage value of b positive
+    c0 = rng.uniform(-0.2, 0.2, n)
+    sr = (1.41244e-2, 1.78932e-4, 3.12696e-5)
+    inp = np.ascontiguousarray(np.stack([b0, F, ds, c0, np.full(n, sr[0]), np.full(n, sr[1]), np.full(n, sr[2])]))
+    for numSteps, numApprox in ((1, 1), (1, 2), (1, 0), (2, 0)):     # sympy gets slow beyond two nested RK4 steps
+        out = np.zeros((12, n))
+        lib.hostsim_eval_interval(n, numSteps, numApprox, inp.ctypes.data, out.ctypes.data)
+        names, fn = _stage_functions(False, numSteps, numApprox, 'none')
+        res = fn(b0, F, np.zeros(n), np.ones(n), ds, c0, *sr, 0.0, 0.0)
+        per = 15
+        ct, cb = names.index('ct') * per, names.index('cb') * per
+        # sympy ordering per row: value, grad(b0,Fel,Fpb,b1), hess pairs (00,01,02,03,11,12,13,22,23,33)
+        ref_tau = [-np.asarray(res[ct + i]) * np.ones(n) for i in (0, 1, 2, 5, 6, 9)]
+        ref_phi = [-np.asarray(res[cb + i]) * np.ones(n) for i in (0, 1, 2, 5, 6, 9)]
+        ref_phi[0] = ref_phi[0] + 1.0                                # the row is b1 - phi with b1 = 1
+        for i in range(6):
+            scale = np.maximum(1e-12, np.abs(ref_tau[i]))
+            assert np.max(np.abs(out[i] - ref_tau[i]) / scale) < 1e-9, (numSteps, numApprox, 'tau', i)
+            scale = np.maximum(1e-12, np.abs(ref_phi[i]))
+            assert np.max(np.abs(out[6 + i] - ref_phi[i]) / scale) < 1e-9, (numSteps, numApprox, 'phi', i)
+
+
+CASES = [
+    ('config1 flat energy', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict()),
+    ('swiss energy', lambda: virm6(), SWISS_JSON, None, 300, 1242.0, True, 1.0, 1.0, dict()),
+    ('swiss time-optimal', lambda: virm6(), SWISS_JSON, None, 300, 2000.0, False, 1.0, 1.0, dict()),
+    ('figure10 no pn brake', fig10_train, FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict()),
+    ('figure5 time-optimal crop', lambda: (lambda t: (setattr(t, 'losses', ('none',)), t)[1])(fig5_train()), FLAT_JSON, 8500, 300,
+     354.0, False, 1.0, 100 / 3.6, dict()),
+    ('unit test energy no power rows', lambda: virm6(forceMinPn=0, powerMax=None, powerMin=None, losses=('none',)), FLAT_JSON, 3475,
+     300, 200.0, True, 1.0, 1.0, dict()),
+    ('rk4 on both states', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict(numApproxSteps=0)),
+    ('two rk steps on both states', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numSteps=2, numApproxSteps=0)),
+    ('two time sub-points', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numSteps=1, numApproxSteps=2)),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_emulated_device_solver_matches_oracle(lib, case):
+    from oracle.problem import load_track
+    name, mk, path, crop, N, T, energy, v0, vN, rk = case
+    track = load_track(path)
+    if crop:
+        track.crop(positionEnd=crop)
+    nlp = oracle_nlp(mk(), track, N, energy=energy, **rk)
+    ref = oracle_solve(nlp, T, v0=v0, vN=vN)
+    assert ref.success, ref.status
+    out = harness.solve([nlp], [T], v0=v0, vN=vN, lib=lib)
+    assert out['status'][0] == 0
+    assert out['kkt'][0] <= 1e-8
+    assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)                       # optimal energy / time: 1e-6 relative
+    z, zr = out['z'][0], ref.x
+    for idx, scale in ((nlp.iB, nlp.limit.max() ** 2), (nlp.iT, T), (nlp.iFel, nlp.forceMax)):
+        assert np.max(np.abs(z[idx] - zr[idx])) <= 1e-4 * scale                  # trajectories: 1e-4 relative to scale
+    # KKT residual of the emulated solution on the ORACLE's formulation, with the emulated multipliers
+    lam = out['lam'][0]
+    J = nlp.jac(z)
+    lbz, ubz, _, _ = nlp.bounds(T, 0.0, v0, vN)
+    free = lbz != ubz
+    r = (nlp.grad_f(z) + J.T @ lam)[free]           # = zL - zU of an exact KKT point
+    sl, su = (z - lbz)[free], (ubz - z)[free]
+    with np.errstate(invalid='ignore'):
+        comp = np.where(r > 0, r * sl, -r * np.where(np.isfinite(su), su, 1.0))
+    assert np.max(comp) < 1e-7                      # stationarity + complementarity on the reference formulation
+    g = nlp.g(z)
+    _, _, lbg, ubg = nlp.bounds(T, 0.0, v0, vN)
+    assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7          # primal feasibility of every reference row
+    with np.errstate(invalid='ignore'):
+        compg = np.where(lam < 0, -lam * (g - lbg), lam * np.where(np.isfinite(ubg), ubg - g, 1.0))
+    eq = lbg == ubg
+    assert np.max(compg[~eq]) < 1e-7                # row multipliers: sign + complementarity
+    a0, amb0 = __import__('common').active_set(nlp, z, T, 0.0, v0, vN)
+    a1, amb1 = __import__('common').active_set(nlp, zr, T, 0.0, v0, vN)
+    sure = ~(amb0 | amb1)
+    assert np.array_equal(a0[sure], a1[sure])                                    # same constraint set active
+
+
+def test_infeasible_trip_time_is_not_reported_as_solved(lib):
+    from oracle.problem import load_track
+    nlp = oracle_nlp(virm6(), load_track(SWISS_JSON), 300)
+    out = harness.solve([nlp], [1000.0], lib=lib, max_iter=200)      # Tmin is 1035.55 s
+    assert out['status'][0] != 0
+
+
+def test_batch_of_mixed_instances_is_independent_and_deterministic(lib):
+    "Instances in one batch do not influence each other; results are bitwise reproducible."
+    from oracle.problem import load_track
+    track = load_track(SWISS_JSON)
+    nlp = oracle_nlp(virm6(), track, 300)
+    Ts = [1242.0, 1100.0, 1300.0, 990.0, 1242.0]
+    a = harness.solve([nlp] * 5, Ts, lib=lib, max_iter=120)
+    b = harness.solve([nlp] * 5, Ts, lib=lib, max_iter=120)
+    assert np.array_equal(a['z'], b['z']) and np.array_equal(a['obj'], b['obj'])
+    assert np.array_equal(a['z'][0], a['z'][4])                     # same instance, different slot
+    single = harness.solve([nlp], [1100.0], lib=lib, max_iter=120)
+    assert np.array_equal(single['z'][0], a['z'][1])
+    assert list(a['status'][[0, 1, 2, 4]]) == [0, 0, 0, 0] and a['status'][3] != 0
+    assert a['obj'][2] < a['obj'][0] < a['obj'][1]                  # more time, less energy
+
+
+def test_mixed_interval_counts_in_one_batch(lib):
+    from oracle.problem import load_track
+    track = load_track(FLAT_JSON)
+    nlps = [oracle_nlp(virm6(), track, N) for N in (100, 300, 200)]
+    out = harness.solve(nlps, [1541.0] * 3, lib=lib)
+    assert list(out['status']) == [0, 0, 0]
+    for i, nlp in enumerate(nlps):
+        ref = oracle_solve(nlp, 1541.0)
+        assert abs(out['obj'][i] - ref.f) <= 1e-6 * ref.f

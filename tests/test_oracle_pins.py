@@ -1,0 +1,123 @@
+"""Pins of the CPU oracle against every known answer the reference holds for this path."""
+import os
+
+import numpy as np
+import pytest
+
+from common import FLAT_JSON, SWISS_JSON, fig5_train, fig10_train, oracle_nlp, oracle_solve, virm6
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_min_time_pin_figure5():
+    """reference simulations/figure5.py:96  minimumTime = 272.4726 s (8.5 km crop, v0 = 1, vN = 100 km/h)."""
+    from oracle.problem import load_track
+    train = fig5_train()
+    train.losses = ('none',)
+    track = load_track(FLAT_JSON).crop(positionEnd=8500)
+    nlp = oracle_nlp(train, track, 300, energy=False)
+    r = oracle_solve(nlp, 354.0, v0=1.0, vN=100 / 3.6)
+    assert r.success and r.kkt <= 1e-8
+    tN = r.x[nlp.iT[-1]]
+    assert abs(tN - 272.4726) < 1e-4          # 7-digit constant; we get 272.472544 (2e-7 relative)
+    # independent of the upper bound on the trip time
+    r2 = oracle_solve(nlp, 600.0, v0=1.0, vN=100 / 3.6)
+    assert r2.success and abs(r2.x[nlp.iT[-1]] - tN) < 1e-6
+
+
+def test_gpops_energy_pin_figure10():
+    """gpops/00_var_speed_limit_100_GPOPS{I,II}.csv: 440.1414723 / 440.1406149 kWh (continuous-time optimum of
+    the figure-10 problem).  The N-interval multiple-shooting optimum converges to it at O(1/N)."""
+    import csv
+    from oracle.problem import load_track
+    energies = []
+    for name in ('00_var_speed_limit_100_GPOPSI.csv', '00_var_speed_limit_100_GPOPSII.csv'):
+        with open(os.path.join(GOLDEN, name)) as fh:
+            rows = list(csv.reader(fh))
+        energies.append(float(rows[1][6]))
+    assert energies == [440.1414723, 440.1406149]
+    track = load_track(FLAT_JSON)
+    gaps = []
+    for N in (150, 300, 600):
+        r = oracle_solve(oracle_nlp(fig10_train(), track, N), 1541.0)
+        assert r.success
+        gaps.append(r.f - energies[1])
+    assert 0 < gaps[2] < gaps[1] < gaps[0]
+    assert gaps[1] / energies[1] < 3e-3        # 0.21 % at N = 300
+    assert gaps[2] < 0.6 * gaps[1]            # first-order convergence towards the GPOPS optimum
+    # velocity profile against the GPOPS-II trajectory
+    with open(os.path.join(GOLDEN, '00_var_speed_limit_100_GPOPSII.csv')) as fh:
+        rows = list(csv.reader(fh))[1:]
+    gp = np.array([[float(x) for x in row[:3]] for row in rows])
+    nlp = oracle_nlp(fig10_train(), track, 600)
+    r = oracle_solve(nlp, 1541.0)
+    v = np.sqrt(np.interp(gp[:, 1], nlp.pos, r.x[nlp.iB]))   # v^2 is close to piecewise linear in position
+    assert np.abs(v - gp[:, 2]).max() < 0.8   # m/s, discretisation-level agreement
+    assert np.abs(v - gp[:, 2]).mean() < 0.1
+
+
+def test_ode_constants_figure4():
+    """reference simulations/figure4.py:22-23: braking at -0.5 N/kg over 100 m from 36.61894 / 37.95880 km/h ends
+    at 1 / 10 km/h (pins the ODE restatement, train.py:251-259)."""
+    from scipy.integrate import solve_ivp
+    t = virm6()
+    M = t.mass * t.rho
+    sr = (t.r0 / M, t.r1 / M, t.r2 / M)
+    for v0_kmh, vend_kmh in ((36.61894, 1.0), (37.95880, 10.0)):
+        rhs = lambda s, b: 2 * (-0.5 - (sr[0] + sr[1] * np.sqrt(b) + sr[2] * b))
+        sol = solve_ivp(rhs, (0, 100), [(v0_kmh / 3.6) ** 2], rtol=1e-12, atol=1e-14)
+        assert abs(np.sqrt(sol.y[0, -1]) * 3.6 - vend_kmh) < 2e-3
+
+
+def test_erk4_time_rule_matches_sympy_and_fine_integration():
+    "ERK4+ (train.py:324-344): b by one RK4 step, t by the average-speed rule; compare with a fine reference."
+    from scipy.integrate import solve_ivp
+    from oracle.nlp import _stage_functions
+    t = virm6()
+    M = t.mass * t.rho
+    sr = (t.r0 / M, t.r1 / M, t.r2 / M)
+    names, fn = _stage_functions(True, 1, 1, 'static')
+    b0, F, ds, c0 = (40 / 3.6) ** 2, 0.3, 150.0, -0.015 * 9.81 / 1.06
+    out = fn(b0, F, 0.0, 200.0, ds, c0, *sr, 0.1, 0.3)
+    per = 15
+    tau = -out[names.index('ct') * per]
+    phib = 200.0 - out[names.index('cb') * per]
+    sol = solve_ivp(lambda s, y: [1 / np.sqrt(y[1]), 2 * (F - (sr[0] + sr[1] * np.sqrt(y[1]) + sr[2] * y[1]) - c0)],
+                    (0, ds), [0.0, b0], rtol=1e-12, atol=1e-14)
+    assert abs(phib - sol.y[1, -1]) < 1e-3      # one RK4 step over 150 m
+    assert abs(tau - sol.y[0, -1]) < 5e-3      # the trapezoid-in-1/v rule is a low-order approximation
+
+
+def test_unit_test_properties_curvature():
+    """reference unitTests/curvatureResistance/curvatureResistance.py:94-201 re-expressed on the oracle."""
+    from oracle.problem import load_track
+    g, rho, K = 9.81, 1.06, 1 / 300
+    fcurv = g * 0.5 * K / ((1 - 30 * K) * rho)
+    # minimum-time: shifting the force limits by the curve resistance reproduces the straight-track speed profile
+    tr = virm6(forceMinPn=0, powerMax=None, powerMin=None)
+    tr.losses = ('none',)
+    straight = load_track(FLAT_JSON).crop(positionEnd=3475)
+    curved = load_track(FLAT_JSON, constant_curvature=K).crop(positionEnd=3475)
+    nlp0 = oracle_nlp(tr, straight, 300, energy=False)
+    r0 = oracle_solve(nlp0, 180.0)
+    tr2 = tr.copy()
+    tr2.forceMax = tr.forceMax + fcurv * tr.mass * tr.rho
+    tr2.forceMin = tr.forceMin + fcurv * tr.mass * tr.rho
+    nlp1 = oracle_nlp(tr2, curved, 300, energy=False)
+    r1 = oracle_solve(nlp1, 180.0)
+    assert r0.success and r1.success
+    v0, v1 = np.sqrt(r0.x[nlp0.iB]), np.sqrt(r1.x[nlp1.iB])
+    assert np.all(np.abs((v0 - v1) / v0) <= 1e-3)
+    # minimum-energy: extra mechanical energy on the curved track = curve-resistance work (within 5 %)
+    tr = virm6(forceMinPn=0)
+    work = fcurv * tr.rho * tr.mass * 3475 / 3.6e6
+    for losses in (('none',), ('static', 0.73, 0.73)):
+        tr.losses = losses
+        e = []
+        for track in (straight, curved):
+            nlp = oracle_nlp(tr, track, 300)
+            r = oracle_solve(nlp, 200.0)
+            assert r.success
+            u = nlp.unpack(r.x)
+            e.append(np.sum(nlp.ds * u['Fel']) * nlp.M / 3.6e6)    # mechanical energy at the wheel [kWh]
+        assert abs((e[1] - e[0]) - work) / work <= 5e-2
