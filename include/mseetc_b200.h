@@ -93,6 +93,10 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);
  *   track_offset_dev  [n_tracks+1]   interval offsets (CSR) into ds/c0; node arrays use offset+track index
  *   ds_dev, c0_dev    [sum N_j]      interval length; g*grad/rho + curvRes/rho   (ocp.py:125, train.py:252-254)
  *   bmax_dev          [sum (N_j+1)]  min(limit_i, vmax, limit_{i-1})^2 at the nodes (ocp.py:266-272)
+ *   tmin_dev          [n_instances] or NULL: known minimum trip duration of each instance (from a time-optimal
+ *                     solve of the same problem).  Instances with T_END - T_START below it are infeasible
+ *                     (terminalTime is an upper bound on t_N, ocp.py:260-261) and are reported as
+ *                     MSEETC_INFEASIBLE_PROBLEM_DETECTED without iterating.
  * outputs (device, caller-owned; each may be NULL except status_out):
  *   z_out_dev    [n_instances * (n_intervals_max*(3+nu)+2)]  reference variable order (ocp.py:166-181,248-249)
  *   lam_g_out_dev[n_instances * n_intervals_max*rows]        multipliers of g in reference row order
@@ -101,7 +105,7 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);
 int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
                        const double* params_dev, const int32_t* n_intervals_dev,
                        const int32_t* track_of_inst_dev, const int32_t* track_offset_dev,
-                       const double* ds_dev, const double* c0_dev, const double* bmax_dev,
+                       const double* ds_dev, const double* c0_dev, const double* bmax_dev, const double* tmin_dev,
                        double* z_out_dev, double* lam_g_out_dev, double* obj_out_dev, double* kkt_out_dev,
                        int32_t* iters_out_dev, int32_t* status_out_dev,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
@@ -109,6 +113,17 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
 /* number of solver ticks (lock-step rounds) and kernel launches of the last mseetc_solve_batch on h */
 int mseetc_last_ticks(mseetc_handle h);
 int mseetc_last_launches(mseetc_handle h);
+
+/* Per-kernel accounting of the last mseetc_solve_batch (measurement support for bench.py):
+ *   kernel classes: 0 cell_trial, 1 inst_decide, 2 cell_eval, 3 inst_step, 4 setup/init/extract
+ *   ms_out[5]        summed device time per class, from cudaEvent pairs recorded on the launch stream
+ *                    (only when profiling was switched on with mseetc_set_profiling; else zeros)
+ *   launches_out[5]  launches per class
+ *   cells_out[5]     (interval, instance) cells actually processed per class (idle/finished instances excluded)
+ *   mseetc_bytes_per_cell(h, cls): algorithmic HBM bytes one processed cell costs in that class */
+int mseetc_set_profiling(mseetc_handle h, int on);
+int mseetc_last_profile(mseetc_handle h, double* ms_out, int32_t* launches_out, int64_t* cells_out);
+double mseetc_bytes_per_cell(mseetc_handle h, int kernel_class);
 
 /* One shooting interval for n points (train.py:347-364): tau = t1 - t0 and b1, with first and second
  * sensitivities w.r.t. (b0, F).  in_dev planes [7*n]: b0, F, ds, c0, sr0, sr1, sr2; out_dev planes [12*n]:

@@ -35,6 +35,14 @@ MS_HD void finish(const Ctx& c, int s, int status) {
 #endif
 }
 
+MS_HD void count_cells(const Ctx& c, int which, int n) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(c.cnt + which, (unsigned long long)n);
+#else
+    c.cnt[which] += (unsigned long long)n;
+#endif
+}
+
 MS_HD double relaxL(double L) { return L - 1e-8 * fmax(1.0, fabs(L)); }   // IPOPT bound_relax_factor
 MS_HD double relaxU(double U) { return U + 1e-8 * fmax(1.0, fabs(U)); }
 
@@ -314,6 +322,7 @@ MS_HD void inst_decide(const Ctx& c, int s) {
         }
     }
     c.I(SI_TICKS, s) += 1;
+    count_cells(c, 0, N + 1);
     if (ok) {
         if (!armijo) {                                    // augment the filter (eq. 22)
             int n = nf;
@@ -858,6 +867,7 @@ MS_HD void inst_step(const Ctx& c, int s) {
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
     const int N = c.I(SI_N_INT, s);
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+    count_cells(c, 1, N + 1);
     double th = 0.0, fo = 0.0, slog = 0.0, sdamp = 0.0, dinf = 0.0, pinf = 0.0, cmin = 1e300, cmax = 0.0, zsum = 0.0, ysum = 0.0;
     double cnPrev = 0.0, ytPrev = 0.0;
     for (int k = 0; k <= N; ++k) {
@@ -911,6 +921,7 @@ MS_HD void inst_step(const Ctx& c, int s) {
     const double dlast = c.D(SD_DELTA_LAST, s);
     bool ok = false;
     for (int tries = 0; tries < 40; ++tries) {
+        count_cells(c, 2, N);
         if (riccati_backward(c, s, N, mu, delta)) { ok = true; break; }
         c.I(SI_NREG, s) += 1;
         if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
@@ -920,6 +931,7 @@ MS_HD void inst_step(const Ctx& c, int s) {
     if (!ok) { finish(c, s, ST_STEP_FAILED); return; }
     if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
     Ftb f;
+    count_cells(c, 3, N);
     riccati_forward(c, s, N, mu, tauF, delta, f);
     if (!isfinite(f.gphid) || !isfinite(f.aP)) { finish(c, s, ST_STEP_FAILED); return; }
     double amin;

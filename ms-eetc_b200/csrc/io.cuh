@@ -13,6 +13,7 @@ struct BatchIO {
     const double* ds;
     const double* c0;
     const double* bmax;
+    const double* tmin;
     double* z_out;
     double* lam_out;
     double* obj;
@@ -27,6 +28,8 @@ MS_HD void inst_setup(const Ctx& c, const BatchIO& io, int s) {
     for (int f = 0; f < PAR_N; ++f) c.P(f, s) = io.params[(size_t)f * g.nInst + s];
     c.I(SI_N_INT, s) = io.nint[s];
     inst_init(c, s);
+    // screening with a known minimum trip duration: terminalTime is an upper bound on t_N (ocp.py:260-261)
+    if (io.tmin && (c.P(P_T, s) - c.P(P_T0, s)) < io.tmin[s] * (1.0 - 1e-9)) finish(c, s, ST_INFEASIBLE);
 }
 
 MS_HD void cell_setup(const Ctx& c, const BatchIO& io, int k, int s) {
@@ -112,7 +115,7 @@ inline WsPlan plan_workspace(int S, int NK) {
     p.off_par = o; o = al(o + sizeof(double) * (size_t)PAR_N * S);
     p.off_sd = o; o = al(o + sizeof(double) * (size_t)SD_N * S);
     p.off_si = o; o = al(o + sizeof(int) * (size_t)SI_N * S);
-    p.off_done = o; o = al(o + 256);
+    p.off_done = o; o = al(o + 256);   // int done; then 4 x uint64 cell counters at +64
     p.total = o;
     return p;
 }

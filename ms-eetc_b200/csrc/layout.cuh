@@ -106,6 +106,7 @@ struct Ctx {
     double* sd;    // SD_N planes of S
     int* si;       // SI_N planes of S
     int* done;     // number of finished instances (device counter polled by the host loop)
+    unsigned long long* cnt;   // [4] processed cells: trial, eval, riccati backward, riccati forward
 
     MS_HD double& W(int field, int k, int slot) const {
         return ws[((size_t)field * cfg.NK + k) * cfg.S + slot];

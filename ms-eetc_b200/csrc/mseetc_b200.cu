@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/mseetc_b200.h"
 #include "io.cuh"
@@ -54,11 +55,18 @@ __global__ void k_eval_interval(int n, int numSteps, int numApprox, const double
 
 }  // namespace
 
+enum { CLS_TRIAL = 0, CLS_DECIDE, CLS_EVAL, CLS_STEP, CLS_MISC, NCLS };
+
 struct mseetc_solver {
     mseetc_problem prob;
-    int* done_host;     // pinned
+    int* done_host;     // pinned: [0] done counter, [16..] 4 x uint64 cell counters
     int last_ticks;
     int last_launches;
+    int profiling;
+    double ms[NCLS];
+    int launches[NCLS];
+    long long cells[NCLS];
+    std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
 };
 
 extern "C" {
@@ -86,7 +94,9 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->prob = *p;
     h->last_ticks = 0;
     h->last_launches = 0;
-    cudaError_t e = cudaHostAlloc((void**)&h->done_host, sizeof(int), cudaHostAllocDefault);
+    h->profiling = 0;
+    for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
+    cudaError_t e = cudaHostAlloc((void**)&h->done_host, 256, cudaHostAllocDefault);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
     *out = h;
     return 0;
@@ -95,6 +105,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
 int mseetc_destroy(mseetc_handle h) {
     if (!h) return 0;
     cudaFreeHost(h->done_host);
+    for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
     delete h;
     return 0;
 }
@@ -107,8 +118,44 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n) {
 int mseetc_last_ticks(mseetc_handle h) { return h ? h->last_ticks : -1; }
 int mseetc_last_launches(mseetc_handle h) { return h ? h->last_launches : -1; }
 
+int mseetc_set_profiling(mseetc_handle h, int on) {
+    if (!h) return fail(-1, "mseetc_set_profiling: null handle");
+    h->profiling = on ? 1 : 0;
+    return 0;
+}
+
+int mseetc_last_profile(mseetc_handle h, double* ms_out, int32_t* launches_out, int64_t* cells_out) {
+    if (!h) return fail(-1, "mseetc_last_profile: null handle");
+    for (int i = 0; i < NCLS; ++i) {
+        if (ms_out) ms_out[i] = h->ms[i];
+        if (launches_out) launches_out[i] = h->launches[i];
+        if (cells_out) cells_out[i] = h->cells[i];
+    }
+    return 0;
+}
+
+// Algorithmic HBM traffic of one processed (interval, instance) cell, in bytes (FP64 planes read + written;
+// per-instance scalars and parameters are warp-uniform broadcasts and not counted).  Derivation in DESIGN.md.
+double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
+    if (!h) return 0.0;
+    const mseetc_problem& p = h->prob;
+    const int rows = (p.with_power_rows ? 2 : 0) + 1 + (p.energy_optimal ? 2 : 0);         // inequality rows
+    const int nz = 2 + (p.with_pn_brake ? 2 : 0) + 1 + 4 + (p.with_power_rows ? 4 : 0) + 2 + (p.energy_optimal ? 2 : 0);
+    const int prim = 4 + (p.with_pn_brake ? 1 : 0);
+    const int iter = prim + rows + 2 + rows + nz;           // x, w, y, yd, z
+    const int step = prim + rows + 2 + rows;
+    switch (cls) {
+        case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
+        case CLS_DECIDE: return 8.0 * 4;
+        case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13));
+        case CLS_STEP:   return 8.0 * (14 + (13 + 6 + 10) + RIC_N + (12 + 9) + (6 + 7 + 11 + rows) + iter + 2 + step);
+        default:         return 0.0;
+    }
+}
+
 int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const int32_t* nint, const int32_t* trk_of,
-                       const int32_t* trk_off, const double* ds, const double* c0, const double* bmax, double* z_out,
+                       const int32_t* trk_off, const double* ds, const double* c0, const double* bmax, const double* tmin,
+                       double* z_out,
                        double* lam_out, double* obj, double* kkt, int32_t* iters, int32_t* status, void* workspace,
                        size_t ws_bytes, void* cuda_stream) {
     if (!h) return fail(-1, "mseetc_solve_batch: null handle");
@@ -136,7 +183,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.sd = (double*)(base + plan.off_sd);
     c.si = (int*)(base + plan.off_si);
     c.done = (int*)(base + plan.off_done);
-    BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, z_out, lam_out, obj, kkt, iters, status};
+    c.cnt = (unsigned long long*)(base + plan.off_done + 64);
+    BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
     const size_t cellThreads = (size_t)g.NK * g.S;
     const unsigned cgrid = (unsigned)((cellThreads + 127) / 128);
@@ -144,20 +192,33 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const unsigned igrid = (unsigned)((g.S + ib - 1) / ib);
     int launches = 0;
     cudaError_t e;
+    for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
+    std::vector<int> evClass;   // class of each recorded event pair
+    auto begin = [&](int cls) {
+        h->launches[cls] += 1;
+        ++launches;
+        if (!h->profiling) return;
+        const size_t need = 2 * (evClass.size() + 1);
+        while (h->ev.size() < need) { cudaEvent_t x; cudaEventCreate(&x); h->ev.push_back(x); }
+        cudaEventRecord(h->ev[2 * evClass.size()], st);
+    };
+    auto end = [&](int cls) {
+        if (!h->profiling) return;
+        cudaEventRecord(h->ev[2 * evClass.size() + 1], st);
+        evClass.push_back(cls);
+    };
     e = cudaMemsetAsync(c.done, 0, 256, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     e = cudaMemsetAsync(c.si, 0, sizeof(int) * (size_t)SI_N * g.S, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    k_insts<OP_SETUP><<<igrid, ib, 0, st>>>(c, io);
-    k_cells<OP_SETUP><<<cgrid, 128, 0, st>>>(c, io);
-    k_cells<OP_INIT><<<cgrid, 128, 0, st>>>(c, io);
-    launches += 3;
+    begin(CLS_MISC); k_insts<OP_SETUP><<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
+    begin(CLS_MISC); k_cells<OP_SETUP><<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    begin(CLS_MISC); k_cells<OP_INIT><<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
     for (;;) {
-        k_cells<OP_EVAL><<<cgrid, 128, 0, st>>>(c, io);
-        k_insts<OP_STEP><<<igrid, ib, 0, st>>>(c, io);
-        launches += 2;
+        begin(CLS_EVAL); k_cells<OP_EVAL><<<cgrid, 128, 0, st>>>(c, io); end(CLS_EVAL);
+        begin(CLS_STEP); k_insts<OP_STEP><<<igrid, ib, 0, st>>>(c, io); end(CLS_STEP);
         if (tick >= maxTicks) break;
         if (tick >= 16 && (tick & 3) == 0) {
             e = cudaMemcpyAsync(h->done_host, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -166,17 +227,30 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
             if (*h->done_host >= n) break;
         }
-        k_cells<OP_TRIAL><<<cgrid, 128, 0, st>>>(c, io);
-        k_insts<OP_DECIDE><<<igrid, ib, 0, st>>>(c, io);
-        launches += 2;
+        begin(CLS_TRIAL); k_cells<OP_TRIAL><<<cgrid, 128, 0, st>>>(c, io); end(CLS_TRIAL);
+        begin(CLS_DECIDE); k_insts<OP_DECIDE><<<igrid, ib, 0, st>>>(c, io); end(CLS_DECIDE);
         ++tick;
     }
-    k_cells<OP_EXTRACT><<<cgrid, 128, 0, st>>>(c, io);
-    launches += 1;
+    begin(CLS_MISC); k_cells<OP_EXTRACT><<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    e = cudaMemcpyAsync(h->done_host, c.done, 128, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(counters)");
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
+    {
+        const unsigned long long* cnt = (const unsigned long long*)((const char*)h->done_host + 64);
+        h->cells[CLS_TRIAL] = (long long)cnt[0];
+        h->cells[CLS_DECIDE] = (long long)cnt[0];
+        h->cells[CLS_EVAL] = (long long)cnt[1];
+        h->cells[CLS_STEP] = (long long)cnt[1];
+        h->cells[CLS_MISC] = 0;
+    }
+    for (size_t i = 0; i < evClass.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]);
+        h->ms[evClass[i]] += ms;
+    }
     h->last_ticks = tick;
     h->last_launches = launches;
     return 0;

@@ -51,9 +51,13 @@ def lib():
     L.mseetc_destroy.argtypes = [vp]
     L.mseetc_workspace_bytes.argtypes = [vp, i32]
     L.mseetc_workspace_bytes.restype = sz
-    L.mseetc_solve_batch.argtypes = [vp, i32] + [vp] * 13 + [vp, sz, vp]
+    L.mseetc_solve_batch.argtypes = [vp, i32] + [vp] * 14 + [vp, sz, vp]
     L.mseetc_last_ticks.argtypes = [vp]
     L.mseetc_last_launches.argtypes = [vp]
+    L.mseetc_set_profiling.argtypes = [vp, ctypes.c_int]
+    L.mseetc_last_profile.argtypes = [vp, vp, vp, vp]
+    L.mseetc_bytes_per_cell.argtypes = [vp, ctypes.c_int]
+    L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
     _lib = L
     return L
@@ -103,14 +107,14 @@ class Handle:
             self._ws = torch.empty(need, dtype=torch.uint8, device=device)
         return self._ws, need
 
-    def solve_device(self, params, nint, trk_of, trk_off, ds, c0, bmax, want_z=True, want_lam=False):
+    def solve_device(self, params, nint, trk_of, trk_off, ds, c0, bmax, want_z=True, want_lam=False, tmin=None, out=None):
         """All arguments are torch CUDA tensors (float64 / int32).  Returns dict of device tensors."""
         torch = _torch_cuda()
         n = int(nint.numel())
         dev = params.device
         Nmax = self.problem.n_intervals_max
         stp = 3 + self.nu
-        out = dict(
+        out = out if out is not None else dict(
             z=torch.zeros((n, Nmax * stp + 2), dtype=torch.float64, device=dev) if want_z else None,
             lam=torch.zeros((n, Nmax * self.rows), dtype=torch.float64, device=dev) if want_lam else None,
             obj=torch.empty(n, dtype=torch.float64, device=dev),
@@ -121,12 +125,29 @@ class Handle:
         ws, need = self.workspace(n, dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib().mseetc_solve_batch(self._h, n, _ptr(params), _ptr(nint), _ptr(trk_of), _ptr(trk_off), _ptr(ds), _ptr(c0),
-                                      _ptr(bmax), _ptr(out['z']), _ptr(out['lam']), _ptr(out['obj']), _ptr(out['kkt']),
+                                      _ptr(bmax), _ptr(tmin), _ptr(out['z']), _ptr(out['lam']), _ptr(out['obj']), _ptr(out['kkt']),
                                       _ptr(out['iters']), _ptr(out['status']), _ptr(ws), need, ctypes.c_void_p(stream))
         _check(rc, 'mseetc_solve_batch')
         out['ticks'] = lib().mseetc_last_ticks(self._h)
         out['launches'] = lib().mseetc_last_launches(self._h)
         return out
+
+
+KERNEL_CLASSES = ('cell_trial', 'inst_decide', 'cell_eval', 'inst_step', 'misc')
+
+
+def set_profiling(handle, on):
+    _check(lib().mseetc_set_profiling(handle._h, int(bool(on))), 'mseetc_set_profiling')
+
+
+def last_profile(handle):
+    "Per-kernel-class (ms, launches, cells, bytes_per_cell) of the last solve on this handle."
+    ms = (ctypes.c_double * 5)()
+    la = (ctypes.c_int32 * 5)()
+    ce = (ctypes.c_int64 * 5)()
+    _check(lib().mseetc_last_profile(handle._h, ms, la, ce), 'mseetc_last_profile')
+    return {name: dict(ms=ms[i], launches=la[i], cells=ce[i], bytes_per_cell=lib().mseetc_bytes_per_cell(handle._h, i))
+            for i, name in enumerate(KERNEL_CLASSES)}
 
 
 def eval_interval(inp, num_steps, num_approx):

@@ -183,8 +183,31 @@ class casadiSolver():
         return self._handle
 
     # ------------------------------------------------------------------ batched solve (additive API)
+    def _time_sibling(self):
+        "The same problem in minimum-time mode (used to certify infeasible trip times)."
+        if getattr(self, '_sibling', None) is None:
+            import copy
+            sib = copy.copy(self)
+            sib.energyOptimal = False
+            sib._lossKind = 'none'
+            sib._handle = None
+            sib._sibling = None
+            sib.scalingFactorObjective = self.trackLength / self._base['velocityMax']
+            self._sibling = sib
+        return self._sibling
+
+    def minimum_time(self, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None, device=None):
+        """Minimum trip duration t_N - t_0 of each instance (time-optimal mode of the same problem,
+        reference ocp.py:146-150).  Returns (durations, status)."""
+        sib = self._time_sibling()
+        horizon = 3.0 * self.trackLength / self._base['velocityMax']
+        t0 = np.atleast_1d(np.asarray(initialTime, dtype=float))
+        res = sib.solve_batch(t0 + horizon, initialTime, terminalVelocity, initialVelocity, overrides=overrides, screen=False,
+                              device=device)
+        return res['z'][:, -2] - np.broadcast_to(t0, res['z'][:, -2].shape), res['status']
+
     def solve_batch(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None,
-                    want_multipliers=False, device=None):
+                    want_multipliers=False, device=None, screen=True):
         """Solve n instances that share this solver's track, options and problem structure.
 
         terminalTime / initialTime / terminalVelocity / initialVelocity: scalars or arrays of length n.
@@ -192,7 +215,12 @@ class casadiSolver():
         mass, rho, r0, r1, r2, forceMax, forceMin, forceMinPn, powerMax, powerMin, accMax, accMin, velocityMax,
         etaTraction, etaRgBrake.
         Returns a dict of numpy arrays: z [n, nz] (reference variable order), cost, kkt, iters, status,
-        plus timing; nothing is post-processed."""
+        plus timing; nothing is post-processed.
+
+        screen=True (energy-optimal mode only): terminalTime is an upper bound on t_N, so an instance is infeasible
+        exactly when it is below the minimum trip time.  The minimum time of every distinct
+        (train, boundary speeds) combination in the batch is computed first by a time-optimal solve and instances
+        below it are reported as 'Infeasible_Problem_Detected' without iterating."""
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -208,9 +236,22 @@ class casadiSolver():
             _, lossT, lossR = classify_losses(self.train)
         else:
             lossT, lossR = (1 - etaT) / etaT, 1 - etaR
+        t_begin = _time.perf_counter()
         P, M = self._planes(n, T, t0, v0, vN, overrides, lossT, lossR)
         dev = torch.device(device if device is not None else 'cuda')
-        t_begin = _time.perf_counter()
+        tmin = None
+        if screen and self.energyOptimal:
+            key = np.delete(P, [_cabi.PARAM_INDEX['T_END'], _cabi.PARAM_INDEX['LOSS_TR'], _cabi.PARAM_INDEX['LOSS_RG'],
+                                _cabi.PARAM_INDEX['OBJ_SCALE']], axis=0)
+            if n == 1 or np.all(key == key[:, :1]):
+                first, inverse = np.array([0]), np.zeros(n, dtype=np.intp)
+            else:
+                _, first, inverse = np.unique(key, axis=1, return_index=True, return_inverse=True)
+                inverse = np.asarray(inverse).reshape(-1)
+            sub = {k: np.broadcast_to(np.asarray(v, dtype=float), (n,))[first] for k, v in overrides.items()}
+            dur, st = self.minimum_time(t0[first], vN[first], v0[first], overrides=sub, device=device)
+            dur = np.where(st == 0, dur, 0.0)            # no certificate when the time-optimal solve did not converge
+            tmin = np.ascontiguousarray(dur[inverse])
         # ---- track tables: shared unless rho / g / velocityMax vary per instance
         per_inst_track = any(k in overrides for k in ('rho', 'velocityMax'))
         N = self.numIntervals
@@ -229,8 +270,22 @@ class casadiSolver():
         h = self._ensure_handle()
         out = h.solve_device(up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
                              up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64),
-                             want_z=True, want_lam=want_multipliers)
-        res = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
+                             want_z=True, want_lam=want_multipliers, tmin=up(tmin, torch.float64) if tmin is not None else None)
+        res = {}
+        for k, v in out.items():                          # device -> pinned host buffers -> numpy
+            if v is None:
+                continue
+            if hasattr(v, 'cpu'):
+                host = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                host.copy_(v, non_blocking=True)
+                res[k] = host
+            else:
+                res[k] = v
+        torch.cuda.synchronize(dev)
+        res = {k: (v.numpy() if hasattr(v, 'numpy') else v) for k, v in res.items()}
+        res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
+        res['d2h_bytes'] = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
+        res['tmin'] = tmin
         res['wall'] = _time.perf_counter() - t_begin
         scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
         # reference ocp.py:361: cost in kWh (energy) or s (time)
@@ -244,8 +299,14 @@ class casadiSolver():
             raise ValueError("Initial time must be a positive number, not {}!".format(initialTime))
         if not isinstance(terminalTime, (int, float)) or terminalTime <= 0:
             raise ValueError("Terminal time must be a strictly positive number, not {}!".format(terminalTime))
-        res = self.solve_batch(terminalTime, initialTime, terminalVelocity, initialVelocity)
+        res = self.solve_batch(terminalTime, initialTime, terminalVelocity, initialVelocity, screen=False)
         status = int(res['status'][0])
+        if status != 0 and self.energyOptimal:
+            # classify the failure: below the minimum trip time the problem is infeasible (what IPOPT's restoration
+            # phase would report); the time-optimal solve is only paid for on failure
+            dur, st = self.minimum_time(initialTime, terminalVelocity, initialVelocity)
+            if st[0] == 0 and (terminalTime - initialTime) < dur[0] * (1 - 1e-9):
+                status = 4
         stats = {'Solver status': _cabi.STATUS_STRINGS.get(status, 'Internal_Error'), 'IP iterations': int(res['iters'][0]),
                  'CPU time [s]': res['wall'], 'Cost': float(res['cost'][0])}
         if status != 0:

@@ -24,7 +24,7 @@ struct hostsim_problem {
 
 int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* params, const int32_t* nint,
                         const int32_t* trk_of, const int32_t* trk_off, const double* ds, const double* c0,
-                        const double* bmax, double* z_out, double* lam_out, double* obj, double* kkt, int32_t* iters,
+                        const double* bmax, const double* tmin, double* z_out, double* lam_out, double* obj, double* kkt, int32_t* iters,
                         int32_t* status, int32_t verbose_inst, int32_t* ticks_out) {
     Config g;
     memset(&g, 0, sizeof g);
@@ -43,7 +43,8 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     c.sd = (double*)(buf.data() + plan.off_sd);
     c.si = (int*)(buf.data() + plan.off_si);
     c.done = (int*)(buf.data() + plan.off_done);
-    BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, z_out, lam_out, obj, kkt, iters, status};
+    c.cnt = (unsigned long long*)(buf.data() + plan.off_done + 64);
+    BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
     for (int s = 0; s < g.S; ++s) inst_setup(c, io, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_init(c, k, s);

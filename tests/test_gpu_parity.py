@@ -1,0 +1,233 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle (-m gpu)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from common import FLAT_JSON, SWISS_JSON, active_set, fig5_train, fig10_train, oracle_nlp, oracle_solve, virm6
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cabi(built_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from mseetc import _cabi
+    _cabi.lib()
+    return _cabi
+
+
+def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True):
+    "Raw C-ABI call with arrays packed from oracle NLP objects (same packing as the CPU emulation harness)."
+    import torch
+    import harness
+    ref = nlps[0]
+    n = len(nlps)
+    Nmax = max(x.N for x in nlps)
+    packs = [harness.pack_instance(x, T, 0.0, v0, vN) for x, T in zip(nlps, Ts)]
+    params = np.ascontiguousarray(np.stack([p[0] for p in packs], axis=1))
+    nint = np.array([x.N for x in nlps], np.int32)
+    trk_off = np.concatenate([[0], np.cumsum(nint)]).astype(np.int32)
+    cu = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to('cuda', dtype=dt)
+    h = cabi.Handle(Nmax, ref.withPn, ref.withPower, ref.energy, {'none': 0, 'static': 1}[ref.lossKind],
+                    ref.opts['numSteps'], ref.opts['numApproxSteps'], max_iter)
+    out = h.solve_device(cu(params, torch.float64), cu(nint, torch.int32), cu(np.arange(n, dtype=np.int32), torch.int32),
+                         cu(trk_off, torch.int32), cu(np.concatenate([p[1] for p in packs]), torch.float64),
+                         cu(np.concatenate([p[2] for p in packs]), torch.float64),
+                         cu(np.concatenate([p[3] for p in packs]), torch.float64), want_z=True, want_lam=want_lam)
+    return {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
+
+
+def test_interval_kernel_matches_sympy(cabi):
+    from oracle.nlp import _stage_functions
+    rng = np.random.default_rng(5)
+    n = 4096
+    b0 = rng.uniform(1.0, 1600.0, n); F = rng.uniform(-0.6, 0.5, n); ds = rng.uniform(0.05, 400.0, n)
+    F = np.maximum(F, (2.0 - b0) / (2 * ds) + 0.3)
+    c0 = rng.uniform(-0.2, 0.2, n)
+    sr = (1.41244e-2, 1.78932e-4, 3.12696e-5)
+    inp = np.stack([b0, F, ds, c0, np.full(n, sr[0]), np.full(n, sr[1]), np.full(n, sr[2])])
+    for numSteps, numApprox in ((1, 1), (1, 0)):
+        out = cabi.eval_interval(inp, numSteps, numApprox)
+        names, fn = _stage_functions(False, numSteps, numApprox, 'none')
+        res = fn(b0, F, np.zeros(n), np.ones(n), ds, c0, *sr, 0.0, 0.0)
+        ct, cb = names.index('ct') * 15, names.index('cb') * 15
+        for a, base in ((0, ct), (1, cb)):
+            for i, j in enumerate((0, 1, 2, 5, 6, 9)):
+                ref = -np.asarray(res[base + j]) * np.ones(n) + (1.0 if (a == 1 and i == 0) else 0.0)
+                assert np.max(np.abs(out[6 * a + i] - ref) / np.maximum(1e-12, np.abs(ref))) < 1e-9
+
+
+def test_interval_kernel_bitwise_equals_host_compilation(cabi):
+    "Same source compiled by nvcc (device) and g++ (tests/hostsim): values agree to the last few ulps (FMA contraction differs)."
+    import harness
+    lib = harness.build()
+    rng = np.random.default_rng(9)
+    n = 1000
+    inp = np.ascontiguousarray(np.stack([rng.uniform(1, 1500, n), rng.uniform(0.0, 0.5, n), rng.uniform(1, 300, n), rng.uniform(-0.1, 0.1, n),
+                                         np.full(n, 1.4e-2), np.full(n, 1.8e-4), np.full(n, 3.1e-5)]))
+    dev = cabi.eval_interval(inp, 1, 1)
+    host = np.zeros((12, n))
+    lib.hostsim_eval_interval(n, 1, 1, inp.ctypes.data, host.ctypes.data)
+    assert np.max(np.abs(dev - host) / np.maximum(1e-300, np.abs(host))) < 1e-11
+
+
+CASES = [
+    ('config1 flat energy', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict()),
+    ('swiss energy', lambda: virm6(), SWISS_JSON, None, 300, 1242.0, True, 1.0, 1.0, dict()),
+    ('swiss time-optimal', lambda: virm6(), SWISS_JSON, None, 300, 2000.0, False, 1.0, 1.0, dict()),
+    ('figure10 no pn brake', fig10_train, FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict()),
+    ('figure5 time-optimal crop', lambda: (lambda t: (setattr(t, 'losses', ('none',)), t)[1])(fig5_train()), FLAT_JSON, 8500, 300,
+     354.0, False, 1.0, 100 / 3.6, dict()),
+    ('unit test energy no power rows', lambda: virm6(forceMinPn=0, powerMax=None, powerMin=None, losses=('none',)), FLAT_JSON, 3475,
+     300, 200.0, True, 1.0, 1.0, dict()),
+    ('rk4 on both states', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict(numApproxSteps=0)),
+    ('two time sub-points', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numSteps=1, numApproxSteps=2)),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_cuda_solver_matches_oracle(cabi, case):
+    """north_star bar: optimal energy 1e-6 relative, trajectories 1e-4 relative, same active set, KKT <= 1e-8."""
+    from oracle.problem import load_track
+    name, mk, path, crop, N, T, energy, v0, vN, rk = case
+    track = load_track(path)
+    if crop:
+        track.crop(positionEnd=crop)
+    nlp = oracle_nlp(mk(), track, N, energy=energy, **rk)
+    ref = oracle_solve(nlp, T, v0=v0, vN=vN)
+    assert ref.success, ref.status
+    out = device_solve(cabi, [nlp], [T], v0=v0, vN=vN)
+    assert out['status'][0] == 0
+    assert out['kkt'][0] <= 1e-8
+    assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
+    z, zr = out['z'][0], ref.x
+    for idx, scale in ((nlp.iB, nlp.limit.max() ** 2), (nlp.iT, T), (nlp.iFel, nlp.forceMax)):
+        assert np.max(np.abs(z[idx] - zr[idx])) <= 1e-4 * scale
+    if name.startswith('figure5'):
+        assert abs(z[nlp.iT[-1]] - 272.4726) < 1e-4          # reference simulations/figure5.py:96
+    lam = out['lam'][0]
+    lbz, ubz, lbg, ubg = nlp.bounds(T, 0.0, v0, vN)
+    free = lbz != ubz
+    r = (nlp.grad_f(z) + nlp.jac(z).T @ lam)[free]
+    sl, su = (z - lbz)[free], (ubz - z)[free]
+    with np.errstate(invalid='ignore'):
+        comp = np.where(r > 0, r * sl, -r * np.where(np.isfinite(su), su, 1.0))
+    assert np.max(comp) < 1e-7
+    g = nlp.g(z)
+    assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7
+    a0, amb0 = active_set(nlp, z, T, 0.0, v0, vN)
+    a1, amb1 = active_set(nlp, zr, T, 0.0, v0, vN)
+    sure = ~(amb0 | amb1)
+    assert np.array_equal(a0[sure], a1[sure])
+
+
+def test_public_api_single_solve_table(cabi):
+    "casadiSolver(train, track, opts).solve(T) -> (DataFrame, stats) as the reference returns (ocp.py:310-409)."
+    import json
+    import os
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from common import PKG
+    with open(os.path.join(PKG, 'simulations', 'config.json')) as fh:
+        opts = json.load(fh)
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    solver = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), opts)
+    df, stats = solver.solve(1541)
+    assert df is not None and stats['Solver status'] == 'Solve_Succeeded'
+    assert set(stats) == {'Solver status', 'IP iterations', 'CPU time [s]', 'Cost'}
+    nlp = oracle_nlp(virm6(), __import__('oracle.problem', fromlist=['load_track']).load_track(FLAT_JSON), 300)
+    ref = oracle_solve(nlp, 1541.0)
+    assert abs(stats['Cost'] - nlp.cost(ref.f)) <= 1e-6 * ref.f
+    assert len(df) == 301 and df.index.name == 'Time [s]'
+    assert np.max(np.abs(df['Velocity [m/s]'].values - np.sqrt(ref.x[nlp.iB]))) < 1e-4 * 38.9
+    assert abs(df.index.values[-1] - 1541) < 1e-3
+    # infeasible trip time: (None, stats), no exception (reference ocp.py:364-370)
+    df2, stats2 = solver.solve(1000)
+    assert df2 is None and stats2['Solver status'] != 'Solve_Succeeded'
+    # same solver object, repeated solve: identical iteration count (reference table3.py:60-62)
+    df3, stats3 = solver.solve(1541)
+    assert stats3['IP iterations'] == stats['IP iterations'] and np.array_equal(df3.values[:, :5], df.values[:, :5])
+
+
+def test_trip_time_sweep_batch_properties(cabi):
+    """BASELINE config 2 at full size: 4096 VIRM6 instances on CH_StGallen_Wil, T in Tmin*[0.8, 1.2].
+    Size-independent properties + oracle spot checks."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from oracle.problem import load_track
+    opts = {'numIntervals': 300, 'maxIterations': 500, 'integrationMethod': 'RK',
+            'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    solver = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), opts)
+    tsolver = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), dict(opts, energyOptimal=False))
+    tmin = tsolver.solve_batch(3000.0)
+    assert tmin['status'][0] == 0
+    Tmin = tmin['z'][0][-2]
+    assert abs(Tmin - 1035.5536) < 2e-3
+    n = 4096
+    T = Tmin * (0.8 + 0.4 * np.arange(n) / (n - 1))
+    res = solver.solve_batch(T)
+    feas = T >= Tmin * (1 + 1e-6)
+    assert np.all(res['status'][feas] == 0)                       # every feasible instance converges
+    assert np.all(res['status'][T < Tmin * (1 - 1e-6)] == 4)      # infeasible instances are flagged, never "solved"
+    assert np.all(res['kkt'][feas] <= 1e-8)
+    cost = res['cost'][feas]
+    assert np.all(np.diff(cost) < 0)                              # energy strictly decreases with trip time
+    tN = res['z'][feas, -2]
+    assert np.all(tN <= T[feas] * (1 + 2e-8))
+    b = res['z'][feas][:, 4::5][:, :300]
+    assert b.min() >= 1 - 1e-6 and np.sqrt(b.max()) <= 125 / 3.6 * (1 + 1e-6)
+    nlp = oracle_nlp(virm6(), load_track(SWISS_JSON), 300)
+    idx = np.where(feas)[0]
+    for i in (idx[3], idx[len(idx) // 2], idx[-1]):
+        ref = oracle_solve(nlp, float(T[i]))
+        assert ref.success
+        assert abs(res['obj'][i] - ref.f) <= 1e-6 * ref.f
+        assert np.max(np.abs(res['z'][i][nlp.iB] - ref.x[nlp.iB])) <= 1e-4 * 1206.0
+    # bitwise determinism for a fixed batch composition
+    res2 = solver.solve_batch(T)
+    assert np.array_equal(res['z'], res2['z']) and np.array_equal(res['iters'], res2['iters'])
+
+
+def test_parameter_monte_carlo_batch(cabi):
+    "BASELINE config 3 (static-efficiency half), reduced to 512 instances + oracle spot checks."
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from oracle.problem import load_track
+    opts = {'numIntervals': 300, 'maxIterations': 500, 'integrationMethod': 'RK',
+            'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    solver = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), opts)
+    rng = np.random.default_rng(20260101)
+    n = 512
+    ov = dict(mass=391000 * rng.uniform(0.85, 1.15, n), r0=train.r0 * rng.uniform(0.8, 1.2, n), r1=train.r1 * rng.uniform(0.8, 1.2, n),
+              r2=train.r2 * rng.uniform(0.8, 1.2, n), etaTraction=rng.uniform(0.80, 0.92, n), etaRgBrake=rng.uniform(0.55, 0.85, n))
+    res = solver.solve_batch(1541.0, overrides=ov)
+    assert np.all(res['status'] == 0) and np.all(res['kkt'] <= 1e-8)
+    for i in (0, 17, 511):
+        t = virm6(mass=ov['mass'][i], r0=ov['r0'][i], r1=ov['r1'][i], r2=ov['r2'][i])
+        t.losses = ('static', ov['etaTraction'][i], ov['etaRgBrake'][i])
+        nlp = oracle_nlp(t, load_track(FLAT_JSON), 300)
+        ref = oracle_solve(nlp, 1541.0)
+        assert ref.success
+        assert abs(res['cost'][i] - nlp.cost(ref.f)) <= 1e-6 * nlp.cost(ref.f)
+
+
+def test_cabi_usage_errors(cabi):
+    lib = cabi.lib()
+    h = ctypes.c_void_p(0)
+    bad = cabi.Problem(1, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1)
+    assert lib.mseetc_create(ctypes.byref(bad), ctypes.byref(h)) < 0
+    assert b'n_intervals_max' in lib.mseetc_last_error()
+    good = cabi.Problem(50, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1)
+    assert lib.mseetc_create(ctypes.byref(good), ctypes.byref(h)) == 0
+    assert lib.mseetc_workspace_bytes(h, 64) > 0
+    null = ctypes.c_void_p(0)
+    rc = lib.mseetc_solve_batch(h, 4, *([null] * 14), null, 0, null)
+    assert rc < 0 and b'null' in lib.mseetc_last_error()
+    assert lib.mseetc_destroy(h) == 0
