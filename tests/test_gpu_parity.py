@@ -149,7 +149,7 @@ def test_public_api_single_solve_table(cabi):
     assert df2 is None and stats2['Solver status'] != 'Solve_Succeeded'
     # same solver object, repeated solve: identical iteration count (reference table3.py:60-62)
     df3, stats3 = solver.solve(1541)
-    assert stats3['IP iterations'] == stats['IP iterations'] and np.array_equal(df3.values[:, :5], df.values[:, :5])
+    assert stats3['IP iterations'] == stats['IP iterations'] and np.array_equal(df3.values[:, :5], df.values[:, :5], equal_nan=True)
 
 
 def test_trip_time_sweep_batch_properties(cabi):
