@@ -294,11 +294,13 @@ MS_HD void inst_decide(const Ctx& c, int s) {
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_TRIAL) return;
     const int N = c.I(SI_N_INT, s);
     double tht = 0.0, ft = 0.0, slog = 0.0, sdamp = 0.0;
-    for (int k = 0; k <= N; ++k) {
-        tht += c.W(WS_PART + PT_TH, k, s);
-        ft += c.W(WS_PART + PT_F, k, s);
-        slog += c.W(WS_PART + PT_SLOG, k, s);
-        sdamp += c.W(WS_PART + PT_SDAMP, k, s);
+    for (int k0 = 0; k0 <= N; k0 += 8) {               // batched loads, sequential (deterministic) sums
+        double q[8][4];
+        for (int j = 0; j < 8; ++j) {
+            const int k = (k0 + j <= N) ? k0 + j : N;
+            for (int f = 0; f < 4; ++f) q[j][f] = c.W(WS_PART + PT_TH + f, k, s);
+        }
+        for (int j = 0; j < 8 && k0 + j <= N; ++j) { tht += q[j][0]; ft += q[j][1]; slog += q[j][2]; sdamp += q[j][3]; }
     }
     const double mu = c.D(SD_MU, s);
     const double pht = ft - mu * slog + MS_KAPPA_D * mu * sdamp;
@@ -603,350 +605,5 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     c.W(WS_PART + PC_OWN_T, k, s) = own_t;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Riccati recursion
-// ------------------------------------------------------------------------------------------------
-struct Sym3 { double tt, tb, tf, bb, bf, ff; };
-
-// dense symmetric 6x6 (t,b,f,Fel,Fpb,sl) in full storage; small enough to live in registers
-MS_HD void load_stage(const Ctx& c, int k, int s, double mu, double delta, double M[6][6], double m[6]) {
-    for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) M[i][j] = 0.0; }
-    M[0][0] = c.W(WS_QP + QP_H_TT, k, s) + delta;
-    M[1][1] = c.W(WS_QP + QP_H_BB, k, s) + delta;
-    M[1][3] = M[3][1] = c.W(WS_QP + QP_H_BFEL, k, s);
-    M[1][4] = M[4][1] = c.W(WS_QP + QP_H_BFPB, k, s);
-    M[1][5] = M[5][1] = c.W(WS_QP + QP_H_BSL, k, s);
-    M[2][2] = c.W(WS_QP + QP_H_FF, k, s);
-    M[2][3] = M[3][2] = c.W(WS_QP + QP_H_FFEL, k, s);
-    M[3][3] = c.W(WS_QP + QP_H_FELFEL, k, s) + delta;
-    M[3][4] = M[4][3] = c.W(WS_QP + QP_H_FELFPB, k, s);
-    M[3][5] = M[5][3] = c.W(WS_QP + QP_H_FELSL, k, s);
-    M[4][4] = c.W(WS_QP + QP_H_FPBFPB, k, s) + delta;
-    M[4][5] = M[5][4] = c.W(WS_QP + QP_H_FPBSL, k, s);
-    M[5][5] = c.W(WS_QP + QP_H_SLSL, k, s) + delta;
-    m[0] = mu * c.W(WS_QP + QP_G1_T, k, s);
-    m[1] = c.W(WS_QP + QP_G0_B, k, s) + mu * c.W(WS_QP + QP_G1_B, k, s);
-    m[2] = c.W(WS_QP + QP_G0_F, k, s);
-    m[3] = c.W(WS_QP + QP_G0_FEL, k, s) + mu * c.W(WS_QP + QP_G1_FEL, k, s);
-    m[4] = c.W(WS_QP + QP_G0_FPB, k, s) + mu * c.W(WS_QP + QP_G1_FPB, k, s);
-    m[5] = c.W(WS_QP + QP_G0_SL, k, s) + mu * c.W(WS_QP + QP_G1_SL, k, s);
-}
-
-// backward sweep; returns false when a reduced control Hessian is not positive definite (wrong inertia)
-MS_HD bool riccati_backward(const Ctx& c, int s, int N, double mu, double delta) {
-    const Config& g = c.cfg;
-    // terminal value function: only t_N is free (b_N fixed, f_N costless)
-    double P[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, p[3] = {0, 0, 0};
-    P[0][0] = c.W(WS_QP + QP_H_TT, N, s) + delta;
-    p[0] = (g.energy ? 0.0 : 1.0 / c.P(P_SCALE, s)) + mu * c.W(WS_QP + QP_G1_T, N, s);
-    for (int i = 0; i < 6; ++i) c.W(WS_RIC + RIC_P + i, N, s) = 0.0;
-    c.W(WS_RIC + RIC_P + 0, N, s) = P[0][0];
-    c.W(WS_RIC + RIC_PV + 0, N, s) = p[0];
-    c.W(WS_RIC + RIC_PV + 1, N, s) = 0.0;
-    c.W(WS_RIC + RIC_PV + 2, N, s) = 0.0;
-    for (int k = N - 1; k >= 0; --k) {
-        double M[6][6], m[6];
-        load_stage(c, k, s, mu, delta, M, m);
-        const double tb = c.W(WS_QP + QP_TAU_B, k, s), tF = c.W(WS_QP + QP_TAU_F, k, s);
-        const double pb = c.W(WS_QP + QP_PHI_B, k, s), pF = c.W(WS_QP + QP_PHI_F, k, s);
-        const double rt = c.W(WS_QP + QP_RT, k, s), rb = c.W(WS_QP + QP_RB, k, s);
-        const double pn = g.withPn ? 1.0 : 0.0;
-        // G = [A B]: rows t,b,f of the next state
-        double G[3][6] = {{1.0, tb, 0.0, tF, pn * tF, 0.0}, {0.0, pb, 0.0, pF, pn * pF, 0.0}, {0.0, 0.0, 0.0, 1.0, 0.0, 0.0}};
-        double r[3] = {rt, rb, 0.0};
-        const bool last = (k == N - 1);
-        if (last) { for (int j = 0; j < 6; ++j) G[1][j] = 0.0; r[1] = 0.0; }   // db_N = 0 handled by elimination
-        // M += G' P G ; m += G' (P r + p)
-        double Y[3][6], pr[3];
-        for (int a = 0; a < 3; ++a) {
-            pr[a] = p[a] + P[a][0] * r[0] + P[a][1] * r[1] + P[a][2] * r[2];
-            for (int j = 0; j < 6; ++j) Y[a][j] = P[a][0] * G[0][j] + P[a][1] * G[1][j] + P[a][2] * G[2][j];
-        }
-        for (int i = 0; i < 6; ++i) {
-            m[i] += G[0][i] * pr[0] + G[1][i] * pr[1] + G[2][i] * pr[2];
-            for (int j = i; j < 6; ++j) {
-                double v = M[i][j] + G[0][i] * Y[0][j] + G[1][i] * Y[1][j] + G[2][i] * Y[2][j];
-                M[i][j] = v; M[j][i] = v;
-            }
-        }
-        double eB = 0.0, ePn = 0.0, e0 = 0.0;
-        if (last) {
-            // terminal speed fixed: Phi_b db + Phi_F (dFel + dFpb) + rb = 0  ->  dFel = eB db + ePn dFpb + e0
-            eB = -pb / pF; ePn = -pn; e0 = -rb / pF;
-            // substitute: column/row Fel distributed onto b and Fpb, then Fel becomes a dummy control
-            double colF[6];
-            for (int i = 0; i < 6; ++i) colF[i] = M[i][3];
-            const double mFF = M[3][3];
-            for (int i = 0; i < 6; ++i) m[i] += colF[i] * e0;
-            const double mF = m[3];
-            double ev[6] = {0.0, eB, 0.0, 0.0, ePn, 0.0};
-            for (int i = 0; i < 6; ++i) m[i] += ev[i] * mF;
-            for (int i = 0; i < 6; ++i)
-                for (int j = 0; j < 6; ++j) M[i][j] += colF[i] * ev[j] + ev[i] * colF[j] + mFF * ev[i] * ev[j];
-            // (m already carries M*t0 through colF*e0; add the (Fel,Fel) part routed through ev)
-            for (int i = 0; i < 6; ++i) { M[i][3] = 0.0; M[3][i] = 0.0; }
-            M[3][3] = 1.0; m[3] = 0.0;
-        }
-        // Cholesky of the control block (indices 3..5)
-        double l00 = M[3][3];
-        if (!(l00 > 0.0) || !isfinite(l00)) return false;
-        l00 = sqrt(l00);
-        double l10 = M[4][3] / l00, l20 = M[5][3] / l00;
-        double l11 = M[4][4] - l10 * l10;
-        if (!(l11 > 0.0) || !isfinite(l11)) return false;
-        l11 = sqrt(l11);
-        double l21 = (M[5][4] - l20 * l10) / l11;
-        double l22 = M[5][5] - l20 * l20 - l21 * l21;
-        if (!(l22 > 0.0) || !isfinite(l22)) return false;
-        l22 = sqrt(l22);
-        // solve Muu X = [Mux mu]  (4 right-hand sides)
-        double K[3][3], kf[3];
-        for (int j = 0; j < 4; ++j) {
-            double r0 = (j < 3) ? M[3][j] : m[3], r1 = (j < 3) ? M[4][j] : m[4], r2 = (j < 3) ? M[5][j] : m[5];
-            double y0 = r0 / l00, y1 = (r1 - l10 * y0) / l11, y2 = (r2 - l20 * y0 - l21 * y1) / l22;
-            double x2 = y2 / l22, x1 = (y1 - l21 * x2) / l11, x0 = (y0 - l10 * x1 - l20 * x2) / l00;
-            if (j < 3) { K[0][j] = -x0; K[1][j] = -x1; K[2][j] = -x2; }
-            else { kf[0] = -x0; kf[1] = -x1; kf[2] = -x2; }
-        }
-        // P = Mxx + Mxu K ; p = mx + Mxu kf
-        double Pn[3][3], pnv[3];
-        for (int i = 0; i < 3; ++i) {
-            pnv[i] = m[i] + M[i][3] * kf[0] + M[i][4] * kf[1] + M[i][5] * kf[2];
-            for (int j = 0; j < 3; ++j) Pn[i][j] = M[i][j] + M[i][3] * K[0][j] + M[i][4] * K[1][j] + M[i][5] * K[2][j];
-        }
-        for (int i = 0; i < 3; ++i) { p[i] = pnv[i]; for (int j = 0; j < 3; ++j) P[i][j] = 0.5 * (Pn[i][j] + Pn[j][i]); }
-        if (last) {   // recover the eliminated control's feedback row
-            for (int j = 0; j < 3; ++j) K[0][j] = ePn * K[1][j];
-            K[0][1] += eB;
-            kf[0] = e0 + ePn * kf[1];
-        }
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) c.W(WS_RIC + RIC_K + 3 * i + j, k, s) = K[i][j];
-            c.W(WS_RIC + RIC_KF + i, k, s) = kf[i];
-            c.W(WS_RIC + RIC_PV + i, k, s) = p[i];
-        }
-        c.W(WS_RIC + RIC_P + 0, k, s) = P[0][0]; c.W(WS_RIC + RIC_P + 1, k, s) = P[0][1];
-        c.W(WS_RIC + RIC_P + 2, k, s) = P[0][2]; c.W(WS_RIC + RIC_P + 3, k, s) = P[1][1];
-        c.W(WS_RIC + RIC_P + 4, k, s) = P[1][2]; c.W(WS_RIC + RIC_P + 5, k, s) = P[2][2];
-    }
-    return true;
-}
-
-struct Ftb {
-    double aP, aZ, gphid;
-};
-MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, double dvSigned, bool oneSided) {
-    // dvSigned = change of the slack; primal fraction-to-boundary, dual step, barrier directional derivative
-    if (dvSigned < 0.0) f.aP = fmin(f.aP, -tau * slack / dvSigned);
-    double dz = mu / slack - z - (z / slack) * dvSigned;
-    if (dz < 0.0) f.aZ = fmin(f.aZ, -tau * z / dz);
-    f.gphid += (-mu / slack + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
-}
-
-// forward sweep: primal step, new multipliers, slack / bound-multiplier steps, step-size limits
-MS_HD void riccati_forward(const Ctx& c, int s, int N, double mu, double tauF, double delta, Ftb& f) {
-    const Config& g = c.cfg;
-    const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
-    const double scale = c.P(P_SCALE, s);
-    double dx[3] = {0.0, 0.0, 0.0};
-    double felPrev = 0.0, dfelPrev = 0.0;
-    f.aP = 1.0; f.aZ = 1.0; f.gphid = 0.0;
-    c.W(WS_ST + ST_T, 0, s) = 0.0;
-    c.W(WS_ST + ST_B, 0, s) = 0.0;
-    for (int k = 0; k < N; ++k) {
-        Bnd B = load_bounds(c, k, s);
-        double du[3];
-        for (int i = 0; i < 3; ++i)
-            du[i] = c.W(WS_RIC + RIC_KF + i, k, s) + c.W(WS_RIC + RIC_K + 3 * i + 0, k, s) * dx[0]
-                  + c.W(WS_RIC + RIC_K + 3 * i + 1, k, s) * dx[1] + c.W(WS_RIC + RIC_K + 3 * i + 2, k, s) * dx[2];
-        if (!g.withPn) du[1] = 0.0;
-        const double tb = c.W(WS_QP + QP_TAU_B, k, s), tF = c.W(WS_QP + QP_TAU_F, k, s);
-        const double pb = c.W(WS_QP + QP_PHI_B, k, s), pF = c.W(WS_QP + QP_PHI_F, k, s);
-        const double dF = du[0] + du[1];
-        double dxn[3];
-        dxn[0] = dx[0] + tb * dx[1] + tF * dF + c.W(WS_QP + QP_RT, k, s);
-        dxn[1] = (k + 1 < N) ? pb * dx[1] + pF * dF + c.W(WS_QP + QP_RB, k, s) : 0.0;
-        dxn[2] = du[0];
-        // costates of the next node
-        double pit = c.W(WS_RIC + RIC_PV + 0, k + 1, s) + c.W(WS_RIC + RIC_P + 0, k + 1, s) * dxn[0]
-                   + c.W(WS_RIC + RIC_P + 1, k + 1, s) * dxn[1] + c.W(WS_RIC + RIC_P + 2, k + 1, s) * dxn[2];
-        double pib;
-        if (k + 1 < N) {
-            pib = c.W(WS_RIC + RIC_PV + 1, k + 1, s) + c.W(WS_RIC + RIC_P + 1, k + 1, s) * dxn[0]
-                + c.W(WS_RIC + RIC_P + 3, k + 1, s) * dxn[1] + c.W(WS_RIC + RIC_P + 4, k + 1, s) * dxn[2];
-            pib += c.W(WS_QP + QP_HC_B, k, s) * dx[1] + c.W(WS_QP + QP_HC_FEL, k, s) * du[0]
-                 + c.W(WS_QP + QP_HC_FPB, k, s) * du[1] + c.W(WS_QP + QP_HC_SL, k, s) * du[2]
-                 + c.W(WS_QP + QP_HPP, k, s) * dxn[1] + c.W(WS_QP + QP_GP0, k, s) + mu * c.W(WS_QP + QP_GP1, k, s);
-        } else {
-            // b_N is fixed: its row multiplier follows from stationarity w.r.t. Fel of the last interval
-            double gF = c.W(WS_QP + QP_G0_FEL, k, s) + mu * c.W(WS_QP + QP_G1_FEL, k, s)
-                      + c.W(WS_QP + QP_H_BFEL, k, s) * dx[1] + c.W(WS_QP + QP_H_FFEL, k, s) * dx[2]
-                      + (c.W(WS_QP + QP_H_FELFEL, k, s) + delta) * du[0] + c.W(WS_QP + QP_H_FELFPB, k, s) * du[1]
-                      + c.W(WS_QP + QP_H_FELSL, k, s) * du[2];
-            pib = -(gF + tF * pit) / pF;
-        }
-        const double ytNew = -pit, ybNew = -pib;
-        // ---- store the primal / equality-multiplier step
-        c.W(WS_ST + ST_FEL, k, s) = du[0];
-        c.W(WS_ST + ST_FPB, k, s) = du[1];
-        c.W(WS_ST + ST_SL, k, s) = du[2];
-        c.W(WS_ST + ST_T, k + 1, s) = dxn[0];
-        c.W(WS_ST + ST_B, k + 1, s) = dxn[1];
-        c.W(WS_ST + ST_YT, k, s) = ytNew - c.W(it + IT_YT, k, s);
-        c.W(WS_ST + ST_YB, k, s) = ybNew - c.W(it + IT_YB, k, s);
-        // ---- bounds on the variables of this interval
-        const double fel = c.W(it + IT_FEL, k, s), fpb = c.W(it + IT_FPB, k, s), sl = c.W(it + IT_SL, k, s);
-        if (k >= 1) {
-            const double t = c.W(it + IT_T, k, s), b = c.W(it + IT_B, k, s);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_L, k, s), t - B.tL, dx[0], false);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_U, k, s), B.tU - t, -dx[0], false);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_B_L, k, s), b - B.bL, dx[1], false);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_B_U, k, s), B.bU - b, -dx[1], false);
-        }
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FEL_L, k, s), fel - B.felL, du[0], false);
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FEL_U, k, s), B.felU - fel, -du[0], false);
-        if (g.withPn) {
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FPB_L, k, s), fpb - B.fpbL, du[1], false);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FPB_U, k, s), B.fpbU - fpb, -du[1], false);
-        }
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_SL_L, k, s), sl - B.slL, du[2], true);
-        // ---- objective part of the barrier directional derivative
-        if (g.energy) {
-            f.gphid += c.W(WS_TRK + TRK_DS, k, s) * (du[0] + du[2]) / scale;
-            if (k >= 1) f.gphid += (2e-3 / scale) * (fel - felPrev) * (du[0] - dfelPrev);
-        } else {
-            f.gphid += (2e-4 / scale) * (fel * du[0] + fpb * du[1]);
-        }
-        felPrev = fel; dfelPrev = du[0];
-        // ---- inequality rows: slack step, multiplier step
-        for (int j = 0; j < NROW; ++j) {
-            c.W(WS_ST + ST_W + j, k, s) = 0.0;
-            c.W(WS_ST + ST_YD + j, k, s) = 0.0;
-            if (!row_on(g, j)) continue;
-            double jd;
-            if (j == R_P0) jd = c.W(WS_QP + QP_J_P0_B, k, s) * dx[1] + c.W(WS_QP + QP_J_P0_FEL, k, s) * du[0];
-            else if (j == R_P1) jd = c.W(WS_QP + QP_J_P1_FEL, k, s) * du[0] + c.W(WS_QP + QP_J_P1_BN, k, s) * dxn[1];
-            else if (j == R_ACC) jd = c.W(WS_QP + QP_J_ACC_B, k, s) * dx[1] + du[0] + du[1];
-            else if (j == R_LTR) jd = du[2] + c.W(WS_QP + QP_J_LTR_FEL, k, s) * du[0] + c.W(WS_QP + QP_J_LTR_B, k, s) * dx[1]
-                                    + c.W(WS_QP + QP_J_LTR_BN, k, s) * dxn[1];
-            else jd = du[2] + c.W(WS_QP + QP_J_LRG_FEL, k, s) * du[0] + c.W(WS_QP + QP_J_LRG_B, k, s) * dx[1]
-                    + c.W(WS_QP + QP_J_LRG_BN, k, s) * dxn[1];
-            const double dw = jd + c.W(WS_QP + QP_RES + j, k, s);
-            double L, U; bool hasU;
-            row_bounds(B, j, L, U, hasU);
-            const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
-            const double w = c.W(it + IT_W + j, k, s);
-            const double vL = c.W(it + IT_Z + zl, k, s), sL = w - L;
-            double sig = vL / sL, gw = -mu / sL + (hasU ? 0.0 : MS_KAPPA_D * mu);
-            ftb_bound(f, tauF, mu, vL, sL, dw, !hasU);
-            if (hasU) {
-                const double vU = c.W(it + IT_Z + zl + 1, k, s), sU = U - w;
-                sig += vU / sU; gw += mu / sU;
-                ftb_bound(f, tauF, mu, vU, sU, -dw, false);
-            }
-            c.W(WS_ST + ST_W + j, k, s) = dw;
-            c.W(WS_ST + ST_YD + j, k, s) = sig * dw + gw - c.W(it + IT_YD + j, k, s);
-        }
-        dx[0] = dxn[0]; dx[1] = dxn[1]; dx[2] = dxn[2];
-    }
-    // terminal node: t_N
-    {
-        Bnd B = load_bounds(c, N, s);
-        const double t = c.W(it + IT_T, N, s);
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_L, N, s), t - B.tL, dx[0], false);
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_U, N, s), B.tU - t, -dx[0], false);
-        if (!g.energy) f.gphid += dx[0] / scale;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// per-instance driver: KKT error, termination, barrier update, search direction   (IPOPT Alg. A, steps A-1..A-4)
-// ------------------------------------------------------------------------------------------------
-MS_HD void inst_step(const Ctx& c, int s) {
-    const Config& g = c.cfg;
-    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
-    const int N = c.I(SI_N_INT, s);
-    const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
-    count_cells(c, 1, N + 1);
-    double th = 0.0, fo = 0.0, slog = 0.0, sdamp = 0.0, dinf = 0.0, pinf = 0.0, cmin = 1e300, cmax = 0.0, zsum = 0.0, ysum = 0.0;
-    double cnPrev = 0.0, ytPrev = 0.0;
-    for (int k = 0; k <= N; ++k) {
-        th += c.W(WS_PART + PC_TH, k, s);
-        fo += c.W(WS_PART + PC_F, k, s);
-        slog += c.W(WS_PART + PC_SLOG, k, s);
-        sdamp += c.W(WS_PART + PC_SDAMP, k, s);
-        dinf = fmax(dinf, c.W(WS_PART + PC_DINF, k, s));
-        pinf = fmax(pinf, c.W(WS_PART + PC_PINF, k, s));
-        cmin = fmin(cmin, c.W(WS_PART + PC_CMIN, k, s));
-        cmax = fmax(cmax, c.W(WS_PART + PC_CMAX, k, s));
-        zsum += c.W(WS_PART + PC_ZSUM, k, s);
-        ysum += c.W(WS_PART + PC_YSUM, k, s);
-        if (k >= 1) {
-            dinf = fmax(dinf, fabs(c.W(WS_PART + PC_OWN_T, k, s) + ytPrev));
-            if (k < N) dinf = fmax(dinf, fabs(c.W(WS_PART + PC_OWN_B, k, s) + cnPrev));
-        }
-        if (k < N) { cnPrev = c.W(WS_PART + PC_CN_B, k, s); ytPrev = c.W(it + IT_YT, k, s); }
-    }
-    // counts for the IPOPT error scaling s_d, s_c (eq. 6)
-    const int nrow = (g.withPower ? 2 : 0) + 1 + (g.energy ? 2 : 0);
-    const int nbRow = (g.withPower ? 4 : 0) + 2 + (g.energy ? 2 : 0);
-    const int nb = N * (2 + (g.withPn ? 2 : 0) + 1 + nbRow) + (N - 1) * 4 + 2;
-    const int mrows = N * (nrow + 2);
-    const double sd = fmax(100.0, (ysum + zsum) / (mrows + nb)) / 100.0;
-    const double sc = fmax(100.0, zsum / nb) / 100.0;
-    const double E0 = fmax(fmax(dinf / sd, pinf), cmax / sc);
-    c.D(SD_THETA, s) = th; c.D(SD_FOBJ, s) = fo; c.D(SD_SLOG, s) = slog; c.D(SD_SDAMP, s) = sdamp;
-    c.D(SD_KKT, s) = E0; c.D(SD_DINF, s) = dinf; c.D(SD_PINF, s) = pinf; c.D(SD_CINF, s) = cmax;
-    if (c.D(SD_THETA_MAX, s) < 0.0) {
-        c.D(SD_THETA_MAX, s) = 1e4 * fmax(1.0, th);
-        c.D(SD_THETA_MIN, s) = 1e-4 * fmax(1.0, th);
-    }
-    if (!isfinite(E0) || !isfinite(fo)) { finish(c, s, ST_INVALID_NUMBER); return; }
-    if (E0 <= g.tol) { finish(c, s, ST_SOLVE_SUCCEEDED); return; }
-    if (c.I(SI_ITERS, s) >= g.maxIter) { finish(c, s, ST_MAXITER); return; }
-    // ---- monotone barrier update (eq. 7), filter reset
-    double mu = c.D(SD_MU, s);
-    for (;;) {
-        double cinf = fmax(cmax - mu, mu - cmin);
-        double Emu = fmax(fmax(dinf / sd, pinf), cinf / sc);
-        if (Emu <= 10.0 * mu && mu > g.tol / 10.0 * (1.0 + 1e-12)) {
-            mu = fmax(g.tol / 10.0, fmin(0.2 * mu, pow(mu, 1.5)));
-            c.I(SI_NFILT, s) = 0;
-        } else break;
-    }
-    const double tauF = fmax(0.99, 1.0 - mu);
-    c.D(SD_MU, s) = mu; c.D(SD_TAU, s) = tauF;
-    // ---- search direction with inertia correction (IPOPT Alg. IC)
-    double delta = 0.0;
-    const double dlast = c.D(SD_DELTA_LAST, s);
-    bool ok = false;
-    for (int tries = 0; tries < 40; ++tries) {
-        count_cells(c, 2, N);
-        if (riccati_backward(c, s, N, mu, delta)) { ok = true; break; }
-        c.I(SI_NREG, s) += 1;
-        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
-        else delta *= (dlast == 0.0) ? 100.0 : 8.0;
-        if (delta > 1e40) break;
-    }
-    if (!ok) { finish(c, s, ST_STEP_FAILED); return; }
-    if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
-    Ftb f;
-    count_cells(c, 3, N);
-    riccati_forward(c, s, N, mu, tauF, delta, f);
-    if (!isfinite(f.gphid) || !isfinite(f.aP)) { finish(c, s, ST_STEP_FAILED); return; }
-    double amin;
-    if (f.gphid < 0.0) {
-        amin = 1e-5;
-        if (th > 0.0) amin = fmin(amin, 1e-8 * th / (-f.gphid));
-        if (th <= c.D(SD_THETA_MIN, s)) amin = fmin(amin, pow(th, 1.1) / pow(-f.gphid, 2.3));
-        amin *= 0.05;
-    } else amin = 0.05 * 1e-5;
-    c.D(SD_GPHID, s) = f.gphid;
-    c.D(SD_ALPHA, s) = f.aP;
-    c.D(SD_ALPHA_Z, s) = f.aZ;
-    c.D(SD_ALPHA_MIN, s) = amin;
-    c.I(SI_NLS, s) = 0;
-    c.I(SI_PHASE, s) = PH_TRIAL;
-}
 
 }  // namespace mseetc

@@ -52,6 +52,7 @@ enum PartField {
     PT_TH = 0, PT_F, PT_SLOG, PT_SDAMP,          // trial point: constraint violation, objective, barrier sums
     PC_TH, PC_F, PC_SLOG, PC_SDAMP,              // current point
     PC_DINF, PC_PINF, PC_CMIN, PC_CMAX, PC_ZSUM, PC_YSUM, PC_OWN_B, PC_CN_B, PC_OWN_T,
+    PS_AP, PS_AZ, PS_GPHID,                      // step: primal / dual fraction-to-boundary limits, barrier slope
     PART_N
 };
 enum TrkField { TRK_DS = 0, TRK_C0, TRK_BMAX, TRK_N };
@@ -81,7 +82,7 @@ enum SdField {
 };
 enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_N };
 
-enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2 };
+enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2, PH_STEPPED = 3 };
 // status codes (mapped to IPOPT's vocabulary by the host shim, ocp.py:362)
 enum Status {
     ST_RUNNING = -1, ST_SOLVE_SUCCEEDED = 0, ST_MAXITER = 1, ST_RESTORATION_FAILED = 2, ST_STEP_FAILED = 3,

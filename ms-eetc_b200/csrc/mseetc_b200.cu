@@ -24,7 +24,7 @@ namespace {
 
 thread_local std::string g_err;
 
-enum Op { OP_SETUP = 0, OP_INIT, OP_TRIAL, OP_DECIDE, OP_EVAL, OP_STEP, OP_EXTRACT };
+enum Op { OP_SETUP = 0, OP_INIT, OP_TRIAL, OP_DECIDE, OP_EVAL, OP_STEP, OP_EXTRACT, OP_CSTEP, OP_ALPHA };
 
 template <int OP>
 __global__ void __launch_bounds__(128) k_cells(Ctx c, BatchIO io) {
@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(128) k_cells(Ctx c, BatchIO io) {
     if (OP == OP_INIT) cell_init(c, k, s);
     if (OP == OP_TRIAL) cell_trial(c, k, s);
     if (OP == OP_EVAL) cell_eval(c, k, s);
+    if (OP == OP_CSTEP) cell_step(c, k, s);
     if (OP == OP_EXTRACT) cell_extract(c, io, k, s);
 }
 
@@ -45,7 +46,20 @@ __global__ void __launch_bounds__(64) k_insts(Ctx c, BatchIO io) {
     if (s >= c.cfg.S) return;
     if (OP == OP_SETUP) inst_setup(c, io, s);
     if (OP == OP_DECIDE) inst_decide(c, s);
-    if (OP == OP_STEP) inst_step(c, s);
+    if (OP == OP_ALPHA) inst_alpha(c, s);
+}
+
+// Riccati sweeps: one thread per instance, stage data prefetched `depth` intervals ahead through a cp.async ring
+// in dynamic shared memory ((depth+1) * RING_NF_MAX * blockDim doubles).
+__global__ void __launch_bounds__(64) k_step(Ctx c, int depth) {
+    extern __shared__ double ring[];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.cfg.S) return;
+    RingFetch<BwdFields> fb;
+    fb.sm = ring; fb.depth = depth; fb.bs = blockDim.x; fb.tid = threadIdx.x; fb.dir = -1; fb.kEnd = 0;
+    RingFetch<FwdFields> ff;
+    ff.sm = ring; ff.depth = depth; ff.bs = blockDim.x; ff.tid = threadIdx.x; ff.dir = 1; ff.kEnd = 0;
+    inst_step(c, s, fb, ff);
 }
 
 __global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out) {
@@ -55,7 +69,7 @@ __global__ void k_eval_interval(int n, int numSteps, int numApprox, const double
 
 }  // namespace
 
-enum { CLS_TRIAL = 0, CLS_DECIDE, CLS_EVAL, CLS_STEP, CLS_MISC, NCLS };
+enum { CLS_TRIAL = 0, CLS_DECIDE, CLS_EVAL, CLS_STEP, CLS_MISC, CLS_CSTEP, CLS_ALPHA, NCLS };
 
 struct mseetc_solver {
     mseetc_problem prob;
@@ -148,7 +162,9 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
         case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
         case CLS_DECIDE: return 8.0 * 4;
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13));
-        case CLS_STEP:   return 8.0 * (14 + (13 + 6 + 10) + RIC_N + (12 + 9) + (6 + 7 + 11 + rows) + iter + 2 + step);
+        case CLS_STEP:   return 8.0 * (14 + BwdFields::NF + RIC_N + FwdFields::NF + 7);
+        case CLS_CSTEP:  return 8.0 * ((7 + 2 + iter + 11 + rows + 2) + (2 * rows + 2 + 3));
+        case CLS_ALPHA:  return 8.0 * 3;
         default:         return 0.0;
     }
 }
@@ -190,6 +206,19 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const unsigned cgrid = (unsigned)((cellThreads + 127) / 128);
     const int ib = (g.S >= 148 * 64 * 2) ? 64 : 32;
     const unsigned igrid = (unsigned)((g.S + ib - 1) / ib);
+    // prefetch depth of the Riccati ring: as deep as shared memory allows for the blocks resident on one SM
+    int nsm = 148;
+    {
+        int devId = 0;
+        cudaGetDevice(&devId);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devId);
+    }
+    const int blocksPerSm = (int)((igrid + nsm - 1) / nsm);
+    const size_t slotBytes = sizeof(double) * RING_NF_MAX * ib;
+    int depth = (int)((size_t)200 * 1024 / ((size_t)(blocksPerSm < 1 ? 1 : blocksPerSm) * slotBytes)) - 1;
+    depth = depth < 1 ? 1 : (depth > 8 ? 8 : depth);
+    const size_t ringBytes = (size_t)(depth + 1) * slotBytes;
+    cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
     int launches = 0;
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -218,7 +247,9 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     int tick = 0;
     for (;;) {
         begin(CLS_EVAL); k_cells<OP_EVAL><<<cgrid, 128, 0, st>>>(c, io); end(CLS_EVAL);
-        begin(CLS_STEP); k_insts<OP_STEP><<<igrid, ib, 0, st>>>(c, io); end(CLS_STEP);
+        begin(CLS_STEP); k_step<<<igrid, ib, ringBytes, st>>>(c, depth); end(CLS_STEP);
+        begin(CLS_CSTEP); k_cells<OP_CSTEP><<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
+        begin(CLS_ALPHA); k_insts<OP_ALPHA><<<igrid, ib, 0, st>>>(c, io); end(CLS_ALPHA);
         if (tick >= maxTicks) break;
         if (tick >= 16 && (tick & 3) == 0) {
             e = cudaMemcpyAsync(h->done_host, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -244,6 +275,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         h->cells[CLS_DECIDE] = (long long)cnt[0];
         h->cells[CLS_EVAL] = (long long)cnt[1];
         h->cells[CLS_STEP] = (long long)cnt[1];
+        h->cells[CLS_CSTEP] = (long long)cnt[3] + (long long)(cnt[3] / (unsigned long long)(p.n_intervals_max));
+        h->cells[CLS_ALPHA] = h->cells[CLS_CSTEP];
         h->cells[CLS_MISC] = 0;
     }
     for (size_t i = 0; i < evClass.size(); ++i) {

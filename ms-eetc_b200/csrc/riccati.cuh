@@ -1,0 +1,456 @@
+// Search direction of one interior-point iteration: Riccati recursion over the shooting intervals.
+//
+// The Newton system of the reference NLP (all rows of ocp.py:183-241 linearised, bound and slack multipliers
+// condensed by cell_eval) is a linear-quadratic OCP in (d t, d b, d Fel_{k-1} | d Fel, d Fpb, d s).  It replaces
+// IPOPT's sparse LDL^T (MUMPS) behind ocp.py:359:
+//   riccati_backward   value functions P_k, p_k and feedback K_k, k_k; positive-definiteness of every reduced
+//                      control Hessian is the inertia test (IPOPT Alg. IC regularises when it fails)
+//   riccati_forward    d x_k, d u_k and the new coupling-row multipliers (costates)
+//   cell_step          (interval-parallel) slack and inequality-multiplier steps, fraction-to-boundary limits,
+//                      directional derivative of the barrier function
+//   inst_alpha         deterministic per-instance reduction of those limits -> first trial step size
+// The two sweeps are sequential in k for one instance; their stage data are prefetched `depth` intervals ahead
+// into a shared-memory ring with cp.async (one column per lane: no block-level synchronisation needed).
+#pragma once
+#include "core.cuh"
+#if defined(__CUDACC__)
+#include <cuda_pipeline_primitives.h>
+#endif
+
+namespace mseetc {
+
+// ---- which planes a sweep consumes per interval ------------------------------------------------------------
+struct BwdFields {   // folded stage Hessian (13), linearised coupling rows (6), gradient parts (5 + 5)
+    enum { NF = 29 };
+    static MS_HD const double* addr(const Ctx& c, int f, int k, int s) { return &c.W(WS_QP + f, k, s); }
+};
+struct FwdFields {   // K, k (12) | P, p of the next node (9) | coupling rows (6) | b_{k+1} terms (7)
+    enum { NF = 34 };
+    static MS_HD const double* addr(const Ctx& c, int f, int k, int s) {
+        if (f < 12) return &c.W(WS_RIC + f, k, s);
+        if (f < 21) return &c.W(WS_RIC + f, k + 1, s);
+        if (f < 27) return &c.W(WS_QP + QP_TAU_B + (f - 21), k, s);
+        return &c.W(WS_QP + QP_HC_B + (f - 27), k, s);
+    }
+};
+enum { RING_NF_MAX = 34 };
+
+// direct loads (host emulation, and the device when no ring is configured)
+template <class FL>
+struct DirectFetch {
+    MS_HD void start(const Ctx&, int, int, int, int) {}
+    MS_HD void get(const Ctx& c, int k, int s, double* v) {
+        for (int f = 0; f < FL::NF; ++f) v[f] = *FL::addr(c, f, k, s);
+    }
+};
+
+#if defined(__CUDACC__)
+// cp.async ring in shared memory: slot (k mod (depth+1)), column = thread; stage k+depth*dir is requested as soon
+// as stage k has been copied to registers, into the slot that was consumed one iteration earlier.
+template <class FL>
+struct RingFetch {
+    double* sm;
+    int depth, bs, tid, dir, kEnd;
+    __device__ void issue(const Ctx& c, int k, int s) {
+        const bool in = (dir < 0) ? (k >= kEnd) : (k <= kEnd);
+        if (in) {
+            double* dst = sm + (size_t)((k % (depth + 1)) * FL::NF) * bs + tid;
+#pragma unroll
+            for (int f = 0; f < FL::NF; ++f) __pipeline_memcpy_async(dst + (size_t)f * bs, FL::addr(c, f, k, s), 8);
+        }
+        __pipeline_commit();
+    }
+    __device__ void start(const Ctx& c, int s, int kFirst, int kLast, int direction) {
+        dir = direction; kEnd = kLast;
+        for (int d = 0; d < depth; ++d) issue(c, kFirst + d * dir, s);
+    }
+    __device__ void get(const Ctx& c, int k, int s, double* v) {
+        switch (depth) {   // cp.async.wait_group needs an immediate
+            case 1: __pipeline_wait_prior(0); break;
+            case 2: __pipeline_wait_prior(1); break;
+            case 3: __pipeline_wait_prior(2); break;
+            case 4: __pipeline_wait_prior(3); break;
+            case 5: __pipeline_wait_prior(4); break;
+            case 6: __pipeline_wait_prior(5); break;
+            case 7: __pipeline_wait_prior(6); break;
+            default: __pipeline_wait_prior(7); break;
+        }
+        const double* src = sm + (size_t)((k % (depth + 1)) * FL::NF) * bs + tid;
+#pragma unroll
+        for (int f = 0; f < FL::NF; ++f) v[f] = src[(size_t)f * bs];
+        issue(c, k + depth * dir, s);
+    }
+};
+#endif
+
+// ---- backward sweep ----------------------------------------------------------------------------------------
+// returns false when a reduced control Hessian is not positive definite (wrong inertia of the KKT matrix)
+template <class Fetch>
+MS_HD bool riccati_backward(const Ctx& c, int s, int N, double mu, double delta, Fetch& fetch) {
+    const Config& g = c.cfg;
+    const double pn = g.withPn ? 1.0 : 0.0;
+    // terminal value function: only t_N is free (b_N fixed, Fel_{N-1} costless)
+    double P[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, p[3] = {0, 0, 0};
+    P[0][0] = c.W(WS_QP + QP_H_TT, N, s) + delta;
+    p[0] = (g.energy ? 0.0 : 1.0 / c.P(P_SCALE, s)) + mu * c.W(WS_QP + QP_G1_T, N, s);
+    for (int i = 0; i < 6; ++i) c.W(WS_RIC + RIC_P + i, N, s) = 0.0;
+    c.W(WS_RIC + RIC_P + 0, N, s) = P[0][0];
+    c.W(WS_RIC + RIC_PV + 0, N, s) = p[0];
+    c.W(WS_RIC + RIC_PV + 1, N, s) = 0.0;
+    c.W(WS_RIC + RIC_PV + 2, N, s) = 0.0;
+    fetch.start(c, s, N - 1, 0, -1);
+    for (int k = N - 1; k >= 0; --k) {
+        double v[BwdFields::NF];
+        fetch.get(c, k, s, v);
+        double M[6][6], m[6];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) M[i][j] = 0.0;
+        M[0][0] = v[QP_H_TT] + delta;
+        M[1][1] = v[QP_H_BB] + delta;
+        M[1][3] = M[3][1] = v[QP_H_BFEL];
+        M[1][4] = M[4][1] = v[QP_H_BFPB];
+        M[1][5] = M[5][1] = v[QP_H_BSL];
+        M[2][2] = v[QP_H_FF];
+        M[2][3] = M[3][2] = v[QP_H_FFEL];
+        M[3][3] = v[QP_H_FELFEL] + delta;
+        M[3][4] = M[4][3] = v[QP_H_FELFPB];
+        M[3][5] = M[5][3] = v[QP_H_FELSL];
+        M[4][4] = v[QP_H_FPBFPB] + delta;
+        M[4][5] = M[5][4] = v[QP_H_FPBSL];
+        M[5][5] = v[QP_H_SLSL] + delta;
+        m[0] = mu * v[QP_G1_T];
+        m[1] = v[QP_G0_B] + mu * v[QP_G1_B];
+        m[2] = v[QP_G0_F];
+        m[3] = v[QP_G0_FEL] + mu * v[QP_G1_FEL];
+        m[4] = v[QP_G0_FPB] + mu * v[QP_G1_FPB];
+        m[5] = v[QP_G0_SL] + mu * v[QP_G1_SL];
+        const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
+        // G = [A B]: rows t, b, f of the next state
+        double G[3][6] = {{1.0, tb, 0.0, tF, pn * tF, 0.0}, {0.0, pb, 0.0, pF, pn * pF, 0.0}, {0.0, 0.0, 0.0, 1.0, 0.0, 0.0}};
+        double r[3] = {v[QP_RT], v[QP_RB], 0.0};
+        const bool last = (k == N - 1);
+        if (last) { for (int j = 0; j < 6; ++j) G[1][j] = 0.0; r[1] = 0.0; }   // d b_N = 0 is handled by elimination
+        // M += G' P G ; m += G' (P r + p)
+        double Y[3][6], pr[3];
+        for (int a = 0; a < 3; ++a) {
+            pr[a] = p[a] + P[a][0] * r[0] + P[a][1] * r[1] + P[a][2] * r[2];
+            for (int j = 0; j < 6; ++j) Y[a][j] = P[a][0] * G[0][j] + P[a][1] * G[1][j] + P[a][2] * G[2][j];
+        }
+        for (int i = 0; i < 6; ++i) {
+            m[i] += G[0][i] * pr[0] + G[1][i] * pr[1] + G[2][i] * pr[2];
+            for (int j = i; j < 6; ++j) {
+                double x = M[i][j] + G[0][i] * Y[0][j] + G[1][i] * Y[1][j] + G[2][i] * Y[2][j];
+                M[i][j] = x; M[j][i] = x;
+            }
+        }
+        double eB = 0.0, ePn = 0.0, e0 = 0.0;
+        if (last) {
+            // terminal speed fixed: Phi_b db + Phi_F (dFel + dFpb) + rb = 0  ->  dFel = eB db + ePn dFpb + e0
+            eB = -pb / pF; ePn = -pn; e0 = -v[QP_RB] / pF;
+            double colF[6];
+            for (int i = 0; i < 6; ++i) colF[i] = M[i][3];
+            const double mFF = M[3][3];
+            for (int i = 0; i < 6; ++i) m[i] += colF[i] * e0;
+            const double mF = m[3];
+            const double ev[6] = {0.0, eB, 0.0, 0.0, ePn, 0.0};
+            for (int i = 0; i < 6; ++i) m[i] += ev[i] * mF;
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) M[i][j] += colF[i] * ev[j] + ev[i] * colF[j] + mFF * ev[i] * ev[j];
+            for (int i = 0; i < 6; ++i) { M[i][3] = 0.0; M[3][i] = 0.0; }
+            M[3][3] = 1.0; m[3] = 0.0;      // Fel of the last interval is now a dummy control
+        }
+        // Cholesky of the control block (indices 3..5), reciprocals of the pivots kept
+        double d0 = M[3][3];
+        if (!(d0 > 0.0) || !isfinite(d0)) return false;
+        const double i00 = 1.0 / sqrt(d0);
+        const double l10 = M[4][3] * i00, l20 = M[5][3] * i00;
+        double d1 = M[4][4] - l10 * l10;
+        if (!(d1 > 0.0) || !isfinite(d1)) return false;
+        const double i11 = 1.0 / sqrt(d1);
+        const double l21 = (M[5][4] - l20 * l10) * i11;
+        double d2 = M[5][5] - l20 * l20 - l21 * l21;
+        if (!(d2 > 0.0) || !isfinite(d2)) return false;
+        const double i22 = 1.0 / sqrt(d2);
+        // solve Muu X = [Mux mu]  (4 right-hand sides)
+        double K[3][3], kf[3];
+        for (int j = 0; j < 4; ++j) {
+            const double r0 = (j < 3) ? M[3][j] : m[3], r1 = (j < 3) ? M[4][j] : m[4], r2 = (j < 3) ? M[5][j] : m[5];
+            const double y0 = r0 * i00, y1 = (r1 - l10 * y0) * i11, y2 = (r2 - l20 * y0 - l21 * y1) * i22;
+            const double x2 = y2 * i22, x1 = (y1 - l21 * x2) * i11, x0 = (y0 - l10 * x1 - l20 * x2) * i00;
+            if (j < 3) { K[0][j] = -x0; K[1][j] = -x1; K[2][j] = -x2; }
+            else { kf[0] = -x0; kf[1] = -x1; kf[2] = -x2; }
+        }
+        // P = Mxx + Mxu K ; p = mx + Mxu kf
+        double Pn[3][3], pnv[3];
+        for (int i = 0; i < 3; ++i) {
+            pnv[i] = m[i] + M[i][3] * kf[0] + M[i][4] * kf[1] + M[i][5] * kf[2];
+            for (int j = 0; j < 3; ++j) Pn[i][j] = M[i][j] + M[i][3] * K[0][j] + M[i][4] * K[1][j] + M[i][5] * K[2][j];
+        }
+        for (int i = 0; i < 3; ++i) { p[i] = pnv[i]; for (int j = 0; j < 3; ++j) P[i][j] = 0.5 * (Pn[i][j] + Pn[j][i]); }
+        if (last) {   // feedback row of the eliminated control
+            for (int j = 0; j < 3; ++j) K[0][j] = ePn * K[1][j];
+            K[0][1] += eB;
+            kf[0] = e0 + ePn * kf[1];
+        }
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) c.W(WS_RIC + RIC_K + 3 * i + j, k, s) = K[i][j];
+            c.W(WS_RIC + RIC_KF + i, k, s) = kf[i];
+            c.W(WS_RIC + RIC_PV + i, k, s) = p[i];
+        }
+        c.W(WS_RIC + RIC_P + 0, k, s) = P[0][0]; c.W(WS_RIC + RIC_P + 1, k, s) = P[0][1];
+        c.W(WS_RIC + RIC_P + 2, k, s) = P[0][2]; c.W(WS_RIC + RIC_P + 3, k, s) = P[1][1];
+        c.W(WS_RIC + RIC_P + 4, k, s) = P[1][2]; c.W(WS_RIC + RIC_P + 5, k, s) = P[2][2];
+    }
+    return true;
+}
+
+// ---- forward sweep: primal step and new coupling-row multipliers -------------------------------------------
+// Writes d Fel, d Fpb, d s, d t, d b into the step planes and the NEW multipliers of the coupling rows into
+// ST_YT / ST_YB (cell_step turns them into steps).
+template <class Fetch>
+MS_HD void riccati_forward(const Ctx& c, int s, int N, double mu, double delta, Fetch& fetch) {
+    const Config& g = c.cfg;
+    double dx[3] = {0.0, 0.0, 0.0};
+    c.W(WS_ST + ST_T, 0, s) = 0.0;
+    c.W(WS_ST + ST_B, 0, s) = 0.0;
+    fetch.start(c, s, 0, N - 1, +1);
+    for (int k = 0; k < N; ++k) {
+        double v[FwdFields::NF];
+        fetch.get(c, k, s, v);
+        double du[3];
+        for (int i = 0; i < 3; ++i) du[i] = v[9 + i] + v[3 * i + 0] * dx[0] + v[3 * i + 1] * dx[1] + v[3 * i + 2] * dx[2];
+        if (!g.withPn) du[1] = 0.0;
+        const double tb = v[21], tF = v[22], pb = v[23], pF = v[24], rt = v[25], rb = v[26];
+        const double dF = du[0] + du[1];
+        double dxn[3];
+        dxn[0] = dx[0] + tb * dx[1] + tF * dF + rt;
+        dxn[1] = (k + 1 < N) ? pb * dx[1] + pF * dF + rb : 0.0;
+        dxn[2] = du[0];
+        // costates of the next node: P (12..17 = tt,tb,tf,bb,bf,ff), p (18..20)
+        const double pit = v[18] + v[12] * dxn[0] + v[13] * dxn[1] + v[14] * dxn[2];
+        double pib;
+        if (k + 1 < N) {
+            pib = v[19] + v[13] * dxn[0] + v[15] * dxn[1] + v[16] * dxn[2];
+            // + the terms of interval k that depend on b_{k+1} directly (27..33 = hc_b, hc_fel, hc_fpb, hc_sl, hpp, gp0, gp1)
+            pib += v[27] * dx[1] + v[28] * du[0] + v[29] * du[1] + v[30] * du[2] + v[31] * dxn[1] + v[32] + mu * v[33];
+        } else {
+            // b_N is fixed: its row multiplier follows from stationarity w.r.t. Fel of the last interval
+            const double gF = c.W(WS_QP + QP_G0_FEL, k, s) + mu * c.W(WS_QP + QP_G1_FEL, k, s)
+                            + c.W(WS_QP + QP_H_BFEL, k, s) * dx[1] + c.W(WS_QP + QP_H_FFEL, k, s) * dx[2]
+                            + (c.W(WS_QP + QP_H_FELFEL, k, s) + delta) * du[0] + c.W(WS_QP + QP_H_FELFPB, k, s) * du[1]
+                            + c.W(WS_QP + QP_H_FELSL, k, s) * du[2];
+            pib = -(gF + tF * pit) / pF;
+        }
+        c.W(WS_ST + ST_FEL, k, s) = du[0];
+        c.W(WS_ST + ST_FPB, k, s) = du[1];
+        c.W(WS_ST + ST_SL, k, s) = du[2];
+        c.W(WS_ST + ST_T, k + 1, s) = dxn[0];
+        c.W(WS_ST + ST_B, k + 1, s) = dxn[1];
+        c.W(WS_ST + ST_YT, k, s) = -pit;
+        c.W(WS_ST + ST_YB, k, s) = -pib;
+        dx[0] = dxn[0]; dx[1] = dxn[1]; dx[2] = dxn[2];
+    }
+}
+
+// ---- per-instance driver: KKT error, termination, barrier update, search direction  (IPOPT Alg. A, A-1..A-4)
+template <class FetchB, class FetchF>
+MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
+    const int N = c.I(SI_N_INT, s);
+    const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+    count_cells(c, 1, N + 1);
+    double th = 0.0, fo = 0.0, slog = 0.0, sdamp = 0.0, dinf = 0.0, pinf = 0.0, cmin = 1e300, cmax = 0.0, zsum = 0.0, ysum = 0.0;
+    double cnPrev = 0.0, ytPrev = 0.0;
+    // sequential (deterministic) reduction of the per-interval partials; loads are batched 4 intervals at a time
+    for (int k0 = 0; k0 <= N; k0 += 4) {
+        double q[4][14];
+        for (int j = 0; j < 4; ++j) {
+            const int k = (k0 + j <= N) ? k0 + j : N;
+            for (int f = 0; f < 13; ++f) q[j][f] = c.W(WS_PART + PC_TH + f, k, s);
+            q[j][13] = c.W(it + IT_YT, k, s);
+        }
+        for (int j = 0; j < 4 && k0 + j <= N; ++j) {
+            const int k = k0 + j;
+            th += q[j][0]; fo += q[j][1]; slog += q[j][2]; sdamp += q[j][3];
+            dinf = fmax(dinf, q[j][4]); pinf = fmax(pinf, q[j][5]);
+            cmin = fmin(cmin, q[j][6]); cmax = fmax(cmax, q[j][7]);
+            zsum += q[j][8]; ysum += q[j][9];
+            if (k >= 1) {
+                dinf = fmax(dinf, fabs(q[j][12] + ytPrev));
+                if (k < N) dinf = fmax(dinf, fabs(q[j][10] + cnPrev));
+            }
+            if (k < N) { cnPrev = q[j][11]; ytPrev = q[j][13]; }
+        }
+    }
+    // counts for the IPOPT error scaling s_d, s_c (eq. 6)
+    const int nrow = (g.withPower ? 2 : 0) + 1 + (g.energy ? 2 : 0);
+    const int nbRow = (g.withPower ? 4 : 0) + 2 + (g.energy ? 2 : 0);
+    const int nb = N * (2 + (g.withPn ? 2 : 0) + 1 + nbRow) + (N - 1) * 4 + 2;
+    const int mrows = N * (nrow + 2);
+    const double sd = fmax(100.0, (ysum + zsum) / (mrows + nb)) / 100.0;
+    const double sc = fmax(100.0, zsum / nb) / 100.0;
+    const double E0 = fmax(fmax(dinf / sd, pinf), cmax / sc);
+    c.D(SD_THETA, s) = th; c.D(SD_FOBJ, s) = fo; c.D(SD_SLOG, s) = slog; c.D(SD_SDAMP, s) = sdamp;
+    c.D(SD_KKT, s) = E0; c.D(SD_DINF, s) = dinf; c.D(SD_PINF, s) = pinf; c.D(SD_CINF, s) = cmax;
+    if (c.D(SD_THETA_MAX, s) < 0.0) {
+        c.D(SD_THETA_MAX, s) = 1e4 * fmax(1.0, th);
+        c.D(SD_THETA_MIN, s) = 1e-4 * fmax(1.0, th);
+    }
+    if (!isfinite(E0) || !isfinite(fo)) { finish(c, s, ST_INVALID_NUMBER); return; }
+    if (E0 <= g.tol) { finish(c, s, ST_SOLVE_SUCCEEDED); return; }
+    if (c.I(SI_ITERS, s) >= g.maxIter) { finish(c, s, ST_MAXITER); return; }
+    // ---- monotone barrier update (eq. 7), filter reset
+    double mu = c.D(SD_MU, s);
+    for (;;) {
+        const double cinf = fmax(cmax - mu, mu - cmin);
+        const double Emu = fmax(fmax(dinf / sd, pinf), cinf / sc);
+        if (Emu <= 10.0 * mu && mu > g.tol / 10.0 * (1.0 + 1e-12)) {
+            mu = fmax(g.tol / 10.0, fmin(0.2 * mu, pow(mu, 1.5)));
+            c.I(SI_NFILT, s) = 0;
+        } else break;
+    }
+    c.D(SD_MU, s) = mu; c.D(SD_TAU, s) = fmax(0.99, 1.0 - mu);
+    // ---- search direction with inertia correction (IPOPT Alg. IC)
+    double delta = 0.0;
+    const double dlast = c.D(SD_DELTA_LAST, s);
+    bool ok = false;
+    for (int tries = 0; tries < 40; ++tries) {
+        count_cells(c, 2, N);
+        if (riccati_backward(c, s, N, mu, delta, fb)) { ok = true; break; }
+        c.I(SI_NREG, s) += 1;
+        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
+        else delta *= (dlast == 0.0) ? 100.0 : 8.0;
+        if (delta > 1e40) break;
+    }
+    if (!ok) { finish(c, s, ST_STEP_FAILED); return; }
+    if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
+    count_cells(c, 3, N);
+    riccati_forward(c, s, N, mu, delta, ff);
+    c.I(SI_PHASE, s) = PH_STEPPED;
+}
+
+// ---- interval-parallel part of the step --------------------------------------------------------------------
+struct Ftb {
+    double aP, aZ, gphid;
+};
+MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, double dvSigned, bool oneSided) {
+    // dvSigned = change of the slack; primal fraction-to-boundary (eq. 15a), dual step (eq. 15b), barrier slope
+    if (dvSigned < 0.0) f.aP = fmin(f.aP, -tau * slack / dvSigned);
+    const double dz = mu / slack - z - (z / slack) * dvSigned;
+    if (dz < 0.0) f.aZ = fmin(f.aZ, -tau * z / dz);
+    f.gphid += (-mu / slack + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
+}
+
+MS_HD void cell_step(const Ctx& c, int k, int s) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_STEPPED) return;
+    const int N = c.I(SI_N_INT, s);
+    if (k > N) return;
+    const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+    const double mu = c.D(SD_MU, s), tauF = c.D(SD_TAU, s), scale = c.P(P_SCALE, s);
+    Bnd B = load_bounds(c, k, s);
+    Ftb f{1.0, 1.0, 0.0};
+    const double dt = c.W(WS_ST + ST_T, k, s), db = c.W(WS_ST + ST_B, k, s);
+    if (k >= 1) {
+        const double t = c.W(it + IT_T, k, s);
+        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_L, k, s), t - B.tL, dt, false);
+        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_U, k, s), B.tU - t, -dt, false);
+        if (k < N) {
+            const double b = c.W(it + IT_B, k, s);
+            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_B_L, k, s), b - B.bL, db, false);
+            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_B_U, k, s), B.bU - b, -db, false);
+        }
+    }
+    if (k == N) {
+        if (!g.energy) f.gphid += dt / scale;
+        c.W(WS_PART + PS_AP, k, s) = f.aP;
+        c.W(WS_PART + PS_AZ, k, s) = f.aZ;
+        c.W(WS_PART + PS_GPHID, k, s) = f.gphid;
+        return;
+    }
+    const double du0 = c.W(WS_ST + ST_FEL, k, s), du1 = c.W(WS_ST + ST_FPB, k, s), du2 = c.W(WS_ST + ST_SL, k, s);
+    const double dbn = c.W(WS_ST + ST_B, k + 1, s);
+    const double fel = c.W(it + IT_FEL, k, s), fpb = c.W(it + IT_FPB, k, s), sl = c.W(it + IT_SL, k, s);
+    // coupling-row multipliers: the forward sweep stored the new values
+    c.W(WS_ST + ST_YT, k, s) = c.W(WS_ST + ST_YT, k, s) - c.W(it + IT_YT, k, s);
+    c.W(WS_ST + ST_YB, k, s) = c.W(WS_ST + ST_YB, k, s) - c.W(it + IT_YB, k, s);
+    ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FEL_L, k, s), fel - B.felL, du0, false);
+    ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FEL_U, k, s), B.felU - fel, -du0, false);
+    if (g.withPn) {
+        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FPB_L, k, s), fpb - B.fpbL, du1, false);
+        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FPB_U, k, s), B.fpbU - fpb, -du1, false);
+    }
+    ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_SL_L, k, s), sl - B.slL, du2, true);
+    // objective part of the barrier directional derivative
+    if (g.energy) {
+        f.gphid += c.W(WS_TRK + TRK_DS, k, s) * (du0 + du2) / scale;
+        if (k >= 1) f.gphid += (2e-3 / scale) * (fel - c.W(it + IT_FEL, k - 1, s)) * (du0 - c.W(WS_ST + ST_FEL, k - 1, s));
+    } else {
+        f.gphid += (2e-4 / scale) * (fel * du0 + fpb * du1);
+    }
+    // inequality rows: slack step d w = J d + (d(x) - w), multiplier step from the condensed equations
+    for (int j = 0; j < NROW; ++j) {
+        c.W(WS_ST + ST_W + j, k, s) = 0.0;
+        c.W(WS_ST + ST_YD + j, k, s) = 0.0;
+        if (!row_on(g, j)) continue;
+        double jd;
+        if (j == R_P0) jd = c.W(WS_QP + QP_J_P0_B, k, s) * db + c.W(WS_QP + QP_J_P0_FEL, k, s) * du0;
+        else if (j == R_P1) jd = c.W(WS_QP + QP_J_P1_FEL, k, s) * du0 + c.W(WS_QP + QP_J_P1_BN, k, s) * dbn;
+        else if (j == R_ACC) jd = c.W(WS_QP + QP_J_ACC_B, k, s) * db + du0 + du1;
+        else if (j == R_LTR) jd = du2 + c.W(WS_QP + QP_J_LTR_FEL, k, s) * du0 + c.W(WS_QP + QP_J_LTR_B, k, s) * db
+                                + c.W(WS_QP + QP_J_LTR_BN, k, s) * dbn;
+        else jd = du2 + c.W(WS_QP + QP_J_LRG_FEL, k, s) * du0 + c.W(WS_QP + QP_J_LRG_B, k, s) * db
+                + c.W(WS_QP + QP_J_LRG_BN, k, s) * dbn;
+        const double dw = jd + c.W(WS_QP + QP_RES + j, k, s);
+        double L, U; bool hasU;
+        row_bounds(B, j, L, U, hasU);
+        const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
+        const double w = c.W(it + IT_W + j, k, s);
+        const double vL = c.W(it + IT_Z + zl, k, s), sL = w - L;
+        double sig = vL / sL, gw = -mu / sL + (hasU ? 0.0 : MS_KAPPA_D * mu);
+        ftb_bound(f, tauF, mu, vL, sL, dw, !hasU);
+        if (hasU) {
+            const double vU = c.W(it + IT_Z + zl + 1, k, s), sU = U - w;
+            sig += vU / sU; gw += mu / sU;
+            ftb_bound(f, tauF, mu, vU, sU, -dw, false);
+        }
+        c.W(WS_ST + ST_W + j, k, s) = dw;
+        c.W(WS_ST + ST_YD + j, k, s) = sig * dw + gw - c.W(it + IT_YD + j, k, s);
+    }
+    c.W(WS_PART + PS_AP, k, s) = f.aP;
+    c.W(WS_PART + PS_AZ, k, s) = f.aZ;
+    c.W(WS_PART + PS_GPHID, k, s) = f.gphid;
+}
+
+// ---- step-size limits of one instance and the first trial step size ----------------------------------------
+MS_HD void inst_alpha(const Ctx& c, int s) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_STEPPED) return;
+    const int N = c.I(SI_N_INT, s);
+    double aP = 1.0, aZ = 1.0, gphid = 0.0;
+    for (int k0 = 0; k0 <= N; k0 += 8) {
+        double q[8][3];
+        for (int j = 0; j < 8; ++j) {
+            const int k = (k0 + j <= N) ? k0 + j : N;
+            for (int f = 0; f < 3; ++f) q[j][f] = c.W(WS_PART + PS_AP + f, k, s);
+        }
+        for (int j = 0; j < 8 && k0 + j <= N; ++j) { aP = fmin(aP, q[j][0]); aZ = fmin(aZ, q[j][1]); gphid += q[j][2]; }
+    }
+    if (!isfinite(gphid) || !isfinite(aP) || !isfinite(aZ)) { finish(c, s, ST_STEP_FAILED); return; }
+    const double th = c.D(SD_THETA, s);
+    double amin;
+    if (gphid < 0.0) {                                   // eq. (23)
+        amin = 1e-5;
+        if (th > 0.0) amin = fmin(amin, 1e-8 * th / (-gphid));
+        if (th <= c.D(SD_THETA_MIN, s)) amin = fmin(amin, pow(th, 1.1) / pow(-gphid, 2.3));
+        amin *= 0.05;
+    } else amin = 0.05 * 1e-5;
+    c.D(SD_GPHID, s) = gphid;
+    c.D(SD_ALPHA, s) = aP;
+    c.D(SD_ALPHA_Z, s) = aZ;
+    c.D(SD_ALPHA_MIN, s) = amin;
+    c.I(SI_NLS, s) = 0;
+    c.I(SI_PHASE, s) = PH_TRIAL;
+}
+
+}  // namespace mseetc

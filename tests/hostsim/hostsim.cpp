@@ -59,7 +59,9 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     };
     for (;;) {
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_eval(c, k, s);
-        for (int s = 0; s < g.S; ++s) inst_step(c, s);
+        for (int s = 0; s < g.S; ++s) { DirectFetch<BwdFields> fb; DirectFetch<FwdFields> ff; inst_step(c, s, fb, ff); }
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_step(c, k, s);
+        for (int s = 0; s < g.S; ++s) inst_alpha(c, s);
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_trial(c, k, s);
