@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define MSEETC_B200_VERSION 100
-#define MSEETC_KERNEL_CLASSES 7
+#define MSEETC_KERNEL_CLASSES 8
 
 /* per-instance parameter planes: params_dev[field * n_instances + instance], specific units (ocp.py:96-116) */
 enum mseetc_param {
@@ -117,11 +117,11 @@ int mseetc_last_launches(mseetc_handle h);
 
 /* Per-kernel accounting of the last mseetc_solve_batch (measurement support for bench.py):
  *   kernel classes: 0 cell_trial, 1 inst_decide, 2 cell_eval, 3 inst_step (Riccati sweeps), 4 setup/init/extract,
- *                   5 cell_step, 6 inst_alpha            (MSEETC_KERNEL_CLASSES = 7 entries in every array)
- *   ms_out[7]        summed device time per class, from cudaEvent pairs recorded on the launch stream
+ *                   5 cell_step, 6 inst_alpha, 7 inst_kkt (MSEETC_KERNEL_CLASSES = 8 entries in every array)
+ *   ms_out[8]        summed device time per class, from cudaEvent pairs recorded on the launch stream
  *                    (only when profiling was switched on with mseetc_set_profiling; else zeros)
- *   launches_out[7]  launches per class
- *   cells_out[7]     (interval, instance) cells actually processed per class (idle/finished instances excluded)
+ *   launches_out[8]  launches per class
+ *   cells_out[8]     (interval, instance) cells actually processed per class (idle/finished instances excluded)
  *   mseetc_bytes_per_cell(h, cls): algorithmic HBM bytes one processed cell costs in that class */
 int mseetc_set_profiling(mseetc_handle h, int on);
 int mseetc_last_profile(mseetc_handle h, double* ms_out, int32_t* launches_out, int64_t* cells_out);

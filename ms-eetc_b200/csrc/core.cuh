@@ -289,19 +289,18 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
 // ------------------------------------------------------------------------------------------------
 // filter acceptance                                                         (IPOPT sec. 2.3, eqs. 18-20)
 // ------------------------------------------------------------------------------------------------
-MS_HD void inst_decide(const Ctx& c, int s) {
+// partial sums of the trial-point quantities over the intervals k = w, w+W, w+2W, ... (ascending)
+MS_HD void trial_partials(const Ctx& c, int s, int N, int w, int W, double* acc) {
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
+    for (int k = w; k <= N; k += W)
+        for (int f = 0; f < 4; ++f) acc[f] += c.W(WS_PART + PT_TH + f, k, s);
+}
+
+MS_HD void inst_decide(const Ctx& c, int s, const double* sums) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_TRIAL) return;
     const int N = c.I(SI_N_INT, s);
-    double tht = 0.0, ft = 0.0, slog = 0.0, sdamp = 0.0;
-    for (int k0 = 0; k0 <= N; k0 += 8) {               // batched loads, sequential (deterministic) sums
-        double q[8][4];
-        for (int j = 0; j < 8; ++j) {
-            const int k = (k0 + j <= N) ? k0 + j : N;
-            for (int f = 0; f < 4; ++f) q[j][f] = c.W(WS_PART + PT_TH + f, k, s);
-        }
-        for (int j = 0; j < 8 && k0 + j <= N; ++j) { tht += q[j][0]; ft += q[j][1]; slog += q[j][2]; sdamp += q[j][3]; }
-    }
+    const double tht = sums[0], ft = sums[1], slog = sums[2], sdamp = sums[3];
     const double mu = c.D(SD_MU, s);
     const double pht = ft - mu * slog + MS_KAPPA_D * mu * sdamp;
     const double theta = c.D(SD_THETA, s);

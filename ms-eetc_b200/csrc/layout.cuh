@@ -82,7 +82,8 @@ enum SdField {
 };
 enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_N };
 
-enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2, PH_STEPPED = 3 };
+enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2, PH_STEPPED = 3, PH_FACTOR = 4 };
+enum { RED_W = 8 };   // interleave factor of the per-instance reductions (fixed -> bitwise reproducible sums)
 // status codes (mapped to IPOPT's vocabulary by the host shim, ocp.py:362)
 enum Status {
     ST_RUNNING = -1, ST_SOLVE_SUCCEEDED = 0, ST_MAXITER = 1, ST_RESTORATION_FAILED = 2, ST_STEP_FAILED = 3,

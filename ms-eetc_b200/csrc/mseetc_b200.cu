@@ -24,29 +24,77 @@ namespace {
 
 thread_local std::string g_err;
 
-enum Op { OP_SETUP = 0, OP_INIT, OP_TRIAL, OP_DECIDE, OP_EVAL, OP_STEP, OP_EXTRACT, OP_CSTEP, OP_ALPHA };
+// ---- interval-parallel kernels: one thread per (interval k, instance), warp = 32 instances at one k ---------
+#define MS_CELL_KERNEL(NAME, CALL)                                              \
+    __global__ void __launch_bounds__(128) NAME(Ctx c, BatchIO io) {            \
+        const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       \
+        const int s = (int)(idx % c.cfg.S);                                     \
+        const int k = (int)(idx / c.cfg.S);                                     \
+        if (k >= c.cfg.NK) return;                                              \
+        CALL;                                                                   \
+    }
+MS_CELL_KERNEL(k_cell_setup, cell_setup(c, io, k, s))
+MS_CELL_KERNEL(k_cell_init, cell_init(c, k, s))
+MS_CELL_KERNEL(k_cell_trial, cell_trial(c, k, s))
+MS_CELL_KERNEL(k_cell_eval, cell_eval(c, k, s))
+MS_CELL_KERNEL(k_cell_step, cell_step(c, k, s))
+MS_CELL_KERNEL(k_cell_extract, cell_extract(c, io, k, s))
 
-template <int OP>
-__global__ void __launch_bounds__(128) k_cells(Ctx c, BatchIO io) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = (int)(idx % c.cfg.S);
-    const int k = (int)(idx / c.cfg.S);
-    if (k >= c.cfg.NK) return;
-    if (OP == OP_SETUP) cell_setup(c, io, k, s);
-    if (OP == OP_INIT) cell_init(c, k, s);
-    if (OP == OP_TRIAL) cell_trial(c, k, s);
-    if (OP == OP_EVAL) cell_eval(c, k, s);
-    if (OP == OP_CSTEP) cell_step(c, k, s);
-    if (OP == OP_EXTRACT) cell_extract(c, io, k, s);
+__global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < c.cfg.S) inst_setup(c, io, s);
 }
 
-template <int OP>
-__global__ void __launch_bounds__(64) k_insts(Ctx c, BatchIO io) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= c.cfg.S) return;
-    if (OP == OP_SETUP) inst_setup(c, io, s);
-    if (OP == OP_DECIDE) inst_decide(c, s);
-    if (OP == OP_ALPHA) inst_alpha(c, s);
+// ---- per-instance reductions: block = 32 instances x RED_W warps; warp w sums the intervals k = w, w+RED_W, ...
+// (coalesced rows), the partials are combined in fixed order by warp 0 -> bitwise reproducible, no atomics.
+__global__ void __launch_bounds__(32 * RED_W) k_inst_decide(Ctx c) {
+    __shared__ double sm[RED_W][4][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
+    const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_TRIAL;
+    double acc[4] = {0, 0, 0, 0};
+    if (on) trial_partials(c, s, c.I(SI_N_INT, s), w, RED_W, acc);
+    for (int f = 0; f < 4; ++f) sm[w][f][lane] = acc[f];
+    __syncthreads();
+    if (w == 0 && on) {
+        double tot[4] = {0, 0, 0, 0};
+        for (int ww = 0; ww < RED_W; ++ww) for (int f = 0; f < 4; ++f) tot[f] += sm[ww][f][lane];
+        inst_decide(c, s, tot);
+    }
+}
+
+__global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c) {
+    __shared__ double sm[RED_W][3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
+    const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_STEPPED;
+    double acc[3] = {1.0, 1.0, 0.0};
+    if (on) alpha_partials(c, s, c.I(SI_N_INT, s), w, RED_W, acc);
+    for (int f = 0; f < 3; ++f) sm[w][f][lane] = acc[f];
+    __syncthreads();
+    if (w == 0 && on) {
+        double tot[3] = {1.0, 1.0, 0.0};
+        for (int ww = 0; ww < RED_W; ++ww) { tot[0] = fmin(tot[0], sm[ww][0][lane]); tot[1] = fmin(tot[1], sm[ww][1][lane]); tot[2] += sm[ww][2][lane]; }
+        inst_alpha(c, s, tot);
+    }
+}
+
+__global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
+    __shared__ KktAcc sm[RED_W][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x * 32 + lane;
+    const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_EVAL;
+    KktAcc acc;
+    kkt_init(acc);
+    if (on) kkt_partials(c, s, c.I(SI_N_INT, s), c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0, w, RED_W, acc);
+    sm[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && on) {
+        KktAcc tot;
+        kkt_init(tot);
+        for (int ww = 0; ww < RED_W; ++ww) kkt_combine(tot, sm[ww][lane]);
+        inst_kkt(c, s, tot);
+    }
 }
 
 // Riccati sweeps: one thread per instance, stage data prefetched `depth` intervals ahead through a cp.async ring
@@ -69,7 +117,7 @@ __global__ void k_eval_interval(int n, int numSteps, int numApprox, const double
 
 }  // namespace
 
-enum { CLS_TRIAL = 0, CLS_DECIDE, CLS_EVAL, CLS_STEP, CLS_MISC, CLS_CSTEP, CLS_ALPHA, NCLS };
+enum { CLS_TRIAL = 0, CLS_DECIDE, CLS_EVAL, CLS_STEP, CLS_MISC, CLS_CSTEP, CLS_ALPHA, CLS_KKT, NCLS };
 
 struct mseetc_solver {
     mseetc_problem prob;
@@ -162,9 +210,10 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
         case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
         case CLS_DECIDE: return 8.0 * 4;
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13));
-        case CLS_STEP:   return 8.0 * (14 + BwdFields::NF + RIC_N + FwdFields::NF + 7);
+        case CLS_STEP:   return 8.0 * (BwdFields::NF + RIC_N + FwdFields::NF + 7);
         case CLS_CSTEP:  return 8.0 * ((7 + 2 + iter + 11 + rows + 2) + (2 * rows + 2 + 3));
         case CLS_ALPHA:  return 8.0 * 3;
+        case CLS_KKT:    return 8.0 * 14;
         default:         return 0.0;
     }
 }
@@ -240,16 +289,18 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     e = cudaMemsetAsync(c.si, 0, sizeof(int) * (size_t)SI_N * g.S, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    begin(CLS_MISC); k_insts<OP_SETUP><<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
-    begin(CLS_MISC); k_cells<OP_SETUP><<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
-    begin(CLS_MISC); k_cells<OP_INIT><<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    const unsigned rgrid = (unsigned)(g.S / 32);
+    begin(CLS_MISC); k_inst_setup<<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
+    begin(CLS_MISC); k_cell_setup<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    begin(CLS_MISC); k_cell_init<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
     for (;;) {
-        begin(CLS_EVAL); k_cells<OP_EVAL><<<cgrid, 128, 0, st>>>(c, io); end(CLS_EVAL);
+        begin(CLS_EVAL); k_cell_eval<<<cgrid, 128, 0, st>>>(c, io); end(CLS_EVAL);
+        begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
         begin(CLS_STEP); k_step<<<igrid, ib, ringBytes, st>>>(c, depth); end(CLS_STEP);
-        begin(CLS_CSTEP); k_cells<OP_CSTEP><<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
-        begin(CLS_ALPHA); k_insts<OP_ALPHA><<<igrid, ib, 0, st>>>(c, io); end(CLS_ALPHA);
+        begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
+        begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);
         if (tick >= maxTicks) break;
         if (tick >= 16 && (tick & 3) == 0) {
             e = cudaMemcpyAsync(h->done_host, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -258,11 +309,11 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
             if (*h->done_host >= n) break;
         }
-        begin(CLS_TRIAL); k_cells<OP_TRIAL><<<cgrid, 128, 0, st>>>(c, io); end(CLS_TRIAL);
-        begin(CLS_DECIDE); k_insts<OP_DECIDE><<<igrid, ib, 0, st>>>(c, io); end(CLS_DECIDE);
+        begin(CLS_TRIAL); k_cell_trial<<<cgrid, 128, 0, st>>>(c, io); end(CLS_TRIAL);
+        begin(CLS_DECIDE); k_inst_decide<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_DECIDE);
         ++tick;
     }
-    begin(CLS_MISC); k_cells<OP_EXTRACT><<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    begin(CLS_MISC); k_cell_extract<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     e = cudaMemcpyAsync(h->done_host, c.done, 128, cudaMemcpyDeviceToHost, st);
@@ -277,6 +328,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         h->cells[CLS_STEP] = (long long)cnt[1];
         h->cells[CLS_CSTEP] = (long long)cnt[3] + (long long)(cnt[3] / (unsigned long long)(p.n_intervals_max));
         h->cells[CLS_ALPHA] = h->cells[CLS_CSTEP];
+        h->cells[CLS_KKT] = (long long)cnt[1];
         h->cells[CLS_MISC] = 0;
     }
     for (size_t i = 0; i < evClass.size(); ++i) {

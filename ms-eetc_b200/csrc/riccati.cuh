@@ -251,37 +251,46 @@ MS_HD void riccati_forward(const Ctx& c, int s, int N, double mu, double delta, 
     }
 }
 
-// ---- per-instance driver: KKT error, termination, barrier update, search direction  (IPOPT Alg. A, A-1..A-4)
-template <class FetchB, class FetchF>
-MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
+// ---- KKT error of the current iterate: partial reduction over k = w, w+W, ... ------------------------------
+struct KktAcc {
+    double th, fo, slog, sdamp, zsum, ysum;   // sums
+    double dinf, pinf, cmin, cmax;            // max / min
+};
+MS_HD void kkt_init(KktAcc& a) {
+    a.th = a.fo = a.slog = a.sdamp = a.zsum = a.ysum = 0.0;
+    a.dinf = a.pinf = a.cmax = 0.0; a.cmin = 1e300;
+}
+MS_HD void kkt_partials(const Ctx& c, int s, int N, int it, int w, int W, KktAcc& a) {
+    kkt_init(a);
+    for (int k = w; k <= N; k += W) {
+        a.th += c.W(WS_PART + PC_TH, k, s);
+        a.fo += c.W(WS_PART + PC_F, k, s);
+        a.slog += c.W(WS_PART + PC_SLOG, k, s);
+        a.sdamp += c.W(WS_PART + PC_SDAMP, k, s);
+        a.zsum += c.W(WS_PART + PC_ZSUM, k, s);
+        a.ysum += c.W(WS_PART + PC_YSUM, k, s);
+        a.dinf = fmax(a.dinf, c.W(WS_PART + PC_DINF, k, s));
+        a.pinf = fmax(a.pinf, c.W(WS_PART + PC_PINF, k, s));
+        a.cmin = fmin(a.cmin, c.W(WS_PART + PC_CMIN, k, s));
+        a.cmax = fmax(a.cmax, c.W(WS_PART + PC_CMAX, k, s));
+        if (k >= 1) {   // stationarity w.r.t. the node variables couples interval k-1 and k
+            a.dinf = fmax(a.dinf, fabs(c.W(WS_PART + PC_OWN_T, k, s) + c.W(it + IT_YT, k - 1, s)));
+            if (k < N) a.dinf = fmax(a.dinf, fabs(c.W(WS_PART + PC_OWN_B, k, s) + c.W(WS_PART + PC_CN_B, k - 1, s)));
+        }
+    }
+}
+MS_HD void kkt_combine(KktAcc& a, const KktAcc& b) {
+    a.th += b.th; a.fo += b.fo; a.slog += b.slog; a.sdamp += b.sdamp; a.zsum += b.zsum; a.ysum += b.ysum;
+    a.dinf = fmax(a.dinf, b.dinf); a.pinf = fmax(a.pinf, b.pinf); a.cmin = fmin(a.cmin, b.cmin); a.cmax = fmax(a.cmax, b.cmax);
+}
+
+// ---- per-instance: KKT error, termination, barrier update                      (IPOPT Alg. A, steps A-1..A-3)
+MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
     const int N = c.I(SI_N_INT, s);
-    const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
     count_cells(c, 1, N + 1);
-    double th = 0.0, fo = 0.0, slog = 0.0, sdamp = 0.0, dinf = 0.0, pinf = 0.0, cmin = 1e300, cmax = 0.0, zsum = 0.0, ysum = 0.0;
-    double cnPrev = 0.0, ytPrev = 0.0;
-    // sequential (deterministic) reduction of the per-interval partials; loads are batched 4 intervals at a time
-    for (int k0 = 0; k0 <= N; k0 += 4) {
-        double q[4][14];
-        for (int j = 0; j < 4; ++j) {
-            const int k = (k0 + j <= N) ? k0 + j : N;
-            for (int f = 0; f < 13; ++f) q[j][f] = c.W(WS_PART + PC_TH + f, k, s);
-            q[j][13] = c.W(it + IT_YT, k, s);
-        }
-        for (int j = 0; j < 4 && k0 + j <= N; ++j) {
-            const int k = k0 + j;
-            th += q[j][0]; fo += q[j][1]; slog += q[j][2]; sdamp += q[j][3];
-            dinf = fmax(dinf, q[j][4]); pinf = fmax(pinf, q[j][5]);
-            cmin = fmin(cmin, q[j][6]); cmax = fmax(cmax, q[j][7]);
-            zsum += q[j][8]; ysum += q[j][9];
-            if (k >= 1) {
-                dinf = fmax(dinf, fabs(q[j][12] + ytPrev));
-                if (k < N) dinf = fmax(dinf, fabs(q[j][10] + cnPrev));
-            }
-            if (k < N) { cnPrev = q[j][11]; ytPrev = q[j][13]; }
-        }
-    }
+    const double th = a.th, fo = a.fo, dinf = a.dinf, pinf = a.pinf, cmin = a.cmin, cmax = a.cmax, zsum = a.zsum, ysum = a.ysum;
     // counts for the IPOPT error scaling s_d, s_c (eq. 6)
     const int nrow = (g.withPower ? 2 : 0) + 1 + (g.energy ? 2 : 0);
     const int nbRow = (g.withPower ? 4 : 0) + 2 + (g.energy ? 2 : 0);
@@ -290,7 +299,7 @@ MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
     const double sd = fmax(100.0, (ysum + zsum) / (mrows + nb)) / 100.0;
     const double sc = fmax(100.0, zsum / nb) / 100.0;
     const double E0 = fmax(fmax(dinf / sd, pinf), cmax / sc);
-    c.D(SD_THETA, s) = th; c.D(SD_FOBJ, s) = fo; c.D(SD_SLOG, s) = slog; c.D(SD_SDAMP, s) = sdamp;
+    c.D(SD_THETA, s) = th; c.D(SD_FOBJ, s) = fo; c.D(SD_SLOG, s) = a.slog; c.D(SD_SDAMP, s) = a.sdamp;
     c.D(SD_KKT, s) = E0; c.D(SD_DINF, s) = dinf; c.D(SD_PINF, s) = pinf; c.D(SD_CINF, s) = cmax;
     if (c.D(SD_THETA_MAX, s) < 0.0) {
         c.D(SD_THETA_MAX, s) = 1e4 * fmax(1.0, th);
@@ -310,7 +319,16 @@ MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
         } else break;
     }
     c.D(SD_MU, s) = mu; c.D(SD_TAU, s) = fmax(0.99, 1.0 - mu);
-    // ---- search direction with inertia correction (IPOPT Alg. IC)
+    c.I(SI_PHASE, s) = PH_FACTOR;
+}
+
+// ---- per-instance: search direction with inertia correction                     (IPOPT Alg. A step A-4, Alg. IC)
+template <class FetchB, class FetchF>
+MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_FACTOR) return;
+    const int N = c.I(SI_N_INT, s);
+    const double mu = c.D(SD_MU, s);
     double delta = 0.0;
     const double dlast = c.D(SD_DELTA_LAST, s);
     bool ok = false;
@@ -423,19 +441,19 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
 }
 
 // ---- step-size limits of one instance and the first trial step size ----------------------------------------
-MS_HD void inst_alpha(const Ctx& c, int s) {
+MS_HD void alpha_partials(const Ctx& c, int s, int N, int w, int W, double* acc) {
+    acc[0] = 1.0; acc[1] = 1.0; acc[2] = 0.0;
+    for (int k = w; k <= N; k += W) {
+        acc[0] = fmin(acc[0], c.W(WS_PART + PS_AP, k, s));
+        acc[1] = fmin(acc[1], c.W(WS_PART + PS_AZ, k, s));
+        acc[2] += c.W(WS_PART + PS_GPHID, k, s);
+    }
+}
+
+MS_HD void inst_alpha(const Ctx& c, int s, const double* red) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_STEPPED) return;
-    const int N = c.I(SI_N_INT, s);
-    double aP = 1.0, aZ = 1.0, gphid = 0.0;
-    for (int k0 = 0; k0 <= N; k0 += 8) {
-        double q[8][3];
-        for (int j = 0; j < 8; ++j) {
-            const int k = (k0 + j <= N) ? k0 + j : N;
-            for (int f = 0; f < 3; ++f) q[j][f] = c.W(WS_PART + PS_AP + f, k, s);
-        }
-        for (int j = 0; j < 8 && k0 + j <= N; ++j) { aP = fmin(aP, q[j][0]); aZ = fmin(aZ, q[j][1]); gphid += q[j][2]; }
-    }
+    const double aP = red[0], aZ = red[1], gphid = red[2];
     if (!isfinite(gphid) || !isfinite(aP) || !isfinite(aZ)) { finish(c, s, ST_STEP_FAILED); return; }
     const double th = c.D(SD_THETA, s);
     double amin;

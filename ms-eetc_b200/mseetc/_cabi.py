@@ -133,7 +133,7 @@ class Handle:
         return out
 
 
-KERNEL_CLASSES = ('cell_trial', 'inst_decide', 'cell_eval', 'inst_step', 'misc', 'cell_step', 'inst_alpha')
+KERNEL_CLASSES = ('cell_trial', 'inst_decide', 'cell_eval', 'inst_step', 'misc', 'cell_step', 'inst_alpha', 'inst_kkt')
 
 
 def set_profiling(handle, on):
@@ -142,9 +142,9 @@ def set_profiling(handle, on):
 
 def last_profile(handle):
     "Per-kernel-class (ms, launches, cells, bytes_per_cell) of the last solve on this handle."
-    ms = (ctypes.c_double * 7)()
-    la = (ctypes.c_int32 * 7)()
-    ce = (ctypes.c_int64 * 7)()
+    ms = (ctypes.c_double * 8)()
+    la = (ctypes.c_int32 * 8)()
+    ce = (ctypes.c_int64 * 8)()
     _check(lib().mseetc_last_profile(handle._h, ms, la, ce), 'mseetc_last_profile')
     return {name: dict(ms=ms[i], launches=la[i], cells=ce[i], bytes_per_cell=lib().mseetc_bytes_per_cell(handle._h, i))
             for i, name in enumerate(KERNEL_CLASSES)}

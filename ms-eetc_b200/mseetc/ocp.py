@@ -200,10 +200,23 @@ class casadiSolver():
         """Minimum trip duration t_N - t_0 of each instance (time-optimal mode of the same problem,
         reference ocp.py:146-150).  Returns (durations, status)."""
         sib = self._time_sibling()
-        horizon = 3.0 * self.trackLength / self._base['velocityMax']
         t0 = np.atleast_1d(np.asarray(initialTime, dtype=float))
-        res = sib.solve_batch(t0 + horizon, initialTime, terminalVelocity, initialVelocity, overrides=overrides, screen=False,
-                              device=device)
+        # upper bound on t_N for the time-optimal solve: a multiple of the free-running time at the speed limits
+        # (the initial guess spreads the nodes linearly up to that bound, ocp.py:325-339, so it should not be loose)
+        lim = np.minimum(self.points['Speed limit [m/s]'].values[:-1], self._base['velocityMax'])
+        running = float(np.sum(self.steps / lim))
+        res = None
+        for factor in (1.5, 2.5, 4.0):
+            cur = sib.solve_batch(t0 + factor * running, initialTime, terminalVelocity, initialVelocity, overrides=overrides,
+                                  screen=False, device=device)
+            if res is None:
+                res = cur
+            else:
+                redo = res['status'] != 0
+                for key in ('z', 'status', 'obj', 'kkt', 'iters'):
+                    res[key][redo] = cur[key][redo]
+            if np.all(res['status'] == 0):
+                break
         return res['z'][:, -2] - np.broadcast_to(t0, res['z'][:, -2].shape), res['status']
 
     def solve_batch(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None,

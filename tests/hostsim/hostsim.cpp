@@ -59,13 +59,33 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     };
     for (;;) {
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_eval(c, k, s);
+        for (int s = 0; s < g.nInst; ++s) {
+            if (c.I(SI_PHASE, s) != PH_EVAL) continue;
+            const int N = c.I(SI_N_INT, s), it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+            KktAcc tot, part;
+            kkt_init(tot);
+            for (int w = 0; w < RED_W; ++w) { kkt_partials(c, s, N, it, w, RED_W, part); kkt_combine(tot, part); }
+            inst_kkt(c, s, tot);
+        }
         for (int s = 0; s < g.S; ++s) { DirectFetch<BwdFields> fb; DirectFetch<FwdFields> ff; inst_step(c, s, fb, ff); }
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_step(c, k, s);
-        for (int s = 0; s < g.S; ++s) inst_alpha(c, s);
+        for (int s = 0; s < g.nInst; ++s) {
+            if (c.I(SI_PHASE, s) != PH_STEPPED) continue;
+            const int N = c.I(SI_N_INT, s);
+            double tot[3] = {1.0, 1.0, 0.0}, part[3];
+            for (int w = 0; w < RED_W; ++w) { alpha_partials(c, s, N, w, RED_W, part); tot[0] = fmin(tot[0], part[0]); tot[1] = fmin(tot[1], part[1]); tot[2] += part[2]; }
+            inst_alpha(c, s, tot);
+        }
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_trial(c, k, s);
-        for (int s = 0; s < g.S; ++s) inst_decide(c, s);
+        for (int s = 0; s < g.nInst; ++s) {
+            if (c.I(SI_PHASE, s) != PH_TRIAL) continue;
+            const int N = c.I(SI_N_INT, s);
+            double tot[4] = {0, 0, 0, 0}, part[4];
+            for (int w = 0; w < RED_W; ++w) { trial_partials(c, s, N, w, RED_W, part); for (int f = 0; f < 4; ++f) tot[f] += part[f]; }
+            inst_decide(c, s, tot);
+        }
         ++tick;
         if (*c.done >= n) break;
     }

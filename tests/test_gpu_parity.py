@@ -164,7 +164,7 @@ def test_trip_time_sweep_batch_properties(cabi):
     train = Train(config={'id': 'NL_Intercity_VIRM6'})
     solver = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), opts)
     tsolver = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), dict(opts, energyOptimal=False))
-    tmin = tsolver.solve_batch(3000.0)
+    tmin = tsolver.solve_batch(1500.0)
     assert tmin['status'][0] == 0
     Tmin = tmin['z'][0][-2]
     assert abs(Tmin - 1035.5536) < 2e-3
