@@ -179,14 +179,23 @@ MS_HD void inst_init(const Ctx& c, int s) {
 }
 
 // slack of a bound and the matching barrier pieces
+// barrier sum of one interval: sum(log slack) is accumulated as the log of products of up to 6 slacks (one
+// log per group instead of one per bound); slacks lie in [1e-20, 1e4] so a group product cannot leave the range
 struct BarAcc {
     double slog, sdamp;
     bool ok;
+    double prod;
+    int nprod;
 };
 MS_HD void bar_add(BarAcc& a, double slack, bool oneSided) {
     if (!(slack > 0.0)) a.ok = false;
-    a.slog += log(slack);
+    a.prod *= slack;
+    if (++a.nprod == 6) { a.slog += log(a.prod); a.prod = 1.0; a.nprod = 0; }
     if (oneSided) a.sdamp += slack;
+}
+MS_HD double bar_finish(BarAcc& a) {
+    if (a.nprod > 0) { a.slog += log(a.prod); a.prod = 1.0; a.nprod = 0; }
+    return a.ok ? a.slog : NAN;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -202,15 +211,18 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
     const double al = c.D(SD_ALPHA, s), az = c.D(SD_ALPHA_Z, s), mu = c.D(SD_MU, s);
     const double scale = c.P(P_SCALE, s);
     Bnd B = load_bounds(c, k, s);
-    BarAcc bar{0.0, 0.0, true};
+    BarAcc bar{0.0, 0.0, true, 1.0, 0};
     double th = 0.0, fo = 0.0;
 
     // multiplier update of one bound: z + az*dz, dz = mu/s - z -+ (z/s) dv, then the kappa_sigma safeguard (eq. 16)
     auto zstep = [&](int zi, double sOld, double sNew, double dvSigned) {
-        double z = c.W(cur + IT_Z + zi, k, s);
-        double dz = mu / sOld - z - (z / sOld) * dvSigned;
+        const double z = c.W(cur + IT_Z + zi, k, s);
+        const double rOld = rcp(sOld);
+        const double dz = mu * rOld - z - (z * rOld) * dvSigned;
         double zn = z + az * dz;
-        zn = fmax(fmin(zn, MS_KAPPA_SIGMA * mu / sNew), mu / (MS_KAPPA_SIGMA * sNew));
+        const double pr = zn * sNew;                 // kappa_sigma safeguard: mu/kappa <= z*slack <= kappa*mu
+        if (pr > MS_KAPPA_SIGMA * mu) zn = MS_KAPPA_SIGMA * mu / sNew;
+        else if (pr < mu * (1.0 / MS_KAPPA_SIGMA)) zn = mu / (MS_KAPPA_SIGMA * sNew);
         c.W(alt + IT_Z + zi, k, s) = zn;
     };
     auto var2 = [&](int itf, int stf, int zl, double L, double U, bool hasU, bool oneSided) -> double {
@@ -236,7 +248,7 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
         if (!g.energy) fo += t / scale;
         c.W(WS_PART + PT_TH, k, s) = 0.0;
         c.W(WS_PART + PT_F, k, s) = fo;
-        c.W(WS_PART + PT_SLOG, k, s) = bar.ok ? bar.slog : NAN;
+        c.W(WS_PART + PT_SLOG, k, s) = bar_finish(bar);
         c.W(WS_PART + PT_SDAMP, k, s) = 0.0;
         return;
     }
@@ -282,7 +294,7 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
     }
     c.W(WS_PART + PT_TH, k, s) = th;
     c.W(WS_PART + PT_F, k, s) = fo;
-    c.W(WS_PART + PT_SLOG, k, s) = bar.ok ? bar.slog : NAN;
+    c.W(WS_PART + PT_SLOG, k, s) = bar_finish(bar);
     c.W(WS_PART + PT_SDAMP, k, s) = bar.sdamp;
 }
 
@@ -362,16 +374,19 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const double scale = c.P(P_SCALE, s);
     Bnd B = load_bounds(c, k, s);
     double H[28], g0[NV7], g1[NV7];
+    #pragma unroll
     for (int i = 0; i < 28; ++i) H[i] = 0.0;
+    #pragma unroll
     for (int i = 0; i < NV7; ++i) { g0[i] = 0.0; g1[i] = 0.0; }
-    BarAcc bar{0.0, 0.0, true};
+    BarAcc bar{0.0, 0.0, true, 1.0, 0};
     double cmin = 1e300, cmax = 0.0, zsum = 0.0;
 
     auto bound = [&](int vi, int zi, double slack, double sign, bool oneSided) {
         // sign = +1 lower bound (slack = v-L), -1 upper bound (slack = U-v)
-        double z = c.W(it + IT_Z + zi, k, s);
-        H[sidx(vi, vi)] += z / slack;
-        g1[vi] += -sign / slack + (oneSided ? MS_KAPPA_D : 0.0);
+        const double z = c.W(it + IT_Z + zi, k, s);
+        const double r = rcp(slack);
+        H[sidx(vi, vi)] += z * r;
+        g1[vi] += -sign * r + (oneSided ? MS_KAPPA_D : 0.0);
         double pr = z * slack;
         cmin = fmin(cmin, pr); cmax = fmax(cmax, pr); zsum += z;
         bar_add(bar, slack, oneSided);
@@ -397,7 +412,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         c.W(WS_QP + QP_G1_T, k, s) = g1[V_T];
         c.W(WS_PART + PC_TH, k, s) = 0.0;
         c.W(WS_PART + PC_F, k, s) = fo;
-        c.W(WS_PART + PC_SLOG, k, s) = bar.ok ? bar.slog : NAN;
+        c.W(WS_PART + PC_SLOG, k, s) = bar_finish(bar);
         c.W(WS_PART + PC_SDAMP, k, s) = 0.0;
         c.W(WS_PART + PC_DINF, k, s) = 0.0;
         c.W(WS_PART + PC_PINF, k, s) = 0.0;
@@ -429,7 +444,8 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
     const double ct = t1 - t - tau.v, cb = b1 - phi.v;
     const double v0 = sqrt(b), v1 = sqrt(b1);
-    const double a_b = -(0.5 * q.sr1 / v0 + q.sr2), a_bb = 0.25 * q.sr1 / (b * v0);
+    const double iv0 = rcp(v0), iv1 = rcp(v1), ib0 = iv0 * iv0, ib1 = iv1 * iv1;
+    const double a_b = -(0.5 * q.sr1 * iv0 + q.sr2), a_bb = 0.25 * q.sr1 * ib0 * iv0;
 
     // ---- Hessian of the Lagrangian: coupling rows (ct = t1 - t - tau, cb = b1 - phi)
     {
@@ -441,20 +457,22 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     }
     // ---- inequality rows: value, gradient over the 7 local variables, Lagrangian-Hessian contribution
     double d[NROW], J[NROW][NV7];
+    #pragma unroll
     for (int j = 0; j < NROW; ++j) for (int i = 0; i < NV7; ++i) J[j][i] = 0.0;
     ineq_values(c, s, fel, fpb, sl, b, b1, q, d);
     double ydv[NROW];
+    #pragma unroll
     for (int j = 0; j < NROW; ++j) ydv[j] = c.W(it + IT_YD + j, k, s);
-    J[R_P0][V_B] = 0.5 * fel / v0; J[R_P0][V_FEL] = v0;
-    J[R_P1][V_BN] = 0.5 * fel / v1; J[R_P1][V_FEL] = v1;
+    J[R_P0][V_B] = 0.5 * fel * iv0; J[R_P0][V_FEL] = v0;
+    J[R_P1][V_BN] = 0.5 * fel * iv1; J[R_P1][V_FEL] = v1;
     J[R_ACC][V_B] = a_b; J[R_ACC][V_FEL] = 1.0; J[R_ACC][V_FPB] = g.withPn ? 1.0 : 0.0;
     J[R_LTR][V_FEL] = -c.P(P_CT, s); J[R_LTR][V_SL] = 1.0;
     J[R_LRG][V_FEL] = c.P(P_CR, s); J[R_LRG][V_SL] = 1.0;
     if (g.withPower) {
-        H[sidx(V_B, V_B)] += ydv[R_P0] * (-0.25 * fel / (b * v0));
-        H[sidx(V_B, V_FEL)] += ydv[R_P0] * (0.5 / v0);
-        H[sidx(V_BN, V_BN)] += ydv[R_P1] * (-0.25 * fel / (b1 * v1));
-        H[sidx(V_FEL, V_BN)] += ydv[R_P1] * (0.5 / v1);
+        H[sidx(V_B, V_B)] += ydv[R_P0] * (-0.25 * fel * ib0 * iv0);
+        H[sidx(V_B, V_FEL)] += ydv[R_P0] * (0.5 * iv0);
+        H[sidx(V_BN, V_BN)] += ydv[R_P1] * (-0.25 * fel * ib1 * iv1);
+        H[sidx(V_FEL, V_BN)] += ydv[R_P1] * (0.5 * iv1);
     }
     H[sidx(V_B, V_B)] += ydv[R_ACC] * a_bb;
 
@@ -489,6 +507,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     own_b += -tau.g0 * yt - phi.g0 * yb;
     own_t += -yt;
     double cn_b = yb;
+    #pragma unroll
     for (int j = 0; j < NROW; ++j) {
         c.W(WS_QP + QP_RES + j, k, s) = 0.0;
         if (!row_on(g, j)) continue;
@@ -497,14 +516,16 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
         const double w = c.W(it + IT_W + j, k, s);
         const double vL = c.W(it + IT_Z + zl, k, s), sL = w - L;
-        double sig = vL / sL, coef = -1.0 / sL + (hasU ? 0.0 : MS_KAPPA_D);
+        const double rL = rcp(sL);
+        double sig = vL * rL, coef = -rL + (hasU ? 0.0 : MS_KAPPA_D);
         double rw = -ydv[j] - vL;
         double pr = vL * sL;
         cmin = fmin(cmin, pr); cmax = fmax(cmax, pr); zsum += vL;
         bar_add(bar, sL, !hasU);
         if (hasU) {
             const double vU = c.W(it + IT_Z + zl + 1, k, s), sU = U - w;
-            sig += vU / sU; coef += 1.0 / sU; rw += vU;
+            const double rU = rcp(sU);
+            sig += vU * rU; coef += rU; rw += vU;
             pr = vU * sU;
             cmin = fmin(cmin, pr); cmax = fmax(cmax, pr); zsum += vU;
             bar_add(bar, sU, false);
@@ -513,10 +534,12 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         c.W(WS_QP + QP_RES + j, k, s) = res;
         th += fabs(res); pinf = fmax(pinf, fabs(res)); ysum += fabs(ydv[j]);
         dinf = fmax(dinf, fabs(rw));
+        #pragma unroll
         for (int a = 0; a < NV7; ++a) {
             if (J[j][a] == 0.0) continue;
             g0[a] += sig * res * J[j][a];
             g1[a] += coef * J[j][a];
+            #pragma unroll
             for (int e = a; e < NV7; ++e) H[sidx(a, e)] += sig * J[j][a] * J[j][e];
         }
         rx_fel += ydv[j] * J[j][V_FEL];
@@ -532,10 +555,13 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const double rt = -ct, rb = -cb;
     double av[6] = {0.0, phi.g0, 0.0, phi.g1, g.withPn ? phi.g1 : 0.0, 0.0};
     double hc[6];
+    #pragma unroll
     for (int i = 0; i < 6; ++i) hc[i] = H[sidx(i, V_BN)];
     const double hpp = H[sidx(V_BN, V_BN)], gp0 = g0[V_BN], gp1 = g1[V_BN];
     if (k + 1 < N) {
+        #pragma unroll
         for (int i = 0; i < 6; ++i) {
+            #pragma unroll
             for (int j = i; j < 6; ++j) H[sidx(i, j)] += hc[i] * av[j] + av[i] * hc[j] + hpp * av[i] * av[j];
             g0[i] += hc[i] * rb + (hpp * rb + gp0) * av[i];
             g1[i] += gp1 * av[i];
@@ -591,7 +617,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     c.W(WS_QP + QP_J_LRG_BN, k, s) = J[R_LRG][V_BN];
     c.W(WS_PART + PC_TH, k, s) = th;
     c.W(WS_PART + PC_F, k, s) = fo;
-    c.W(WS_PART + PC_SLOG, k, s) = bar.ok ? bar.slog : NAN;
+    c.W(WS_PART + PC_SLOG, k, s) = bar_finish(bar);
     c.W(WS_PART + PC_SDAMP, k, s) = bar.sdamp;
     c.W(WS_PART + PC_DINF, k, s) = dinf;
     c.W(WS_PART + PC_PINF, k, s) = pinf;

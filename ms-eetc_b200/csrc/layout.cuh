@@ -1,11 +1,12 @@
 // HBM data layout of the batched solver.
 //
-// All per-(instance, interval) data live in one FP64 workspace as field-major SoA planes:
-//     plane(field)[k][slot]      k = interval / node index (0..NK-1), slot = instance (padded to 32)
-// so a warp that works on 32 consecutive instances at the same k touches one contiguous 256-byte
-// segment per field -- both in the interval-parallel kernels (thread = (k, slot)) and in the
-// instance-parallel Riccati sweeps (thread = slot, loop over k).  Per-instance scalars and parameters
-// are planes of length S.
+// All per-(instance, interval) data live in one FP64 workspace, tiled by 32 instances:
+//     ws[tile = slot/32][k][field][lane = slot%32]      k = interval / node index (0..NK-1)
+// A warp that works on 32 consecutive instances at the same k touches one contiguous 256-byte segment per
+// field -- both in the interval-parallel kernels (thread = (k, slot)) and in the instance-parallel Riccati
+// sweeps (thread = slot, loop over k) -- and all fields of one (tile, k) are contiguous, so a field access is
+// `cell base + compile-time offset` (no per-access address arithmetic) and the per-interval data of a sweep is
+// one contiguous block.  Per-instance scalars and parameters are planes of length S.
 #pragma once
 #include <stdint.h>
 #include "jet.cuh"
@@ -111,7 +112,7 @@ struct Ctx {
     unsigned long long* cnt;   // [4] processed cells: trial, eval, riccati backward, riccati forward
 
     MS_HD double& W(int field, int k, int slot) const {
-        return ws[((size_t)field * cfg.NK + k) * cfg.S + slot];
+        return ws[((size_t)(slot >> 5) * cfg.NK + k) * (WS_FIELDS * 32) + (slot & 31) + field * 32];
     }
     MS_HD double& P(int field, int slot) const { return par[(size_t)field * cfg.S + slot]; }
     MS_HD double& D(int field, int slot) const { return sd[(size_t)field * cfg.S + slot]; }

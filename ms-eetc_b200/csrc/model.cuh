@@ -20,7 +20,7 @@ struct IntervalCoef {
 
 MS_HD double msqrt(double x) { return sqrt(x); }
 MS_HD Jet2 msqrt(const Jet2& x) { return jsqrt(x); }
-MS_HD double mrecip(double x) { return 1.0 / x; }
+MS_HD double mrecip(double x) { return rcp(x); }
 MS_HD Jet2 mrecip(const Jet2& x) { return jrecip(x); }
 
 // a(b, F) = F - (sr0 + sr1*sqrt(b) + sr2*b) - c0                     (train.py:251,254)

@@ -25,20 +25,20 @@ namespace {
 thread_local std::string g_err;
 
 // ---- interval-parallel kernels: one thread per (interval k, instance), warp = 32 instances at one k ---------
-#define MS_CELL_KERNEL(NAME, CALL)                                              \
-    __global__ void __launch_bounds__(128) NAME(Ctx c, BatchIO io) {            \
+#define MS_CELL_KERNEL(NAME, MINB, CALL)                                        \
+    __global__ void __launch_bounds__(128, MINB) NAME(Ctx c, BatchIO io) {      \
         const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       \
         const int s = (int)(idx % c.cfg.S);                                     \
         const int k = (int)(idx / c.cfg.S);                                     \
         if (k >= c.cfg.NK) return;                                              \
         CALL;                                                                   \
     }
-MS_CELL_KERNEL(k_cell_setup, cell_setup(c, io, k, s))
-MS_CELL_KERNEL(k_cell_init, cell_init(c, k, s))
-MS_CELL_KERNEL(k_cell_trial, cell_trial(c, k, s))
-MS_CELL_KERNEL(k_cell_eval, cell_eval(c, k, s))
-MS_CELL_KERNEL(k_cell_step, cell_step(c, k, s))
-MS_CELL_KERNEL(k_cell_extract, cell_extract(c, io, k, s))
+MS_CELL_KERNEL(k_cell_setup, 4, cell_setup(c, io, k, s))
+MS_CELL_KERNEL(k_cell_init, 4, cell_init(c, k, s))
+MS_CELL_KERNEL(k_cell_trial, 4, cell_trial(c, k, s))
+MS_CELL_KERNEL(k_cell_eval, 3, cell_eval(c, k, s))
+MS_CELL_KERNEL(k_cell_step, 4, cell_step(c, k, s))
+MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
 
 __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;

@@ -354,9 +354,10 @@ struct Ftb {
 MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, double dvSigned, bool oneSided) {
     // dvSigned = change of the slack; primal fraction-to-boundary (eq. 15a), dual step (eq. 15b), barrier slope
     if (dvSigned < 0.0) f.aP = fmin(f.aP, -tau * slack / dvSigned);
-    const double dz = mu / slack - z - (z / slack) * dvSigned;
+    const double r = rcp(slack);
+    const double dz = mu * r - z - (z * r) * dvSigned;
     if (dz < 0.0) f.aZ = fmin(f.aZ, -tau * z / dz);
-    f.gphid += (-mu / slack + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
+    f.gphid += (-mu * r + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
 }
 
 MS_HD void cell_step(const Ctx& c, int k, int s) {
@@ -425,11 +426,13 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
         const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
         const double w = c.W(it + IT_W + j, k, s);
         const double vL = c.W(it + IT_Z + zl, k, s), sL = w - L;
-        double sig = vL / sL, gw = -mu / sL + (hasU ? 0.0 : MS_KAPPA_D * mu);
+        const double rL = rcp(sL);
+        double sig = vL * rL, gw = -mu * rL + (hasU ? 0.0 : MS_KAPPA_D * mu);
         ftb_bound(f, tauF, mu, vL, sL, dw, !hasU);
         if (hasU) {
             const double vU = c.W(it + IT_Z + zl + 1, k, s), sU = U - w;
-            sig += vU / sU; gw += mu / sU;
+            const double rU = rcp(sU);
+            sig += vU * rU; gw += mu * rU;
             ftb_bound(f, tauF, mu, vU, sU, -dw, false);
         }
         c.W(WS_ST + ST_W + j, k, s) = dw;
