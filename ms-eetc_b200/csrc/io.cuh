@@ -1,7 +1,7 @@
 // Batch input scatter (caller arrays -> SoA planes) and result gather in the reference's own layout
 // (zOpt of ocp.py:360, interleaved as ocp.py:166-181,248-249; g-row order of ocp.py:183-241).
 #pragma once
-#include "riccati.cuh"
+#include "pit.cuh"
 
 namespace mseetc {
 

@@ -83,137 +83,189 @@ struct RingFetch {
 };
 #endif
 
-// ---- backward sweep ----------------------------------------------------------------------------------------
-// returns false when a reduced control Hessian is not positive definite (wrong inertia of the KKT matrix)
-template <class Fetch>
-MS_HD bool riccati_backward(const Ctx& c, int s, int N, double mu, double delta, Fetch& fetch) {
-    const Config& g = c.cfg;
-    const double pn = g.withPn ? 1.0 : 0.0;
-    // terminal value function: only t_N is free (b_N fixed, Fel_{N-1} costless)
-    double P[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, p[3] = {0, 0, 0};
+// ---- one interval of the stage QP in registers --------------------------------------------------------------
+struct StageQP {
+    double M[6][6], m[6];     // Hessian / gradient over (t,b,f | Fel,Fpb,sl), delta_w included
+    double G[3][6], r[3];     // next state = G (x;u) + r
+    double pb, pF, rb;        // Phi_b, Phi_F, b residual (needed by the terminal-speed elimination)
+};
+
+MS_HD void stage_build(const double* v, double mu, double delta, double pn, bool last, StageQP& q) {
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) q.M[i][j] = 0.0;
+    q.M[0][0] = v[QP_H_TT] + delta;
+    q.M[1][1] = v[QP_H_BB] + delta;
+    q.M[1][3] = q.M[3][1] = v[QP_H_BFEL];
+    q.M[1][4] = q.M[4][1] = v[QP_H_BFPB];
+    q.M[1][5] = q.M[5][1] = v[QP_H_BSL];
+    q.M[2][2] = v[QP_H_FF];
+    q.M[2][3] = q.M[3][2] = v[QP_H_FFEL];
+    q.M[3][3] = v[QP_H_FELFEL] + delta;
+    q.M[3][4] = q.M[4][3] = v[QP_H_FELFPB];
+    q.M[3][5] = q.M[5][3] = v[QP_H_FELSL];
+    q.M[4][4] = v[QP_H_FPBFPB] + delta;
+    q.M[4][5] = q.M[5][4] = v[QP_H_FPBSL];
+    q.M[5][5] = v[QP_H_SLSL] + delta;
+    q.m[0] = mu * v[QP_G1_T];
+    q.m[1] = v[QP_G0_B] + mu * v[QP_G1_B];
+    q.m[2] = v[QP_G0_F];
+    q.m[3] = v[QP_G0_FEL] + mu * v[QP_G1_FEL];
+    q.m[4] = v[QP_G0_FPB] + mu * v[QP_G1_FPB];
+    q.m[5] = v[QP_G0_SL] + mu * v[QP_G1_SL];
+    const double tb = v[QP_TAU_B], tF = v[QP_TAU_F];
+    q.pb = v[QP_PHI_B]; q.pF = v[QP_PHI_F]; q.rb = v[QP_RB];
+    // G = [A B]: rows t, b, f of the next state
+    const double G0[6] = {1.0, tb, 0.0, tF, pn * tF, 0.0};
+    const double G1[6] = {0.0, q.pb, 0.0, q.pF, pn * q.pF, 0.0};
+    const double G2[6] = {0.0, 0.0, 0.0, 1.0, 0.0, 0.0};
+    for (int j = 0; j < 6; ++j) { q.G[0][j] = G0[j]; q.G[1][j] = last ? 0.0 : G1[j]; q.G[2][j] = G2[j]; }
+    q.r[0] = v[QP_RT]; q.r[1] = last ? 0.0 : v[QP_RB]; q.r[2] = 0.0;   // d b_N = 0 is handled by elimination
+}
+
+// One backward Riccati step: (P, p) of the next node in, (P, p) of this node out, feedback K, kf.
+// Returns false when the reduced control Hessian is not positive definite (wrong inertia of the KKT matrix).
+MS_HD bool stage_riccati(StageQP& q, bool last, double pn, double P[3][3], double p[3], double K[3][3], double kf[3]) {
+    double (*M)[6] = q.M;
+    double* m = q.m;
+    // M += G' P G ; m += G' (P r + p)
+    double Y[3][6], pr[3];
+    for (int a = 0; a < 3; ++a) {
+        pr[a] = p[a] + P[a][0] * q.r[0] + P[a][1] * q.r[1] + P[a][2] * q.r[2];
+        for (int j = 0; j < 6; ++j) Y[a][j] = P[a][0] * q.G[0][j] + P[a][1] * q.G[1][j] + P[a][2] * q.G[2][j];
+    }
+    for (int i = 0; i < 6; ++i) {
+        m[i] += q.G[0][i] * pr[0] + q.G[1][i] * pr[1] + q.G[2][i] * pr[2];
+        for (int j = i; j < 6; ++j) {
+            const double x = M[i][j] + q.G[0][i] * Y[0][j] + q.G[1][i] * Y[1][j] + q.G[2][i] * Y[2][j];
+            M[i][j] = x; M[j][i] = x;
+        }
+    }
+    double eB = 0.0, ePn = 0.0, e0 = 0.0;
+    if (last) {
+        // terminal speed fixed: Phi_b db + Phi_F (dFel + dFpb) + rb = 0  ->  dFel = eB db + ePn dFpb + e0
+        const double ipF = rcp(q.pF);
+        eB = -q.pb * ipF; ePn = -pn; e0 = -q.rb * ipF;
+        double colF[6];
+        for (int i = 0; i < 6; ++i) colF[i] = M[i][3];
+        const double mFF = M[3][3];
+        for (int i = 0; i < 6; ++i) m[i] += colF[i] * e0;
+        const double mF = m[3];
+        const double ev[6] = {0.0, eB, 0.0, 0.0, ePn, 0.0};
+        for (int i = 0; i < 6; ++i) m[i] += ev[i] * mF;
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) M[i][j] += colF[i] * ev[j] + ev[i] * colF[j] + mFF * ev[i] * ev[j];
+        for (int i = 0; i < 6; ++i) { M[i][3] = 0.0; M[3][i] = 0.0; }
+        M[3][3] = 1.0; m[3] = 0.0;      // Fel of the last interval is now a dummy control
+    }
+    // Cholesky of the control block (indices 3..5), reciprocals of the pivots kept
+    const double d0 = M[3][3];
+    if (!(d0 > 0.0) || !isfinite(d0)) return false;
+    const double i00 = rcp(sqrt(d0));
+    const double l10 = M[4][3] * i00, l20 = M[5][3] * i00;
+    const double d1 = M[4][4] - l10 * l10;
+    if (!(d1 > 0.0) || !isfinite(d1)) return false;
+    const double i11 = rcp(sqrt(d1));
+    const double l21 = (M[5][4] - l20 * l10) * i11;
+    const double d2 = M[5][5] - l20 * l20 - l21 * l21;
+    if (!(d2 > 0.0) || !isfinite(d2)) return false;
+    const double i22 = rcp(sqrt(d2));
+    // solve Muu X = [Mux mu]  (4 right-hand sides)
+    for (int j = 0; j < 4; ++j) {
+        const double r0 = (j < 3) ? M[3][j] : m[3], r1 = (j < 3) ? M[4][j] : m[4], r2 = (j < 3) ? M[5][j] : m[5];
+        const double y0 = r0 * i00, y1 = (r1 - l10 * y0) * i11, y2 = (r2 - l20 * y0 - l21 * y1) * i22;
+        const double x2 = y2 * i22, x1 = (y1 - l21 * x2) * i11, x0 = (y0 - l10 * x1 - l20 * x2) * i00;
+        if (j < 3) { K[0][j] = -x0; K[1][j] = -x1; K[2][j] = -x2; }
+        else { kf[0] = -x0; kf[1] = -x1; kf[2] = -x2; }
+    }
+    // P = Mxx + Mxu K ; p = mx + Mxu kf
+    double Pn[3][3], pnv[3];
+    for (int i = 0; i < 3; ++i) {
+        pnv[i] = m[i] + M[i][3] * kf[0] + M[i][4] * kf[1] + M[i][5] * kf[2];
+        for (int j = 0; j < 3; ++j) Pn[i][j] = M[i][j] + M[i][3] * K[0][j] + M[i][4] * K[1][j] + M[i][5] * K[2][j];
+    }
+    for (int i = 0; i < 3; ++i) { p[i] = pnv[i]; for (int j = 0; j < 3; ++j) P[i][j] = 0.5 * (Pn[i][j] + Pn[j][i]); }
+    if (last) {   // feedback row of the eliminated control
+        for (int j = 0; j < 3; ++j) K[0][j] = ePn * K[1][j];
+        K[0][1] += eB;
+        kf[0] = e0 + ePn * kf[1];
+    }
+    return true;
+}
+
+MS_HD void stage_store(const Ctx& c, int k, int s, const double K[3][3], const double kf[3], const double P[3][3], const double p[3]) {
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) c.W(WS_RIC + RIC_K + 3 * i + j, k, s) = K[i][j];
+        c.W(WS_RIC + RIC_KF + i, k, s) = kf[i];
+        c.W(WS_RIC + RIC_PV + i, k, s) = p[i];
+    }
+    c.W(WS_RIC + RIC_P + 0, k, s) = P[0][0]; c.W(WS_RIC + RIC_P + 1, k, s) = P[0][1];
+    c.W(WS_RIC + RIC_P + 2, k, s) = P[0][2]; c.W(WS_RIC + RIC_P + 3, k, s) = P[1][1];
+    c.W(WS_RIC + RIC_P + 4, k, s) = P[1][2]; c.W(WS_RIC + RIC_P + 5, k, s) = P[2][2];
+}
+
+// terminal value function: only t_N is free (b_N fixed, Fel_{N-1} costless)
+MS_HD void terminal_value(const Ctx& c, int s, int N, double mu, double delta, double P[3][3], double p[3]) {
+    for (int i = 0; i < 3; ++i) { p[i] = 0.0; for (int j = 0; j < 3; ++j) P[i][j] = 0.0; }
     P[0][0] = c.W(WS_QP + QP_H_TT, N, s) + delta;
-    p[0] = (g.energy ? 0.0 : 1.0 / c.P(P_SCALE, s)) + mu * c.W(WS_QP + QP_G1_T, N, s);
+    p[0] = (c.cfg.energy ? 0.0 : 1.0 / c.P(P_SCALE, s)) + mu * c.W(WS_QP + QP_G1_T, N, s);
     for (int i = 0; i < 6; ++i) c.W(WS_RIC + RIC_P + i, N, s) = 0.0;
     c.W(WS_RIC + RIC_P + 0, N, s) = P[0][0];
     c.W(WS_RIC + RIC_PV + 0, N, s) = p[0];
     c.W(WS_RIC + RIC_PV + 1, N, s) = 0.0;
     c.W(WS_RIC + RIC_PV + 2, N, s) = 0.0;
-    fetch.start(c, s, N - 1, 0, -1);
-    for (int k = N - 1; k >= 0; --k) {
+}
+
+// ---- backward sweep over the intervals kHi-1 .. kLo, starting from (P, p) of node kHi ------------------------
+// Optionally accumulates the closed-loop transition of the range: x_{kHi} = Mc x_{kLo} + mc.
+template <class Fetch>
+MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch,
+                                  double P[3][3], double p[3], double* Mc, double* mc) {
+    const double pn = c.cfg.withPn ? 1.0 : 0.0;
+    if (kHi <= kLo) return true;
+    fetch.start(c, s, kHi - 1, kLo, -1);
+    for (int k = kHi - 1; k >= kLo; --k) {
         double v[BwdFields::NF];
         fetch.get(c, k, s, v);
-        double M[6][6], m[6];
-        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) M[i][j] = 0.0;
-        M[0][0] = v[QP_H_TT] + delta;
-        M[1][1] = v[QP_H_BB] + delta;
-        M[1][3] = M[3][1] = v[QP_H_BFEL];
-        M[1][4] = M[4][1] = v[QP_H_BFPB];
-        M[1][5] = M[5][1] = v[QP_H_BSL];
-        M[2][2] = v[QP_H_FF];
-        M[2][3] = M[3][2] = v[QP_H_FFEL];
-        M[3][3] = v[QP_H_FELFEL] + delta;
-        M[3][4] = M[4][3] = v[QP_H_FELFPB];
-        M[3][5] = M[5][3] = v[QP_H_FELSL];
-        M[4][4] = v[QP_H_FPBFPB] + delta;
-        M[4][5] = M[5][4] = v[QP_H_FPBSL];
-        M[5][5] = v[QP_H_SLSL] + delta;
-        m[0] = mu * v[QP_G1_T];
-        m[1] = v[QP_G0_B] + mu * v[QP_G1_B];
-        m[2] = v[QP_G0_F];
-        m[3] = v[QP_G0_FEL] + mu * v[QP_G1_FEL];
-        m[4] = v[QP_G0_FPB] + mu * v[QP_G1_FPB];
-        m[5] = v[QP_G0_SL] + mu * v[QP_G1_SL];
-        const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
-        // G = [A B]: rows t, b, f of the next state
-        double G[3][6] = {{1.0, tb, 0.0, tF, pn * tF, 0.0}, {0.0, pb, 0.0, pF, pn * pF, 0.0}, {0.0, 0.0, 0.0, 1.0, 0.0, 0.0}};
-        double r[3] = {v[QP_RT], v[QP_RB], 0.0};
         const bool last = (k == N - 1);
-        if (last) { for (int j = 0; j < 6; ++j) G[1][j] = 0.0; r[1] = 0.0; }   // d b_N = 0 is handled by elimination
-        // M += G' P G ; m += G' (P r + p)
-        double Y[3][6], pr[3];
-        for (int a = 0; a < 3; ++a) {
-            pr[a] = p[a] + P[a][0] * r[0] + P[a][1] * r[1] + P[a][2] * r[2];
-            for (int j = 0; j < 6; ++j) Y[a][j] = P[a][0] * G[0][j] + P[a][1] * G[1][j] + P[a][2] * G[2][j];
-        }
-        for (int i = 0; i < 6; ++i) {
-            m[i] += G[0][i] * pr[0] + G[1][i] * pr[1] + G[2][i] * pr[2];
-            for (int j = i; j < 6; ++j) {
-                double x = M[i][j] + G[0][i] * Y[0][j] + G[1][i] * Y[1][j] + G[2][i] * Y[2][j];
-                M[i][j] = x; M[j][i] = x;
-            }
-        }
-        double eB = 0.0, ePn = 0.0, e0 = 0.0;
-        if (last) {
-            // terminal speed fixed: Phi_b db + Phi_F (dFel + dFpb) + rb = 0  ->  dFel = eB db + ePn dFpb + e0
-            eB = -pb / pF; ePn = -pn; e0 = -v[QP_RB] / pF;
-            double colF[6];
-            for (int i = 0; i < 6; ++i) colF[i] = M[i][3];
-            const double mFF = M[3][3];
-            for (int i = 0; i < 6; ++i) m[i] += colF[i] * e0;
-            const double mF = m[3];
-            const double ev[6] = {0.0, eB, 0.0, 0.0, ePn, 0.0};
-            for (int i = 0; i < 6; ++i) m[i] += ev[i] * mF;
-            for (int i = 0; i < 6; ++i)
-                for (int j = 0; j < 6; ++j) M[i][j] += colF[i] * ev[j] + ev[i] * colF[j] + mFF * ev[i] * ev[j];
-            for (int i = 0; i < 6; ++i) { M[i][3] = 0.0; M[3][i] = 0.0; }
-            M[3][3] = 1.0; m[3] = 0.0;      // Fel of the last interval is now a dummy control
-        }
-        // Cholesky of the control block (indices 3..5), reciprocals of the pivots kept
-        double d0 = M[3][3];
-        if (!(d0 > 0.0) || !isfinite(d0)) return false;
-        const double i00 = 1.0 / sqrt(d0);
-        const double l10 = M[4][3] * i00, l20 = M[5][3] * i00;
-        double d1 = M[4][4] - l10 * l10;
-        if (!(d1 > 0.0) || !isfinite(d1)) return false;
-        const double i11 = 1.0 / sqrt(d1);
-        const double l21 = (M[5][4] - l20 * l10) * i11;
-        double d2 = M[5][5] - l20 * l20 - l21 * l21;
-        if (!(d2 > 0.0) || !isfinite(d2)) return false;
-        const double i22 = 1.0 / sqrt(d2);
-        // solve Muu X = [Mux mu]  (4 right-hand sides)
+        StageQP q;
+        stage_build(v, mu, delta, pn, last, q);
         double K[3][3], kf[3];
-        for (int j = 0; j < 4; ++j) {
-            const double r0 = (j < 3) ? M[3][j] : m[3], r1 = (j < 3) ? M[4][j] : m[4], r2 = (j < 3) ? M[5][j] : m[5];
-            const double y0 = r0 * i00, y1 = (r1 - l10 * y0) * i11, y2 = (r2 - l20 * y0 - l21 * y1) * i22;
-            const double x2 = y2 * i22, x1 = (y1 - l21 * x2) * i11, x0 = (y0 - l10 * x1 - l20 * x2) * i00;
-            if (j < 3) { K[0][j] = -x0; K[1][j] = -x1; K[2][j] = -x2; }
-            else { kf[0] = -x0; kf[1] = -x1; kf[2] = -x2; }
+        if (!stage_riccati(q, last, pn, P, p, K, kf)) return false;
+        stage_store(c, k, s, K, kf, P, p);
+        if (Mc) {
+            // closed loop of this interval: x+ = (A + B K) x + (B kf + r); compose: acc <- acc o this
+            double Mk[9], mk[3];
+            for (int i = 0; i < 3; ++i) {
+                mk[i] = q.r[i] + q.G[i][3] * kf[0] + q.G[i][4] * kf[1] + q.G[i][5] * kf[2];
+                for (int j = 0; j < 3; ++j) Mk[3 * i + j] = q.G[i][j] + q.G[i][3] * K[0][j] + q.G[i][4] * K[1][j] + q.G[i][5] * K[2][j];
+            }
+            double Mn[9], mn[3];
+            for (int i = 0; i < 3; ++i) {
+                mn[i] = mc[i] + Mc[3 * i] * mk[0] + Mc[3 * i + 1] * mk[1] + Mc[3 * i + 2] * mk[2];
+                for (int j = 0; j < 3; ++j) Mn[3 * i + j] = Mc[3 * i] * Mk[j] + Mc[3 * i + 1] * Mk[3 + j] + Mc[3 * i + 2] * Mk[6 + j];
+            }
+            for (int i = 0; i < 9; ++i) Mc[i] = Mn[i];
+            for (int i = 0; i < 3; ++i) mc[i] = mn[i];
         }
-        // P = Mxx + Mxu K ; p = mx + Mxu kf
-        double Pn[3][3], pnv[3];
-        for (int i = 0; i < 3; ++i) {
-            pnv[i] = m[i] + M[i][3] * kf[0] + M[i][4] * kf[1] + M[i][5] * kf[2];
-            for (int j = 0; j < 3; ++j) Pn[i][j] = M[i][j] + M[i][3] * K[0][j] + M[i][4] * K[1][j] + M[i][5] * K[2][j];
-        }
-        for (int i = 0; i < 3; ++i) { p[i] = pnv[i]; for (int j = 0; j < 3; ++j) P[i][j] = 0.5 * (Pn[i][j] + Pn[j][i]); }
-        if (last) {   // feedback row of the eliminated control
-            for (int j = 0; j < 3; ++j) K[0][j] = ePn * K[1][j];
-            K[0][1] += eB;
-            kf[0] = e0 + ePn * kf[1];
-        }
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) c.W(WS_RIC + RIC_K + 3 * i + j, k, s) = K[i][j];
-            c.W(WS_RIC + RIC_KF + i, k, s) = kf[i];
-            c.W(WS_RIC + RIC_PV + i, k, s) = p[i];
-        }
-        c.W(WS_RIC + RIC_P + 0, k, s) = P[0][0]; c.W(WS_RIC + RIC_P + 1, k, s) = P[0][1];
-        c.W(WS_RIC + RIC_P + 2, k, s) = P[0][2]; c.W(WS_RIC + RIC_P + 3, k, s) = P[1][1];
-        c.W(WS_RIC + RIC_P + 4, k, s) = P[1][2]; c.W(WS_RIC + RIC_P + 5, k, s) = P[2][2];
     }
     return true;
 }
 
-// ---- forward sweep: primal step and new coupling-row multipliers -------------------------------------------
+template <class Fetch>
+MS_HD bool riccati_backward(const Ctx& c, int s, int N, double mu, double delta, Fetch& fetch) {
+    double P[3][3], p[3];
+    terminal_value(c, s, N, mu, delta, P, p);
+    return riccati_backward_range(c, s, N, 0, N, mu, delta, fetch, P, p, nullptr, nullptr);
+}
+
+// ---- forward sweep over the intervals kLo .. kHi-1 from d x_{kLo}: primal step, new coupling-row multipliers ---
 // Writes d Fel, d Fpb, d s, d t, d b into the step planes and the NEW multipliers of the coupling rows into
 // ST_YT / ST_YB (cell_step turns them into steps).
 template <class Fetch>
-MS_HD void riccati_forward(const Ctx& c, int s, int N, double mu, double delta, Fetch& fetch) {
+MS_HD void riccati_forward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch, double dx[3]) {
     const Config& g = c.cfg;
-    double dx[3] = {0.0, 0.0, 0.0};
-    c.W(WS_ST + ST_T, 0, s) = 0.0;
-    c.W(WS_ST + ST_B, 0, s) = 0.0;
-    fetch.start(c, s, 0, N - 1, +1);
-    for (int k = 0; k < N; ++k) {
+    if (kHi <= kLo) return;
+    fetch.start(c, s, kLo, kHi - 1, +1);
+    for (int k = kLo; k < kHi; ++k) {
         double v[FwdFields::NF];
         fetch.get(c, k, s, v);
         double du[3];
@@ -249,6 +301,14 @@ MS_HD void riccati_forward(const Ctx& c, int s, int N, double mu, double delta, 
         c.W(WS_ST + ST_YB, k, s) = -pib;
         dx[0] = dxn[0]; dx[1] = dxn[1]; dx[2] = dxn[2];
     }
+}
+
+template <class Fetch>
+MS_HD void riccati_forward(const Ctx& c, int s, int N, double mu, double delta, Fetch& fetch) {
+    double dx[3] = {0.0, 0.0, 0.0};
+    c.W(WS_ST + ST_T, 0, s) = 0.0;
+    c.W(WS_ST + ST_B, 0, s) = 0.0;
+    riccati_forward_range(c, s, N, 0, N, mu, delta, fetch, dx);
 }
 
 // ---- KKT error of the current iterate: partial reduction over k = w, w+W, ... ------------------------------

@@ -25,7 +25,7 @@ struct hostsim_problem {
 int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* params, const int32_t* nint,
                         const int32_t* trk_of, const int32_t* trk_off, const double* ds, const double* c0,
                         const double* bmax, const double* tmin, double* z_out, double* lam_out, double* obj, double* kkt, int32_t* iters,
-                        int32_t* status, int32_t verbose_inst, int32_t* ticks_out) {
+                        int32_t* status, int32_t verbose_inst, int32_t* ticks_out, int32_t pit_lanes) {
     Config g;
     memset(&g, 0, sizeof g);
     g.S = pad_slots(n);
@@ -67,7 +67,11 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
             for (int w = 0; w < RED_W; ++w) { kkt_partials(c, s, N, it, w, RED_W, part); kkt_combine(tot, part); }
             inst_kkt(c, s, tot);
         }
-        for (int s = 0; s < g.S; ++s) { DirectFetch<BwdFields> fb; DirectFetch<FwdFields> ff; inst_step(c, s, fb, ff); }
+        for (int s = 0; s < g.S; ++s) {
+            DirectFetch<BwdFields> fb; DirectFetch<FwdFields> ff;
+            if (pit_lanes > 1) inst_step_pit_emulated(c, s, pit_lanes, fb, ff);   // lanes-per-instance (parallel-in-time) variant
+            else inst_step(c, s, fb, ff);
+        }
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_step(c, k, s);
         for (int s = 0; s < g.nInst; ++s) {
             if (c.I(SI_PHASE, s) != PH_STEPPED) continue;
