@@ -49,7 +49,12 @@ enum mseetc_param {
     MSEETC_P_T_START,   /* initialTime                        ocp.py:347 */
     MSEETC_P_B_START,   /* clipped v0^2                       ocp.py:343,348 */
     MSEETC_P_B_END,     /* clipped vN^2                       ocp.py:344,349 */
-    MSEETC_P_MASS,      /* mass*rho (informational)           ocp.py:97 */
+    MSEETC_P_MASS,      /* mass*rho                           ocp.py:97 */
+    MSEETC_P_DYN_AUX,   /* auxiliaries [W]        (loss_kind 2, efficiency.py:101) */
+    MSEETC_P_DYN_ETAG,  /* etaGear                (efficiency.py:101) */
+    MSEETC_P_DYN_FMAX,  /* forceMax of the measured drive [N]  (efficiency.py:64) */
+    MSEETC_P_DYN_PMAX,  /* powerMax of the measured drive [W]  (efficiency.py:65) */
+    MSEETC_P_DYN_SCALE, /* scale of the measured loss table (1 = reference map) */
     MSEETC_PARAM_COUNT
 };
 
@@ -83,6 +88,18 @@ const char* mseetc_last_error(void);
 
 int mseetc_create(const mseetc_problem* problem, mseetc_handle* out);
 int mseetc_destroy(mseetc_handle h);
+
+/* Dynamic loss map (loss_kind 2): the cubic tensor-product B-spline that efficiency.createSpline builds
+ * (efficiency.py:23-51): knots over load [%] (n_load+4) and speed [m/s] (n_speed+4), coefficients [n_load][n_speed].
+ * Host pointers; the library keeps a device copy until mseetc_destroy. */
+int mseetc_set_loss_map(mseetc_handle h, int32_t n_load, int32_t n_speed, const double* knots_load,
+                        const double* knots_speed, const double* coef);
+
+/* Kernel-level parity hook for the loss rows: G(Fel, b_k, b_{k+1}) = PL{tr,rgb}(Fel, vMid)/vMid with gradient and
+ * Hessian.  in_dev planes [3*n]: Fel, b_k, b_{k+1}; params_dev planes [MSEETC_PARAM_COUNT*n];
+ * out_dev planes [20*n]: traction row (value, dFel, db0, db1, FF, F0, F1, 00, 01, 11) then the braking row. */
+int mseetc_eval_loss_rows(mseetc_handle h, int32_t n, const double* in_dev, const double* params_dev, double* out_dev,
+                          void* cuda_stream);
 
 /* bytes of device workspace needed to solve `n_instances` at once */
 size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);

@@ -98,14 +98,30 @@ MS_HD double init_t(const Ctx& c, int j, int s, int N) {
     return push2(t0 + j * ((T - t0) / N), relaxL(t0), relaxU(T));
 }
 
+MS_HD LossPar load_losspar(const Ctx& c, int s) {
+    LossPar p;
+    const double eg = c.P(P_DYN_ETAG, s);
+    p.M = c.P(P_MASS, s); p.aux = c.P(P_DYN_AUX, s); p.cgT = (1.0 - eg) / eg; p.cgB = 1.0 - eg;
+    p.fMax = c.P(P_DYN_FMAX, s); p.pMax = c.P(P_DYN_PMAX, s); p.scale = c.P(P_DYN_SCALE, s);
+    return p;
+}
+
 // values of the inequality rows at a point                                  (ocp.py:189,199,225-226)
+template <bool DYN>
 MS_HD void ineq_values(const Ctx& c, int s, double fel, double fpb, double sl, double b0, double b1,
                        const IntervalCoef& q, double* d) {
     d[R_P0] = fel * sqrt(b0);
     d[R_P1] = fel * sqrt(b1);
     d[R_ACC] = accel(b0, fel + fpb, q);
-    d[R_LTR] = sl - c.P(P_CT, s) * fel;
-    d[R_LRG] = sl + c.P(P_CR, s) * fel;
+    if (DYN) {
+        LossRow tr, rg;
+        loss_rows_dynamic(c.lm, load_losspar(c, s), fel, b0, b1, tr, rg);
+        d[R_LTR] = sl - tr.v;
+        d[R_LRG] = sl - rg.v;
+    } else {
+        d[R_LTR] = sl - c.P(P_CT, s) * fel;
+        d[R_LRG] = sl + c.P(P_CR, s) * fel;
+    }
 }
 
 MS_HD bool row_on(const Config& g, int j) {
@@ -123,6 +139,7 @@ MS_HD void row_bounds(const Bnd& B, int j, double& L, double& U, bool& hasU) {
 // ------------------------------------------------------------------------------------------------
 // initialisation: x0 pushed inside the bounds, slacks from d(x0), multipliers 1 / 0   (IPOPT sec. 3.6)
 // ------------------------------------------------------------------------------------------------
+template <bool DYN>
 MS_HD void cell_init(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     const int N = c.I(SI_N_INT, s);
@@ -149,7 +166,7 @@ MS_HD void cell_init(const Ctx& c, int k, int s) {
     c.W(it + IT_Z + Z_SL_L, k, s) = 1.0;
     IntervalCoef q = load_coef(c, k, s);
     double d[NROW];
-    ineq_values(c, s, fel, fpb, sl, b, init_b(c, k + 1, s, N), q, d);
+    ineq_values<DYN>(c, s, fel, fpb, sl, b, init_b(c, k + 1, s, N), q, d);
     for (int j = 0; j < NROW; ++j) {
         if (!row_on(g, j)) continue;
         double L, U; bool hasU;
@@ -201,6 +218,7 @@ MS_HD double bar_finish(BarAcc& a) {
 // ------------------------------------------------------------------------------------------------
 // trial point                                                                 (IPOPT sec. 2.3, Alg. A step A-5)
 // ------------------------------------------------------------------------------------------------
+template <bool DYN>
 MS_HD void cell_trial(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_TRIAL) return;
@@ -268,7 +286,7 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
     c.W(alt + IT_YT, k, s) = c.W(cur + IT_YT, k, s) + al * c.W(WS_ST + ST_YT, k, s);
     c.W(alt + IT_YB, k, s) = c.W(cur + IT_YB, k, s) + al * c.W(WS_ST + ST_YB, k, s);
     double d[NROW];
-    ineq_values(c, s, fel, fpb, sl, b, b1, q, d);
+    ineq_values<DYN>(c, s, fel, fpb, sl, b, b1, q, d);
     for (int j = 0; j < NROW; ++j) {
         if (!row_on(g, j)) continue;
         double L, U; bool hasU;
@@ -365,6 +383,7 @@ enum { V_T = 0, V_B, V_F, V_FEL, V_FPB, V_SL, V_BN, NV7 };
 // ------------------------------------------------------------------------------------------------
 // interval evaluation: RK4 + sensitivities, Hessian of the Lagrangian, condensed stage QP, KKT partials
 // ------------------------------------------------------------------------------------------------
+template <bool DYN>
 MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
@@ -459,7 +478,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     double d[NROW], J[NROW][NV7];
     #pragma unroll
     for (int j = 0; j < NROW; ++j) for (int i = 0; i < NV7; ++i) J[j][i] = 0.0;
-    ineq_values(c, s, fel, fpb, sl, b, b1, q, d);
+    ineq_values<false>(c, s, fel, fpb, sl, b, b1, q, d);
     double ydv[NROW];
     #pragma unroll
     for (int j = 0; j < NROW; ++j) ydv[j] = c.W(it + IT_YD + j, k, s);
@@ -468,6 +487,24 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     J[R_ACC][V_B] = a_b; J[R_ACC][V_FEL] = 1.0; J[R_ACC][V_FPB] = g.withPn ? 1.0 : 0.0;
     J[R_LTR][V_FEL] = -c.P(P_CT, s); J[R_LTR][V_SL] = 1.0;
     J[R_LRG][V_FEL] = c.P(P_CR, s); J[R_LRG][V_SL] = 1.0;
+    if (DYN && g.energy) {
+        // loss map of efficiency.py: rows s - G(Fel, b_k, b_{k+1}) with full first and second derivatives
+        LossRow lr[2];
+        loss_rows_dynamic(c.lm, load_losspar(c, s), fel, b, b1, lr[0], lr[1]);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int row = (a == 0) ? R_LTR : R_LRG;
+            d[row] = sl - lr[a].v;
+            J[row][V_FEL] = -lr[a].gF; J[row][V_B] = -lr[a].g0; J[row][V_BN] = -lr[a].g1;
+            const double y = ydv[row];
+            H[sidx(V_FEL, V_FEL)] -= y * lr[a].hFF;
+            H[sidx(V_B, V_FEL)] -= y * lr[a].hF0;
+            H[sidx(V_FEL, V_BN)] -= y * lr[a].hF1;
+            H[sidx(V_B, V_B)] -= y * lr[a].h00;
+            H[sidx(V_B, V_BN)] -= y * lr[a].h01;
+            H[sidx(V_BN, V_BN)] -= y * lr[a].h11;
+        }
+    }
     if (g.withPower) {
         H[sidx(V_B, V_B)] += ydv[R_P0] * (-0.25 * fel * ib0 * iv0);
         H[sidx(V_B, V_FEL)] += ydv[R_P0] * (0.5 * iv0);

@@ -103,6 +103,21 @@ MS_HD void eval_interval_point(int i, int n, int numSteps, int numApprox, const 
     }
 }
 
+// kernel-level parity hook of the dynamic loss rows
+MS_HD void eval_loss_rows_point(const LossMapDev& lm, int i, int n, const double* in, const double* par, double* out) {
+    if (i >= n) return;
+    LossPar p;
+    const double eg = par[(size_t)P_DYN_ETAG * n + i];
+    p.M = par[(size_t)P_MASS * n + i]; p.aux = par[(size_t)P_DYN_AUX * n + i]; p.cgT = (1.0 - eg) / eg; p.cgB = 1.0 - eg;
+    p.fMax = par[(size_t)P_DYN_FMAX * n + i]; p.pMax = par[(size_t)P_DYN_PMAX * n + i]; p.scale = par[(size_t)P_DYN_SCALE * n + i];
+    LossRow r[2];
+    loss_rows_dynamic(lm, p, in[i], in[n + i], in[2 * (size_t)n + i], r[0], r[1]);
+    for (int a = 0; a < 2; ++a) {
+        const double vals[10] = {r[a].v, r[a].gF, r[a].g0, r[a].g1, r[a].hFF, r[a].hF0, r[a].hF1, r[a].h00, r[a].h01, r[a].h11};
+        for (int j = 0; j < 10; ++j) out[(size_t)(10 * a + j) * n + i] = vals[j];
+    }
+}
+
 // workspace carving (all sizes in bytes, 256-byte aligned sections)
 struct WsPlan {
     size_t off_ws, off_par, off_sd, off_si, off_done, total;

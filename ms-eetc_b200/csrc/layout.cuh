@@ -10,6 +10,7 @@
 #pragma once
 #include <stdint.h>
 #include "jet.cuh"
+#include "lossmap.cuh"
 
 namespace mseetc {
 
@@ -72,7 +73,9 @@ enum WsBase {
 // ---- per-instance parameters (specific units, ocp.py:96-116)
 enum ParField {
     P_SR0 = 0, P_SR1, P_SR2, P_FEL_L, P_FEL_U, P_FPB_L, P_P_LO, P_P_UP, P_A_LO, P_A_UP, P_CT, P_CR,
-    P_BMIN, P_SCALE, P_T, P_T0, P_B0, P_BN, P_MASS, PAR_N
+    P_BMIN, P_SCALE, P_T, P_T0, P_B0, P_BN, P_MASS,
+    P_DYN_AUX, P_DYN_ETAG, P_DYN_FMAX, P_DYN_PMAX, P_DYN_SCALE,   // dynamic loss map (efficiency.py:64-65,101)
+    PAR_N
 };
 // ---- per-instance solver state (doubles)
 enum SdField {
@@ -110,6 +113,7 @@ struct Ctx {
     int* si;       // SI_N planes of S
     int* done;     // number of finished instances (device counter polled by the host loop)
     unsigned long long* cnt;   // [4] processed cells: trial, eval, riccati backward, riccati forward
+    LossMapDev lm;             // spline of the dynamic loss map (lossKind 2), device pointers
 
     MS_HD double& W(int field, int k, int slot) const {
         return ws[((size_t)(slot >> 5) * cfg.NK + k) * (WS_FIELDS * 32) + (slot & 31) + field * 32];

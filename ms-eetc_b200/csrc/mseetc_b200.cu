@@ -34,9 +34,12 @@ thread_local std::string g_err;
         CALL;                                                                   \
     }
 MS_CELL_KERNEL(k_cell_setup, 4, cell_setup(c, io, k, s))
-MS_CELL_KERNEL(k_cell_init, 4, cell_init(c, k, s))
-MS_CELL_KERNEL(k_cell_trial, 4, cell_trial(c, k, s))
-MS_CELL_KERNEL(k_cell_eval, 3, cell_eval(c, k, s))
+MS_CELL_KERNEL(k_cell_init, 4, cell_init<false>(c, k, s))
+MS_CELL_KERNEL(k_cell_init_dyn, 2, cell_init<true>(c, k, s))
+MS_CELL_KERNEL(k_cell_trial, 4, cell_trial<false>(c, k, s))
+MS_CELL_KERNEL(k_cell_trial_dyn, 2, cell_trial<true>(c, k, s))
+MS_CELL_KERNEL(k_cell_eval, 3, cell_eval<false>(c, k, s))
+MS_CELL_KERNEL(k_cell_eval_dyn, 2, cell_eval<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_step, 4, cell_step(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
 
@@ -110,6 +113,11 @@ __global__ void __launch_bounds__(64) k_step(Ctx c, int depth) {
     inst_step(c, s, fb, ff);
 }
 
+__global__ void k_eval_loss_rows(LossMapDev lm, int n, const double* in, const double* par, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    eval_loss_rows_point(lm, i, n, in, par, out);
+}
+
 __global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     eval_interval_point(i, n, numSteps, numApprox, in, out);
@@ -129,6 +137,8 @@ struct mseetc_solver {
     int launches[NCLS];
     long long cells[NCLS];
     std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
+    double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
+    LossMapDev lm;
 };
 
 extern "C" {
@@ -149,7 +159,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     if (!p || !out) return fail(-1, "mseetc_create: null argument");
     if (p->n_intervals_max < 2) return fail(-2, "mseetc_create: n_intervals_max must be >= 2");
     if (p->num_steps < 1 || p->num_approx_steps < 0) return fail(-3, "mseetc_create: bad RK options");
-    if (p->loss_kind < 0 || p->loss_kind > 1) return fail(-4, "mseetc_create: loss_kind not supported by this build");
+    if (p->loss_kind < 0 || p->loss_kind > 2) return fail(-4, "mseetc_create: loss_kind must be 0, 1 or 2");
     if (p->max_iterations < 1 || !(p->tol > 0.0) || !(p->mu_init > 0.0)) return fail(-5, "mseetc_create: bad IP options");
     mseetc_solver* h = new (std::nothrow) mseetc_solver;
     if (!h) return fail(-6, "mseetc_create: out of host memory");
@@ -157,6 +167,8 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->last_ticks = 0;
     h->last_launches = 0;
     h->profiling = 0;
+    h->lm_dev = nullptr;
+    memset(&h->lm, 0, sizeof h->lm);
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
     cudaError_t e = cudaHostAlloc((void**)&h->done_host, 256, cudaHostAllocDefault);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
@@ -167,6 +179,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
 int mseetc_destroy(mseetc_handle h) {
     if (!h) return 0;
     cudaFreeHost(h->done_host);
+    if (h->lm_dev) cudaFree(h->lm_dev);
     for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
     delete h;
     return 0;
@@ -179,6 +192,36 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n) {
 
 int mseetc_last_ticks(mseetc_handle h) { return h ? h->last_ticks : -1; }
 int mseetc_last_launches(mseetc_handle h) { return h ? h->last_launches : -1; }
+
+int mseetc_set_loss_map(mseetc_handle h, int32_t nl, int32_t nv, const double* tl, const double* tv, const double* coef) {
+    if (!h || !tl || !tv || !coef) return fail(-1, "mseetc_set_loss_map: null argument");
+    if (nl < 4 || nv < 4) return fail(-2, "mseetc_set_loss_map: a cubic spline needs at least 4 coefficients per direction");
+    const size_t count = (size_t)(nl + 4) + (nv + 4) + (size_t)nl * nv;
+    if (h->lm_dev) { cudaFree(h->lm_dev); h->lm_dev = nullptr; }
+    cudaError_t e = cudaMalloc((void**)&h->lm_dev, count * sizeof(double));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(loss map)");
+    std::vector<double> host(count);
+    memcpy(host.data(), tl, sizeof(double) * (nl + 4));
+    memcpy(host.data() + nl + 4, tv, sizeof(double) * (nv + 4));
+    memcpy(host.data() + nl + 4 + nv + 4, coef, sizeof(double) * (size_t)nl * nv);
+    e = cudaMemcpy(h->lm_dev, host.data(), count * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(loss map)");
+    h->lm.tl = h->lm_dev; h->lm.tv = h->lm_dev + nl + 4; h->lm.coef = h->lm_dev + nl + 4 + nv + 4;
+    h->lm.nl = nl; h->lm.nv = nv;
+    return 0;
+}
+
+int mseetc_eval_loss_rows(mseetc_handle h, int32_t n, const double* in, const double* par, double* out, void* cuda_stream) {
+    if (!h || n < 1 || !in || !par || !out) return fail(-1, "mseetc_eval_loss_rows: bad argument");
+    if (!h->lm_dev) return fail(-2, "mseetc_eval_loss_rows: no loss map set (mseetc_set_loss_map)");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    k_eval_loss_rows<<<(n + 127) / 128, 128, 0, st>>>(h->lm, n, in, par, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "k_eval_loss_rows launch");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "k_eval_loss_rows");
+    return 0;
+}
 
 int mseetc_set_profiling(mseetc_handle h, int on) {
     if (!h) return fail(-1, "mseetc_set_profiling: null handle");
@@ -228,6 +271,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     if (!params || !nint || !trk_of || !trk_off || !ds || !c0 || !bmax || !status || !workspace)
         return fail(-3, "mseetc_solve_batch: null device pointer");
     const mseetc_problem& p = h->prob;
+    if (p.loss_kind == 2 && p.energy_optimal && !h->lm_dev) return fail(-6, "mseetc_solve_batch: loss_kind 2 needs mseetc_set_loss_map first");
     Config g;
     memset(&g, 0, sizeof g);
     g.S = pad_slots(n);
@@ -249,6 +293,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.si = (int*)(base + plan.off_si);
     c.done = (int*)(base + plan.off_done);
     c.cnt = (unsigned long long*)(base + plan.off_done + 64);
+    c.lm = h->lm;
+    const bool dyn = (p.loss_kind == 2 && p.energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
     const size_t cellThreads = (size_t)g.NK * g.S;
@@ -292,11 +338,15 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const unsigned rgrid = (unsigned)(g.S / 32);
     begin(CLS_MISC); k_inst_setup<<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
     begin(CLS_MISC); k_cell_setup<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
-    begin(CLS_MISC); k_cell_init<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    begin(CLS_MISC);
+    if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
+    end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
     for (;;) {
-        begin(CLS_EVAL); k_cell_eval<<<cgrid, 128, 0, st>>>(c, io); end(CLS_EVAL);
+        begin(CLS_EVAL);
+        if (dyn) k_cell_eval_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_eval<<<cgrid, 128, 0, st>>>(c, io);
+        end(CLS_EVAL);
         begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
         begin(CLS_STEP); k_step<<<igrid, ib, ringBytes, st>>>(c, depth); end(CLS_STEP);
         begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
@@ -309,7 +359,9 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
             if (*h->done_host >= n) break;
         }
-        begin(CLS_TRIAL); k_cell_trial<<<cgrid, 128, 0, st>>>(c, io); end(CLS_TRIAL);
+        begin(CLS_TRIAL);
+        if (dyn) k_cell_trial_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_trial<<<cgrid, 128, 0, st>>>(c, io);
+        end(CLS_TRIAL);
         begin(CLS_DECIDE); k_inst_decide<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_DECIDE);
         ++tick;
     }

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmseetc_b200.so')
 
 PARAMS = ['SR0', 'SR1', 'SR2', 'FEL_LO', 'FEL_UP', 'FPB_LO', 'POW_LO', 'POW_UP', 'ACC_LO', 'ACC_UP', 'LOSS_TR', 'LOSS_RG',
-          'BMIN', 'OBJ_SCALE', 'T_END', 'T_START', 'B_START', 'B_END', 'MASS']
+          'BMIN', 'OBJ_SCALE', 'T_END', 'T_START', 'B_START', 'B_END', 'MASS', 'DYN_AUX', 'DYN_ETAG', 'DYN_FMAX', 'DYN_PMAX',
+          'DYN_SCALE']
 PARAM_INDEX = {name: i for i, name in enumerate(PARAMS)}
 
 STATUS_STRINGS = {   # IPOPT's return_status vocabulary (what stats['Solver status'] holds in the reference, ocp.py:362)
@@ -59,6 +60,8 @@ def lib():
     L.mseetc_bytes_per_cell.argtypes = [vp, ctypes.c_int]
     L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.mseetc_eval_loss_rows.argtypes = [vp, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -99,6 +102,26 @@ class Handle:
                 self._h = ctypes.c_void_p(0)
         except Exception:
             pass
+
+    def set_loss_map(self, knots_load, knots_speed, coef):
+        "Upload the motor-loss spline (efficiency.createSpline) used by loss_kind 2."
+        tl = np.ascontiguousarray(knots_load, dtype=np.float64)
+        tv = np.ascontiguousarray(knots_speed, dtype=np.float64)
+        cf = np.ascontiguousarray(coef, dtype=np.float64)
+        assert cf.shape == (len(tl) - 4, len(tv) - 4)
+        _torch_cuda()
+        _check(lib().mseetc_set_loss_map(self._h, cf.shape[0], cf.shape[1], tl.ctypes.data, tv.ctypes.data, cf.ctypes.data),
+               'mseetc_set_loss_map')
+
+    def eval_loss_rows(self, fel, b0, b1, params):
+        "Kernel-level parity hook: numpy in ([n] each, params [PARAM_COUNT, n]) -> numpy [20, n]."
+        torch = _torch_cuda()
+        inp = torch.from_numpy(np.ascontiguousarray(np.stack([fel, b0, b1]), dtype=np.float64)).cuda()
+        par = torch.from_numpy(np.ascontiguousarray(params, dtype=np.float64)).cuda()
+        out = torch.empty((20, inp.shape[1]), dtype=torch.float64, device=inp.device)
+        _check(lib().mseetc_eval_loss_rows(self._h, inp.shape[1], _ptr(inp), _ptr(par), _ptr(out),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'mseetc_eval_loss_rows')
+        return out.cpu().numpy()
 
     def workspace(self, n, device):
         torch = _torch_cuda()

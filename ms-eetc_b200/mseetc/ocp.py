@@ -64,6 +64,8 @@ def classify_losses(train):
         raise ValueError("Power losses function of train must by either explicitly or implicitly defined!")
     fun = train.powerLosses
     kind = getattr(fun, 'mseetc_kind', None)
+    if kind == 'dynamic':
+        return 'dynamic', 0.0, 0.0
     if kind is not None:
         raise NotImplementedError("loss model '{}' is not available in this build of the device library".format(kind))
     fmax = train.forceMax if train.forceMax is not None else _ACC_INF * train.mass * train.rho
@@ -158,6 +160,13 @@ class casadiSolver():
         rows = dict(SR0=get('r0') / M, SR1=get('r1') / M, SR2=get('r2') / M, FEL_LO=fMin, FEL_UP=fMax, FPB_LO=fMinPn,
                     POW_LO=pLo, POW_UP=pUp, ACC_LO=accMin, ACC_UP=accMax, LOSS_TR=lossT, LOSS_RG=lossR,
                     BMIN=float(self.velocityMin) ** 2, OBJ_SCALE=scale, T_END=T, T_START=t0, B_START=v0c ** 2, B_END=vNc ** 2, MASS=M)
+        dyn = dict(DYN_AUX=0.0, DYN_ETAG=1.0, DYN_FMAX=1.0, DYN_PMAX=1.0, DYN_SCALE=1.0)
+        if self._lossKind == 'dynamic':
+            dp = self.train.powerLosses.device_params
+            pick = lambda key, dflt: np.broadcast_to(np.asarray(overrides[key], dtype=float), (n,)) if key in overrides else dflt
+            dyn = dict(DYN_AUX=pick('auxiliaries', dp['auxiliaries']), DYN_ETAG=pick('etaGear', dp['etaGear']), DYN_FMAX=dp['forceMax'],
+                       DYN_PMAX=dp['powerMax'], DYN_SCALE=pick('tableScale', dp['tableScale']))
+        rows.update(dyn)
         for name, val in rows.items():
             P[_cabi.PARAM_INDEX[name]] = val
         return P, M
@@ -178,8 +187,11 @@ class casadiSolver():
         if self._handle is None:
             io = self.opts.integrationOptions
             self._handle = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
-                                        {'none': 0, 'static': 1}[self._lossKind], io.numSteps, io.numApproxSteps,
+                                        {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], io.numSteps, io.numApproxSteps,
                                         int(self.opts.maxIterations))
+            if self._lossKind == 'dynamic' and self.energyOptimal:
+                dp = self.train.powerLosses.device_params
+                self._handle.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
         return self._handle
 
     # ------------------------------------------------------------------ batched solve (additive API)
@@ -226,7 +238,7 @@ class casadiSolver():
         terminalTime / initialTime / terminalVelocity / initialVelocity: scalars or arrays of length n.
         overrides: optional dict of per-instance train attributes (arrays of length n), any of
         mass, rho, r0, r1, r2, forceMax, forceMin, forceMinPn, powerMax, powerMin, accMax, accMin, velocityMax,
-        etaTraction, etaRgBrake.
+        etaTraction, etaRgBrake; with the dynamic loss map also auxiliaries, etaGear, tableScale.
         Returns a dict of numpy arrays: z [n, nz] (reference variable order), cost, kkt, iters, status,
         plus timing; nothing is post-processed.
 
@@ -243,7 +255,7 @@ class casadiSolver():
         T, t0, vN, v0 = [np.broadcast_to(a, (n,)) for a in arrs]
         etaT = np.asarray(overrides.pop('etaTraction', getattr(self.train, 'etaTraction', 1.0)), dtype=float)
         etaR = np.asarray(overrides.pop('etaRgBrake', getattr(self.train, 'etaRgBrake', 1.0)), dtype=float)
-        if not self.energyOptimal:
+        if not self.energyOptimal or self._lossKind == 'dynamic':
             lossT, lossR = 0.0, 0.0
         elif hasattr(self.train, 'powerLosses'):
             _, lossT, lossR = classify_losses(self.train)

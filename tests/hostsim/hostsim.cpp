@@ -25,7 +25,8 @@ struct hostsim_problem {
 int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* params, const int32_t* nint,
                         const int32_t* trk_of, const int32_t* trk_off, const double* ds, const double* c0,
                         const double* bmax, const double* tmin, double* z_out, double* lam_out, double* obj, double* kkt, int32_t* iters,
-                        int32_t* status, int32_t verbose_inst, int32_t* ticks_out, int32_t pit_lanes) {
+                        int32_t* status, int32_t verbose_inst, int32_t* ticks_out, int32_t pit_lanes,
+                        int32_t lm_nl, int32_t lm_nv, const double* lm_tl, const double* lm_tv, const double* lm_coef) {
     Config g;
     memset(&g, 0, sizeof g);
     g.S = pad_slots(n);
@@ -44,10 +45,12 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     c.si = (int*)(buf.data() + plan.off_si);
     c.done = (int*)(buf.data() + plan.off_done);
     c.cnt = (unsigned long long*)(buf.data() + plan.off_done + 64);
+    c.lm.tl = lm_tl; c.lm.tv = lm_tv; c.lm.coef = lm_coef; c.lm.nl = lm_nl; c.lm.nv = lm_nv;
+    const bool dyn = (pr->loss_kind == 2 && pr->energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
     for (int s = 0; s < g.S; ++s) inst_setup(c, io, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
-    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_init(c, k, s);
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
     int tick = 0;
     const int maxTicks = 20 * pr->max_iterations + 50;
     auto report = [&](const char* tag) {
@@ -58,7 +61,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
                c.D(SD_MU, s), c.D(SD_ALPHA, s), c.D(SD_ALPHA_Z, s), c.D(SD_KKT, s), c.I(SI_NLS, s), c.I(SI_NREG, s));
     };
     for (;;) {
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_eval(c, k, s);
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_eval<true>(c, k, s); else cell_eval<false>(c, k, s); }
         for (int s = 0; s < g.nInst; ++s) {
             if (c.I(SI_PHASE, s) != PH_EVAL) continue;
             const int N = c.I(SI_N_INT, s), it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
@@ -82,7 +85,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         }
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_trial(c, k, s);
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_trial<true>(c, k, s); else cell_trial<false>(c, k, s); }
         for (int s = 0; s < g.nInst; ++s) {
             if (c.I(SI_PHASE, s) != PH_TRIAL) continue;
             const int N = c.I(SI_N_INT, s);
@@ -95,6 +98,13 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     }
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_extract(c, io, k, s);
     if (ticks_out) *ticks_out = tick;
+    return 0;
+}
+
+int hostsim_eval_loss_rows(int32_t n, int32_t nl, int32_t nv, const double* tl, const double* tv, const double* coef,
+                           const double* in, const double* par, double* out) {
+    LossMapDev lm{tl, tv, coef, nl, nv};
+    for (int i = 0; i < n; ++i) eval_loss_rows_point(lm, i, n, in, par, out);
     return 0;
 }
 

@@ -231,3 +231,51 @@ def test_cabi_usage_errors(cabi):
     rc = lib.mseetc_solve_batch(h, 4, *([null] * 14), null, 0, null)
     assert rc < 0 and b'null' in lib.mseetc_last_error()
     assert lib.mseetc_destroy(h) == 0
+
+
+def test_dynamic_loss_rows_kernel_matches_oracle(cabi):
+    from test_hostsim_parity import _dynamic_params, loss_row_points, check_loss_rows
+    import harness
+    tr = fig5_train()
+    M = tr.mass * tr.rho
+    Fel, b0, b1 = loss_row_points(4096, seed=3)
+    tl, tv, cf = harness.loss_map_arrays()
+    h = cabi.Handle(300, 0, 1, 1, 2, 1, 1, 500)
+    h.set_loss_map(tl, tv, cf)
+    out = h.eval_loss_rows(Fel, b0, b1, _dynamic_params(len(Fel), M, tr.forceMax))
+    check_loss_rows(out, Fel, b0, b1, M, tr.forceMax)
+
+
+def test_dynamic_loss_map_public_api_matches_golden(cabi):
+    """reference simulations/table3.py:14-31 through the drop-in API: Train, totalLossesFunction (with its side effects on
+    the train), casadiSolver(...).solve(1541) -- against the oracle fixture tests/golden/table3_dynamic_flat_N300.json."""
+    import json, os
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from mseetc.efficiency import totalLossesFunction
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, '..', 'ms-eetc_b200', 'simulations', 'config.json')) as fh:
+        opts = json.load(fh)
+    opts['minimumVelocity'] = 1
+    for name, track_id in (('table3_dynamic_flat_N300', '00_var_speed_limit_100'), ('dynamic_swiss_N300', 'CH_StGallen_Wil')):
+        gold = json.load(open(os.path.join(here, 'golden', name + '.json')))
+        train = Train(config={'id': 'NL_Intercity_VIRM6'})
+        train.forceMinPn = 0
+        train.powerLosses = totalLossesFunction(train, auxiliaries=27000, etaGear=0.96)
+        solver = casadiSolver(train, Track(config={'id': track_id}), opts)
+        df, stats = solver.solve(gold['T'], terminalVelocity=1, initialVelocity=1)
+        assert df is not None
+        assert abs(stats['Cost'] - gold['cost_kwh']) <= 1e-6 * gold['cost_kwh']
+        assert stats['IP iterations'] == gold['iterations']
+        assert np.max(np.abs(df['Velocity [m/s]'].values - np.sqrt(np.array(gold['b'])))) <= 1e-4 * 44.5
+        # the table's energy column: sum = J - smoothing penalty (the epigraph rows are active at the optimum)
+        Fel = np.array(gold['Fel'])
+        pen = 1e-3 * np.sum(np.diff(Fel) ** 2) * (1e-6 * solver.totalMass / 3.6)
+        assert abs(df['Energy [kWh]'].sum() - (gold['cost_kwh'] - pen)) <= 2e-6 * gold['cost_kwh']
+    # parameter study on the loss map (BASELINE config 3, dynamic half): per-instance auxiliaries and table scale
+    rng = np.random.default_rng(5)
+    n = 64
+    res = solver.solve_batch(1242.0, overrides=dict(auxiliaries=rng.uniform(20e3, 35e3, n), tableScale=rng.uniform(0.9, 1.1, n)))
+    assert np.all(res['status'] == 0) and np.all(res['kkt'] <= 1e-8)
+    assert res['cost'].std() > 0.05

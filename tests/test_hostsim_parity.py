@@ -143,3 +143,63 @@ def test_parallel_in_time_direction_emulated(lib):
         assert seq['status'][0] == 0 and pit['status'][0] == 0
         assert abs(pit['obj'][0] - seq['obj'][0]) <= 1e-9 * abs(seq['obj'][0])
         assert pit['kkt'][0] <= 1e-8
+
+
+def _dynamic_params(n, M, fmax, aux=27000.0, etag=0.96, scale=1.0):
+    par = np.zeros((len(harness.PARAMS), n))
+    ix = {k: i for i, k in enumerate(harness.PARAMS)}
+    par[ix['MASS']] = M; par[ix['DYN_AUX']] = aux; par[ix['DYN_ETAG']] = etag; par[ix['DYN_FMAX']] = fmax
+    par[ix['DYN_PMAX']] = fmax * ((((55 - 20) / 150) * 140 + 20) / 3.6); par[ix['DYN_SCALE']] = scale
+    return par
+
+
+def loss_row_points(n, seed=1):
+    rng = np.random.default_rng(seed)
+    Fel = rng.uniform(-0.5, 0.5, n); b0 = rng.uniform(2, 1900, n); b1 = np.maximum(1.5, b0 + rng.uniform(-60, 60, n))
+    Fel[:5] = 0.0; Fel[5:10] = 1e-12; Fel[10:15] = -1e-12; Fel[15:20] = 0.55       # kink, both tangents, outside the load range
+    return Fel, b0, b1
+
+
+def check_loss_rows(out, Fel, b0, b1, M, fmax):
+    "device rows (value, gradient, Hessian of G) against the oracle's torch-autograd restatement of efficiency.py + splitLosses"
+    from oracle.lossmap import DynamicLossMap
+    ref = DynamicLossMap(fmax, 27000.0, 0.96).rows(M)(Fel, b0, b1)
+    for a in range(2):
+        val, g, H = ref[a]
+        refs = [-val, -g[0], -g[1], -g[2], -H[0], -H[1], -H[2], -H[3], -H[4], -H[5]]     # the oracle returns -G
+        for i in range(10):
+            scale = np.maximum(np.abs(refs[i]), np.abs(refs[i]).mean() + 1e-300)
+            assert np.max(np.abs(out[10 * a + i] - refs[i]) / scale) < 2e-8, (a, i)
+
+
+def test_dynamic_loss_rows_match_oracle(lib):
+    import ctypes
+    tr = fig5_train()
+    M = tr.mass * tr.rho
+    Fel, b0, b1 = loss_row_points(400)
+    tl, tv, cf = harness.loss_map_arrays()
+    par = _dynamic_params(len(Fel), M, tr.forceMax)
+    inp = np.ascontiguousarray(np.stack([Fel, b0, b1])); out = np.zeros((20, len(Fel)))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.hostsim_eval_loss_rows(len(Fel), cf.shape[0], cf.shape[1], P(tl), P(tv), P(cf), P(inp), P(par), P(out))
+    check_loss_rows(out, Fel, b0, b1, M, tr.forceMax)
+
+
+def test_dynamic_loss_map_solve_matches_golden(lib):
+    "reference simulations/table3.py problem (pn brake off, totalLossesFunction(train, 27000, 0.96)), N = 300"
+    import json, os
+    from oracle.problem import load_track
+    for name, path in (('table3_dynamic_flat_N300', FLAT_JSON), ('dynamic_swiss_N300', SWISS_JSON)):
+        gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name + '.json')))
+        tr = fig5_train()
+        tr.losses = ('dynamic', gold['auxiliaries'], gold['etaGear'], 1.0)
+        nlp = oracle_nlp(tr, load_track(path), gold['N'])
+        nlp.lossKind = 'dynamic'
+        out = harness.solve([nlp], [gold['T']], lib=lib)
+        assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8
+        assert abs(nlp.cost(out['obj'][0]) - gold['cost_kwh']) <= 1e-6 * gold['cost_kwh']
+        assert out['iters'][0] == gold['iterations']
+        z = out['z'][0]
+        assert np.max(np.abs(z[nlp.iB] - np.array(gold['b']))) <= 1e-4 * 1975.0
+        assert np.max(np.abs(z[nlp.iFel] - np.array(gold['Fel']))) <= 1e-4 * nlp.forceMax
+        assert np.max(np.abs(z[nlp.iT] - np.array(gold['t']))) <= 1e-4 * gold['T']

@@ -121,3 +121,36 @@ def test_unit_test_properties_curvature():
             u = nlp.unpack(r.x)
             e.append(np.sum(nlp.ds * u['Fel']) * nlp.M / 3.6e6)    # mechanical energy at the wheel [kWh]
         assert abs((e[1] - e[0]) - work) / work <= 5e-2
+
+
+def test_loss_map_pins_figure3():
+    """reference simulations/figure3.py:113-115: max static(eta=0.73) loss / max dynamic loss on the plotted grid must lie in
+    [0.99, 1.01].  Checked for the oracle's torch restatement of efficiency.py AND for the product's efficiency.py."""
+    import torch
+    from oracle.lossmap import DynamicLossMap
+    from mseetc.train import Train
+    from mseetc.efficiency import totalLossesFunction, loadToForce, motorLossesFunction
+    tr = Train(config={'id': 'NL_Intercity_VIRM6'})
+    fun = totalLossesFunction(tr, auxiliaries=27000, etaGear=0.96)
+    assert abs(tr.powerMax - 213900 * 52.6666666666666 / 3.6) < 1e-3 and tr.powerMin == -tr.powerMax      # efficiency.py:64-71 side effects
+    assert tr.forceMin == -213900 and abs(tr.velocityMax - 160 / 3.6) < 1e-12
+    eta = 0.73
+    L, V = np.meshgrid(np.linspace(-100, 100, 200), np.linspace(1, 170, 170) / 3.6, indexing='ij')
+    F = loadToForce(L, V, tr.forceMax, tr.powerMax)
+    stat = F * V * (F > 0) * (1 - eta) / eta - (1 - eta) * F * V * (F < 0)
+    lm = DynamicLossMap(tr.forceMax, 27000.0, 0.96)
+    dyn_oracle = lm.total(torch.tensor(F), torch.tensor(V)).numpy()
+    dyn_product = fun(F, V)
+    for dyn in (dyn_oracle, dyn_product):
+        assert 0.99 <= stat.max() / dyn.max() <= 1.01
+    assert np.max(np.abs(dyn_oracle - dyn_product)) < 1e-6 * dyn_oracle.max()      # two independent spline constructions
+    # the interpolant reproduces the measured table (min of the two converter configurations, 4 motors)
+    from mseetc.data import dataLosses
+    A, B = dataLosses()
+    best = np.minimum(np.array(A['losses']), np.array(B['losses'])) * 4
+    lut = motorLossesFunction(Train(config={'id': 'NL_Intercity_VIRM6'})).lut
+    loads = np.array(A['loads'], float); loads[-1] += 1e-4
+    speeds = (((np.array(A['frequencies']) - 20) / 150) * 140 + 20) / 3.6
+    LL, SS = np.meshgrid(loads, speeds, indexing='ij')
+    assert np.max(np.abs(lut(LL, SS) - best)) < 1e-8
+    assert lut(150.0, 20.0) == 0.0 and fun(3e5, 20.0) == 0.0                      # zero outside the measured box
