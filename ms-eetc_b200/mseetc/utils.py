@@ -225,9 +225,11 @@ def postProcessDataFrame(dfIn, points, train, CVODES=True, integrateLosses=False
     ds = np.append(np.diff(pos), np.nan)
     loss_fun = train.powerLossesFuns(split=False)          # specific, unsplit (utils.py:247-248)
     v_mid = 0.5 * (vel + v_next)
+    last = np.isnan(fel) | np.isnan(v_mid)                   # the terminal row has no control / no mid-point speed
+    f_eval, v_eval = np.where(last, 0.0, fel), np.where(last, 1.0, v_mid)
     with np.errstate(invalid='ignore', divide='ignore'):
-        losses = kWh * ds * totalMass * np.asarray(loss_fun(fel / totalMass, v_mid), dtype=float) / v_mid
-    losses = np.where(np.isnan(fel), np.nan, losses)
+        losses = kWh * ds * totalMass * np.asarray(loss_fun(f_eval / totalMass, v_eval), dtype=float) / v_eval
+    losses = np.where(last, np.nan, losses)
     df['Losses [kWh]'] = losses
     df['Energy [kWh]'] = kWh * ds * f_acc + kWh * ds * f_rgb + losses
     df['Energy (pnb) [kWh]'] = -kWh * ds * df['Force (pnb) [N]'].values
