@@ -79,6 +79,8 @@ typedef struct mseetc_problem {
     int32_t max_iterations;     /* opts.maxIterations -> ipopt max_iter  ocp.py:290 */
     double tol;                 /* IPOPT tol (default 1e-8) */
     double mu_init;             /* IPOPT mu_init (default 0.1) */
+    int32_t initial_guess;      /* 0: the reference's starting point (ocp.py:325-339); 1: dynamically consistent
+                                 * speed-envelope profile built on the device (same optimum, about half the iterations) */
 } mseetc_problem;
 
 typedef struct mseetc_solver* mseetc_handle;

@@ -86,16 +86,94 @@ MS_HD IntervalCoef load_coef(const Ctx& c, int k, int s) {
     return q;
 }
 
-// initial guess of the reference (ocp.py:325-339) pushed into the relaxed bounds
+// initial guess pushed into the relaxed bounds: the reference's (ocp.py:325-339) or, with initMode 1, the speed-envelope
+// profile that inst_profile left in the planes of iterate buffer 0
 MS_HD double init_b(const Ctx& c, int j, int s, int N) {
     if (j == 0) return c.P(P_B0, s);
     if (j == N) return c.P(P_BN, s);
-    return push2(MS_VEL0SQ, relaxL(c.P(P_BMIN, s)), relaxU(c.W(WS_TRK + TRK_BMAX, j, s)));
+    const double guess = c.cfg.initMode ? c.W(WS_IT1 + IT_B, j, s) : MS_VEL0SQ;
+    return push2(guess, relaxL(c.P(P_BMIN, s)), relaxU(c.W(WS_TRK + TRK_BMAX, j, s)));
 }
 MS_HD double init_t(const Ctx& c, int j, int s, int N) {
     double t0 = c.P(P_T0, s), T = c.P(P_T, s);
     if (j == 0) return t0;
-    return push2(t0 + j * ((T - t0) / N), relaxL(t0), relaxU(T));
+    const double guess = c.cfg.initMode ? c.W(WS_IT1 + IT_T, j, s) : t0 + j * ((T - t0) / N);
+    return push2(guess, relaxL(t0), relaxU(T));
+}
+
+// Dynamically consistent starting profile (initMode 1): speed envelope from the limits with bounded acceleration and
+// braking, cruise speed capped so that the trip takes the available time, times and forces from the ODE.  It replaces
+// the constant-speed guess of the reference only as a starting point; the NLP and its optimum are unchanged.
+MS_HD void inst_profile(const Ctx& c, int s) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || !g.initMode) return;
+    const int N = c.I(SI_N_INT, s);
+    const int P = WS_IT1;                       // scratch: buffer 1 holds the profile until cell_init has consumed it
+    const double sr0 = c.P(P_SR0, s), sr1 = c.P(P_SR1, s), sr2 = c.P(P_SR2, s);
+    const double felU = c.P(P_FEL_U, s), felL = c.P(P_FEL_L, s), fpbL = g.withPn ? c.P(P_FPB_L, s) : 0.0;
+    const double pUp = g.withPower ? c.P(P_P_UP, s) : 1e30, pLo = g.withPower ? c.P(P_P_LO, s) : -1e30;
+    const double aLo = c.P(P_A_LO, s), aUp = c.P(P_A_UP, s);
+    const double b0 = c.P(P_B0, s), bN = c.P(P_BN, s), bmin = c.P(P_BMIN, s);
+    const double Tav = c.P(P_T, s) - c.P(P_T0, s);
+    // ---- fastest admissible profile: accelerate / brake with 80 % of what the force, power and acceleration limits allow
+    double b = b0, bmaxAll = 0.0;
+    c.W(P + IT_B, 0, s) = b0;
+    for (int k = 0; k < N; ++k) {
+        const double v = sqrt(b), ds = c.W(WS_TRK + TRK_DS, k, s);
+        const double r = sr0 + sr1 * v + sr2 * b + c.W(WS_TRK + TRK_C0, k, s);
+        const double a = fmin(0.8 * (fmin(felU, pUp / fmax(v, 1.0)) - r), 0.8 * aUp);
+        const double lim = (k + 1 < N) ? 0.97 * c.W(WS_TRK + TRK_BMAX, k + 1, s) : bN;
+        b = fmax(bmin, fmin(lim, b + 2.0 * ds * a));
+        c.W(P + IT_B, k + 1, s) = b;
+    }
+    b = bN;
+    c.W(P + IT_B, N, s) = bN;
+    for (int k = N - 1; k >= 1; --k) {
+        const double v = sqrt(b), ds = c.W(WS_TRK + TRK_DS, k, s);
+        const double r = sr0 + sr1 * v + sr2 * b + c.W(WS_TRK + TRK_C0, k, s);
+        const double a = fmax(0.8 * (fmax(felL, pLo / fmax(v, 1.0)) + fpbL - r), 0.8 * aLo);      // negative
+        b = fmin(c.W(P + IT_B, k, s), b - 2.0 * ds * a);
+        c.W(P + IT_B, k, s) = b;
+        bmaxAll = fmax(bmaxAll, b);
+    }
+    // ---- energy mode: cap the cruise speed so that the trip uses (almost all of) the available time
+    double cap = 1e30;
+    if (g.energy) {
+        double lo = bmin, hi = bmaxAll;
+        for (int it = 0; it < 22; ++it) {
+            const double trial = (it == 0) ? 1e30 : 0.5 * (lo + hi);
+            double tt = 0.0, vp = sqrt(fmin(b0, fmax(trial, b0)));
+            for (int k = 0; k < N; ++k) {
+                const double bn = c.W(P + IT_B, k + 1, s);
+                const double vn = sqrt((k + 1 < N) ? fmin(bn, trial) : bn);
+                tt += 2.0 * c.W(WS_TRK + TRK_DS, k, s) / (vp + vn);
+                vp = vn;
+            }
+            if (it == 0) { if (tt >= 0.995 * Tav) break; continue; }    // no slack in the timetable: keep the fastest profile
+            if (tt > 0.995 * Tav) lo = trial; else hi = trial;
+            cap = hi;
+            if (hi - lo < 1e-3 * hi) break;
+        }
+    }
+    // ---- times, forces and epigraph variable of the profile
+    double t = c.P(P_T0, s);
+    c.W(P + IT_T, 0, s) = t;
+    b = b0;
+    for (int k = 0; k < N; ++k) {
+        double bn = c.W(P + IT_B, k + 1, s);
+        if (k + 1 < N) { bn = fmin(bn, cap); c.W(P + IT_B, k + 1, s) = bn; }
+        const double ds = c.W(WS_TRK + TRK_DS, k, s);
+        t += 2.0 * ds / (sqrt(b) + sqrt(bn));
+        c.W(P + IT_T, k + 1, s) = t;
+        const double bm = 0.5 * (b + bn);
+        const double F = (bn - b) / (2.0 * ds) + sr0 + sr1 * sqrt(bm) + sr2 * bm + c.W(WS_TRK + TRK_C0, k, s);
+        const double vmx = fmax(sqrt(fmax(b, bn)), 1.0);
+        const double fel = fmin(fmax(F, fmax(0.97 * felL, 0.97 * pLo / vmx)), fmin(0.97 * felU, 0.97 * pUp / vmx));
+        c.W(P + IT_FEL, k, s) = fel;
+        c.W(P + IT_FPB, k, s) = g.withPn ? fmin(0.0, fmax(0.97 * fpbL, F - fel)) : 0.0;
+        c.W(P + IT_SL, k, s) = 0.5 * fabs(fel) + 0.02;
+        b = bn;
+    }
 }
 
 MS_HD LossPar load_losspar(const Ctx& c, int s) {
@@ -145,7 +223,7 @@ MS_HD void cell_init(const Ctx& c, int k, int s) {
     const int N = c.I(SI_N_INT, s);
     if (s >= g.nInst || k > N) return;
     const int it = WS_IT0;
-    for (int f = 0; f < IT_N; ++f) { c.W(WS_IT0 + f, k, s) = 0.0; c.W(WS_IT1 + f, k, s) = 0.0; }
+    for (int f = 0; f < IT_N; ++f) c.W(WS_IT0 + f, k, s) = 0.0;      // buffer 1 may hold the starting profile (read by neighbours)
     for (int f = 0; f < ST_N; ++f) c.W(WS_ST + f, k, s) = 0.0;
     Bnd B = load_bounds(c, k, s);
     double t = init_t(c, k, s, N), b = init_b(c, k, s, N);
@@ -154,9 +232,9 @@ MS_HD void cell_init(const Ctx& c, int k, int s) {
     if (k >= 1 && k <= N) { c.W(it + IT_Z + Z_T_L, k, s) = 1.0; c.W(it + IT_Z + Z_T_U, k, s) = 1.0; }
     if (k >= 1 && k < N) { c.W(it + IT_Z + Z_B_L, k, s) = 1.0; c.W(it + IT_Z + Z_B_U, k, s) = 1.0; }
     if (k == N) return;
-    double fel = push2(0.5, B.felL, B.felU);
-    double fpb = g.withPn ? push2(-0.1, B.fpbL, B.fpbU) : 0.0;
-    double sl = push1(1.0, B.slL);
+    double fel = push2(g.initMode ? c.W(WS_IT1 + IT_FEL, k, s) : 0.5, B.felL, B.felU);
+    double fpb = g.withPn ? push2(g.initMode ? c.W(WS_IT1 + IT_FPB, k, s) : -0.1, B.fpbL, B.fpbU) : 0.0;
+    double sl = push1(g.initMode ? c.W(WS_IT1 + IT_SL, k, s) : 1.0, B.slL);
     c.W(it + IT_FEL, k, s) = fel;
     c.W(it + IT_FPB, k, s) = fpb;
     c.W(it + IT_SL, k, s) = sl;

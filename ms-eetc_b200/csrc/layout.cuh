@@ -102,7 +102,7 @@ struct Config {
     int numSteps, numApprox;
     int maxIter;
     double tol, muInit;
-    double trackLenOverVmax;  // unused placeholder for ABI stability
+    int initMode;     // 0: initial guess of the reference (ocp.py:325-339); 1: dynamically consistent speed-envelope guess
 };
 
 struct Ctx {

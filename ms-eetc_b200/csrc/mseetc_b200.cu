@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < c.cfg.S) inst_setup(c, io, s);
 }
+__global__ void __launch_bounds__(64) k_inst_profile(Ctx c) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < c.cfg.S) inst_profile(c, s);
+}
 
 // ---- per-instance reductions: block = 32 instances x RED_W warps; warp w sums the intervals k = w, w+RED_W, ...
 // (coalesced rows), the partials are combined in fixed order by warp 0 -> bitwise reproducible, no atomics.
@@ -161,6 +165,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     if (p->num_steps < 1 || p->num_approx_steps < 0) return fail(-3, "mseetc_create: bad RK options");
     if (p->loss_kind < 0 || p->loss_kind > 2) return fail(-4, "mseetc_create: loss_kind must be 0, 1 or 2");
     if (p->max_iterations < 1 || !(p->tol > 0.0) || !(p->mu_init > 0.0)) return fail(-5, "mseetc_create: bad IP options");
+    if (p->initial_guess < 0 || p->initial_guess > 1) return fail(-7, "mseetc_create: initial_guess must be 0 or 1");
     mseetc_solver* h = new (std::nothrow) mseetc_solver;
     if (!h) return fail(-6, "mseetc_create: out of host memory");
     h->prob = *p;
@@ -279,7 +284,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     g.nInst = n;
     g.withPn = p.with_pn_brake; g.withPower = p.with_power_rows; g.energy = p.energy_optimal; g.lossKind = p.loss_kind;
     g.numSteps = p.num_steps; g.numApprox = p.num_approx_steps; g.maxIter = p.max_iterations;
-    g.tol = p.tol; g.muInit = p.mu_init;
+    g.tol = p.tol; g.muInit = p.mu_init; g.initMode = p.initial_guess;
     WsPlan plan = plan_workspace(g.S, g.NK);
     if (ws_bytes < plan.total) return fail(-4, "mseetc_solve_batch: workspace too small (see mseetc_workspace_bytes)");
     if (((uintptr_t)workspace & 255) != 0) return fail(-5, "mseetc_solve_batch: workspace must be 256-byte aligned");
@@ -338,6 +343,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const unsigned rgrid = (unsigned)(g.S / 32);
     begin(CLS_MISC); k_inst_setup<<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
     begin(CLS_MISC); k_cell_setup<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    if (g.initMode) { begin(CLS_MISC); k_inst_profile<<<igrid, ib, 0, st>>>(c); end(CLS_MISC); }
     begin(CLS_MISC);
     if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
     end(CLS_MISC);

@@ -20,6 +20,11 @@ from mseetc import _cabi
 
 _ACC_INF = 10   # stand-in for an absent force / acceleration limit (reference ocp.py:104)
 
+# Starting point of the interior-point iteration: 'profile' = dynamically consistent speed-envelope profile built on the
+# device (same optimum, about half the iterations); 'reference' = the constant guess of the reference (ocp.py:325-339),
+# which reproduces IPOPT-like iteration counts.  Per solver: set `solver.initialGuess` before the first solve.
+DEFAULT_INITIAL_GUESS = 'profile'
+
 
 class OptionsCasadiSolver(Options):
 
@@ -121,6 +126,7 @@ class casadiSolver():
         self._base = self._train_scalars(train)
         self._handle = None
         self._dev = {}
+        self.initialGuess = DEFAULT_INITIAL_GUESS
 
     # ------------------------------------------------------------------ packing
     @staticmethod
@@ -188,7 +194,7 @@ class casadiSolver():
             io = self.opts.integrationOptions
             self._handle = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
                                         {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], io.numSteps, io.numApproxSteps,
-                                        int(self.opts.maxIterations))
+                                        int(self.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[self.initialGuess])
             if self._lossKind == 'dynamic' and self.energyOptimal:
                 dp = self.train.powerLosses.device_params
                 self._handle.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])

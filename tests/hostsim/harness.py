@@ -66,7 +66,7 @@ def loss_map_arrays():
     return np.ascontiguousarray(lut.tx), np.ascontiguousarray(lut.ty), np.ascontiguousarray(lut.coef)
 
 
-def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst=-1, lib=None, tmin=None, pit_lanes=0):
+def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst=-1, lib=None, tmin=None, pit_lanes=0, init_mode=0):
     """Solve instances (one NLP object per instance, equal structure flags) with the emulated device code."""
     lib = lib or build()
     n = len(nlps)
@@ -96,5 +96,5 @@ def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst
         lm = (0, 0, ctypes.c_void_p(0), ctypes.c_void_p(0), ctypes.c_void_p(0))
     lib.hostsim_solve_batch(ctypes.byref(pr), n, P(params), P(nint), P(trk_of), P(trk_off), P(ds), P(c0), P(bmax),
                             P(np.ascontiguousarray(tmin, dtype=float)) if tmin is not None else ctypes.c_void_p(0), P(z), P(lam),
-                            P(obj), P(kkt), P(iters), P(status), verbose_inst, ctypes.byref(ticks), int(pit_lanes), *lm)
+                            P(obj), P(kkt), P(iters), P(status), verbose_inst, ctypes.byref(ticks), int(pit_lanes), *lm, int(init_mode))
     return dict(z=z, lam=lam, obj=obj, kkt=kkt, iters=iters, status=status, ticks=ticks.value)

@@ -26,7 +26,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
                         const int32_t* trk_of, const int32_t* trk_off, const double* ds, const double* c0,
                         const double* bmax, const double* tmin, double* z_out, double* lam_out, double* obj, double* kkt, int32_t* iters,
                         int32_t* status, int32_t verbose_inst, int32_t* ticks_out, int32_t pit_lanes,
-                        int32_t lm_nl, int32_t lm_nv, const double* lm_tl, const double* lm_tv, const double* lm_coef) {
+                        int32_t lm_nl, int32_t lm_nv, const double* lm_tl, const double* lm_tv, const double* lm_coef, int32_t init_mode) {
     Config g;
     memset(&g, 0, sizeof g);
     g.S = pad_slots(n);
@@ -34,7 +34,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     g.nInst = n;
     g.withPn = pr->with_pn_brake; g.withPower = pr->with_power_rows; g.energy = pr->energy_optimal;
     g.lossKind = pr->loss_kind; g.numSteps = pr->num_steps; g.numApprox = pr->num_approx_steps;
-    g.maxIter = pr->max_iterations; g.tol = pr->tol; g.muInit = pr->mu_init;
+    g.maxIter = pr->max_iterations; g.tol = pr->tol; g.muInit = pr->mu_init; g.initMode = init_mode;
     WsPlan plan = plan_workspace(g.S, g.NK);
     std::vector<char> buf(plan.total, 0);
     Ctx c;
@@ -50,6 +50,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
     for (int s = 0; s < g.S; ++s) inst_setup(c, io, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
+    for (int s = 0; s < g.S; ++s) inst_profile(c, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
     int tick = 0;
     const int maxTicks = 20 * pr->max_iterations + 50;

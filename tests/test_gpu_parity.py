@@ -18,7 +18,7 @@ def cabi(built_lib):
     return _cabi
 
 
-def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True):
+def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True, initial_guess=0):
     "Raw C-ABI call with arrays packed from oracle NLP objects (same packing as the CPU emulation harness)."
     import torch
     import harness
@@ -31,7 +31,7 @@ def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True):
     trk_off = np.concatenate([[0], np.cumsum(nint)]).astype(np.int32)
     cu = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to('cuda', dtype=dt)
     h = cabi.Handle(Nmax, ref.withPn, ref.withPower, ref.energy, {'none': 0, 'static': 1}[ref.lossKind],
-                    ref.opts['numSteps'], ref.opts['numApproxSteps'], max_iter)
+                    ref.opts['numSteps'], ref.opts['numApproxSteps'], max_iter, initial_guess=initial_guess)
     out = h.solve_device(cu(params, torch.float64), cu(nint, torch.int32), cu(np.arange(n, dtype=np.int32), torch.int32),
                          cu(trk_off, torch.int32), cu(np.concatenate([p[1] for p in packs]), torch.float64),
                          cu(np.concatenate([p[2] for p in packs]), torch.float64),
@@ -87,8 +87,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize('guess', [0, 1], ids=['reference-guess', 'profile-guess'])
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
-def test_cuda_solver_matches_oracle(cabi, case):
+def test_cuda_solver_matches_oracle(cabi, case, guess):
     """north_star bar: optimal energy 1e-6 relative, trajectories 1e-4 relative, same active set, KKT <= 1e-8."""
     from oracle.problem import load_track
     name, mk, path, crop, N, T, energy, v0, vN, rk = case
@@ -98,9 +99,11 @@ def test_cuda_solver_matches_oracle(cabi, case):
     nlp = oracle_nlp(mk(), track, N, energy=energy, **rk)
     ref = oracle_solve(nlp, T, v0=v0, vN=vN)
     assert ref.success, ref.status
-    out = device_solve(cabi, [nlp], [T], v0=v0, vN=vN)
+    out = device_solve(cabi, [nlp], [T], v0=v0, vN=vN, initial_guess=guess)
     assert out['status'][0] == 0
     assert out['kkt'][0] <= 1e-8
+    if guess == 0:
+        assert abs(int(out['iters'][0]) - ref.iters) <= max(3, ref.iters // 4)     # same algorithm, same start: IPOPT-like counts
     assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
     z, zr = out['z'][0], ref.x
     for idx, scale in ((nlp.iB, nlp.limit.max() ** 2), (nlp.iT, T), (nlp.iFel, nlp.forceMax)):
@@ -221,10 +224,10 @@ def test_parameter_monte_carlo_batch(cabi):
 def test_cabi_usage_errors(cabi):
     lib = cabi.lib()
     h = ctypes.c_void_p(0)
-    bad = cabi.Problem(1, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1)
+    bad = cabi.Problem(1, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1, 0)
     assert lib.mseetc_create(ctypes.byref(bad), ctypes.byref(h)) < 0
     assert b'n_intervals_max' in lib.mseetc_last_error()
-    good = cabi.Problem(50, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1)
+    good = cabi.Problem(50, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1, 1)
     assert lib.mseetc_create(ctypes.byref(good), ctypes.byref(h)) == 0
     assert lib.mseetc_workspace_bytes(h, 64) > 0
     null = ctypes.c_void_p(0)
@@ -264,10 +267,16 @@ def test_dynamic_loss_map_public_api_matches_golden(cabi):
         train.forceMinPn = 0
         train.powerLosses = totalLossesFunction(train, auxiliaries=27000, etaGear=0.96)
         solver = casadiSolver(train, Track(config={'id': track_id}), opts)
+        solver.initialGuess = 'reference'          # same starting point as the oracle -> same iteration count
         df, stats = solver.solve(gold['T'], terminalVelocity=1, initialVelocity=1)
         assert df is not None
         assert abs(stats['Cost'] - gold['cost_kwh']) <= 1e-6 * gold['cost_kwh']
         assert stats['IP iterations'] == gold['iterations']
+        fast = casadiSolver(train, Track(config={'id': track_id}), opts)      # default: speed-envelope starting profile
+        df2, stats2 = fast.solve(gold['T'], terminalVelocity=1, initialVelocity=1)
+        assert abs(stats2['Cost'] - gold['cost_kwh']) <= 1e-6 * gold['cost_kwh']
+        assert stats2['IP iterations'] < gold['iterations']
+        assert np.max(np.abs(df2['Velocity [m/s]'].values - np.sqrt(np.array(gold['b'])))) <= 1e-4 * 44.5
         assert np.max(np.abs(df['Velocity [m/s]'].values - np.sqrt(np.array(gold['b'])))) <= 1e-4 * 44.5
         # the table's energy column: sum = J - smoothing penalty (the epigraph rows are active at the optimum)
         Fel = np.array(gold['Fel'])

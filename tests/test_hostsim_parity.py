@@ -203,3 +203,16 @@ def test_dynamic_loss_map_solve_matches_golden(lib):
         assert np.max(np.abs(z[nlp.iB] - np.array(gold['b']))) <= 1e-4 * 1975.0
         assert np.max(np.abs(z[nlp.iFel] - np.array(gold['Fel']))) <= 1e-4 * nlp.forceMax
         assert np.max(np.abs(z[nlp.iT] - np.array(gold['t']))) <= 1e-4 * gold['T']
+
+
+def test_profile_starting_point_reaches_the_same_optimum_in_fewer_iterations(lib):
+    "initial_guess = 1 (speed-envelope profile) vs the reference's constant guess (ocp.py:325-339)"
+    from oracle.problem import load_track
+    for path, Ts, energy in ((SWISS_JSON, [1036.0, 1100.0, 1242.0, 1400.0], True), (FLAT_JSON, [1541.0], True), (SWISS_JSON, [1500.0], False)):
+        nlp = oracle_nlp(virm6(), load_track(path), 300, energy=energy)
+        a = harness.solve([nlp] * len(Ts), Ts, lib=lib)
+        b = harness.solve([nlp] * len(Ts), Ts, lib=lib, init_mode=1)
+        assert np.all(a['status'] == 0) and np.all(b['status'] == 0) and np.all(b['kkt'] <= 1e-8)
+        assert np.all(np.abs(a['obj'] - b['obj']) <= 1e-9 * np.abs(a['obj']))
+        assert np.max(np.abs(a['z'] - b['z'])) < 1e-4
+        assert np.all(b['iters'] < 0.8 * a['iters'])
