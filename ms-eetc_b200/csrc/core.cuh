@@ -304,27 +304,44 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
     if (k > N) return;
     const int cur = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
     const int alt = c.I(SI_PARITY, s) ? WS_IT0 : WS_IT1;
+    // ---- all loads first (independent, dozens in flight per thread), then arithmetic, then all stores
+    const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
+    double CI[IT_N], CS[ST_N], AO[IT_N];
+    {
+        const double* ip = &c.W(cur, k, s);
+        const double* sp = &c.W(WS_ST, k, s);
+#pragma unroll
+        for (int f = 0; f < IT_N; ++f) CI[f] = ip[f * 32];
+#pragma unroll
+        for (int f = 0; f < ST_N; ++f) CS[f] = sp[f * 32];
+    }
+    const double nT = c.W(cur + IT_T, kn, s), nB = c.W(cur + IT_B, kn, s);
+    const double nDT = c.W(WS_ST + ST_T, kn, s), nDB = c.W(WS_ST + ST_B, kn, s);
+    const double pFel = c.W(cur + IT_FEL, km, s), pDFel = c.W(WS_ST + ST_FEL, km, s);
+    const IntervalCoef q = load_coef(c, k, s);
+    const Bnd B = load_bounds(c, k, s);
     const double al = c.D(SD_ALPHA, s), az = c.D(SD_ALPHA_Z, s), mu = c.D(SD_MU, s);
     const double scale = c.P(P_SCALE, s);
-    Bnd B = load_bounds(c, k, s);
+#pragma unroll
+    for (int f = 0; f < IT_N; ++f) AO[f] = 0.0;
     BarAcc bar{0.0, 0.0, true, 1.0, 0};
     double th = 0.0, fo = 0.0;
 
     // multiplier update of one bound: z + az*dz, dz = mu/s - z -+ (z/s) dv, then the kappa_sigma safeguard (eq. 16)
     auto zstep = [&](int zi, double sOld, double sNew, double dvSigned) {
-        const double z = c.W(cur + IT_Z + zi, k, s);
+        const double z = CI[IT_Z + zi];
         const double rOld = rcp(sOld);
         const double dz = mu * rOld - z - (z * rOld) * dvSigned;
         double zn = z + az * dz;
         const double pr = zn * sNew;                 // kappa_sigma safeguard: mu/kappa <= z*slack <= kappa*mu
         if (pr > MS_KAPPA_SIGMA * mu) zn = MS_KAPPA_SIGMA * mu / sNew;
         else if (pr < mu * (1.0 / MS_KAPPA_SIGMA)) zn = mu / (MS_KAPPA_SIGMA * sNew);
-        c.W(alt + IT_Z + zi, k, s) = zn;
+        AO[IT_Z + zi] = zn;
     };
     auto var2 = [&](int itf, int stf, int zl, double L, double U, bool hasU, bool oneSided) -> double {
-        double v = c.W(cur + itf, k, s), dv = c.W(WS_ST + stf, k, s);
-        double vn = v + al * dv;
-        c.W(alt + itf, k, s) = vn;
+        const double v = CI[itf], dv = CS[stf];
+        const double vn = v + al * dv;
+        AO[itf] = vn;
         zstep(zl, v - L, vn - L, dv);
         bar_add(bar, vn - L, oneSided);
         if (hasU) { zstep(zl + 1, U - v, U - vn, -dv); bar_add(bar, U - vn, false); }
@@ -333,65 +350,65 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
 
     double t, b;
     if (k == 0) {
-        t = c.W(cur + IT_T, k, s); b = c.W(cur + IT_B, k, s);
-        c.W(alt + IT_T, k, s) = t; c.W(alt + IT_B, k, s) = b;
+        t = CI[IT_T]; b = CI[IT_B];
+        AO[IT_T] = t; AO[IT_B] = b;
     } else {
         t = var2(IT_T, ST_T, Z_T_L, B.tL, B.tU, true, false);
         if (k < N) b = var2(IT_B, ST_B, Z_B_L, B.bL, B.bU, true, false);
-        else { b = c.W(cur + IT_B, k, s); c.W(alt + IT_B, k, s) = b; }
+        else { b = CI[IT_B]; AO[IT_B] = b; }
     }
-    if (k == N) {
-        if (!g.energy) fo += t / scale;
-        c.W(WS_PART + PT_TH, k, s) = 0.0;
-        c.W(WS_PART + PT_F, k, s) = fo;
-        c.W(WS_PART + PT_SLOG, k, s) = bar_finish(bar);
-        c.W(WS_PART + PT_SDAMP, k, s) = 0.0;
-        return;
-    }
-    double fel = var2(IT_FEL, ST_FEL, Z_FEL_L, B.felL, B.felU, true, false);
-    double fpb = 0.0;
-    if (g.withPn) fpb = var2(IT_FPB, ST_FPB, Z_FPB_L, B.fpbL, B.fpbU, true, false);
-    else c.W(alt + IT_FPB, k, s) = 0.0;
-    double sl = var2(IT_SL, ST_SL, Z_SL_L, B.slL, 0.0, false, true);
-    // neighbours at the trial point
-    double t1 = c.W(cur + IT_T, k + 1, s) + al * c.W(WS_ST + ST_T, k + 1, s);
-    double b1 = (k + 1 < N) ? c.W(cur + IT_B, k + 1, s) + al * c.W(WS_ST + ST_B, k + 1, s) : c.W(cur + IT_B, k + 1, s);
-    IntervalCoef q = load_coef(c, k, s);
-    double tau, phib;
-    shoot<double>(b, fel + fpb, q, g.numSteps, g.numApprox, tau, phib);
-    double ct = t1 - t - tau, cb = b1 - phib;
-    th += fabs(ct) + fabs(cb);
-    c.W(alt + IT_YT, k, s) = c.W(cur + IT_YT, k, s) + al * c.W(WS_ST + ST_YT, k, s);
-    c.W(alt + IT_YB, k, s) = c.W(cur + IT_YB, k, s) + al * c.W(WS_ST + ST_YB, k, s);
-    double d[NROW];
-    ineq_values<DYN>(c, s, fel, fpb, sl, b, b1, q, d);
-    for (int j = 0; j < NROW; ++j) {
-        if (!row_on(g, j)) continue;
-        double L, U; bool hasU;
-        row_bounds(B, j, L, U, hasU);
-        const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
-        double w = c.W(cur + IT_W + j, k, s), dw = c.W(WS_ST + ST_W + j, k, s);
-        double wn = w + al * dw;
-        c.W(alt + IT_W + j, k, s) = wn;
-        zstep(zl, w - L, wn - L, dw);
-        bar_add(bar, wn - L, !hasU);
-        if (hasU) { zstep(zl + 1, U - w, U - wn, -dw); bar_add(bar, U - wn, false); }
-        c.W(alt + IT_YD + j, k, s) = c.W(cur + IT_YD + j, k, s) + al * c.W(WS_ST + ST_YD + j, k, s);
-        th += fabs(d[j] - wn);
-    }
-    if (g.energy) {                                                            // ocp.py:223,243-245
-        fo += q.ds * (fel + sl) / scale;
-        if (k >= 1) {
-            double fprev = c.W(cur + IT_FEL, k - 1, s) + al * c.W(WS_ST + ST_FEL, k - 1, s);
-            fo += 1e-3 * (fel - fprev) * (fel - fprev) / scale;
+    if (k < N) {
+        const double fel = var2(IT_FEL, ST_FEL, Z_FEL_L, B.felL, B.felU, true, false);
+        double fpb = 0.0;
+        if (g.withPn) fpb = var2(IT_FPB, ST_FPB, Z_FPB_L, B.fpbL, B.fpbU, true, false);
+        const double sl = var2(IT_SL, ST_SL, Z_SL_L, B.slL, 0.0, false, true);
+        // neighbours at the trial point
+        const double t1 = nT + al * nDT;
+        const double b1 = (k + 1 < N) ? nB + al * nDB : nB;
+        double tau, phib;
+        shoot<double>(b, fel + fpb, q, g.numSteps, g.numApprox, tau, phib);
+        const double ct = t1 - t - tau, cb = b1 - phib;
+        th += fabs(ct) + fabs(cb);
+        AO[IT_YT] = CI[IT_YT] + al * CS[ST_YT];
+        AO[IT_YB] = CI[IT_YB] + al * CS[ST_YB];
+        double d[NROW];
+        ineq_values<DYN>(c, s, fel, fpb, sl, b, b1, q, d);
+#pragma unroll
+        for (int j = 0; j < NROW; ++j) {
+            if (!row_on(g, j)) continue;
+            double L, U; bool hasU;
+            row_bounds(B, j, L, U, hasU);
+            const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
+            const double w = CI[IT_W + j], dw = CS[ST_W + j];
+            const double wn = w + al * dw;
+            AO[IT_W + j] = wn;
+            zstep(zl, w - L, wn - L, dw);
+            bar_add(bar, wn - L, !hasU);
+            if (hasU) { zstep(zl + 1, U - w, U - wn, -dw); bar_add(bar, U - wn, false); }
+            AO[IT_YD + j] = CI[IT_YD + j] + al * CS[ST_YD + j];
+            th += fabs(d[j] - wn);
         }
-    } else {                                                                   // ocp.py:146-150
-        fo += 1e-4 * (fel * fel + fpb * fpb) / scale;
+        if (g.energy) {                                                            // ocp.py:223,243-245
+            fo += q.ds * (fel + sl) / scale;
+            if (k >= 1) {
+                const double fprev = pFel + al * pDFel;
+                fo += 1e-3 * (fel - fprev) * (fel - fprev) / scale;
+            }
+        } else {                                                                   // ocp.py:146-150
+            fo += 1e-4 * (fel * fel + fpb * fpb) / scale;
+        }
+    } else if (!g.energy) {
+        fo += t / scale;
+    }
+    {
+        double* op = &c.W(alt, k, s);
+#pragma unroll
+        for (int f = 0; f < IT_N; ++f) op[f * 32] = AO[f];
     }
     c.W(WS_PART + PT_TH, k, s) = th;
     c.W(WS_PART + PT_F, k, s) = fo;
     c.W(WS_PART + PT_SLOG, k, s) = bar_finish(bar);
-    c.W(WS_PART + PT_SDAMP, k, s) = bar.sdamp;
+    c.W(WS_PART + PT_SDAMP, k, s) = (k < N) ? bar.sdamp : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,6 +485,16 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const int N = c.I(SI_N_INT, s);
     if (k > N) return;
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+    // ---- all loads first (independent, in flight together); the stores of this kernel are at the very end
+    const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
+    double CI[IT_N];
+    {
+        const double* ip = &c.W(it, k, s);
+#pragma unroll
+        for (int f = 0; f < IT_N; ++f) CI[f] = ip[f * 32];
+    }
+    const double nT = c.W(it + IT_T, kn, s), nB = c.W(it + IT_B, kn, s);
+    const double pFel = c.W(it + IT_FEL, km, s), nFel = c.W(it + IT_FEL, (k + 1 < N) ? k + 1 : k, s);
     const double scale = c.P(P_SCALE, s);
     Bnd B = load_bounds(c, k, s);
     double H[28], g0[NV7], g1[NV7];
@@ -480,7 +507,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
 
     auto bound = [&](int vi, int zi, double slack, double sign, bool oneSided) {
         // sign = +1 lower bound (slack = v-L), -1 upper bound (slack = U-v)
-        const double z = c.W(it + IT_Z + zi, k, s);
+        const double z = CI[IT_Z + zi];
         const double r = rcp(slack);
         H[sidx(vi, vi)] += z * r;
         g1[vi] += -sign * r + (oneSided ? MS_KAPPA_D : 0.0);
@@ -489,16 +516,16 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         bar_add(bar, slack, oneSided);
     };
 
-    const double t = c.W(it + IT_T, k, s), b = c.W(it + IT_B, k, s);
+    const double t = CI[IT_T], b = CI[IT_B];
     double own_t = 0.0, own_b = 0.0;
     if (k >= 1) {
         bound(V_T, Z_T_L, t - B.tL, 1.0, false);
         bound(V_T, Z_T_U, B.tU - t, -1.0, false);
-        own_t = -c.W(it + IT_Z + Z_T_L, k, s) + c.W(it + IT_Z + Z_T_U, k, s);
+        own_t = -CI[IT_Z + Z_T_L] + CI[IT_Z + Z_T_U];
         if (k < N) {
             bound(V_B, Z_B_L, b - B.bL, 1.0, false);
             bound(V_B, Z_B_U, B.bU - b, -1.0, false);
-            own_b = -c.W(it + IT_Z + Z_B_L, k, s) + c.W(it + IT_Z + Z_B_U, k, s);
+            own_b = -CI[IT_Z + Z_B_L] + CI[IT_Z + Z_B_U];
         }
     }
     if (k == N) {
@@ -522,9 +549,9 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         c.W(WS_PART + PC_OWN_T, k, s) = own_t;
         return;
     }
-    const double fel = c.W(it + IT_FEL, k, s), fpb = c.W(it + IT_FPB, k, s), sl = c.W(it + IT_SL, k, s);
-    const double t1 = c.W(it + IT_T, k + 1, s), b1 = c.W(it + IT_B, k + 1, s);
-    const double yt = c.W(it + IT_YT, k, s), yb = c.W(it + IT_YB, k, s);
+    const double fel = CI[IT_FEL], fpb = CI[IT_FPB], sl = CI[IT_SL];
+    const double t1 = nT, b1 = nB;
+    const double yt = CI[IT_YT], yb = CI[IT_YB];
     bound(V_FEL, Z_FEL_L, fel - B.felL, 1.0, false);
     bound(V_FEL, Z_FEL_U, B.felU - fel, -1.0, false);
     if (g.withPn) {
@@ -559,7 +586,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     ineq_values<false>(c, s, fel, fpb, sl, b, b1, q, d);
     double ydv[NROW];
     #pragma unroll
-    for (int j = 0; j < NROW; ++j) ydv[j] = c.W(it + IT_YD + j, k, s);
+    for (int j = 0; j < NROW; ++j) ydv[j] = CI[IT_YD + j];
     J[R_P0][V_B] = 0.5 * fel * iv0; J[R_P0][V_FEL] = v0;
     J[R_P1][V_BN] = 0.5 * fel * iv1; J[R_P1][V_FEL] = v1;
     J[R_ACC][V_B] = a_b; J[R_ACC][V_FEL] = 1.0; J[R_ACC][V_FPB] = g.withPn ? 1.0 : 0.0;
@@ -599,13 +626,13 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         gf_fel = q.ds / scale; gf_sl = q.ds / scale;
         g0[V_FEL] += q.ds / scale; g0[V_SL] += q.ds / scale;
         if (k >= 1) {
-            double df = fel - c.W(it + IT_FEL, k - 1, s);
+            double df = fel - pFel;
             fo += 1e-3 * df * df / scale;
             H[sidx(V_FEL, V_FEL)] += w2; H[sidx(V_F, V_F)] += w2; H[sidx(V_F, V_FEL)] -= w2;
             g0[V_FEL] += w2 * df; g0[V_F] -= w2 * df;
             gf_fel += w2 * df;
         }
-        if (k + 1 < N) gf_fel -= w2 * (c.W(it + IT_FEL, k + 1, s) - fel);
+        if (k + 1 < N) gf_fel -= w2 * (nFel - fel);
     } else {
         const double w4 = 2e-4 / scale;
         fo = 1e-4 * (fel * fel + fpb * fpb) / scale;
@@ -616,9 +643,9 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     // ---- condensation of the inequality rows (slack w, multiplier v_L/v_U)
     double th = fabs(ct) + fabs(cb), pinf = fmax(fabs(ct), fabs(cb));
     double ysum = fabs(yt) + fabs(yb), dinf = 0.0;
-    double rx_fel = gf_fel - tau.g1 * yt - phi.g1 * yb - c.W(it + IT_Z + Z_FEL_L, k, s) + c.W(it + IT_Z + Z_FEL_U, k, s);
-    double rx_fpb = gf_fpb - tau.g1 * yt - phi.g1 * yb - c.W(it + IT_Z + Z_FPB_L, k, s) + c.W(it + IT_Z + Z_FPB_U, k, s);
-    double rx_sl = gf_sl - c.W(it + IT_Z + Z_SL_L, k, s);
+    double rx_fel = gf_fel - tau.g1 * yt - phi.g1 * yb - CI[IT_Z + Z_FEL_L] + CI[IT_Z + Z_FEL_U];
+    double rx_fpb = gf_fpb - tau.g1 * yt - phi.g1 * yb - CI[IT_Z + Z_FPB_L] + CI[IT_Z + Z_FPB_U];
+    double rx_sl = gf_sl - CI[IT_Z + Z_SL_L];
     own_b += -tau.g0 * yt - phi.g0 * yb;
     own_t += -yt;
     double cn_b = yb;
@@ -629,8 +656,8 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         double L, U; bool hasU;
         row_bounds(B, j, L, U, hasU);
         const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
-        const double w = c.W(it + IT_W + j, k, s);
-        const double vL = c.W(it + IT_Z + zl, k, s), sL = w - L;
+        const double w = CI[IT_W + j];
+        const double vL = CI[IT_Z + zl], sL = w - L;
         const double rL = rcp(sL);
         double sig = vL * rL, coef = -rL + (hasU ? 0.0 : MS_KAPPA_D);
         double rw = -ydv[j] - vL;
@@ -638,7 +665,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         cmin = fmin(cmin, pr); cmax = fmax(cmax, pr); zsum += vL;
         bar_add(bar, sL, !hasU);
         if (hasU) {
-            const double vU = c.W(it + IT_Z + zl + 1, k, s), sU = U - w;
+            const double vU = CI[IT_Z + zl + 1], sU = U - w;
             const double rU = rcp(sU);
             sig += vU * rU; coef += rU; rw += vU;
             pr = vU * sU;

@@ -33,14 +33,23 @@ thread_local std::string g_err;
         if (k >= c.cfg.NK) return;                                              \
         CALL;                                                                   \
     }
+#ifndef MS_MINB_TRIAL
+#define MS_MINB_TRIAL 4
+#endif
+#ifndef MS_MINB_EVAL
+#define MS_MINB_EVAL 3
+#endif
+#ifndef MS_MINB_STEP
+#define MS_MINB_STEP 4
+#endif
 MS_CELL_KERNEL(k_cell_setup, 4, cell_setup(c, io, k, s))
 MS_CELL_KERNEL(k_cell_init, 4, cell_init<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_init_dyn, 2, cell_init<true>(c, k, s))
-MS_CELL_KERNEL(k_cell_trial, 4, cell_trial<false>(c, k, s))
+MS_CELL_KERNEL(k_cell_trial, MS_MINB_TRIAL, cell_trial<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_trial_dyn, 2, cell_trial<true>(c, k, s))
-MS_CELL_KERNEL(k_cell_eval, 3, cell_eval<false>(c, k, s))
+MS_CELL_KERNEL(k_cell_eval, MS_MINB_EVAL, cell_eval<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_eval_dyn, 2, cell_eval<true>(c, k, s))
-MS_CELL_KERNEL(k_cell_step, 4, cell_step(c, k, s))
+MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
 
 __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {

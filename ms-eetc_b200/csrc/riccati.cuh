@@ -426,77 +426,98 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     const int N = c.I(SI_N_INT, s);
     if (k > N) return;
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+    // ---- all loads first, then arithmetic, then all stores (loads must not queue behind stores through the same base)
+    const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
+    double CI[IT_N], CS[ST_N], QJ[QP_N - QP_J_P0_B];
+    {
+        const double* ip = &c.W(it, k, s);
+        const double* sp = &c.W(WS_ST, k, s);
+        const double* qp = &c.W(WS_QP + QP_J_P0_B, k, s);
+#pragma unroll
+        for (int f = 0; f < IT_N; ++f) CI[f] = ip[f * 32];
+#pragma unroll
+        for (int f = 0; f < ST_N; ++f) CS[f] = sp[f * 32];
+#pragma unroll
+        for (int f = 0; f < QP_N - QP_J_P0_B; ++f) QJ[f] = qp[f * 32];
+    }
+    const double dbn = c.W(WS_ST + ST_B, kn, s);
+    const double pFel = c.W(it + IT_FEL, km, s), pDFel = c.W(WS_ST + ST_FEL, km, s);
+    const double dsk = c.W(WS_TRK + TRK_DS, k, s);
+    const Bnd B = load_bounds(c, k, s);
     const double mu = c.D(SD_MU, s), tauF = c.D(SD_TAU, s), scale = c.P(P_SCALE, s);
-    Bnd B = load_bounds(c, k, s);
+#define MS_QJ(F) QJ[(F) - QP_J_P0_B]
     Ftb f{1.0, 1.0, 0.0};
-    const double dt = c.W(WS_ST + ST_T, k, s), db = c.W(WS_ST + ST_B, k, s);
+    double OW[NROW], OYD[NROW], oyt = 0.0, oyb = 0.0;
+#pragma unroll
+    for (int j = 0; j < NROW; ++j) { OW[j] = 0.0; OYD[j] = 0.0; }
+    const double dt = CS[ST_T], db = CS[ST_B];
     if (k >= 1) {
-        const double t = c.W(it + IT_T, k, s);
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_L, k, s), t - B.tL, dt, false);
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_T_U, k, s), B.tU - t, -dt, false);
+        const double t = CI[IT_T];
+        ftb_bound(f, tauF, mu, CI[IT_Z + Z_T_L], t - B.tL, dt, false);
+        ftb_bound(f, tauF, mu, CI[IT_Z + Z_T_U], B.tU - t, -dt, false);
         if (k < N) {
-            const double b = c.W(it + IT_B, k, s);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_B_L, k, s), b - B.bL, db, false);
-            ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_B_U, k, s), B.bU - b, -db, false);
+            const double b = CI[IT_B];
+            ftb_bound(f, tauF, mu, CI[IT_Z + Z_B_L], b - B.bL, db, false);
+            ftb_bound(f, tauF, mu, CI[IT_Z + Z_B_U], B.bU - b, -db, false);
         }
     }
-    if (k == N) {
-        if (!g.energy) f.gphid += dt / scale;
-        c.W(WS_PART + PS_AP, k, s) = f.aP;
-        c.W(WS_PART + PS_AZ, k, s) = f.aZ;
-        c.W(WS_PART + PS_GPHID, k, s) = f.gphid;
-        return;
-    }
-    const double du0 = c.W(WS_ST + ST_FEL, k, s), du1 = c.W(WS_ST + ST_FPB, k, s), du2 = c.W(WS_ST + ST_SL, k, s);
-    const double dbn = c.W(WS_ST + ST_B, k + 1, s);
-    const double fel = c.W(it + IT_FEL, k, s), fpb = c.W(it + IT_FPB, k, s), sl = c.W(it + IT_SL, k, s);
-    // coupling-row multipliers: the forward sweep stored the new values
-    c.W(WS_ST + ST_YT, k, s) = c.W(WS_ST + ST_YT, k, s) - c.W(it + IT_YT, k, s);
-    c.W(WS_ST + ST_YB, k, s) = c.W(WS_ST + ST_YB, k, s) - c.W(it + IT_YB, k, s);
-    ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FEL_L, k, s), fel - B.felL, du0, false);
-    ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FEL_U, k, s), B.felU - fel, -du0, false);
-    if (g.withPn) {
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FPB_L, k, s), fpb - B.fpbL, du1, false);
-        ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_FPB_U, k, s), B.fpbU - fpb, -du1, false);
-    }
-    ftb_bound(f, tauF, mu, c.W(it + IT_Z + Z_SL_L, k, s), sl - B.slL, du2, true);
-    // objective part of the barrier directional derivative
-    if (g.energy) {
-        f.gphid += c.W(WS_TRK + TRK_DS, k, s) * (du0 + du2) / scale;
-        if (k >= 1) f.gphid += (2e-3 / scale) * (fel - c.W(it + IT_FEL, k - 1, s)) * (du0 - c.W(WS_ST + ST_FEL, k - 1, s));
-    } else {
-        f.gphid += (2e-4 / scale) * (fel * du0 + fpb * du1);
-    }
-    // inequality rows: slack step d w = J d + (d(x) - w), multiplier step from the condensed equations
-    for (int j = 0; j < NROW; ++j) {
-        c.W(WS_ST + ST_W + j, k, s) = 0.0;
-        c.W(WS_ST + ST_YD + j, k, s) = 0.0;
-        if (!row_on(g, j)) continue;
-        double jd;
-        if (j == R_P0) jd = c.W(WS_QP + QP_J_P0_B, k, s) * db + c.W(WS_QP + QP_J_P0_FEL, k, s) * du0;
-        else if (j == R_P1) jd = c.W(WS_QP + QP_J_P1_FEL, k, s) * du0 + c.W(WS_QP + QP_J_P1_BN, k, s) * dbn;
-        else if (j == R_ACC) jd = c.W(WS_QP + QP_J_ACC_B, k, s) * db + du0 + du1;
-        else if (j == R_LTR) jd = du2 + c.W(WS_QP + QP_J_LTR_FEL, k, s) * du0 + c.W(WS_QP + QP_J_LTR_B, k, s) * db
-                                + c.W(WS_QP + QP_J_LTR_BN, k, s) * dbn;
-        else jd = du2 + c.W(WS_QP + QP_J_LRG_FEL, k, s) * du0 + c.W(WS_QP + QP_J_LRG_B, k, s) * db
-                + c.W(WS_QP + QP_J_LRG_BN, k, s) * dbn;
-        const double dw = jd + c.W(WS_QP + QP_RES + j, k, s);
-        double L, U; bool hasU;
-        row_bounds(B, j, L, U, hasU);
-        const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
-        const double w = c.W(it + IT_W + j, k, s);
-        const double vL = c.W(it + IT_Z + zl, k, s), sL = w - L;
-        const double rL = rcp(sL);
-        double sig = vL * rL, gw = -mu * rL + (hasU ? 0.0 : MS_KAPPA_D * mu);
-        ftb_bound(f, tauF, mu, vL, sL, dw, !hasU);
-        if (hasU) {
-            const double vU = c.W(it + IT_Z + zl + 1, k, s), sU = U - w;
-            const double rU = rcp(sU);
-            sig += vU * rU; gw += mu * rU;
-            ftb_bound(f, tauF, mu, vU, sU, -dw, false);
+    if (k < N) {
+        const double du0 = CS[ST_FEL], du1 = CS[ST_FPB], du2 = CS[ST_SL];
+        const double fel = CI[IT_FEL], fpb = CI[IT_FPB], sl = CI[IT_SL];
+        // coupling-row multipliers: the forward sweep stored the new values
+        oyt = CS[ST_YT] - CI[IT_YT];
+        oyb = CS[ST_YB] - CI[IT_YB];
+        ftb_bound(f, tauF, mu, CI[IT_Z + Z_FEL_L], fel - B.felL, du0, false);
+        ftb_bound(f, tauF, mu, CI[IT_Z + Z_FEL_U], B.felU - fel, -du0, false);
+        if (g.withPn) {
+            ftb_bound(f, tauF, mu, CI[IT_Z + Z_FPB_L], fpb - B.fpbL, du1, false);
+            ftb_bound(f, tauF, mu, CI[IT_Z + Z_FPB_U], B.fpbU - fpb, -du1, false);
         }
-        c.W(WS_ST + ST_W + j, k, s) = dw;
-        c.W(WS_ST + ST_YD + j, k, s) = sig * dw + gw - c.W(it + IT_YD + j, k, s);
+        ftb_bound(f, tauF, mu, CI[IT_Z + Z_SL_L], sl - B.slL, du2, true);
+        // objective part of the barrier directional derivative
+        if (g.energy) {
+            f.gphid += dsk * (du0 + du2) / scale;
+            if (k >= 1) f.gphid += (2e-3 / scale) * (fel - pFel) * (du0 - pDFel);
+        } else {
+            f.gphid += (2e-4 / scale) * (fel * du0 + fpb * du1);
+        }
+        // inequality rows: slack step d w = J d + (d(x) - w), multiplier step from the condensed equations
+#pragma unroll
+        for (int j = 0; j < NROW; ++j) {
+            if (!row_on(g, j)) continue;
+            double jd;
+            if (j == R_P0) jd = MS_QJ(QP_J_P0_B) * db + MS_QJ(QP_J_P0_FEL) * du0;
+            else if (j == R_P1) jd = MS_QJ(QP_J_P1_FEL) * du0 + MS_QJ(QP_J_P1_BN) * dbn;
+            else if (j == R_ACC) jd = MS_QJ(QP_J_ACC_B) * db + du0 + du1;
+            else if (j == R_LTR) jd = du2 + MS_QJ(QP_J_LTR_FEL) * du0 + MS_QJ(QP_J_LTR_B) * db + MS_QJ(QP_J_LTR_BN) * dbn;
+            else jd = du2 + MS_QJ(QP_J_LRG_FEL) * du0 + MS_QJ(QP_J_LRG_B) * db + MS_QJ(QP_J_LRG_BN) * dbn;
+            const double dw = jd + MS_QJ(QP_RES + j);
+            double L, U; bool hasU;
+            row_bounds(B, j, L, U, hasU);
+            const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
+            const double w = CI[IT_W + j];
+            const double vL = CI[IT_Z + zl], sL = w - L;
+            const double rL = rcp(sL);
+            double sig = vL * rL, gw = -mu * rL + (hasU ? 0.0 : MS_KAPPA_D * mu);
+            ftb_bound(f, tauF, mu, vL, sL, dw, !hasU);
+            if (hasU) {
+                const double vU = CI[IT_Z + zl + 1], sU = U - w;
+                const double rU = rcp(sU);
+                sig += vU * rU; gw += mu * rU;
+                ftb_bound(f, tauF, mu, vU, sU, -dw, false);
+            }
+            OW[j] = dw;
+            OYD[j] = sig * dw + gw - CI[IT_YD + j];
+        }
+    } else if (!g.energy) {
+        f.gphid += dt / scale;
+    }
+#undef MS_QJ
+    if (k < N) {
+        c.W(WS_ST + ST_YT, k, s) = oyt;
+        c.W(WS_ST + ST_YB, k, s) = oyb;
+#pragma unroll
+        for (int j = 0; j < NROW; ++j) { c.W(WS_ST + ST_W + j, k, s) = OW[j]; c.W(WS_ST + ST_YD + j, k, s) = OYD[j]; }
     }
     c.W(WS_PART + PS_AP, k, s) = f.aP;
     c.W(WS_PART + PS_AZ, k, s) = f.aZ;

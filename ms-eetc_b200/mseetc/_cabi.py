@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmseetc_b200.so')
+LIB_PATH = os.environ.get('MSEETC_B200_LIB', os.path.join(_HERE, 'libmseetc_b200.so'))   # override: tuning experiments only
 
 PARAMS = ['SR0', 'SR1', 'SR2', 'FEL_LO', 'FEL_UP', 'FPB_LO', 'POW_LO', 'POW_UP', 'ACC_LO', 'ACC_UP', 'LOSS_TR', 'LOSS_RG',
           'BMIN', 'OBJ_SCALE', 'T_END', 'T_START', 'B_START', 'B_END', 'MASS', 'DYN_AUX', 'DYN_ETAG', 'DYN_FMAX', 'DYN_PMAX',
