@@ -34,10 +34,10 @@ thread_local std::string g_err;
         CALL;                                                                   \
     }
 #ifndef MS_MINB_TRIAL
-#define MS_MINB_TRIAL 4
+#define MS_MINB_TRIAL 3
 #endif
 #ifndef MS_MINB_EVAL
-#define MS_MINB_EVAL 3
+#define MS_MINB_EVAL 2
 #endif
 #ifndef MS_MINB_STEP
 #define MS_MINB_STEP 4
@@ -150,6 +150,7 @@ struct mseetc_solver {
     int launches[NCLS];
     long long cells[NCLS];
     std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
+    cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
     double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
     LossMapDev lm;
 };
@@ -186,6 +187,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
     cudaError_t e = cudaHostAlloc((void**)&h->done_host, 256, cudaHostAllocDefault);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
+    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming);
     *out = h;
     return 0;
 }
@@ -194,6 +196,7 @@ int mseetc_destroy(mseetc_handle h) {
     if (!h) return 0;
     cudaFreeHost(h->done_host);
     if (h->lm_dev) cudaFree(h->lm_dev);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(h->poll_ev[i]);
     for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
     delete h;
     return 0;
@@ -367,12 +370,19 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
         begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);
         if (tick >= maxTicks) break;
-        if (tick >= 16 && (tick & 3) == 0) {
-            e = cudaMemcpyAsync(h->done_host, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
+        // completion polling without draining the queue: the counter is copied every tick into a small pinned ring and the
+        // copy made two ticks ago is tested (its event has normally completed), so kernels of the next ticks are already queued
+        {
+            const int slot = tick % 4;
+            e = cudaMemcpyAsync(h->done_host + 32 + slot, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
             if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(done)");
-            e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
-            if (*h->done_host >= n) break;
+            cudaEventRecord(h->poll_ev[slot], st);
+            if (tick >= 2) {
+                const int old = (tick - 2) % 4;
+                e = cudaEventSynchronize(h->poll_ev[old]);
+                if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
+                if (h->done_host[32 + old] >= n) break;
+            }
         }
         begin(CLS_TRIAL);
         if (dyn) k_cell_trial_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_trial<<<cgrid, 128, 0, st>>>(c, io);
