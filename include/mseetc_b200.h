@@ -116,7 +116,9 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);
  *   tmin_dev          [n_instances] or NULL: known minimum trip duration of each instance (from a time-optimal
  *                     solve of the same problem).  Instances with T_END - T_START below it are infeasible
  *                     (terminalTime is an upper bound on t_N, ocp.py:260-261) and are reported as
- *                     MSEETC_INFEASIBLE_PROBLEM_DETECTED without iterating.
+ *                     MSEETC_INFEASIBLE_PROBLEM_DETECTED without iterating.  An entry of 0 means "not known yet": the
+ *                     array is re-read once per iteration, so the minimum times may be produced concurrently (another
+ *                     stream / thread) while this call is running.
  * outputs (device, caller-owned; each may be NULL except status_out):
  *   z_out_dev    [n_instances * (n_intervals_max*(3+nu)+2)]  reference variable order (ocp.py:166-181,248-249)
  *   lam_g_out_dev[n_instances * n_intervals_max*rows]        multipliers of g in reference row order

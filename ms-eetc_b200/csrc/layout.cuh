@@ -87,7 +87,7 @@ enum SdField {
 enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_N };
 
 enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2, PH_STEPPED = 3, PH_FACTOR = 4 };
-enum { RED_W = 8 };   // interleave factor of the per-instance reductions (fixed -> bitwise reproducible sums)
+enum { RED_W = 16 };   // interleave factor of the per-instance reductions (fixed -> bitwise reproducible sums)
 // status codes (mapped to IPOPT's vocabulary by the host shim, ocp.py:362)
 enum Status {
     ST_RUNNING = -1, ST_SOLVE_SUCCEEDED = 0, ST_MAXITER = 1, ST_RESTORATION_FAILED = 2, ST_STEP_FAILED = 3,
@@ -114,6 +114,7 @@ struct Ctx {
     int* done;     // number of finished instances (device counter polled by the host loop)
     unsigned long long* cnt;   // [4] processed cells: trial, eval, riccati backward, riccati forward
     LossMapDev lm;             // spline of the dynamic loss map (lossKind 2), device pointers
+    const double* tmin;        // [nInst] or null: minimum trip duration once known (0 = not known yet), see inst_kkt
 
     MS_HD double& W(int field, int k, int slot) const {
         return ws[((size_t)(slot >> 5) * cfg.NK + k) * (WS_FIELDS * 32) + (slot & 31) + field * 32];

@@ -311,6 +311,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.done = (int*)(base + plan.off_done);
     c.cnt = (unsigned long long*)(base + plan.off_done + 64);
     c.lm = h->lm;
+    c.tmin = tmin;
     const bool dyn = (p.loss_kind == 2 && p.energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 

@@ -350,6 +350,12 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
     const int N = c.I(SI_N_INT, s);
     count_cells(c, 1, N + 1);
+    // screening against a minimum trip duration that may arrive while the batch is running (computed concurrently by a
+    // time-optimal solve on another stream): terminalTime is an upper bound on t_N (ocp.py:260-261)
+    if (c.tmin) {
+        const double tm = c.tmin[s];
+        if (tm > 0.0 && (c.P(P_T, s) - c.P(P_T0, s)) < tm * (1.0 - 1e-9)) { finish(c, s, ST_INFEASIBLE); return; }
+    }
     const double th = a.th, fo = a.fo, dinf = a.dinf, pinf = a.pinf, cmin = a.cmin, cmax = a.cmax, zsum = a.zsum, ysum = a.ysum;
     // counts for the IPOPT error scaling s_d, s_c (eq. 6)
     const int nrow = (g.withPower ? 2 : 0) + 1 + (g.energy ? 2 : 0);

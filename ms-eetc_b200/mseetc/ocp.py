@@ -87,6 +87,41 @@ def classify_losses(train):
     return ('none' if cT == 0 and cR == 0 else 'static'), cT, cR
 
 
+class _Presolve:
+    "Time-optimal solve of the distinct problems of a batch on a side stream, in a second host thread."
+
+    def __init__(self, solver, dev, tmin_dev, args, inverse):
+        import threading
+        self.solver, self.dev, self.tmin_dev, self.args, self.inverse = solver, dev, tmin_dev, args, inverse
+        self.tmin, self.error = None, None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def start(self):
+        self.thread.start()
+
+    def _run(self):
+        import torch
+        try:
+            torch.cuda.set_device(self.dev)
+            side = torch.cuda.Stream(device=self.dev)
+            with torch.cuda.stream(side):
+                t0, vN, v0, sub, device = self.args
+                dur, st = self.solver.minimum_time(t0, vN, v0, overrides=sub, device=device)
+                dur = np.where(st == 0, dur, 0.0)        # no certificate when the time-optimal solve did not converge
+                full = np.ascontiguousarray(dur[self.inverse])
+                self.tmin_dev.copy_(torch.from_numpy(full).to(self.tmin_dev.device, non_blocking=False))
+                side.synchronize()
+            self.tmin = full
+        except Exception as exc:      # surfaced by join()
+            self.error = exc
+
+    def join(self):
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        return self.tmin
+
+
 def _curve_res(kappa, g):
     k = np.abs(kappa)
     return np.where(k <= 1 / 300, g * 0.5 * k / (1 - 30 * k), g * 0.65 * k / (1 - 55 * k))
@@ -269,20 +304,24 @@ class casadiSolver():
             lossT, lossR = (1 - etaT) / etaT, 1 - etaR
         t_begin = _time.perf_counter()
         P, M = self._planes(n, T, t0, v0, vN, overrides, lossT, lossR)
-        dev = torch.device(device if device is not None else 'cuda')
+        dev = torch.device(device if device is not None else 'cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         tmin = None
+        presolve = None
         if screen and self.energyOptimal:
+            # minimum trip time of every distinct problem, computed CONCURRENTLY (second host thread + second stream) with
+            # the energy-optimal batch; the kernels pick the values up as soon as they are in device memory
             key = np.delete(P, [_cabi.PARAM_INDEX['T_END'], _cabi.PARAM_INDEX['LOSS_TR'], _cabi.PARAM_INDEX['LOSS_RG'],
-                                _cabi.PARAM_INDEX['OBJ_SCALE']], axis=0)
+                                _cabi.PARAM_INDEX['OBJ_SCALE'], _cabi.PARAM_INDEX['DYN_AUX'], _cabi.PARAM_INDEX['DYN_ETAG'],
+                                _cabi.PARAM_INDEX['DYN_SCALE']], axis=0)
             if n == 1 or np.all(key == key[:, :1]):
                 first, inverse = np.array([0]), np.zeros(n, dtype=np.intp)
             else:
                 _, first, inverse = np.unique(key, axis=1, return_index=True, return_inverse=True)
                 inverse = np.asarray(inverse).reshape(-1)
             sub = {k: np.broadcast_to(np.asarray(v, dtype=float), (n,))[first] for k, v in overrides.items()}
-            dur, st = self.minimum_time(t0[first], vN[first], v0[first], overrides=sub, device=device)
-            dur = np.where(st == 0, dur, 0.0)            # no certificate when the time-optimal solve did not converge
-            tmin = np.ascontiguousarray(dur[inverse])
+            tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)      # 0 = "not known yet"
+            presolve = _Presolve(self, dev, tmin_dev, (t0[first], vN[first], v0[first], sub, device), inverse)
+            presolve.start()
         # ---- track tables: shared unless rho / g / velocityMax vary per instance
         per_inst_track = any(k in overrides for k in ('rho', 'velocityMax'))
         N = self.numIntervals
@@ -301,7 +340,9 @@ class casadiSolver():
         h = self._ensure_handle()
         out = h.solve_device(up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
                              up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64),
-                             want_z=True, want_lam=want_multipliers, tmin=up(tmin, torch.float64) if tmin is not None else None)
+                             want_z=True, want_lam=want_multipliers, tmin=presolve.tmin_dev if presolve is not None else None)
+        if presolve is not None:
+            tmin = presolve.join()
         res = {}
         for k, v in out.items():                          # device -> pinned host buffers -> numpy
             if v is None:
@@ -312,8 +353,15 @@ class casadiSolver():
                 res[k] = host
             else:
                 res[k] = v
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         res = {k: (v.numpy() if hasattr(v, 'numpy') else v) for k, v in res.items()}
+        if tmin is not None:
+            # an instance below its minimum trip time is infeasible whatever the iteration did before the certificate arrived
+            infeasible = (res['status'] != 0) & (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
+            res['status'][infeasible] = 4
+        failed = res['status'] != 0
+        if failed.any():
+            res['z'][failed] = 0.0          # the reference returns no trajectory for a failed solve (ocp.py:364-370)
         res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
         res['d2h_bytes'] = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
         res['tmin'] = tmin
