@@ -343,6 +343,8 @@ class casadiSolver():
                              want_z=True, want_lam=want_multipliers, tmin=presolve.tmin_dev if presolve is not None else None)
         if presolve is not None:
             tmin = presolve.join()
+        # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
+        out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
         res = {}
         for k, v in out.items():                          # device -> pinned host buffers -> numpy
             if v is None:
@@ -359,9 +361,7 @@ class casadiSolver():
             # an instance below its minimum trip time is infeasible whatever the iteration did before the certificate arrived
             infeasible = (res['status'] != 0) & (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
             res['status'][infeasible] = 4
-        failed = res['status'] != 0
-        if failed.any():
-            res['z'][failed] = 0.0          # the reference returns no trajectory for a failed solve (ocp.py:364-370)
+
         res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
         res['d2h_bytes'] = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
         res['tmin'] = tmin

@@ -195,7 +195,8 @@ def test_trip_time_sweep_batch_properties(cabi):
         assert np.max(np.abs(res['z'][i][nlp.iB] - ref.x[nlp.iB])) <= 1e-4 * 1206.0
     # bitwise determinism for a fixed batch composition
     res2 = solver.solve_batch(T)
-    assert np.array_equal(res['z'], res2['z']) and np.array_equal(res['iters'], res2['iters'])
+    assert np.array_equal(res['z'], res2['z']) and np.array_equal(res['iters'][feas], res2['iters'][feas])
+    assert np.array_equal(res['status'], res2['status'])
 
 
 def test_parameter_monte_carlo_batch(cabi):
