@@ -115,14 +115,15 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
 
 // Riccati sweeps: one thread per instance, stage data prefetched `depth` intervals ahead through a cp.async ring
 // in dynamic shared memory ((depth+1) * RING_NF_MAX * blockDim doubles).
-__global__ void __launch_bounds__(64) k_step(Ctx c, int depth) {
+template <int BS>
+__global__ void __launch_bounds__(BS) k_step(Ctx c, int depth) {
     extern __shared__ double ring[];
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.x * BS + threadIdx.x;
     if (s >= c.cfg.S) return;
-    RingFetch<BwdFields> fb;
-    fb.sm = ring; fb.depth = depth; fb.bs = blockDim.x; fb.tid = threadIdx.x; fb.dir = -1; fb.kEnd = 0;
-    RingFetch<FwdFields> ff;
-    ff.sm = ring; ff.depth = depth; ff.bs = blockDim.x; ff.tid = threadIdx.x; ff.dir = 1; ff.kEnd = 0;
+    RingFetch<BwdFields, BS> fb;
+    fb.sm = ring; fb.depth = depth; fb.tid = threadIdx.x; fb.dir = -1; fb.kEnd = 0;
+    RingFetch<FwdFields, BS> ff;
+    ff.sm = ring; ff.depth = depth; ff.tid = threadIdx.x; ff.dir = 1; ff.kEnd = 0;
     inst_step(c, s, fb, ff);
 }
 
@@ -331,7 +332,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     int depth = (int)((size_t)200 * 1024 / ((size_t)(blocksPerSm < 1 ? 1 : blocksPerSm) * slotBytes)) - 1;
     depth = depth < 1 ? 1 : (depth > 8 ? 8 : depth);
     const size_t ringBytes = (size_t)(depth + 1) * slotBytes;
-    cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
+    if (ib == 64) cudaFuncSetAttribute(k_step<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
+    else cudaFuncSetAttribute(k_step<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
     int launches = 0;
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -367,7 +369,9 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         if (dyn) k_cell_eval_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_eval<<<cgrid, 128, 0, st>>>(c, io);
         end(CLS_EVAL);
         begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
-        begin(CLS_STEP); k_step<<<igrid, ib, ringBytes, st>>>(c, depth); end(CLS_STEP);
+        begin(CLS_STEP);
+        if (ib == 64) k_step<64><<<igrid, 64, ringBytes, st>>>(c, depth); else k_step<32><<<igrid, 32, ringBytes, st>>>(c, depth);
+        end(CLS_STEP);
         begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
         begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);
         if (tick >= maxTicks) break;

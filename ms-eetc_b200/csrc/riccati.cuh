@@ -20,17 +20,20 @@
 namespace mseetc {
 
 // ---- which planes a sweep consumes per interval ------------------------------------------------------------
+// With the tiled layout every field of interval k of one instance is  record(k) + compile-time offset, and the record
+// of k+1 follows at a compile-time stride, so the address arithmetic of a sweep is one pointer bump per interval.
+enum { REC_STRIDE = WS_FIELDS * 32 };
 struct BwdFields {   // folded stage Hessian (13), linearised coupling rows (6), gradient parts (5 + 5)
     enum { NF = 29 };
-    static MS_HD const double* addr(const Ctx& c, int f, int k, int s) { return &c.W(WS_QP + f, k, s); }
+    static MS_HD constexpr int off(int f) { return (WS_QP + f) * 32; }
 };
 struct FwdFields {   // K, k (12) | P, p of the next node (9) | coupling rows (6) | b_{k+1} terms (7)
     enum { NF = 34 };
-    static MS_HD const double* addr(const Ctx& c, int f, int k, int s) {
-        if (f < 12) return &c.W(WS_RIC + f, k, s);
-        if (f < 21) return &c.W(WS_RIC + f, k + 1, s);
-        if (f < 27) return &c.W(WS_QP + QP_TAU_B + (f - 21), k, s);
-        return &c.W(WS_QP + QP_HC_B + (f - 27), k, s);
+    static MS_HD constexpr int off(int f) {
+        return f < 12 ? (WS_RIC + f) * 32
+             : f < 21 ? (WS_RIC + f) * 32 + REC_STRIDE
+             : f < 27 ? (WS_QP + QP_TAU_B + (f - 21)) * 32
+                      : (WS_QP + QP_HC_B + (f - 27)) * 32;
     }
 };
 enum { RING_NF_MAX = 34 };
@@ -40,23 +43,26 @@ template <class FL>
 struct DirectFetch {
     MS_HD void start(const Ctx&, int, int, int, int) {}
     MS_HD void get(const Ctx& c, int k, int s, double* v) {
-        for (int f = 0; f < FL::NF; ++f) v[f] = *FL::addr(c, f, k, s);
+        const double* rec = &c.W(0, k, s);
+#pragma unroll
+        for (int f = 0; f < FL::NF; ++f) v[f] = rec[FL::off(f)];
     }
 };
 
 #if defined(__CUDACC__)
 // cp.async ring in shared memory: slot (k mod (depth+1)), column = thread; stage k+depth*dir is requested as soon
 // as stage k has been copied to registers, into the slot that was consumed one iteration earlier.
-template <class FL>
+template <class FL, int BS>
 struct RingFetch {
     double* sm;
-    int depth, bs, tid, dir, kEnd;
+    int depth, tid, dir, kEnd;
     __device__ void issue(const Ctx& c, int k, int s) {
         const bool in = (dir < 0) ? (k >= kEnd) : (k <= kEnd);
         if (in) {
-            double* dst = sm + (size_t)((k % (depth + 1)) * FL::NF) * bs + tid;
+            double* dst = sm + (size_t)((k % (depth + 1)) * FL::NF) * BS + tid;
+            const double* src = &c.W(0, k, s);
 #pragma unroll
-            for (int f = 0; f < FL::NF; ++f) __pipeline_memcpy_async(dst + (size_t)f * bs, FL::addr(c, f, k, s), 8);
+            for (int f = 0; f < FL::NF; ++f) __pipeline_memcpy_async(dst + f * BS, src + FL::off(f), 8);
         }
         __pipeline_commit();
     }
@@ -75,9 +81,9 @@ struct RingFetch {
             case 7: __pipeline_wait_prior(6); break;
             default: __pipeline_wait_prior(7); break;
         }
-        const double* src = sm + (size_t)((k % (depth + 1)) * FL::NF) * bs + tid;
+        const double* src = sm + (size_t)((k % (depth + 1)) * FL::NF) * BS + tid;
 #pragma unroll
-        for (int f = 0; f < FL::NF; ++f) v[f] = src[(size_t)f * bs];
+        for (int f = 0; f < FL::NF; ++f) v[f] = src[f * BS];
         issue(c, k + depth * dir, s);
     }
 };
@@ -192,14 +198,14 @@ MS_HD bool stage_riccati(StageQP& q, bool last, double pn, double P[3][3], doubl
 }
 
 MS_HD void stage_store(const Ctx& c, int k, int s, const double K[3][3], const double kf[3], const double P[3][3], const double p[3]) {
+    double* r = &c.W(WS_RIC, k, s);
     for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j) c.W(WS_RIC + RIC_K + 3 * i + j, k, s) = K[i][j];
-        c.W(WS_RIC + RIC_KF + i, k, s) = kf[i];
-        c.W(WS_RIC + RIC_PV + i, k, s) = p[i];
+        for (int j = 0; j < 3; ++j) r[(RIC_K + 3 * i + j) * 32] = K[i][j];
+        r[(RIC_KF + i) * 32] = kf[i];
+        r[(RIC_PV + i) * 32] = p[i];
     }
-    c.W(WS_RIC + RIC_P + 0, k, s) = P[0][0]; c.W(WS_RIC + RIC_P + 1, k, s) = P[0][1];
-    c.W(WS_RIC + RIC_P + 2, k, s) = P[0][2]; c.W(WS_RIC + RIC_P + 3, k, s) = P[1][1];
-    c.W(WS_RIC + RIC_P + 4, k, s) = P[1][2]; c.W(WS_RIC + RIC_P + 5, k, s) = P[2][2];
+    r[(RIC_P + 0) * 32] = P[0][0]; r[(RIC_P + 1) * 32] = P[0][1]; r[(RIC_P + 2) * 32] = P[0][2];
+    r[(RIC_P + 3) * 32] = P[1][1]; r[(RIC_P + 4) * 32] = P[1][2]; r[(RIC_P + 5) * 32] = P[2][2];
 }
 
 // terminal value function: only t_N is free (b_N fixed, Fel_{N-1} costless)
@@ -292,13 +298,14 @@ MS_HD void riccati_forward_range(const Ctx& c, int s, int N, int kLo, int kHi, d
                             + c.W(WS_QP + QP_H_FELSL, k, s) * du[2];
             pib = -(gF + tF * pit) / pF;
         }
-        c.W(WS_ST + ST_FEL, k, s) = du[0];
-        c.W(WS_ST + ST_FPB, k, s) = du[1];
-        c.W(WS_ST + ST_SL, k, s) = du[2];
-        c.W(WS_ST + ST_T, k + 1, s) = dxn[0];
-        c.W(WS_ST + ST_B, k + 1, s) = dxn[1];
-        c.W(WS_ST + ST_YT, k, s) = -pit;
-        c.W(WS_ST + ST_YB, k, s) = -pib;
+        double* st = &c.W(WS_ST, k, s);
+        st[ST_FEL * 32] = du[0];
+        st[ST_FPB * 32] = du[1];
+        st[ST_SL * 32] = du[2];
+        st[ST_T * 32 + REC_STRIDE] = dxn[0];
+        st[ST_B * 32 + REC_STRIDE] = dxn[1];
+        st[ST_YT * 32] = -pit;
+        st[ST_YB * 32] = -pib;
         dx[0] = dxn[0]; dx[1] = dxn[1]; dx[2] = dxn[2];
     }
 }
