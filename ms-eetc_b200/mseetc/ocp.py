@@ -414,6 +414,81 @@ class casadiSolver():
         return df
 
 
+def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, screen=True, device=None):
+    """Additive API: one device call for instances that live on DIFFERENT tracks and/or interval counts
+    (BASELINE config 5: random tracks, mixed numIntervals).  `solvers` is a list of casadiSolver objects with the same
+    problem structure (brakes, power rows, objective, loss family, integrator options); instance i is
+    solvers[i].solve(terminalTime[i], ...).  Returns the same dictionary as casadiSolver.solve_batch; z rows are padded
+    to the largest interval count."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    n = len(solvers)
+    ref = solvers[0]
+    sig = lambda s: (s.withPnBrake, s.withRgBrake, s.withPower, s.energyOptimal, s._lossKind, int(s.opts.integrationOptions.numSteps),
+                     int(s.opts.integrationOptions.numApproxSteps))
+    if any(sig(s) != sig(ref) for s in solvers):
+        raise ValueError("solve_instances needs solvers with identical problem structure")
+    bc = [np.broadcast_to(np.atleast_1d(np.asarray(a, dtype=float)), (n,)) for a in (terminalTime, initialTime, terminalVelocity, initialVelocity)]
+    T, t0, vN, v0 = bc
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    t_begin = _time.perf_counter()
+    Nmax = max(s.numIntervals for s in solvers)
+    planes, Ms, tabs = [], [], []
+    for i, s in enumerate(solvers):
+        if s.energyOptimal and s._lossKind == 'static':
+            _, lossT, lossR = classify_losses(s.train)
+        else:
+            lossT, lossR = 0.0, 0.0
+        P, M = s._planes(1, T[i:i + 1], t0[i:i + 1], v0[i:i + 1], vN[i:i + 1], {}, lossT, lossR)
+        planes.append(P); Ms.append(float(np.atleast_1d(M)[0]))
+        tabs.append(s._tables(s._base['rho'], s._base['g'], s._base['velocityMax']))
+    P = np.ascontiguousarray(np.concatenate(planes, axis=1))
+    nint = np.array([s.numIntervals for s in solvers], dtype=np.int32)
+    trk_off = np.concatenate([[0], np.cumsum(nint)]).astype(np.int32)
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    io = ref.opts.integrationOptions
+    mk = lambda energy, loss: _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
+                                           int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess])
+    dev_tabs = dict(nint=up(nint, torch.int32), trk_of=up(np.arange(n, dtype=np.int32), torch.int32), trk_off=up(trk_off, torch.int32),
+                    ds=up(np.concatenate([t[0] for t in tabs]), torch.float64), c0=up(np.concatenate([t[1] for t in tabs]), torch.float64),
+                    bmax=up(np.concatenate([t[2] for t in tabs]), torch.float64))
+    tmin = None
+    if screen and ref.energyOptimal:
+        # minimum trip time of every instance (tracks differ, so there is nothing to share): time-optimal batch first
+        ht = mk(False, 0)
+        Pt = P.copy()
+        lim = [np.minimum(s.points['Speed limit [m/s]'].values[:-1], s._base['velocityMax']) for s in solvers]
+        Pt[_cabi.PARAM_INDEX['T_END']] = t0 + 1.5 * np.array([float(np.sum(s.steps / l)) for s, l in zip(solvers, lim)])
+        Pt[_cabi.PARAM_INDEX['OBJ_SCALE']] = np.array([s.trackLength / s._base['velocityMax'] for s in solvers])
+        tr = ht.solve_device(up(Pt, torch.float64), dev_tabs['nint'], dev_tabs['trk_of'], dev_tabs['trk_off'], dev_tabs['ds'], dev_tabs['c0'],
+                             dev_tabs['bmax'])
+        stp = 4 + int(ref.withPnBrake)
+        idx = torch.from_numpy(nint.astype(np.int64) * stp).to(dev)
+        tN = tr['z'].gather(1, idx.unsqueeze(1)).squeeze(1)
+        tmin_dev = torch.where(tr['status'] == 0, tN - up(t0, torch.float64), torch.zeros_like(tN))
+        tmin = tmin_dev.cpu().numpy()
+    else:
+        tmin_dev = None
+    h = mk(ref.energyOptimal, {'none': 0, 'static': 1, 'dynamic': 2}[ref._lossKind])
+    if ref._lossKind == 'dynamic' and ref.energyOptimal:
+        dp = ref.train.powerLosses.device_params
+        h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
+    out = h.solve_device(up(P, torch.float64), dev_tabs['nint'], dev_tabs['trk_of'], dev_tabs['trk_off'], dev_tabs['ds'], dev_tabs['c0'],
+                         dev_tabs['bmax'], tmin=tmin_dev)
+    out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
+    res = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
+    if tmin is not None:
+        res['status'][(res['status'] != 0) & (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))] = 4
+    res['wall'] = _time.perf_counter() - t_begin
+    scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
+    M = np.array(Ms)
+    res['cost'] = ((1e-6 / 3.6) * M if ref.energyOptimal else 1.0) * res['obj'] * scale
+    res['tmin'] = tmin
+    res['n_intervals'] = nint
+    return res
+
+
 if __name__ == '__main__':
     from mseetc.train import Train
     from mseetc.track import Track

@@ -119,6 +119,21 @@ class Track():
         self.updateLimits(convertUnit(stops['values'][iFrom], stops['unit']), convertUnit(stops['values'][iTo], stops['unit']))
         self.checkFields()
 
+    @classmethod
+    def fromData(cls, length, speedLimits, gradients=((0.0, 0.0),), curvatures=((0.0, "infinity", "infinity"),), title='synthetic',
+                 altitude=0, speedUnit='km/h', clothoidSamplingInterval=None):
+        """Additive constructor (no reference analogue): a track from in-memory section lists instead of a TTOBench JSON file.
+        speedLimits [(position m, limit)], gradients [(position m, permil)], curvatures [(position m, Rstart m, Rend m)]."""
+        self = cls.__new__(cls)
+        self.length = float(length)
+        self.altitude = altitude
+        self.title = title
+        self.importSpeedLimitTuples([tuple(x) for x in speedLimits], speedUnit)
+        self.importGradientTuples([tuple(x) for x in gradients], 'permil')
+        self.importCurvatureTuples([tuple(x) for x in curvatures], 'm', 'm', clothoidSamplingInterval)
+        self.checkFields()
+        return self
+
     # ------------------------------------------------------------------ validation
     def lengthOk(self):
         return bool(self.length is not None and self.length > 0 and not np.isinf(self.length))
