@@ -80,11 +80,11 @@ enum ParField {
 // ---- per-instance solver state (doubles)
 enum SdField {
     SD_MU = 0, SD_TAU, SD_ALPHA, SD_ALPHA_Z, SD_ALPHA_MIN, SD_THETA, SD_FOBJ, SD_SLOG, SD_SDAMP, SD_GPHID,
-    SD_THETA_MIN, SD_THETA_MAX, SD_DELTA_LAST, SD_KKT, SD_DINF, SD_PINF, SD_CINF,
+    SD_THETA_MIN, SD_THETA_MAX, SD_DELTA_LAST, SD_KKT, SD_DINF, SD_PINF, SD_CINF, SD_KKT_BEST,
     SD_FILTER,                                   // SD_FILTER + 2*i : (theta_i, phi_i)
     SD_N = SD_FILTER + 2 * 12
 };
-enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_N };
+enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_LAST_GAIN, SI_N };
 
 enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2, PH_STEPPED = 3, PH_FACTOR = 4 };
 enum { RED_W = 16 };   // interleave factor of the per-instance reductions (fixed -> bitwise reproducible sums)
@@ -102,6 +102,7 @@ struct Config {
     int numSteps, numApprox;
     int maxIter;
     double tol, muInit;
+    int stallIters;   // > 0: give up (status MAXITER) after that many iterations without a 10 % gain of the best KKT error
     int initMode;     // 0: initial guess of the reference (ocp.py:325-339); 1: dynamically consistent speed-envelope guess
 };
 

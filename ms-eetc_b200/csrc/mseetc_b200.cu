@@ -297,7 +297,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     g.nInst = n;
     g.withPn = p.with_pn_brake; g.withPower = p.with_power_rows; g.energy = p.energy_optimal; g.lossKind = p.loss_kind;
     g.numSteps = p.num_steps; g.numApprox = p.num_approx_steps; g.maxIter = p.max_iterations;
-    g.tol = p.tol; g.muInit = p.mu_init; g.initMode = p.initial_guess;
+    g.tol = p.tol; g.muInit = p.mu_init; g.initMode = p.initial_guess; g.stallIters = p.stall_iterations;
     WsPlan plan = plan_workspace(g.S, g.NK);
     if (ws_bytes < plan.total) return fail(-4, "mseetc_solve_batch: workspace too small (see mseetc_workspace_bytes)");
     if (((uintptr_t)workspace & 255) != 0) return fail(-5, "mseetc_solve_batch: workspace must be 256-byte aligned");

@@ -381,6 +381,13 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     if (!isfinite(E0) || !isfinite(fo)) { finish(c, s, ST_INVALID_NUMBER); return; }
     if (E0 <= g.tol) { finish(c, s, ST_SOLVE_SUCCEEDED); return; }
     if (c.I(SI_ITERS, s) >= g.maxIter) { finish(c, s, ST_MAXITER); return; }
+    // stall watchdog (batch throughput): an instance that cycles around a kink of a non-smooth loss map would otherwise hold
+    // the whole lock-step batch until max_iter; it ends with the status it would end with anyway
+    if (g.stallIters > 0) {
+        const double best = c.D(SD_KKT_BEST, s);
+        if (best <= 0.0 || E0 < 0.9 * best) { c.D(SD_KKT_BEST, s) = E0; c.I(SI_LAST_GAIN, s) = c.I(SI_ITERS, s); }
+        else if (c.I(SI_ITERS, s) - c.I(SI_LAST_GAIN, s) > g.stallIters) { finish(c, s, ST_MAXITER); return; }
+    }
     // ---- monotone barrier update (eq. 7), filter reset
     double mu = c.D(SD_MU, s);
     for (;;) {

@@ -30,7 +30,7 @@ STATUS_STRINGS = {   # IPOPT's return_status vocabulary (what stats['Solver stat
 class Problem(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ('n_intervals_max', 'with_pn_brake', 'with_power_rows', 'energy_optimal',
                                                'loss_kind', 'num_steps', 'num_approx_steps', 'max_iterations')] + \
-               [('tol', ctypes.c_double), ('mu_init', ctypes.c_double), ('initial_guess', ctypes.c_int32)]
+               [('tol', ctypes.c_double), ('mu_init', ctypes.c_double), ('initial_guess', ctypes.c_int32), ('stall_iterations', ctypes.c_int32)]
 
 
 _lib = None
@@ -86,9 +86,9 @@ class Handle:
     "Owns one mseetc_handle plus the device workspace (a torch uint8 tensor, re-used across solves)."
 
     def __init__(self, n_intervals_max, with_pn, with_power, energy, loss_kind, num_steps, num_approx, max_iter,
-                 tol=1e-8, mu_init=0.1, initial_guess=0):
+                 tol=1e-8, mu_init=0.1, initial_guess=0, stall_iterations=0):
         self.problem = Problem(int(n_intervals_max), int(with_pn), int(with_power), int(energy), int(loss_kind),
-                               int(num_steps), int(num_approx), int(max_iter), float(tol), float(mu_init), int(initial_guess))
+                               int(num_steps), int(num_approx), int(max_iter), float(tol), float(mu_init), int(initial_guess), int(stall_iterations))
         self._h = ctypes.c_void_p(0)
         _check(lib().mseetc_create(ctypes.byref(self.problem), ctypes.byref(self._h)), 'mseetc_create')
         self._ws = None

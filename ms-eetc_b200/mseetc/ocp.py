@@ -24,6 +24,10 @@ _ACC_INF = 10   # stand-in for an absent force / acceleration limit (reference o
 # device (same optimum, about half the iterations); 'reference' = the constant guess of the reference (ocp.py:325-339),
 # which reproduces IPOPT-like iteration counts.  Per solver: set `solver.initialGuess` before the first solve.
 DEFAULT_INITIAL_GUESS = 'profile'
+# Iterations without a 10 % gain of the best KKT error after which an instance is abandoned with the status it would reach
+# anyway (Maximum_Iterations_Exceeded); otherwise one instance cycling around a kink of a non-smooth loss map holds the whole
+# lock-step batch until maxIterations.  0 disables the watchdog (`solver.stallIterations = 0`).
+DEFAULT_STALL_ITERATIONS = 80
 
 
 class OptionsCasadiSolver(Options):
@@ -162,6 +166,7 @@ class casadiSolver():
         self._handle = None
         self._dev = {}
         self.initialGuess = DEFAULT_INITIAL_GUESS
+        self.stallIterations = DEFAULT_STALL_ITERATIONS
 
     # ------------------------------------------------------------------ packing
     @staticmethod
@@ -229,7 +234,8 @@ class casadiSolver():
             io = self.opts.integrationOptions
             self._handle = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
                                         {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], io.numSteps, io.numApproxSteps,
-                                        int(self.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[self.initialGuess])
+                                        int(self.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[self.initialGuess],
+                                        stall_iterations=int(self.stallIterations))
             if self._lossKind == 'dynamic' and self.energyOptimal:
                 dp = self.train.powerLosses.device_params
                 self._handle.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
@@ -449,7 +455,8 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
     io = ref.opts.integrationOptions
     mk = lambda energy, loss: _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
-                                           int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess])
+                                           int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess],
+                                           stall_iterations=int(ref.stallIterations))
     dev_tabs = dict(nint=up(nint, torch.int32), trk_of=up(np.arange(n, dtype=np.int32), torch.int32), trk_off=up(trk_off, torch.int32),
                     ds=up(np.concatenate([t[0] for t in tabs]), torch.float64), c0=up(np.concatenate([t[1] for t in tabs]), torch.float64),
                     bmax=up(np.concatenate([t[2] for t in tabs]), torch.float64))

@@ -227,10 +227,10 @@ def test_parameter_monte_carlo_batch(cabi):
 def test_cabi_usage_errors(cabi):
     lib = cabi.lib()
     h = ctypes.c_void_p(0)
-    bad = cabi.Problem(1, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1, 0)
+    bad = cabi.Problem(1, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1, 0, 0)
     assert lib.mseetc_create(ctypes.byref(bad), ctypes.byref(h)) < 0
     assert b'n_intervals_max' in lib.mseetc_last_error()
-    good = cabi.Problem(50, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1, 1)
+    good = cabi.Problem(50, 1, 1, 1, 1, 1, 1, 100, 1e-8, 0.1, 1, 0)
     assert lib.mseetc_create(ctypes.byref(good), ctypes.byref(h)) == 0
     assert lib.mseetc_workspace_bytes(h, 64) > 0
     null = ctypes.c_void_p(0)
