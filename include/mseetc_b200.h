@@ -81,7 +81,7 @@ typedef struct mseetc_problem {
     double mu_init;             /* IPOPT mu_init (default 0.1) */
     int32_t initial_guess;      /* 0: the reference's starting point (ocp.py:325-339); 1: dynamically consistent
                                  * speed-envelope profile built on the device (same optimum, about half the iterations) */
-    int32_t stall_iterations;   /* > 0: stop an instance (status MAXIMUM_ITERATIONS_EXCEEDED) after that many iterations without
+    int32_t stall_iterations;   /* > 0: stop an instance (status MAXIMUM_ITERATIONS_EXCEEDED) after that many trial evaluations without
                                  * a 10 % gain of its best KKT error -- keeps one cycling instance from holding a whole batch;
                                  * 0 = run to max_iterations like the reference */
 } mseetc_problem;

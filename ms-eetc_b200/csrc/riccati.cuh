@@ -385,8 +385,9 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     // the whole lock-step batch until max_iter; it ends with the status it would end with anyway
     if (g.stallIters > 0) {
         const double best = c.D(SD_KKT_BEST, s);
-        if (best <= 0.0 || E0 < 0.9 * best) { c.D(SD_KKT_BEST, s) = E0; c.I(SI_LAST_GAIN, s) = c.I(SI_ITERS, s); }
-        else if (c.I(SI_ITERS, s) - c.I(SI_LAST_GAIN, s) > g.stallIters) { finish(c, s, ST_MAXITER); return; }
+        // counted in trial evaluations (lock-step ticks), which is what a straggler costs the batch
+        if (best <= 0.0 || E0 < 0.9 * best) { c.D(SD_KKT_BEST, s) = E0; c.I(SI_LAST_GAIN, s) = c.I(SI_TICKS, s); }
+        else if (c.I(SI_TICKS, s) - c.I(SI_LAST_GAIN, s) > g.stallIters) { finish(c, s, ST_MAXITER); return; }
     }
     // ---- monotone barrier update (eq. 7), filter reset
     double mu = c.D(SD_MU, s);

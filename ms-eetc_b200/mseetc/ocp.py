@@ -24,7 +24,7 @@ _ACC_INF = 10   # stand-in for an absent force / acceleration limit (reference o
 # device (same optimum, about half the iterations); 'reference' = the constant guess of the reference (ocp.py:325-339),
 # which reproduces IPOPT-like iteration counts.  Per solver: set `solver.initialGuess` before the first solve.
 DEFAULT_INITIAL_GUESS = 'profile'
-# Iterations without a 10 % gain of the best KKT error after which an instance is abandoned with the status it would reach
+# Trial evaluations (iterations + line-search back-tracks) without a 10 % gain of the best KKT error after which an instance is abandoned with the status it would reach
 # anyway (Maximum_Iterations_Exceeded); otherwise one instance cycling around a kink of a non-smooth loss map holds the whole
 # lock-step batch until maxIterations.  0 disables the watchdog (`solver.stallIterations = 0`).
 DEFAULT_STALL_ITERATIONS = 80
