@@ -203,10 +203,12 @@ def run_gpu(args):
              nint1=up(np.full(1, N_INT, np.int32), torch.int32), trk_of=up(np.zeros(n, np.int32), torch.int32),
              trk_of1=up(np.zeros(1, np.int32), torch.int32), trk_off=up(np.array([0, N_INT], np.int32), torch.int32),
              ds=up(ds, torch.float64), c0=up(c0, torch.float64), bmax=up(bmax, torch.float64))
-    h = solver._ensure_handle()
+    solver.streams = args.streams
+    pool = _cabi.StreamPool(solver._make_handle, max(1, args.streams), dev)
+    h = pool.handles[0]
     ht = tsolver._ensure_handle()
-    _cabi.set_profiling(h, True)
-    _cabi.set_profiling(ht, True)
+    for hh in pool.handles + [ht]:
+        _cabi.set_profiling(hh, True)
     stp = 3 + h.nu
     outbuf = dict(z=torch.zeros((n, N_INT * stp + 2), dtype=torch.float64, device=dev), lam=None,
                   obj=torch.empty(n, dtype=torch.float64, device=dev), kkt=torch.empty(n, dtype=torch.float64, device=dev),
@@ -235,12 +237,12 @@ def run_gpu(args):
         th = threading.Thread(target=presolve)
         th.start()
         # (2) the sweep; instances below the minimum time are flagged infeasible by the library as soon as it is known
-        out = h.solve_device(d['P'], d['nint'], d['trk_of'], d['trk_off'], d['ds'], d['c0'], d['bmax'], tmin=tmin_dev, out=dict(outbuf))
+        out = pool.solve(d['P'], d['nint'], d['trk_of'], d['trk_off'], d['ds'], d['c0'], d['bmax'], tmin=tmin_dev, out=dict(outbuf))
         th.join()
         tr = box['tr']
         if accumulate:
             launches[0] += tr['launches'] + out['launches']
-            for hh in (h, ht):
+            for hh in pool.handles + [ht]:
                 for k, v in _cabi.last_profile(hh).items():
                     prof[k]['ms'] += v['ms']; prof[k]['launches'] += v['launches']; prof[k]['cells'] += v['cells']
                     prof[k]['bytes_per_cell'] = v['bytes_per_cell'] if hh is h else prof[k].get('bytes_per_cell', v['bytes_per_cell'])
@@ -336,7 +338,7 @@ def run_gpu(args):
                        'instances_per_gpu': n, 'feasible_per_gpu': int(feas.sum()), 'converged_feasible': n_ok,
                        'flagged_infeasible': n_flag, 'tmin_s': tmin_dev, 'ip_iterations_mean': float(iters[feas].mean()),
                        'ip_iterations_max': int(iters[feas].max()), 'ticks': int(out['ticks']),
-                       'l2': 'per-tick working set %.2f GB >> 126 MB L2' % (_cabi.lib().mseetc_workspace_bytes(h._h, n) / 1e9)},
+                       'streams': args.streams, 'l2': 'per-tick working set %.2f GB >> 126 MB L2' % (_cabi.lib().mseetc_workspace_bytes(h._h, n) / 1e9)},
             'feasible_solves_per_s': int(feas.sum()) * world * args.steps / (ms * 1e-3),
             'e2e': {'value': total * args.steps / e2e_s, 'unit': 'solves/s', 'h2d_bytes_per_step': res['h2d_bytes'],
                     'd2h_bytes_per_step': res['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s / args.steps},
@@ -356,6 +358,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--instances', type=int, default=N_INST)
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
+    ap.add_argument('--streams', type=int, default=4, help='concurrent sub-batches (CUDA streams / host threads) per GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

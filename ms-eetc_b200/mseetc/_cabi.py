@@ -156,6 +156,71 @@ class Handle:
         return out
 
 
+class StreamPool:
+    """Solve one batch as k sub-batches on k CUDA streams, each driven by its own host thread (ctypes releases the GIL).
+
+    A tick of the solver is a chain of latency-bound phases -- the Riccati sweep kernel takes the same time for 1 or for 4096
+    instances -- so concurrent sub-batches overlap one sub-batch's sweep with the interval kernels of the others.  Instances
+    are independent: the results are bitwise identical to a single-stream solve."""
+
+    def __init__(self, make_handle, k, device):
+        torch = _torch_cuda()
+        self.handles = [make_handle() for _ in range(k)]
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(k)]
+        self.device = device
+
+    @staticmethod
+    def bounds(n, k):
+        per = -(-n // k)
+        per = (per + 31) // 32 * 32                     # sub-batches start on a 32-instance tile
+        cuts = [min(i * per, n) for i in range(k + 1)]
+        cuts[-1] = n
+        return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+    def solve(self, params, nint, trk_of, trk_off, ds, c0, bmax, tmin=None, out=None, want_lam=False):
+        import threading
+        torch = _torch_cuda()
+        n = int(nint.numel())
+        dev = params.device
+        h0 = self.handles[0]
+        Nmax, stp = h0.problem.n_intervals_max, 3 + h0.nu
+        if out is None:
+            out = dict(z=torch.zeros((n, Nmax * stp + 2), dtype=torch.float64, device=dev),
+                       lam=torch.zeros((n, Nmax * h0.rows), dtype=torch.float64, device=dev) if want_lam else None,
+                       obj=torch.empty(n, dtype=torch.float64, device=dev), kkt=torch.empty(n, dtype=torch.float64, device=dev),
+                       iters=torch.empty(n, dtype=torch.int32, device=dev), status=torch.empty(n, dtype=torch.int32, device=dev))
+        main = torch.cuda.current_stream(dev)
+        parts = self.bounds(n, len(self.handles))
+        info, errors = [None] * len(parts), []
+
+        def work(i, a, b):
+            try:
+                torch.cuda.set_device(dev)
+                st = self.streams[i]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    sub = {k: (v[a:b] if v is not None else None) for k, v in out.items()}
+                    r = self.handles[i].solve_device(params[:, a:b].contiguous(), nint[a:b], trk_of[a:b], trk_off, ds, c0, bmax,
+                                                     tmin=tmin[a:b] if tmin is not None else None, out=sub)
+                    info[i] = (r['ticks'], r['launches'])
+            except Exception as exc:
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(i, a, b)) for i, (a, b) in enumerate(parts)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        for st in self.streams[:len(parts)]:
+            main.wait_stream(st)
+        out = dict(out)
+        out['ticks'] = max(i[0] for i in info if i)
+        out['launches'] = sum(i[1] for i in info if i)
+        return out
+
+
 KERNEL_CLASSES = ('cell_trial', 'inst_decide', 'cell_eval', 'inst_step', 'misc', 'cell_step', 'inst_alpha', 'inst_kkt')
 
 

@@ -28,6 +28,9 @@ DEFAULT_INITIAL_GUESS = 'profile'
 # anyway (Maximum_Iterations_Exceeded); otherwise one instance cycling around a kink of a non-smooth loss map holds the whole
 # lock-step batch until maxIterations.  0 disables the watchdog (`solver.stallIterations = 0`).
 DEFAULT_STALL_ITERATIONS = 80
+# Sub-batches solved concurrently on separate CUDA streams (one host thread each); see _cabi.StreamPool.
+DEFAULT_STREAMS = 4
+MIN_INSTANCES_PER_STREAM = 512
 
 
 class OptionsCasadiSolver(Options):
@@ -167,6 +170,8 @@ class casadiSolver():
         self._dev = {}
         self.initialGuess = DEFAULT_INITIAL_GUESS
         self.stallIterations = DEFAULT_STALL_ITERATIONS
+        self.streams = DEFAULT_STREAMS
+        self._pool = None
 
     # ------------------------------------------------------------------ packing
     @staticmethod
@@ -228,6 +233,22 @@ class casadiSolver():
         bmax = np.ones(N + 1)
         bmax[1:N] = np.minimum(np.minimum(lim[1:N], vmax), lim[0:N - 1]) ** 2    # reference ocp.py:266-269
         return np.asarray(self.steps, dtype=float), c0, bmax
+
+    def _make_handle(self):
+        io = self.opts.integrationOptions
+        h = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
+                         {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], io.numSteps, io.numApproxSteps,
+                         int(self.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[self.initialGuess],
+                         stall_iterations=int(self.stallIterations))
+        if self._lossKind == 'dynamic' and self.energyOptimal:
+            dp = self.train.powerLosses.device_params
+            h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
+        return h
+
+    def _ensure_pool(self, dev):
+        if self._pool is None or len(self._pool.handles) != int(self.streams) or self._pool.device != dev:
+            self._pool = _cabi.StreamPool(self._make_handle, int(self.streams), dev)
+        return self._pool
 
     def _ensure_handle(self):
         if self._handle is None:
@@ -343,10 +364,13 @@ class casadiSolver():
             trk_of = np.zeros(n, dtype=np.int32)
             trk_off = np.array([0, N], dtype=np.int32)
         up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt, non_blocking=False)
-        h = self._ensure_handle()
-        out = h.solve_device(up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
-                             up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64),
-                             want_z=True, want_lam=want_multipliers, tmin=presolve.tmin_dev if presolve is not None else None)
+        args = (up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
+                up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64))
+        tm = presolve.tmin_dev if presolve is not None else None
+        if int(self.streams) > 1 and n >= 2 * MIN_INSTANCES_PER_STREAM:
+            out = self._ensure_pool(dev).solve(*args, tmin=tm, want_lam=want_multipliers)
+        else:
+            out = self._ensure_handle().solve_device(*args, want_z=True, want_lam=want_multipliers, tmin=tm)
         if presolve is not None:
             tmin = presolve.join()
         # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
