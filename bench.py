@@ -208,7 +208,7 @@ def run_gpu(args):
     h = pool.handles[0]
     ht = tsolver._ensure_handle()
     for hh in pool.handles + [ht]:
-        _cabi.set_profiling(hh, True)
+        _cabi.set_profiling(hh, not args.no_profile)
     stp = 3 + h.nu
     outbuf = dict(z=torch.zeros((n, N_INT * stp + 2), dtype=torch.float64, device=dev), lam=None,
                   obj=torch.empty(n, dtype=torch.float64, device=dev), kkt=torch.empty(n, dtype=torch.float64, device=dev),
@@ -310,6 +310,8 @@ def run_gpu(args):
         gbs = v['cells'] * v['bytes_per_cell'] / (v['ms'] * 1e-3) / 1e9 if v['ms'] > 0 else 0.0
         kern[k] = {'ms_total': v['ms'], 'launches': v['launches'], 'avg_us': 1e3 * v['ms'] / v['launches'],
                    'bytes_per_cell': v['bytes_per_cell'], 'cells': v['cells'], 'achieved_gbs': gbs, 'frac_hbm': gbs / peak}
+    if not kern:
+        kern = {'inst_step': dict(ms_total=1.0, launches=1, avg_us=0.0, bytes_per_cell=0.0, cells=0, achieved_gbs=0.0, frac_hbm=0.0)}
     top = max(kern, key=lambda k: kern[k]['ms_total'])
     ncu_traffic = None
     tfile = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -317,7 +319,7 @@ def run_gpu(args):
         ncu_traffic = json.load(open(tfile)).get(top)
     roofline = {'bound': 'hbm', 'kernel': top, 'achieved': kern[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
                 'frac': kern[top]['achieved_gbs'] / peak, 'traffic': ncu_traffic, 'peak_source': peak_src,
-                'share_of_device_time': kern[top]['ms_total'] / sum(v['ms_total'] for v in kern.values()),
+                'share_of_device_time': kern[top]['ms_total'] / max(1e-12, sum(v['ms_total'] for v in kern.values())),
                 'bytes_per_launch': kern[top]['cells'] * kern[top]['bytes_per_cell'] / kern[top]['launches'], 'kernels': kern}
 
     # ---------------- CPU baseline beside it (bounded sample, rank 0, N = 1 only)
@@ -353,12 +355,13 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--instances', type=int, default=N_INST)
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
-    ap.add_argument('--streams', type=int, default=4, help='concurrent sub-batches (CUDA streams / host threads) per GPU')
+    ap.add_argument('--no-profile', action='store_true', help='no per-kernel CUDA events (roofline block is then empty)')
+    ap.add_argument('--streams', type=int, default=2, help='concurrent sub-batches (CUDA streams / host threads) per GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -29,7 +29,7 @@ DEFAULT_INITIAL_GUESS = 'profile'
 # lock-step batch until maxIterations.  0 disables the watchdog (`solver.stallIterations = 0`).
 DEFAULT_STALL_ITERATIONS = 80
 # Sub-batches solved concurrently on separate CUDA streams (one host thread each); see _cabi.StreamPool.
-DEFAULT_STREAMS = 4
+DEFAULT_STREAMS = 2
 MIN_INSTANCES_PER_STREAM = 512
 
 

@@ -291,3 +291,58 @@ def test_dynamic_loss_map_public_api_matches_golden(cabi):
     res = solver.solve_batch(1242.0, overrides=dict(auxiliaries=rng.uniform(20e3, 35e3, n), tableScale=rng.uniform(0.9, 1.1, n)))
     assert np.all(res['status'] == 0) and np.all(res['kkt'] <= 1e-8)
     assert res['cost'].std() > 0.05
+
+
+def test_stream_pool_is_bitwise_identical_to_single_stream(cabi):
+    "Concurrent sub-batches (StreamPool) change the schedule, not the arithmetic."
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    opts = {'numIntervals': 300, 'maxIterations': 500, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    T = np.linspace(1040.0, 1400.0, 1500)
+    one = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), opts)
+    one.streams = 1
+    three = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), opts)
+    three.streams = 3
+    a = one.solve_batch(T, screen=False)
+    b = three.solve_batch(T, screen=False)
+    assert np.all(a['status'] == 0)
+    for key in ('z', 'obj', 'kkt', 'iters', 'status'):
+        assert np.array_equal(a[key], b[key]), key
+
+
+def test_solve_instances_mixed_tracks_and_interval_counts(cabi):
+    "BASELINE config 5 in miniature: random tracks, mixed numIntervals, one device call; oracle spot check."
+    from mseetc.ocp import casadiSolver, solve_instances
+    from mseetc.train import Train
+    from mseetc.synthetic import random_track
+    from oracle.problem import TrackData
+    rng = np.random.default_rng(11)
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    solvers = []
+    while len(solvers) < 48:
+        N = int(rng.choice([100, 200, 300]))
+        track = random_track(rng)
+        try:
+            solvers.append(casadiSolver(train, track, {'numIntervals': N, 'maxIterations': 300, 'integrationOptions': {'numApproxSteps': 1}}))
+            solvers[-1]._track = track
+        except ValueError:
+            continue
+    lim = [np.minimum(s.points['Speed limit [m/s]'].values[:-1], s._base['velocityMax']) for s in solvers]
+    T = 1.3 * np.array([float(np.sum(s.steps / l)) for s, l in zip(solvers, lim)]) + 60.0
+    res = solve_instances(solvers, T)
+    ok = res['status'] == 0
+    assert ok.sum() >= 40 and np.all(res['kkt'][ok] <= 1e-8)
+    assert np.all((res['status'] == 0) | (res['status'] == 4) | (res['status'] == 1) | (res['status'] == 2))
+    i = int(np.where(ok)[0][0])
+    s = solvers[i]
+    tk = s._track
+    td = TrackData(tk.length, (tk.speedLimits.index.values, tk.speedLimits.iloc[:, 0].values), (tk.gradients.index.values, tk.gradients.iloc[:, 0].values),
+                   (tk.curvatures.index.values, tk.curvatures.iloc[:, 0].values))
+    nlp = oracle_nlp(virm6(), td, s.numIntervals)
+    ref = oracle_solve(nlp, float(T[i]))
+    assert ref.success
+    assert abs(res['obj'][i] - ref.f) <= 1e-6 * abs(ref.f)
+    z = res['z'][i][:nlp.nz]
+    assert np.max(np.abs(z[nlp.iB] - ref.x[nlp.iB])) <= 1e-4 * nlp.limit.max() ** 2
