@@ -343,6 +343,7 @@ def run_gpu(args):
                        'streams': args.streams, 'l2': 'per-tick working set %.2f GB >> 126 MB L2' % (_cabi.lib().mseetc_workspace_bytes(h._h, n) / 1e9)},
             'feasible_solves_per_s': int(feas.sum()) * world * args.steps / (ms * 1e-3),
             'e2e': {'value': total * args.steps / e2e_s, 'unit': 'solves/s', 'h2d_bytes_per_step': res['h2d_bytes'],
+                    'last_call_breakdown_s': res.get('timing'),
                     'd2h_bytes_per_step': res['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s / args.steps},
             'gpu_launches': launches[0], 'clocks': clocks, 'roofline': roofline}
     if cpu is not None:

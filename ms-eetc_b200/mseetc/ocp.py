@@ -364,15 +364,19 @@ class casadiSolver():
             trk_of = np.zeros(n, dtype=np.int32)
             trk_off = np.array([0, N], dtype=np.int32)
         up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt, non_blocking=False)
+        t_pack = _time.perf_counter() - t_begin
         args = (up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
                 up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64))
         tm = presolve.tmin_dev if presolve is not None else None
+        t_up = _time.perf_counter() - t_begin
         if int(self.streams) > 1 and n >= 2 * MIN_INSTANCES_PER_STREAM:
             out = self._ensure_pool(dev).solve(*args, tmin=tm, want_lam=want_multipliers)
         else:
             out = self._ensure_handle().solve_device(*args, want_z=True, want_lam=want_multipliers, tmin=tm)
+        t_solve = _time.perf_counter() - t_begin
         if presolve is not None:
             tmin = presolve.join()
+        t_join = _time.perf_counter() - t_begin
         # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
         out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
         res = {}
@@ -395,6 +399,8 @@ class casadiSolver():
         res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
         res['d2h_bytes'] = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
         res['tmin'] = tmin
+        res['timing'] = dict(pack=t_pack, upload=t_up - t_pack, solve=t_solve - t_up, presolve_join=t_join - t_solve,
+                             d2h=_time.perf_counter() - t_begin - t_join)
         res['wall'] = _time.perf_counter() - t_begin
         scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
         # reference ocp.py:361: cost in kWh (energy) or s (time)
