@@ -135,6 +135,12 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
                        int32_t* iters_out_dev, int32_t* status_out_dev,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
 
+/* Sweep variant: 1 = sequential Riccati sweeps, one thread per instance (default); 8 or 32 = parallel-in-time sweeps with that
+ * many lanes per instance (associative scan over chunk elements + exact in-chunk recursions + a-posteriori check with
+ * sequential fallback per instance).  Pays for long horizons and small batches. */
+int mseetc_set_sweep_lanes(mseetc_handle h, int lanes);
+long long mseetc_last_sweep_fallbacks(mseetc_handle h);
+
 /* number of solver ticks (lock-step rounds) and kernel launches of the last mseetc_solve_batch on h */
 int mseetc_last_ticks(mseetc_handle h);
 int mseetc_last_launches(mseetc_handle h);

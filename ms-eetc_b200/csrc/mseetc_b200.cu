@@ -127,6 +127,137 @@ __global__ void __launch_bounds__(BS) k_step(Ctx c, int depth) {
     inst_step(c, s, fb, ff);
 }
 
+// ---- parallel-in-time sweeps: G lanes per instance (pit.cuh).  Chunk elements -> suffix scan (warp shuffles) -> exact
+// Riccati inside every chunk (twice: the second pass takes its end value from the neighbour's first pass, a block-Jacobi
+// refinement) -> prefix scan of the closed-loop chunk transitions -> chunk-local forward sweeps.  An a-posteriori check of
+// the chunk-end value functions decides per instance whether the result is trusted; otherwise lane 0 redoes the
+// sequential sweeps (same kernel), so accuracy never depends on the scan.
+template <int G>
+__device__ __forceinline__ void shfl_down_arr(const double* src, double* dst, int n, int d) {
+    for (int i = 0; i < n; ++i) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d, G);
+}
+template <int G>
+__device__ __forceinline__ void shfl_up_arr(const double* src, double* dst, int n, int d) {
+    for (int i = 0; i < n; ++i) dst[i] = __shfl_up_sync(0xffffffffu, src[i], d, G);
+}
+
+template <int G>
+__global__ void __launch_bounds__(64) k_step_pit(Ctx c, int* fallbackCount) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = gtid / G, cl = gtid % G;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const Config& g = c.cfg;
+    const bool active = s < g.nInst && c.I(SI_PHASE, s) == PH_FACTOR;
+    const int N = active ? c.I(SI_N_INT, s) : 2;
+    const double mu = active ? c.D(SD_MU, s) : 0.1;
+    const double dlast = active ? c.D(SD_DELTA_LAST, s) : 0.0;
+    int kLo, kHi;
+    pit_chunk(N, G, cl, kLo, kHi);
+    DirectFetch<BwdFields> fb;
+    DirectFetch<FwdFields> ff;
+    double delta = 0.0;
+    bool pending = active, failedForGood = false, fallback = false;
+    Aff T;
+    aff_identity(T);
+    for (int tries = 0; tries < 40; ++tries) {
+        if (!__any_sync(0xffffffffu, pending)) break;
+        bool ok = true;
+        Elem E;
+        elem_identity(E);
+        double Pl[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, pl[3] = {0, 0, 0};
+        if (pending) {
+            if (cl == 0) count_cells(c, 2, N);
+            if (cl == G - 1) {      // interval N-1 (terminal-speed elimination): value function of node N-1
+                terminal_value(c, s, N, mu, delta, Pl, pl);
+                ok = riccati_backward_range(c, s, N, N - 1, N, mu, delta, fb, Pl, pl, nullptr, nullptr);
+                if (ok) elem_from_value(E, Pl, pl);
+            }
+            if (ok) ok = pit_phase_a(c, s, kLo, kHi, mu, delta, fb, cl == G - 1, E);
+        }
+        // suffix scan of the chunk elements (all lanes take part in the shuffles)
+        for (int d = 1; d < G; d <<= 1) {
+            Elem O;
+            shfl_down_arr<G>((const double*)&E, (double*)&O, sizeof(Elem) / sizeof(double), d);
+            const bool okO = __shfl_down_sync(0xffffffffu, ok ? 1 : 0, d, G) != 0;
+            if (cl + d < G) {
+                Elem R;
+                ok = ok && okO && elem_combine(E, O, R);
+                E = R;
+            }
+        }
+        Elem En;
+        shfl_down_arr<G>((const double*)&E, (double*)&En, sizeof(Elem) / sizeof(double), 1);
+        const bool okN = __shfl_down_sync(0xffffffffu, ok ? 1 : 0, 1, G) != 0;
+        double P[3][3], p[3];
+        if (cl == G - 1) { for (int i = 0; i < 3; ++i) { p[i] = pl[i]; for (int j = 0; j < 3; ++j) P[i][j] = Pl[i][j]; } }
+        else { sym_to_full(En.J, P); for (int i = 0; i < 3; ++i) p[i] = -En.eta[i]; ok = ok && okN; }
+        double P0[3][3], p0[3];
+        for (int i = 0; i < 3; ++i) { p0[i] = p[i]; for (int j = 0; j < 3; ++j) P0[i][j] = P[i][j]; }
+        // pass 0: in-chunk recursion from the scan's end value (only (P,p) at the chunk start is kept)
+        if (pending && ok) ok = riccati_backward_range(c, s, N, kLo, kHi, mu, delta, fb, P, p, nullptr, nullptr, false);
+        __syncwarp();
+        // pass 1: end value = what the next lane's stable recursion produced at that node
+        double dev = 0.0;
+        if (pending && ok && cl < G - 1 && kHi > kLo) {
+            double sy[6];
+            for (int i = 0; i < 6; ++i) sy[i] = c.W(WS_RIC + RIC_P + i, kHi, s);
+            sym_to_full(sy, P);
+            for (int i = 0; i < 3; ++i) p[i] = c.W(WS_RIC + RIC_PV + i, kHi, s);
+            double num = 0.0, den = 1e-300;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { num = fmax(num, fabs(P[i][j] - P0[i][j])); den = fmax(den, fabs(P[i][j])); }
+            dev = num / den;
+        } else if (cl == G - 1) {
+            for (int i = 0; i < 3; ++i) { p[i] = pl[i]; for (int j = 0; j < 3; ++j) P[i][j] = Pl[i][j]; }
+        } else {
+            for (int i = 0; i < 3; ++i) { p[i] = p0[i]; for (int j = 0; j < 3; ++j) P[i][j] = P0[i][j]; }
+        }
+        __syncwarp();
+        aff_identity(T);
+        if (pending && ok) ok = riccati_backward_range(c, s, N, kLo, kHi, mu, delta, fb, P, p, T.M, T.m, true);
+        // group decisions: wrong inertia -> regularise and retry; scan not trustworthy -> sequential fallback
+        const unsigned bad = __ballot_sync(0xffffffffu, pending && !ok);
+        const unsigned sus = __ballot_sync(0xffffffffu, pending && ok && dev > 1e-6);
+        if (pending) {
+            if (bad & gmask) {
+                if (cl == 0) c.I(SI_NREG, s) += 1;
+                if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
+                else delta *= (dlast == 0.0) ? 100.0 : 8.0;
+                if (delta > 1e40) { failedForGood = true; pending = false; }
+            } else {
+                fallback = (sus & gmask) != 0;
+                pending = false;
+            }
+        }
+    }
+    if (pending) failedForGood = true;
+    // ---- sequential fallback for the instances whose scan was not accurate enough (lane 0 of the group works)
+    if (__any_sync(0xffffffffu, fallback)) {
+        if (fallback && cl == 0) {
+            atomicAdd(fallbackCount, 1);
+            inst_step(c, s, fb, ff);            // complete sequential direction incl. its own inertia ladder and phase change
+        }
+        __syncwarp();
+    }
+    if (fallback || !active) return;
+    if (failedForGood) { if (cl == 0) finish(c, s, ST_STEP_FAILED); return; }
+    // ---- prefix scan of the closed-loop chunk transitions -> state step at every chunk start
+    // (lanes of finished groups left above; the shuffles below use the group mask)
+    for (int d = 1; d < G; d <<= 1) {
+        Aff O;
+        for (int i = 0; i < 12; ++i) ((double*)&O)[i] = __shfl_up_sync(gmask, ((const double*)&T)[i], d, G);
+        if (cl >= d) { Aff R; aff_compose(O, T, R); T = R; }
+    }
+    double dx[3];
+    for (int i = 0; i < 3; ++i) { const double v = __shfl_up_sync(gmask, T.m[i], 1, G); dx[i] = (cl > 0) ? v : 0.0; }
+    if (cl == 0) { c.W(WS_ST + ST_T, 0, s) = 0.0; c.W(WS_ST + ST_B, 0, s) = 0.0; count_cells(c, 3, N); if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta; }
+    __syncwarp(gmask);
+    riccati_forward_range(c, s, N, kLo, kHi, mu, delta, ff, dx);
+    if (cl == G - 1) riccati_forward_range(c, s, N, N - 1, N, mu, delta, ff, dx);
+    __syncwarp(gmask);
+    if (cl == 0) c.I(SI_PHASE, s) = PH_STEPPED;
+}
+
 __global__ void k_eval_loss_rows(LossMapDev lm, int n, const double* in, const double* par, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     eval_loss_rows_point(lm, i, n, in, par, out);
@@ -152,6 +283,8 @@ struct mseetc_solver {
     long long cells[NCLS];
     std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
     cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
+    int sweep_lanes;               // 1: sequential sweeps; 8 / 32: lanes per instance of the parallel-in-time sweeps
+    long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
     double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
     LossMapDev lm;
 };
@@ -183,6 +316,8 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->last_ticks = 0;
     h->last_launches = 0;
     h->profiling = 0;
+    h->sweep_lanes = 1;
+    h->last_fallbacks = 0;
     h->lm_dev = nullptr;
     memset(&h->lm, 0, sizeof h->lm);
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -240,6 +375,14 @@ int mseetc_eval_loss_rows(mseetc_handle h, int32_t n, const double* in, const do
     if (e != cudaSuccess) return cuda_fail(e, "k_eval_loss_rows");
     return 0;
 }
+
+int mseetc_set_sweep_lanes(mseetc_handle h, int lanes) {
+    if (!h) return fail(-1, "mseetc_set_sweep_lanes: null handle");
+    if (lanes != 1 && lanes != 8 && lanes != 32) return fail(-2, "mseetc_set_sweep_lanes: lanes must be 1, 8 or 32");
+    h->sweep_lanes = lanes;
+    return 0;
+}
+long long mseetc_last_sweep_fallbacks(mseetc_handle h) { return h ? h->last_fallbacks : -1; }
 
 int mseetc_set_profiling(mseetc_handle h, int on) {
     if (!h) return fail(-1, "mseetc_set_profiling: null handle");
@@ -370,7 +513,10 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         end(CLS_EVAL);
         begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
         begin(CLS_STEP);
-        if (ib == 64) k_step<64><<<igrid, 64, ringBytes, st>>>(c, depth); else k_step<32><<<igrid, 32, ringBytes, st>>>(c, depth);
+        if (h->sweep_lanes == 8) k_step_pit<8><<<(unsigned)(((size_t)g.S * 8 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
+        else if (h->sweep_lanes == 32) k_step_pit<32><<<(unsigned)(((size_t)g.S * 32 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
+        else if (ib == 64) k_step<64><<<igrid, 64, ringBytes, st>>>(c, depth);
+        else k_step<32><<<igrid, 32, ringBytes, st>>>(c, depth);
         end(CLS_STEP);
         begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
         begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);
@@ -398,7 +544,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     begin(CLS_MISC); k_cell_extract<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-    e = cudaMemcpyAsync(h->done_host, c.done, 128, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(h->done_host, c.done, 256, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(counters)");
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
@@ -412,6 +558,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         h->cells[CLS_ALPHA] = h->cells[CLS_CSTEP];
         h->cells[CLS_KKT] = (long long)cnt[1];
         h->cells[CLS_MISC] = 0;
+        h->last_fallbacks = (long long)h->done_host[48];
     }
     for (size_t i = 0; i < evClass.size(); ++i) {
         float ms = 0.f;

@@ -224,7 +224,7 @@ MS_HD void terminal_value(const Ctx& c, int s, int N, double mu, double delta, d
 // Optionally accumulates the closed-loop transition of the range: x_{kHi} = Mc x_{kLo} + mc.
 template <class Fetch>
 MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch,
-                                  double P[3][3], double p[3], double* Mc, double* mc) {
+                                  double P[3][3], double p[3], double* Mc, double* mc, bool storeAll = true) {
     const double pn = c.cfg.withPn ? 1.0 : 0.0;
     if (kHi <= kLo) return true;
     fetch.start(c, s, kHi - 1, kLo, -1);
@@ -236,7 +236,7 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
         stage_build(v, mu, delta, pn, last, q);
         double K[3][3], kf[3];
         if (!stage_riccati(q, last, pn, P, p, K, kf)) return false;
-        stage_store(c, k, s, K, kf, P, p);
+        if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
             // closed loop of this interval: x+ = (A + B K) x + (B kf + r); compose: acc <- acc o this
             double Mk[9], mk[3];

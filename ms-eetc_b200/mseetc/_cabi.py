@@ -61,6 +61,9 @@ def lib():
     L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
     L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.mseetc_set_sweep_lanes.argtypes = [vp, ctypes.c_int]
+    L.mseetc_last_sweep_fallbacks.argtypes = [vp]
+    L.mseetc_last_sweep_fallbacks.restype = ctypes.c_longlong
     L.mseetc_eval_loss_rows.argtypes = [vp, i32, vp, vp, vp, vp]
     _lib = L
     return L
@@ -102,6 +105,13 @@ class Handle:
                 self._h = ctypes.c_void_p(0)
         except Exception:
             pass
+
+    def set_sweep_lanes(self, lanes):
+        "1 = sequential Riccati sweeps; 8 / 32 = parallel-in-time sweeps with that many lanes per instance."
+        _check(lib().mseetc_set_sweep_lanes(self._h, int(lanes)), 'mseetc_set_sweep_lanes')
+
+    def last_sweep_fallbacks(self):
+        return int(lib().mseetc_last_sweep_fallbacks(self._h))
 
     def set_loss_map(self, knots_load, knots_speed, coef):
         "Upload the motor-loss spline (efficiency.createSpline) used by loss_kind 2."

@@ -172,6 +172,7 @@ class casadiSolver():
         self.stallIterations = DEFAULT_STALL_ITERATIONS
         self.streams = DEFAULT_STREAMS
         self._pool = None
+        self.sweepLanes = 'auto'      # 1 sequential sweeps | 8 | 32 lanes per instance (parallel in time) | 'auto'
 
     # ------------------------------------------------------------------ packing
     @staticmethod
@@ -243,6 +244,10 @@ class casadiSolver():
         if self._lossKind == 'dynamic' and self.energyOptimal:
             dp = self.train.powerLosses.device_params
             h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
+        lanes = self.sweepLanes
+        if lanes == 'auto':
+            lanes = 32 if self.numIntervals >= 2048 else 1     # long horizons: chunks of >= 64 intervals per lane
+        h.set_sweep_lanes(int(lanes))
         return h
 
     def _ensure_pool(self, dev):
@@ -252,14 +257,7 @@ class casadiSolver():
 
     def _ensure_handle(self):
         if self._handle is None:
-            io = self.opts.integrationOptions
-            self._handle = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
-                                        {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], io.numSteps, io.numApproxSteps,
-                                        int(self.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[self.initialGuess],
-                                        stall_iterations=int(self.stallIterations))
-            if self._lossKind == 'dynamic' and self.energyOptimal:
-                dp = self.train.powerLosses.device_params
-                self._handle.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
+            self._handle = self._make_handle()
         return self._handle
 
     # ------------------------------------------------------------------ batched solve (additive API)
