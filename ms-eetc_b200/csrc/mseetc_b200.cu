@@ -252,8 +252,22 @@ __global__ void __launch_bounds__(64) k_step_pit(Ctx c, int* fallbackCount) {
     for (int i = 0; i < 3; ++i) { const double v = __shfl_up_sync(gmask, T.m[i], 1, G); dx[i] = (cl > 0) ? v : 0.0; }
     if (cl == 0) { c.W(WS_ST + ST_T, 0, s) = 0.0; c.W(WS_ST + ST_B, 0, s) = 0.0; count_cells(c, 3, N); if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta; }
     __syncwarp(gmask);
+    double dxs[3] = {dx[0], dx[1], dx[2]};
     riccati_forward_range(c, s, N, kLo, kHi, mu, delta, ff, dx);
-    if (cl == G - 1) riccati_forward_range(c, s, N, N - 1, N, mu, delta, ff, dx);
+    // consistency of the scan with the exact in-chunk recursion: the state step at my chunk end must equal the next lane's start
+    double nxt[3];
+    for (int i = 0; i < 3; ++i) nxt[i] = __shfl_down_sync(gmask, dxs[i], 1, G);
+    double mism = 0.0, mag = 1e-300;
+    if (cl < G - 1) for (int i = 0; i < 3; ++i) { mism = fmax(mism, fabs(dx[i] - nxt[i])); mag = fmax(mag, fmax(fabs(dx[i]), fabs(nxt[i]))); }
+    const bool offF = __ballot_sync(gmask, mism > 1e-9 * mag + 1e-14) & gmask;
+    if (offF) {
+        // the feedback gains are exact (stable in-chunk recursions); only the chunk start states were off: lane 0 redoes the
+        // forward sweep sequentially
+        __syncwarp(gmask);
+        if (cl == 0) { atomicAdd(fallbackCount + 1, 1); riccati_forward(c, s, N, mu, delta, ff); }
+    } else if (cl == G - 1) {
+        riccati_forward_range(c, s, N, N - 1, N, mu, delta, ff, dx);
+    }
     __syncwarp(gmask);
     if (cl == 0) c.I(SI_PHASE, s) = PH_STEPPED;
 }
