@@ -346,3 +346,24 @@ def test_solve_instances_mixed_tracks_and_interval_counts(cabi):
     assert abs(res['obj'][i] - ref.f) <= 1e-6 * abs(ref.f)
     z = res['z'][i][:nlp.nz]
     assert np.max(np.abs(z[nlp.iB] - ref.x[nlp.iB])) <= 1e-4 * nlp.limit.max() ** 2
+
+
+def test_parallel_in_time_sweeps_long_horizon(cabi):
+    """BASELINE config 4 in miniature: one instance, synthetic 200 km track, N = 2000.  The parallel-in-time sweeps
+    (32 lanes per instance, default for N >= 2048, forced here) must reproduce the sequential sweeps."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.synthetic import random_track
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    track = random_track(np.random.default_rng(7), length=200e3)
+    o = {'numIntervals': 2000, 'maxIterations': 1000, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    out = {}
+    for lanes in (1, 32):
+        s = casadiSolver(train, track, o)
+        s.sweepLanes = lanes
+        out[lanes] = s.solve_batch(8240.0, screen=False)
+        assert out[lanes]['status'][0] == 0 and out[lanes]['kkt'][0] <= 1e-8
+    assert abs(out[32]['obj'][0] - out[1]['obj'][0]) <= 1e-9 * abs(out[1]['obj'][0])
+    assert np.max(np.abs(out[32]['z'] - out[1]['z'])) < 1e-5
+    auto = casadiSolver(train, track, dict(o, numIntervals=2048))
+    assert auto._make_handle is not None and auto.sweepLanes == 'auto'
