@@ -255,6 +255,20 @@ class casadiSolver():
             self._pool = _cabi.StreamPool(self._make_handle, int(self.streams), dev)
         return self._pool
 
+    def _pinned(self, key, like):
+        """Page-locked staging buffers are kept per solver in a ring of two per output (allocating 50 MB of pinned memory per call
+        costs more than the solve): a returned array stays valid until the second-next solve_batch call on this solver."""
+        import torch
+        ring = self._dev.setdefault('pinned', {})
+        slot = ring.setdefault(key, {'bufs': [None, None], 'next': 0})
+        i = slot['next']
+        slot['next'] = 1 - i
+        buf = slot['bufs'][i]
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+            slot['bufs'][i] = buf
+        return buf
+
     def _ensure_handle(self):
         if self._handle is None:
             self._handle = self._make_handle()
@@ -306,7 +320,8 @@ class casadiSolver():
         mass, rho, r0, r1, r2, forceMax, forceMin, forceMinPn, powerMax, powerMin, accMax, accMin, velocityMax,
         etaTraction, etaRgBrake; with the dynamic loss map also auxiliaries, etaGear, tableScale.
         Returns a dict of numpy arrays: z [n, nz] (reference variable order), cost, kkt, iters, status,
-        plus timing; nothing is post-processed.
+        plus timing; nothing is post-processed.  The arrays are views of page-locked staging buffers that are reused by the
+        second-next call on this solver -- copy them if they must live longer.
 
         screen=True (energy-optimal mode only): terminalTime is an upper bound on t_N, so an instance is infeasible
         exactly when it is below the minimum trip time.  The minimum time of every distinct
@@ -382,7 +397,7 @@ class casadiSolver():
             if v is None:
                 continue
             if hasattr(v, 'cpu'):
-                host = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                host = self._pinned(k, v)
                 host.copy_(v, non_blocking=True)
                 res[k] = host
             else:
