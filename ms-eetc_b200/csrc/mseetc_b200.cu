@@ -115,15 +115,15 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
 
 // Riccati sweeps: one thread per instance, stage data prefetched `depth` intervals ahead through a cp.async ring
 // in dynamic shared memory ((depth+1) * RING_NF_MAX * blockDim doubles).
-template <int BS>
-__global__ void __launch_bounds__(BS) k_step(Ctx c, int depth) {
+template <int BS, int DEPTH>
+__global__ void __launch_bounds__(BS) k_step(Ctx c) {
     extern __shared__ double ring[];
     const int s = blockIdx.x * BS + threadIdx.x;
     if (s >= c.cfg.S) return;
-    RingFetch<BwdFields, BS> fb;
-    fb.sm = ring; fb.depth = depth; fb.tid = threadIdx.x; fb.dir = -1; fb.kEnd = 0;
-    RingFetch<FwdFields, BS> ff;
-    ff.sm = ring; ff.depth = depth; ff.tid = threadIdx.x; ff.dir = 1; ff.kEnd = 0;
+    RingFetch<BwdFields, BS, DEPTH> fb;
+    fb.sm = ring + threadIdx.x;
+    RingFetch<FwdFields, BS, DEPTH> ff;
+    ff.sm = ring + threadIdx.x;
     inst_step(c, s, fb, ff);
 }
 
@@ -487,10 +487,17 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const int blocksPerSm = (int)((igrid + nsm - 1) / nsm);
     const size_t slotBytes = sizeof(double) * RING_NF_MAX * ib;
     int depth = (int)((size_t)200 * 1024 / ((size_t)(blocksPerSm < 1 ? 1 : blocksPerSm) * slotBytes)) - 1;
-    depth = depth < 1 ? 1 : (depth > 8 ? 8 : depth);
+    // the depth is a compile-time constant of the kernel: largest instantiated value that fits
+    void (*stepKernel)(Ctx);
+    if (ib == 32) {
+        if (depth >= 8) { depth = 8; stepKernel = k_step<32, 8>; } else { depth = 4; stepKernel = k_step<32, 4>; }
+    } else {
+        if (depth >= 4) { depth = 4; stepKernel = k_step<64, 4>; }
+        else if (depth >= 2) { depth = 2; stepKernel = k_step<64, 2>; }
+        else { depth = 1; stepKernel = k_step<64, 1>; }
+    }
     const size_t ringBytes = (size_t)(depth + 1) * slotBytes;
-    if (ib == 64) cudaFuncSetAttribute(k_step<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
-    else cudaFuncSetAttribute(k_step<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
+    cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
     int launches = 0;
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -529,8 +536,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_STEP);
         if (h->sweep_lanes == 8) k_step_pit<8><<<(unsigned)(((size_t)g.S * 8 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
         else if (h->sweep_lanes == 32) k_step_pit<32><<<(unsigned)(((size_t)g.S * 32 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
-        else if (ib == 64) k_step<64><<<igrid, 64, ringBytes, st>>>(c, depth);
-        else k_step<32><<<igrid, 32, ringBytes, st>>>(c, depth);
+        else stepKernel<<<igrid, ib, ringBytes, st>>>(c);
         end(CLS_STEP);
         begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
         begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);

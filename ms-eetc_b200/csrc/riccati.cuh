@@ -50,41 +50,42 @@ struct DirectFetch {
 };
 
 #if defined(__CUDACC__)
-// cp.async ring in shared memory: slot (k mod (depth+1)), column = thread; stage k+depth*dir is requested as soon
-// as stage k has been copied to registers, into the slot that was consumed one iteration earlier.
-template <class FL, int BS>
+// cp.async ring in shared memory with DEPTH + 1 slots, column = thread: stage k + DEPTH*dir is requested as soon as
+// stage k has been copied to registers, into the slot that was consumed one iteration earlier.  Slot indices and the
+// global record pointer are running counters (no division, one pointer bump per interval).
+template <class FL, int BS, int DEPTH>
 struct RingFetch {
-    double* sm;
-    int depth, tid, dir, kEnd;
-    __device__ void issue(const Ctx& c, int k, int s) {
-        const bool in = (dir < 0) ? (k >= kEnd) : (k <= kEnd);
-        if (in) {
-            double* dst = sm + (size_t)((k % (depth + 1)) * FL::NF) * BS + tid;
-            const double* src = &c.W(0, k, s);
+    double* sm;          // this thread's column of slot 0
+    const double* next;  // record of the next interval to request
+    int left;            // intervals not yet requested
+    int head, tail;      // slot to consume next / slot to fill next
+    long step;           // +-REC_STRIDE
+    __device__ void issue() {
+        if (left > 0) {
+            double* dst = sm + tail * (FL::NF * BS);
 #pragma unroll
-            for (int f = 0; f < FL::NF; ++f) __pipeline_memcpy_async(dst + f * BS, src + FL::off(f), 8);
+            for (int f = 0; f < FL::NF; ++f) __pipeline_memcpy_async(dst + f * BS, next + FL::off(f), 8);
+            next += step;
+            --left;
         }
         __pipeline_commit();
+        tail = (tail == DEPTH) ? 0 : tail + 1;
     }
     __device__ void start(const Ctx& c, int s, int kFirst, int kLast, int direction) {
-        dir = direction; kEnd = kLast;
-        for (int d = 0; d < depth; ++d) issue(c, kFirst + d * dir, s);
+        next = &c.W(0, kFirst, s);
+        step = (long)direction * REC_STRIDE;
+        left = (direction < 0 ? kFirst - kLast : kLast - kFirst) + 1;
+        head = tail = 0;
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) issue();
     }
-    __device__ void get(const Ctx& c, int k, int s, double* v) {
-        switch (depth) {   // cp.async.wait_group needs an immediate
-            case 1: __pipeline_wait_prior(0); break;
-            case 2: __pipeline_wait_prior(1); break;
-            case 3: __pipeline_wait_prior(2); break;
-            case 4: __pipeline_wait_prior(3); break;
-            case 5: __pipeline_wait_prior(4); break;
-            case 6: __pipeline_wait_prior(5); break;
-            case 7: __pipeline_wait_prior(6); break;
-            default: __pipeline_wait_prior(7); break;
-        }
-        const double* src = sm + (size_t)((k % (depth + 1)) * FL::NF) * BS + tid;
+    __device__ void get(const Ctx&, int, int, double* v) {
+        __pipeline_wait_prior(DEPTH - 1);
+        const double* src = sm + head * (FL::NF * BS);
 #pragma unroll
         for (int f = 0; f < FL::NF; ++f) v[f] = src[f * BS];
-        issue(c, k + depth * dir, s);
+        head = (head == DEPTH) ? 0 : head + 1;
+        issue();
     }
 };
 #endif
@@ -197,6 +198,88 @@ MS_HD bool stage_riccati(StageQP& q, bool last, double pn, double P[3][3], doubl
     return true;
 }
 
+// Backward Riccati step of a regular interval (k < N-1), exploiting the structure of the stage QP:
+//   t+ = t + tau_b b + tau_F w + rt,   b+ = phi_b b + phi_F w + rb,   f+ = Fel,     w = Fel + pn Fpb
+// and the sparsity of the folded Hessian (QpField lists its non-zero entries).  The control block is factorised as
+// L D L' (no square roots); its pivots are the inertia test.  Same mathematics as stage_build + stage_riccati, about a
+// third of the arithmetic; the sequential sweeps spend most of their time here.
+MS_HD void ldl3_solve(double l10, double l20, double l21, double i0, double i1, double i2,
+                      double r0, double r1, double r2, double& x0, double& x1, double& x2) {
+    const double y1 = r1 - l10 * r0, y2 = r2 - l20 * r0 - l21 * y1;
+    x2 = y2 * i2;
+    x1 = y1 * i1 - l21 * x2;
+    x0 = r0 * i0 - l10 * x1 - l20 * x2;
+}
+
+MS_HD bool stage_riccati_sparse(const double* v, double mu, double delta, double pn,
+                                double P[3][3], double p[3], double K[3][3], double kf[3]) {
+    const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F], rt = v[QP_RT], rb = v[QP_RB];
+    const double P00 = P[0][0], P01 = P[0][1], P02 = P[0][2], P11 = P[1][1], P12 = P[1][2], P22 = P[2][2];
+    // P times the b- and w-columns of the transition
+    const double y0b = P00 * tb + P01 * pb, y1b = P01 * tb + P11 * pb, y2b = P02 * tb + P12 * pb;
+    const double y0w = P00 * tF + P01 * pF, y1w = P01 * tF + P11 * pF, y2w = P02 * tF + P12 * pF;
+    const double ww = tF * y0w + pF * y1w, bw = tb * y0w + pb * y1w;
+    // stage Hessian + G' P G, non-zero entries only (t, b, f | F = Fel, Q = Fpb, S = slack)
+    const double Mtt = v[QP_H_TT] + delta + P00;
+    const double Mtb = y0b;
+    const double MtF = y0w + P02;
+    const double MtQ = pn * y0w;
+    const double Mbb = v[QP_H_BB] + delta + (tb * y0b + pb * y1b);
+    const double MbF = v[QP_H_BFEL] + (bw + y2b);
+    const double MbQ = v[QP_H_BFPB] + pn * bw;
+    const double MbS = v[QP_H_BSL];
+    const double Mff = v[QP_H_FF];
+    const double MfF = v[QP_H_FFEL];
+    const double MFF = v[QP_H_FELFEL] + delta + (ww + 2.0 * y2w + P22);
+    const double MFQ = v[QP_H_FELFPB] + pn * (ww + y2w);
+    const double MFS = v[QP_H_FELSL];
+    const double MQQ = v[QP_H_FPBFPB] + delta + pn * (pn * ww);
+    const double MQS = v[QP_H_FPBSL];
+    const double MSS = v[QP_H_SLSL] + delta;
+    // gradient + G' (P r + p)
+    const double pr0 = p[0] + P00 * rt + P01 * rb, pr1 = p[1] + P01 * rt + P11 * rb, pr2 = p[2] + P02 * rt + P12 * rb;
+    const double gw = tF * pr0 + pF * pr1;
+    const double mt = mu * v[QP_G1_T] + pr0;
+    const double mb = v[QP_G0_B] + mu * v[QP_G1_B] + (tb * pr0 + pb * pr1);
+    const double mf = v[QP_G0_F];
+    const double mF = v[QP_G0_FEL] + mu * v[QP_G1_FEL] + (gw + pr2);
+    const double mQ = v[QP_G0_FPB] + mu * v[QP_G1_FPB] + pn * gw;
+    const double mS = v[QP_G0_SL] + mu * v[QP_G1_SL];
+    // L D L' of the control block
+    if (!(MFF > 0.0) || !isfinite(MFF)) return false;
+    const double i0 = rcp(MFF);
+    const double l10 = MFQ * i0, l20 = MFS * i0;
+    const double d1 = MQQ - l10 * MFQ;
+    if (!(d1 > 0.0) || !isfinite(d1)) return false;
+    const double i1 = rcp(d1);
+    const double u21 = MQS - l20 * MFQ;
+    const double l21 = u21 * i1;
+    const double d2 = MSS - l20 * MFS - l21 * u21;
+    if (!(d2 > 0.0) || !isfinite(d2)) return false;
+    const double i2 = rcp(d2);
+    // feedback: Muu [K kf] = -[Mux mu]
+    double x0, x1, x2;
+    ldl3_solve(l10, l20, l21, i0, i1, i2, MtF, MtQ, 0.0, x0, x1, x2);
+    K[0][0] = -x0; K[1][0] = -x1; K[2][0] = -x2;
+    ldl3_solve(l10, l20, l21, i0, i1, i2, MbF, MbQ, MbS, x0, x1, x2);
+    K[0][1] = -x0; K[1][1] = -x1; K[2][1] = -x2;
+    ldl3_solve(l10, l20, l21, i0, i1, i2, MfF, 0.0, 0.0, x0, x1, x2);
+    K[0][2] = -x0; K[1][2] = -x1; K[2][2] = -x2;
+    ldl3_solve(l10, l20, l21, i0, i1, i2, mF, mQ, mS, x0, x1, x2);
+    kf[0] = -x0; kf[1] = -x1; kf[2] = -x2;
+    // value function of this node (upper triangle, mirrored)
+    P[0][0] = Mtt + MtF * K[0][0] + MtQ * K[1][0];
+    P[0][1] = P[1][0] = Mtb + MtF * K[0][1] + MtQ * K[1][1];
+    P[0][2] = P[2][0] = MtF * K[0][2] + MtQ * K[1][2];
+    P[1][1] = Mbb + MbF * K[0][1] + MbQ * K[1][1] + MbS * K[2][1];
+    P[1][2] = P[2][1] = MbF * K[0][2] + MbQ * K[1][2] + MbS * K[2][2];
+    P[2][2] = Mff + MfF * K[0][2];
+    p[0] = mt + MtF * kf[0] + MtQ * kf[1];
+    p[1] = mb + MbF * kf[0] + MbQ * kf[1] + MbS * kf[2];
+    p[2] = mf + MfF * kf[0];
+    return true;
+}
+
 MS_HD void stage_store(const Ctx& c, int k, int s, const double K[3][3], const double kf[3], const double P[3][3], const double p[3]) {
     double* r = &c.W(WS_RIC, k, s);
     for (int i = 0; i < 3; ++i) {
@@ -222,35 +305,58 @@ MS_HD void terminal_value(const Ctx& c, int s, int N, double mu, double delta, d
 
 // ---- backward sweep over the intervals kHi-1 .. kLo, starting from (P, p) of node kHi ------------------------
 // Optionally accumulates the closed-loop transition of the range: x_{kHi} = Mc x_{kLo} + mc.
+MS_HD void closed_loop_compose(double* Mc, double* mc, const double* Mk, const double* mk) {
+    // closed loop of one interval: x+ = (A + B K) x + (B kf + r) = Mk x + mk; compose: acc <- acc o this
+    double Mn[9], mn[3];
+    for (int i = 0; i < 3; ++i) {
+        mn[i] = mc[i] + Mc[3 * i] * mk[0] + Mc[3 * i + 1] * mk[1] + Mc[3 * i + 2] * mk[2];
+        for (int j = 0; j < 3; ++j) Mn[3 * i + j] = Mc[3 * i] * Mk[j] + Mc[3 * i + 1] * Mk[3 + j] + Mc[3 * i + 2] * Mk[6 + j];
+    }
+    for (int i = 0; i < 9; ++i) Mc[i] = Mn[i];
+    for (int i = 0; i < 3; ++i) mc[i] = mn[i];
+}
+
 template <class Fetch>
 MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch,
                                   double P[3][3], double p[3], double* Mc, double* mc, bool storeAll = true) {
     const double pn = c.cfg.withPn ? 1.0 : 0.0;
     if (kHi <= kLo) return true;
     fetch.start(c, s, kHi - 1, kLo, -1);
-    for (int k = kHi - 1; k >= kLo; --k) {
-        double v[BwdFields::NF];
+    int k = kHi - 1;
+    double v[BwdFields::NF], K[3][3], kf[3];
+    if (k == N - 1) {
+        // last interval: terminal speed fixed, Fel eliminated (dense algebra, once per sweep)
         fetch.get(c, k, s, v);
-        const bool last = (k == N - 1);
         StageQP q;
-        stage_build(v, mu, delta, pn, last, q);
-        double K[3][3], kf[3];
-        if (!stage_riccati(q, last, pn, P, p, K, kf)) return false;
+        stage_build(v, mu, delta, pn, true, q);
+        if (!stage_riccati(q, true, pn, P, p, K, kf)) return false;
         if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
-            // closed loop of this interval: x+ = (A + B K) x + (B kf + r); compose: acc <- acc o this
             double Mk[9], mk[3];
             for (int i = 0; i < 3; ++i) {
                 mk[i] = q.r[i] + q.G[i][3] * kf[0] + q.G[i][4] * kf[1] + q.G[i][5] * kf[2];
                 for (int j = 0; j < 3; ++j) Mk[3 * i + j] = q.G[i][j] + q.G[i][3] * K[0][j] + q.G[i][4] * K[1][j] + q.G[i][5] * K[2][j];
             }
-            double Mn[9], mn[3];
-            for (int i = 0; i < 3; ++i) {
-                mn[i] = mc[i] + Mc[3 * i] * mk[0] + Mc[3 * i + 1] * mk[1] + Mc[3 * i + 2] * mk[2];
-                for (int j = 0; j < 3; ++j) Mn[3 * i + j] = Mc[3 * i] * Mk[j] + Mc[3 * i + 1] * Mk[3 + j] + Mc[3 * i + 2] * Mk[6 + j];
+            closed_loop_compose(Mc, mc, Mk, mk);
+        }
+        --k;
+    }
+    for (; k >= kLo; --k) {
+        fetch.get(c, k, s, v);
+        if (!stage_riccati_sparse(v, mu, delta, pn, P, p, K, kf)) return false;
+        if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
+        if (Mc) {
+            const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
+            const double kfw = kf[0] + pn * kf[1];
+            double Mk[9], mk[3];
+            mk[0] = v[QP_RT] + tF * kfw; mk[1] = v[QP_RB] + pF * kfw; mk[2] = kf[0];
+            for (int j = 0; j < 3; ++j) {
+                const double kw = K[0][j] + pn * K[1][j];
+                Mk[j] = (j == 0 ? 1.0 : j == 1 ? tb : 0.0) + tF * kw;
+                Mk[3 + j] = (j == 1 ? pb : 0.0) + pF * kw;
+                Mk[6 + j] = K[0][j];
             }
-            for (int i = 0; i < 9; ++i) Mc[i] = Mn[i];
-            for (int i = 0; i < 3; ++i) mc[i] = mn[i];
+            closed_loop_compose(Mc, mc, Mk, mk);
         }
     }
     return true;
