@@ -101,12 +101,62 @@ MS_HD double init_t(const Ctx& c, int j, int s, int N) {
     return push2(guess, relaxL(t0), relaxU(T));
 }
 
+// Early infeasibility screening (only when the caller asked for screening by passing a tmin plane): a lower bound on the
+// trip duration from the speed envelope at 100 % of the force, power, acceleration and speed limits -- fastest
+// acceleration from b_0, latest braking into b_N, never above the limits.  No admissible run is faster, up to
+// discretisation effects that MS_SCREEN_MARGIN covers, and terminalTime is an upper bound on t_N (ocp.py:260-261): an
+// instance whose available time is below (1 - margin) * bound is reported infeasible before a single iteration is
+// spent on it.  The exact certificate is the minimum trip time (time-optimal solve, running concurrently); the host
+// layer checks every early flag against it and re-solves an instance without screening should a flag ever be wrong.
+#define MS_SCREEN_MARGIN 0.02
+MS_HD void inst_screen(const Ctx& c, int s) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || !g.energy || !c.tmin || c.I(SI_PHASE, s) == PH_DONE) return;
+    const int N = c.I(SI_N_INT, s);
+    const int P = WS_IT1;                       // scratch plane, overwritten by inst_profile / the first trial point
+    const double sr0 = c.P(P_SR0, s), sr1 = c.P(P_SR1, s), sr2 = c.P(P_SR2, s);
+    const double felU = c.P(P_FEL_U, s), felL = c.P(P_FEL_L, s), fpbL = g.withPn ? c.P(P_FPB_L, s) : 0.0;
+    const double pUp = g.withPower ? c.P(P_P_UP, s) : 1e30, pLo = g.withPower ? c.P(P_P_LO, s) : -1e30;
+    const double aLo = c.P(P_A_LO, s), aUp = c.P(P_A_UP, s);
+    const double b0 = c.P(P_B0, s), bN = c.P(P_BN, s), bmin = c.P(P_BMIN, s);
+    double b = b0;
+    c.W(P + IT_B, 0, s) = b0;
+    for (int k = 0; k < N; ++k) {
+        const double v = sqrt(b), ds = c.W(WS_TRK + TRK_DS, k, s);
+        const double r = sr0 + sr1 * v + sr2 * b + c.W(WS_TRK + TRK_C0, k, s);
+        const double a = fmin(fmin(felU, pUp / fmax(v, 1e-3)) - r, aUp);
+        const double lim = (k + 1 < N) ? c.W(WS_TRK + TRK_BMAX, k + 1, s) : bN;
+        b = fmax(bmin, fmin(lim, b + 2.0 * ds * a));
+        c.W(P + IT_B, k + 1, s) = b;
+    }
+    b = bN;
+    double vn = sqrt(bN), tLow = 0.0;
+    for (int k = N - 1; k >= 0; --k) {
+        const double ds = c.W(WS_TRK + TRK_DS, k, s);
+        double bk = b0;
+        if (k >= 1) {
+            bk = b;
+            for (int it = 0; it < 3; ++it) {        // the braking deceleration depends on the speed at the start of the interval
+                const double v = sqrt(bk);
+                const double r = sr0 + sr1 * v + sr2 * bk + c.W(WS_TRK + TRK_C0, k, s);
+                const double a = fmax(fmax(felL, pLo / fmax(v, 1e-3)) + fpbL - r, aLo);      // negative
+                bk = b - 2.0 * ds * a;
+            }
+            bk = fmin(c.W(P + IT_B, k, s), bk);
+        }
+        const double vk = sqrt(bk);
+        tLow += 2.0 * ds / (vk + vn);
+        b = bk; vn = vk;
+    }
+    if (isfinite(tLow) && (c.P(P_T, s) - c.P(P_T0, s)) < (1.0 - MS_SCREEN_MARGIN) * tLow) finish(c, s, ST_INFEASIBLE);
+}
+
 // Dynamically consistent starting profile (initMode 1): speed envelope from the limits with bounded acceleration and
 // braking, cruise speed capped so that the trip takes the available time, times and forces from the ODE.  It replaces
 // the constant-speed guess of the reference only as a starting point; the NLP and its optimum are unchanged.
 MS_HD void inst_profile(const Ctx& c, int s) {
     const Config& g = c.cfg;
-    if (s >= g.nInst || !g.initMode) return;
+    if (s >= g.nInst || !g.initMode || c.I(SI_PHASE, s) == PH_DONE) return;
     const int N = c.I(SI_N_INT, s);
     const int P = WS_IT1;                       // scratch: buffer 1 holds the profile until cell_init has consumed it
     const double sr0 = c.P(P_SR0, s), sr1 = c.P(P_SR1, s), sr2 = c.P(P_SR2, s);

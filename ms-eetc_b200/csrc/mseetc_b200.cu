@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
 }
 __global__ void __launch_bounds__(64) k_inst_profile(Ctx c) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < c.cfg.S) inst_profile(c, s);
+    if (s < c.cfg.S) { inst_screen(c, s); inst_profile(c, s); }
 }
 
 // ---- per-instance reductions: block = 32 instances x RED_W warps; warp w sums the intervals k = w, w+RED_W, ...
@@ -522,7 +522,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const unsigned rgrid = (unsigned)(g.S / 32);
     begin(CLS_MISC); k_inst_setup<<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
     begin(CLS_MISC); k_cell_setup<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
-    if (g.initMode) { begin(CLS_MISC); k_inst_profile<<<igrid, ib, 0, st>>>(c); end(CLS_MISC); }
+    if (g.initMode || (tmin && g.energy)) { begin(CLS_MISC); k_inst_profile<<<igrid, ib, 0, st>>>(c); end(CLS_MISC); }
     begin(CLS_MISC);
     if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
     end(CLS_MISC);

@@ -331,6 +331,7 @@ class casadiSolver():
         if not torch.cuda.is_available():
             raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         overrides = dict(overrides or {})
+        overrides_in = dict(overrides)
         arrs = [np.atleast_1d(np.asarray(a, dtype=float)) for a in (terminalTime, initialTime, terminalVelocity, initialVelocity)]
         n = max([len(a) for a in arrs] + [len(np.atleast_1d(v)) for v in overrides.values()])
         T, t0, vN, v0 = [np.broadcast_to(a, (n,)) for a in arrs]
@@ -406,8 +407,18 @@ class casadiSolver():
         res = {k: (v.numpy() if hasattr(v, 'numpy') else v) for k, v in res.items()}
         if tmin is not None:
             # an instance below its minimum trip time is infeasible whatever the iteration did before the certificate arrived
-            infeasible = (res['status'] != 0) & (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
-            res['status'][infeasible] = 4
+            short = (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
+            res['status'][(res['status'] != 0) & short] = 4
+            # the device also screens with a speed-envelope bound before the first iteration (inst_screen, core.cuh); every such
+            # flag is checked against the exact certificate and an instance flagged wrongly is solved again without screening
+            wrong = np.flatnonzero((res['status'] == 4) & ~short)
+            if len(wrong):
+                pick = lambda a: np.broadcast_to(np.asarray(a, dtype=float), (n,))[wrong]
+                redo = self.solve_batch(T[wrong], t0[wrong], vN[wrong], v0[wrong], overrides={k: pick(v) for k, v in overrides_in.items()},
+                                        want_multipliers=want_multipliers, device=device, screen=False)
+                for key in ('z', 'lam', 'obj', 'kkt', 'iters', 'status'):
+                    if key in res and isinstance(res[key], np.ndarray):
+                        res[key][wrong] = redo[key]
 
         res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
         res['d2h_bytes'] = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
@@ -529,7 +540,18 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
     out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
     res = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
     if tmin is not None:
-        res['status'][(res['status'] != 0) & (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))] = 4
+        short = (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
+        res['status'][(res['status'] != 0) & short] = 4
+        wrong = np.flatnonzero((res['status'] == 4) & ~short)      # early envelope flag without an exact certificate: solve again
+        if len(wrong):
+            pick = lambda a: np.broadcast_to(np.asarray(a, dtype=float), (n,))[wrong]
+            redo = solve_instances([solvers[i] for i in wrong], pick(terminalTime), pick(initialTime), pick(terminalVelocity),
+                                   pick(initialVelocity), screen=False, device=device)
+            w = redo['z'].shape[1]
+            for key in ('obj', 'kkt', 'iters', 'status'):
+                res[key][wrong] = redo[key]
+            res['z'][wrong] = 0.0
+            res['z'][wrong, :w] = redo['z']
     res['wall'] = _time.perf_counter() - t_begin
     scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
     M = np.array(Ms)

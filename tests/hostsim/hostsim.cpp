@@ -51,7 +51,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
     for (int s = 0; s < g.S; ++s) inst_setup(c, io, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
-    for (int s = 0; s < g.S; ++s) inst_profile(c, s);
+    for (int s = 0; s < g.S; ++s) { inst_screen(c, s); inst_profile(c, s); }
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
     int tick = 0;
     const int maxTicks = 20 * pr->max_iterations + 50;

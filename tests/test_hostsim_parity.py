@@ -104,6 +104,21 @@ def test_infeasible_trip_time_is_not_reported_as_solved(lib):
     assert out['status'][0] != 0
 
 
+def test_envelope_screening_flags_only_trips_clearly_below_the_minimum_time(lib):
+    """With screening requested (a tmin plane, all zeros = "not known yet") an instance whose available time is more than the
+    margin below the speed-envelope bound is reported infeasible before the first iteration; the bound itself stays below the
+    true minimum time (1035.55 s, simulations/figure5.py:96 of the reference), so feasible trips are never touched."""
+    from oracle.problem import load_track
+    nlp = oracle_nlp(virm6(), load_track(SWISS_JSON), 300)
+    Ts = [900.0, 1000.0, 1030.0, 1036.0, 1100.0]
+    out = harness.solve([nlp] * 5, Ts, lib=lib, max_iter=150, tmin=np.zeros(5))
+    assert list(out['status'][:2]) == [4, 4] and list(out['iters'][:2]) == [0, 0]      # 0.98 * bound is about 1012.6 s
+    assert out['status'][2] != 4 and out['status'][2] != 0                             # inside the margin: left to the iteration
+    assert list(out['status'][3:]) == [0, 0]
+    plain = harness.solve([nlp] * 2, Ts[3:], lib=lib, max_iter=150)
+    assert np.array_equal(plain['z'], out['z'][3:])                                    # screening does not change a feasible solve
+
+
 def test_batch_of_mixed_instances_is_independent_and_deterministic(lib):
     "Instances in one batch do not influence each other; results are bitwise reproducible."
     from oracle.problem import load_track
