@@ -283,8 +283,11 @@ def run_gpu(args):
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         res = solver.solve_batch(T)
+        e2e_steps.append(round(1e3 * (time.perf_counter() - ts), 2))
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -344,7 +347,7 @@ def run_gpu(args):
             'feasible_solves_per_s': int(feas.sum()) * world * args.steps / (ms * 1e-3),
             'e2e': {'value': total * args.steps / e2e_s, 'unit': 'solves/s', 'h2d_bytes_per_step': res['h2d_bytes'],
                     'last_call_breakdown_s': res.get('timing'),
-                    'd2h_bytes_per_step': res['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s / args.steps},
+                    'd2h_bytes_per_step': res['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s / args.steps, 'steps_ms': e2e_steps},
             'gpu_launches': launches[0], 'clocks': clocks, 'roofline': roofline}
     if cpu is not None:
         line['cpu_baseline'] = cpu

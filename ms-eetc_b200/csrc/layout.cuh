@@ -80,7 +80,7 @@ enum ParField {
 // ---- per-instance solver state (doubles)
 enum SdField {
     SD_MU = 0, SD_TAU, SD_ALPHA, SD_ALPHA_Z, SD_ALPHA_MIN, SD_THETA, SD_FOBJ, SD_SLOG, SD_SDAMP, SD_GPHID,
-    SD_THETA_MIN, SD_THETA_MAX, SD_DELTA_LAST, SD_KKT, SD_DINF, SD_PINF, SD_CINF, SD_KKT_BEST,
+    SD_THETA_MIN, SD_THETA_MAX, SD_DELTA_LAST, SD_DELTA, SD_KKT, SD_DINF, SD_PINF, SD_CINF, SD_KKT_BEST,
     SD_FILTER,                                   // SD_FILTER + 2*i : (theta_i, phi_i)
     SD_N = SD_FILTER + 2 * 12
 };

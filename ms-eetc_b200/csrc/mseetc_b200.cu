@@ -40,7 +40,7 @@ thread_local std::string g_err;
 #define MS_MINB_EVAL 2
 #endif
 #ifndef MS_MINB_STEP
-#define MS_MINB_STEP 4
+#define MS_MINB_STEP 3
 #endif
 MS_CELL_KERNEL(k_cell_setup, 4, cell_setup(c, io, k, s))
 MS_CELL_KERNEL(k_cell_init, 4, cell_init<false>(c, k, s))
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(64) k_step_pit(Ctx c, int* fallbackCount) {
     }
     double dx[3];
     for (int i = 0; i < 3; ++i) { const double v = __shfl_up_sync(gmask, T.m[i], 1, G); dx[i] = (cl > 0) ? v : 0.0; }
-    if (cl == 0) { c.W(WS_ST + ST_T, 0, s) = 0.0; c.W(WS_ST + ST_B, 0, s) = 0.0; count_cells(c, 3, N); if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta; }
+    if (cl == 0) { c.W(WS_ST + ST_T, 0, s) = 0.0; c.W(WS_ST + ST_B, 0, s) = 0.0; count_cells(c, 3, N); if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta; c.D(SD_DELTA, s) = delta; }
     __syncwarp(gmask);
     double dxs[3] = {dx[0], dx[1], dx[2]};
     riccati_forward_range(c, s, N, kLo, kHi, mu, delta, ff, dx);
@@ -428,8 +428,8 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
         case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
         case CLS_DECIDE: return 8.0 * 4;
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13));
-        case CLS_STEP:   return 8.0 * (BwdFields::NF + RIC_N + FwdFields::NF + 7);
-        case CLS_CSTEP:  return 8.0 * ((7 + 2 + iter + 11 + rows + 2) + (2 * rows + 2 + 3));
+        case CLS_STEP:   return 8.0 * (BwdFields::NF + RIC_N + FwdFields::NF + 5);
+        case CLS_CSTEP:  return 8.0 * ((7 + 3 + iter + 11 + rows + 2 + 7 + 9) + (2 * rows + 2 + 3));
         case CLS_ALPHA:  return 8.0 * 3;
         case CLS_KKT:    return 8.0 * 14;
         default:         return 0.0;

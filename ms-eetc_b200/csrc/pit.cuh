@@ -299,6 +299,7 @@ inline void inst_step_pit_emulated(const Ctx& c, int s, int G, FetchB& fb, Fetch
     }
     if (!ok) { finish(c, s, ST_STEP_FAILED); return; }
     if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
+    c.D(SD_DELTA, s) = delta;
     count_cells(c, 3, N);
     c.I(SI_PHASE, s) = PH_STEPPED;
 }

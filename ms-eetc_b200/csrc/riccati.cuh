@@ -27,16 +27,11 @@ struct BwdFields {   // folded stage Hessian (13), linearised coupling rows (6),
     enum { NF = 29 };
     static MS_HD constexpr int off(int f) { return (WS_QP + f) * 32; }
 };
-struct FwdFields {   // K, k (12) | P, p of the next node (9) | coupling rows (6) | b_{k+1} terms (7)
-    enum { NF = 34 };
-    static MS_HD constexpr int off(int f) {
-        return f < 12 ? (WS_RIC + f) * 32
-             : f < 21 ? (WS_RIC + f) * 32 + REC_STRIDE
-             : f < 27 ? (WS_QP + QP_TAU_B + (f - 21)) * 32
-                      : (WS_QP + QP_HC_B + (f - 27)) * 32;
-    }
+struct FwdFields {   // K, k (12) | linearised coupling rows (6)
+    enum { NF = 18 };
+    static MS_HD constexpr int off(int f) { return f < 12 ? (WS_RIC + f) * 32 : (WS_QP + QP_TAU_B + (f - 12)) * 32; }
 };
-enum { RING_NF_MAX = 34 };
+enum { RING_NF_MAX = 29 };
 
 // direct loads (host emulation, and the device when no ring is configured)
 template <class FL>
@@ -369,50 +364,32 @@ MS_HD bool riccati_backward(const Ctx& c, int s, int N, double mu, double delta,
     return riccati_backward_range(c, s, N, 0, N, mu, delta, fetch, P, p, nullptr, nullptr);
 }
 
-// ---- forward sweep over the intervals kLo .. kHi-1 from d x_{kLo}: primal step, new coupling-row multipliers ---
-// Writes d Fel, d Fpb, d s, d t, d b into the step planes and the NEW multipliers of the coupling rows into
-// ST_YT / ST_YB (cell_step turns them into steps).
+// ---- forward sweep over the intervals kLo .. kHi-1 from d x_{kLo}: primal step ---------------------------------
+// Writes d Fel, d Fpb, d s of interval k and d t, d b of node k+1 into the step planes.  The new coupling-row multipliers
+// (costates of the stepped state) need nothing sequential and are evaluated by the interval-parallel cell_step.
 template <class Fetch>
 MS_HD void riccati_forward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch, double dx[3]) {
     const Config& g = c.cfg;
+    (void)mu; (void)delta;
     if (kHi <= kLo) return;
     fetch.start(c, s, kLo, kHi - 1, +1);
-    for (int k = kLo; k < kHi; ++k) {
+    double* st = &c.W(WS_ST, kLo, s);
+    for (int k = kLo; k < kHi; ++k, st += REC_STRIDE) {
         double v[FwdFields::NF];
         fetch.get(c, k, s, v);
         double du[3];
         for (int i = 0; i < 3; ++i) du[i] = v[9 + i] + v[3 * i + 0] * dx[0] + v[3 * i + 1] * dx[1] + v[3 * i + 2] * dx[2];
         if (!g.withPn) du[1] = 0.0;
-        const double tb = v[21], tF = v[22], pb = v[23], pF = v[24], rt = v[25], rb = v[26];
+        const double tb = v[12], tF = v[13], pb = v[14], pF = v[15], rt = v[16], rb = v[17];
         const double dF = du[0] + du[1];
-        double dxn[3];
-        dxn[0] = dx[0] + tb * dx[1] + tF * dF + rt;
-        dxn[1] = (k + 1 < N) ? pb * dx[1] + pF * dF + rb : 0.0;
-        dxn[2] = du[0];
-        // costates of the next node: P (12..17 = tt,tb,tf,bb,bf,ff), p (18..20)
-        const double pit = v[18] + v[12] * dxn[0] + v[13] * dxn[1] + v[14] * dxn[2];
-        double pib;
-        if (k + 1 < N) {
-            pib = v[19] + v[13] * dxn[0] + v[15] * dxn[1] + v[16] * dxn[2];
-            // + the terms of interval k that depend on b_{k+1} directly (27..33 = hc_b, hc_fel, hc_fpb, hc_sl, hpp, gp0, gp1)
-            pib += v[27] * dx[1] + v[28] * du[0] + v[29] * du[1] + v[30] * du[2] + v[31] * dxn[1] + v[32] + mu * v[33];
-        } else {
-            // b_N is fixed: its row multiplier follows from stationarity w.r.t. Fel of the last interval
-            const double gF = c.W(WS_QP + QP_G0_FEL, k, s) + mu * c.W(WS_QP + QP_G1_FEL, k, s)
-                            + c.W(WS_QP + QP_H_BFEL, k, s) * dx[1] + c.W(WS_QP + QP_H_FFEL, k, s) * dx[2]
-                            + (c.W(WS_QP + QP_H_FELFEL, k, s) + delta) * du[0] + c.W(WS_QP + QP_H_FELFPB, k, s) * du[1]
-                            + c.W(WS_QP + QP_H_FELSL, k, s) * du[2];
-            pib = -(gF + tF * pit) / pF;
-        }
-        double* st = &c.W(WS_ST, k, s);
+        const double dtn = dx[0] + tb * dx[1] + tF * dF + rt;
+        const double dbn = (k + 1 < N) ? pb * dx[1] + pF * dF + rb : 0.0;
         st[ST_FEL * 32] = du[0];
         st[ST_FPB * 32] = du[1];
         st[ST_SL * 32] = du[2];
-        st[ST_T * 32 + REC_STRIDE] = dxn[0];
-        st[ST_B * 32 + REC_STRIDE] = dxn[1];
-        st[ST_YT * 32] = -pit;
-        st[ST_YB * 32] = -pib;
-        dx[0] = dxn[0]; dx[1] = dxn[1]; dx[2] = dxn[2];
+        st[ST_T * 32 + REC_STRIDE] = dtn;
+        st[ST_B * 32 + REC_STRIDE] = dbn;
+        dx[0] = dtn; dx[1] = dbn; dx[2] = du[0];
     }
 }
 
@@ -529,6 +506,7 @@ MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
     }
     if (!ok) { finish(c, s, ST_STEP_FAILED); return; }
     if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
+    c.D(SD_DELTA, s) = delta;
     count_cells(c, 3, N);
     riccati_forward(c, s, N, mu, delta, ff);
     c.I(SI_PHASE, s) = PH_STEPPED;
@@ -555,24 +533,35 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
     // ---- all loads first, then arithmetic, then all stores (loads must not queue behind stores through the same base)
     const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
-    double CI[IT_N], CS[ST_N], QJ[QP_N - QP_J_P0_B];
+    double CI[IT_N], CS[ST_N], QJ[QP_N - QP_HC_B], RP[9];
     {
         const double* ip = &c.W(it, k, s);
         const double* sp = &c.W(WS_ST, k, s);
-        const double* qp = &c.W(WS_QP + QP_J_P0_B, k, s);
+        const double* qp = &c.W(WS_QP + QP_HC_B, k, s);
+        const double* rp = &c.W(WS_RIC + RIC_P, kn, s);       // value function of the next node: P (tt,tb,tf,bb,bf,ff), p
 #pragma unroll
         for (int f = 0; f < IT_N; ++f) CI[f] = ip[f * 32];
 #pragma unroll
         for (int f = 0; f < ST_N; ++f) CS[f] = sp[f * 32];
 #pragma unroll
-        for (int f = 0; f < QP_N - QP_J_P0_B; ++f) QJ[f] = qp[f * 32];
+        for (int f = 0; f < QP_N - QP_HC_B; ++f) QJ[f] = qp[f * 32];
+#pragma unroll
+        for (int f = 0; f < 9; ++f) RP[f] = rp[f * 32];
     }
-    const double dbn = c.W(WS_ST + ST_B, kn, s);
+    const double dbn = c.W(WS_ST + ST_B, kn, s), dtn = c.W(WS_ST + ST_T, kn, s);
+    // last interval only: b_N is fixed, the multiplier of its row follows from stationarity w.r.t. Fel (see below)
+    double LQ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0};
+    if (k == N - 1) {
+        const double* q = &c.W(WS_QP, k, s);
+        LQ[0] = q[QP_G0_FEL * 32]; LQ[1] = q[QP_G1_FEL * 32]; LQ[2] = q[QP_H_BFEL * 32]; LQ[3] = q[QP_H_FFEL * 32];
+        LQ[4] = q[QP_H_FELFEL * 32]; LQ[5] = q[QP_H_FELFPB * 32]; LQ[6] = q[QP_H_FELSL * 32]; LQ[7] = q[QP_TAU_F * 32];
+        LQ[8] = q[QP_PHI_F * 32];
+    }
     const double pFel = c.W(it + IT_FEL, km, s), pDFel = c.W(WS_ST + ST_FEL, km, s);
     const double dsk = c.W(WS_TRK + TRK_DS, k, s);
     const Bnd B = load_bounds(c, k, s);
     const double mu = c.D(SD_MU, s), tauF = c.D(SD_TAU, s), scale = c.P(P_SCALE, s);
-#define MS_QJ(F) QJ[(F) - QP_J_P0_B]
+#define MS_QJ(F) QJ[(F) - QP_HC_B]
     Ftb f{1.0, 1.0, 0.0};
     double OW[NROW], OYD[NROW], oyt = 0.0, oyb = 0.0;
 #pragma unroll
@@ -591,9 +580,21 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     if (k < N) {
         const double du0 = CS[ST_FEL], du1 = CS[ST_FPB], du2 = CS[ST_SL];
         const double fel = CI[IT_FEL], fpb = CI[IT_FPB], sl = CI[IT_SL];
-        // coupling-row multipliers: the forward sweep stored the new values
-        oyt = CS[ST_YT] - CI[IT_YT];
-        oyb = CS[ST_YB] - CI[IT_YB];
+        // new coupling-row multipliers = minus the costates of the stepped state: gradient of the value function of the
+        // backward sweep at node k+1, plus the terms of this interval that depend on b_{k+1} directly
+        const double pit = RP[6] + RP[0] * dtn + RP[1] * dbn + RP[2] * du0;
+        double pib;
+        if (k + 1 < N) {
+            pib = RP[7] + RP[1] * dtn + RP[3] * dbn + RP[4] * du0
+                + MS_QJ(QP_HC_B) * db + MS_QJ(QP_HC_FEL) * du0 + MS_QJ(QP_HC_FPB) * du1 + MS_QJ(QP_HC_SL) * du2
+                + MS_QJ(QP_HPP) * dbn + MS_QJ(QP_GP0) + mu * MS_QJ(QP_GP1);
+        } else {
+            const double dfk = (k >= 1) ? pDFel : 0.0;        // d f_k = d Fel_{k-1}
+            const double gF = LQ[0] + mu * LQ[1] + LQ[2] * db + LQ[3] * dfk + (LQ[4] + c.D(SD_DELTA, s)) * du0 + LQ[5] * du1 + LQ[6] * du2;
+            pib = -(gF + LQ[7] * pit) / LQ[8];
+        }
+        oyt = -pit - CI[IT_YT];
+        oyb = -pib - CI[IT_YB];
         ftb_bound(f, tauF, mu, CI[IT_Z + Z_FEL_L], fel - B.felL, du0, false);
         ftb_bound(f, tauF, mu, CI[IT_Z + Z_FEL_U], B.felU - fel, -du0, false);
         if (g.withPn) {

@@ -199,13 +199,76 @@ def simulateCVODES(dfIn, model, totalMass, accumulatedErrors=True):
     return dfOut
 
 
-def postProcessDataFrame(dfIn, points, train, CVODES=True, integrateLosses=False, integrateRollingResistance=False):
-    """Derived columns of the trajectory table (reference utils.py:223-336), vectorised.
+def _rk4_richardson(rhs, y0, h, substeps=64, tol=1e-7):
+    """Integrate a batch of independent ODEs over [0, h] (arrays, one entry per member; ``rhs(y, sel)`` evaluates the members
+    ``sel``).  Classic RK4 with ``substeps`` and with twice as many steps, combined by Richardson extrapolation, for the whole
+    batch at once; members whose two runs disagree by more than ``tol`` (a loss map with kinks or jumps along the path, a
+    start from very low speed) are redone one by one with an adaptive integrator at rtol 1e-10 -- the reference asks CVODES
+    for 1e-8/1e-6 (train.py:396, :437)."""
+    everyone = slice(None)
 
-    ``integrateLosses=True`` / ``integrateRollingResistance=True`` (utils.py:261-289,296-320) are not part of the
-    ``simulations/config.json`` hot path and raise NotImplementedError here."""
-    if integrateLosses or integrateRollingResistance:
-        raise NotImplementedError("integrated losses / rolling resistance post-processing is outside the accelerated path")
+    def run(m):
+        y = [np.array(c, dtype=float) for c in y0]
+        dt = h / m
+        for _ in range(m):
+            k1 = rhs(y, everyone)
+            k2 = rhs([a + 0.5 * dt * k for a, k in zip(y, k1)], everyone)
+            k3 = rhs([a + 0.5 * dt * k for a, k in zip(y, k2)], everyone)
+            k4 = rhs([a + dt * k for a, k in zip(y, k3)], everyone)
+            y = [a + dt / 6 * (p + 2 * q + 2 * r + w) for a, p, q, r, w in zip(y, k1, k2, k3, k4)]
+        return y
+    coarse, fine = run(substeps), run(2 * substeps)
+    out = [f + (f - c) / 15 for c, f in zip(coarse, fine)]
+    rough = np.zeros(np.shape(out[0]), dtype=bool)
+    for c, f in zip(coarse, fine):
+        rough |= ~(np.abs(f - c) <= tol * np.maximum(np.abs(f), 1e-12))
+    if np.any(rough):
+        from scipy.integrate import solve_ivp
+        for j in np.flatnonzero(rough):
+            one = np.array([j])
+            single = lambda _, y: [float(np.asarray(d).reshape(-1)[0]) for d in rhs([np.array([v]) for v in y], one)]
+            sol = solve_ivp(single, (0.0, float(h[j])), [float(np.asarray(c)[j]) for c in y0], method='LSODA', rtol=1e-10, atol=1e-13)
+            for comp, val in zip(out, sol.y[:, -1]):
+                comp[j] = val
+    return out
+
+
+def _integrated_losses(time, vel, fel, fpb, grad, curv, train, totalMass):
+    """Energy lost in the drive over every interval, integrated along the time-domain trajectory under the interval's constant
+    forces (reference utils.py:261-289 with train.py:367-413): d v/dt = a(v), d e/dt = PL(F, v).  The reference integrates
+    the traction and the braking branch of splitLosses separately and picks by the sign of the force; each branch is the true
+    map on its own side, so this is the unsplit map along the trajectory."""
+    loss_fun = train.powerLossesFuns(split=False)                        # specific: W/kg from (N/kg, m/s)
+    drive = fel + fpb - train.g * grad / train.rho - _curve_resistance(train, curv)
+
+    def rhs(y, sel):
+        v, _ = y
+        return [drive[sel] - _rolling(train, v, totalMass), np.asarray(loss_fun(fel[sel], v), dtype=float)]
+
+    _, e = _rk4_richardson(rhs, [vel, np.zeros_like(vel)], time)
+    return totalMass * e
+
+
+def _integrated_rolling_resistance(pos, vel, facc, fpb, grad, curv, train, totalMass):
+    """Work of the rolling resistance over every interval in the position domain (reference utils.py:296-320 with
+    train.py:415-456): d b/ds = 2 a(b), d e/ds = sr0 + sr1 sqrt(b) + sr2 b, driven -- as in the reference -- by the traction
+    part of the electric force and the pneumatic brake only."""
+    drive = facc + fpb - train.g * grad / train.rho - _curve_resistance(train, curv)
+
+    def rhs(y, sel):
+        b, _ = y
+        roll = _rolling(train, np.sqrt(np.maximum(b, 0.0)), totalMass)
+        return [2.0 * (drive[sel] - roll), roll]
+
+    _, e = _rk4_richardson(rhs, [vel ** 2, np.zeros_like(vel)], pos)
+    return totalMass * e
+
+
+def postProcessDataFrame(dfIn, points, train, CVODES=True, integrateLosses=False, integrateRollingResistance=False):
+    """Derived columns of the trajectory table (reference utils.py:223-336), vectorised over the rows.
+
+    ``integrateLosses=True`` replaces the mid-point loss estimate by the losses integrated along the time-domain trajectory
+    (utils.py:261-289), ``integrateRollingResistance=True`` adds the 'Rolling resistance [kWh]' column (utils.py:296-320)."""
     kWh = 1e-6 / 3.6
     totalMass = train.mass * train.rho
     df = dfIn.copy()
@@ -227,13 +290,25 @@ def postProcessDataFrame(dfIn, points, train, CVODES=True, integrateLosses=False
     v_mid = 0.5 * (vel + v_next)
     last = np.isnan(fel) | np.isnan(v_mid)                   # the terminal row has no control / no mid-point speed
     f_eval, v_eval = np.where(last, 0.0, fel), np.where(last, 1.0, v_mid)
-    with np.errstate(invalid='ignore', divide='ignore'):
-        losses = kWh * ds * totalMass * np.asarray(loss_fun(f_eval / totalMass, v_eval), dtype=float) / v_eval
-    losses = np.where(last, np.nan, losses)
+    if not integrateLosses:
+        with np.errstate(invalid='ignore', divide='ignore'):
+            losses = kWh * ds * totalMass * np.asarray(loss_fun(f_eval / totalMass, v_eval), dtype=float) / v_eval
+        losses = np.where(last, np.nan, losses)
+    else:
+        t = df.index.values.astype(float)
+        n = len(t) - 1
+        e = _integrated_losses(np.diff(t), vel[:n], fel[:n] / totalMass, df['Force (pnb) [N]'].values[:n].astype(float) / totalMass,
+                               df['Gradient [permil]'].values[:n] / 1e3, df['Curvature [1/m]'].values[:n].astype(float), train, totalMass)
+        losses = np.append(kWh * e, np.nan)
     df['Losses [kWh]'] = losses
     df['Energy [kWh]'] = kWh * ds * f_acc + kWh * ds * f_rgb + losses
     df['Energy (pnb) [kWh]'] = -kWh * ds * df['Force (pnb) [N]'].values
     df['Energy (kin) [kWh]'] = kWh * 0.5 * train.mass * vel ** 2
+    if integrateRollingResistance:
+        n = len(pos) - 1
+        e = _integrated_rolling_resistance(np.diff(pos), vel[:n], f_acc[:n] / totalMass, df['Force (pnb) [N]'].values[:n].astype(float) / totalMass,
+                                           df['Gradient [permil]'].values[:n] / 1e3, df['Curvature [1/m]'].values[:n].astype(float), train, totalMass)
+        df['Rolling resistance [kWh]'] = np.append(kWh * e, np.nan)
     grad_res = train.g * (df['Gradient [permil]'].values / 1000) / train.rho
     df['Acceleration [m/s^2]'] = df['Force [N]'].values / totalMass - _rolling(train, vel, totalMass) - grad_res \
         - _curve_resistance(train, df['Curvature [1/m]'].values)

@@ -222,3 +222,54 @@ def test_postprocess_table_columns():
     assert abs(df['Energy [kWh]'].sum() - (r.f - pen)) / r.f < 1e-6
     # the re-simulated trajectory stays close to the RK4 multiple-shooting one
     assert df['Error velocity [m/s]'].max() < 0.5
+
+
+def test_postprocess_integrated_losses_and_rolling_resistance():
+    """postProcessDataFrame(integrateLosses=True, integrateRollingResistance=True) (reference utils.py:261-320): the columns are
+    checked against an independent adaptive integration (scipy DOP853, rtol 1e-12) of the same ODEs (train.py:367-413, :415-456)."""
+    from scipy.integrate import solve_ivp
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from mseetc.efficiency import totalLossesFunction
+    from mseetc.utils import postProcessDataFrame
+    from common import virm6, oracle_nlp, oracle_solve
+    from oracle.problem import load_track
+    N = 60
+    nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), N)
+    r = oracle_solve(nlp, 1541.0)
+    assert r.success
+    for dynamic in (False, True):
+        train = Train(config={'id': 'NL_Intercity_VIRM6'})
+        s = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), {'numIntervals': N, 'integrationOptions': {'numApproxSteps': 1}})
+        if dynamic:
+            train.powerLosses = totalLossesFunction(train, auxiliaries=27000, etaGear=0.96)
+        raw = s.table_from_z(r.x)
+        mid = postProcessDataFrame(raw, s.points, train, CVODES=False)
+        df = postProcessDataFrame(raw, s.points, train, CVODES=False, integrateLosses=True, integrateRollingResistance=True)
+        assert list(df.columns) == list(mid.columns[:-1]) + ['Rolling resistance [kWh]', 'Acceleration [m/s^2]']
+        assert np.isnan(df['Losses [kWh]'].values[-1]) and np.isnan(df['Rolling resistance [kWh]'].values[-1])
+        M = train.mass * train.rho
+        kWh = 1e-6 / 3.6
+        loss = train.powerLossesFuns(split=False)
+        t = df.index.values
+        roll = lambda v: (train.r0 + train.r1 * v + train.r2 * v * v) / M
+        for j in (0, 7, 23, 41, N - 1):
+            f = df['Force (el) [N]'].values[j] / M
+            p = df['Force (pnb) [N]'].values[j] / M
+            gd = train.g * df['Gradient [permil]'].values[j] / 1e3 / train.rho
+            v0 = df['Velocity [m/s]'].values[j]
+            rhs = lambda _, y: [f + p - roll(y[0]) - gd, float(loss(f, y[0]))]
+            ref = solve_ivp(rhs, (0.0, t[j + 1] - t[j]), [v0, 0.0], method='DOP853', rtol=1e-12, atol=1e-14).y[1, -1] * M * kWh
+            assert abs(df['Losses [kWh]'].values[j] - ref) <= 1e-6 * abs(ref) + 1e-9      # the reference asks CVODES for reltol 1e-6
+            fa = df['Force (acc) [N]'].values[j] / M
+            rhs = lambda _, y: [2.0 * (fa + p - roll(np.sqrt(y[0])) - gd), roll(np.sqrt(y[0]))]
+            ds = df['Position [m]'].values[j + 1] - df['Position [m]'].values[j]
+            ref = solve_ivp(rhs, (0.0, ds), [v0 * v0, 0.0], method='DOP853', rtol=1e-12, atol=1e-14).y[1, -1] * M * kWh
+            assert abs(df['Rolling resistance [kWh]'].values[j] - ref) <= 1e-6 * abs(ref) + 1e-9
+        if not dynamic:
+            # constant efficiencies: losses are proportional to force x distance, so the two estimates differ only by the
+            # distance the time-domain re-simulation covers versus the grid step
+            rel = np.nanmax(np.abs(df['Losses [kWh]'] - mid['Losses [kWh]'])) / np.nanmax(mid['Losses [kWh]'])
+            assert rel < 2e-2
+        assert abs(np.nansum(df['Energy [kWh]']) - np.nansum(mid['Energy [kWh]'])) / np.nansum(mid['Energy [kWh]']) < 2e-2
