@@ -198,6 +198,11 @@ def run_gpu(args):
     horizon = 1.5 * float(np.sum(solver.steps / lim))      # same bound as casadiSolver.minimum_time
     Pt, _ = tsolver._planes(1, np.array([horizon]), np.zeros(1), np.ones(1), np.ones(1), {}, 0.0, 0.0)
     ds, c0, bmax = solver._tables(solver._base['rho'], solver._base['g'], solver._base['velocityMax'])
+    # several streams: instances are dealt to the sub-batches tile by tile, exactly as casadiSolver.solve_batch does; the resident
+    # inputs are stored in that order and the per-instance results are put back in sweep order for the checks below
+    perm, parts = _cabi.StreamPool.interleave(n, max(1, args.streams)) if args.streams > 1 else (np.arange(n), None)
+    back = np.argsort(perm)
+    P = np.ascontiguousarray(P[:, perm])
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
     d = dict(P=up(P, torch.float64), Pt=up(Pt, torch.float64), nint=up(np.full(n, N_INT, np.int32), torch.int32),
              nint1=up(np.full(1, N_INT, np.int32), torch.int32), trk_of=up(np.zeros(n, np.int32), torch.int32),
@@ -217,7 +222,7 @@ def run_gpu(args):
     launches = [0]
 
     tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=-5)
 
     def step(accumulate):
         # (1) minimum trip time of the (single) distinct problem of this sweep: time-optimal solve on a side stream, driven by
@@ -237,7 +242,7 @@ def run_gpu(args):
         th = threading.Thread(target=presolve)
         th.start()
         # (2) the sweep; instances below the minimum time are flagged infeasible by the library as soon as it is known
-        out = pool.solve(d['P'], d['nint'], d['trk_of'], d['trk_off'], d['ds'], d['c0'], d['bmax'], tmin=tmin_dev, out=dict(outbuf))
+        out = pool.solve(d['P'], d['nint'], d['trk_of'], d['trk_off'], d['ds'], d['c0'], d['bmax'], tmin=tmin_dev, out=dict(outbuf), parts=parts)
         th.join()
         tr = box['tr']
         if accumulate:
@@ -268,9 +273,9 @@ def run_gpu(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    status = out['status'].cpu().numpy()
-    iters = out['iters'].cpu().numpy()
-    kkt = out['kkt'].cpu().numpy()
+    status = out['status'].cpu().numpy()[back]
+    iters = out['iters'].cpu().numpy()[back]
+    kkt = out['kkt'].cpu().numpy()[back]
     tmin_dev = float(tr['z'][0, -2].item())
     feas = T >= tmin_dev
     n_ok = int(np.sum((status == 0) & feas & (kkt <= 1e-8)))

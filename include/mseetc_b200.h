@@ -156,6 +156,10 @@ int mseetc_last_launches(mseetc_handle h);
 int mseetc_set_profiling(mseetc_handle h, int on);
 int mseetc_last_profile(mseetc_handle h, double* ms_out, int32_t* launches_out, int64_t* cells_out);
 double mseetc_bytes_per_cell(mseetc_handle h, int kernel_class);
+/* Diagnostic: the launches of the last solve on `h` as (class, start_ms, end_ms) triples in out[3*max_entries], times taken
+ * from the same event pairs relative to the first launch of the last solve on `origin` (another handle of the same device,
+ * e.g. the first stream of a pool, or `h` itself).  Returns the number of entries written; needs profiling switched on. */
+int mseetc_last_timeline(mseetc_handle h, mseetc_handle origin, double* out, int32_t max_entries);
 
 /* One shooting interval for n points (train.py:347-364): tau = t1 - t0 and b1, with first and second
  * sensitivities w.r.t. (b0, F).  in_dev planes [7*n]: b0, F, ds, c0, sr0, sr1, sr2; out_dev planes [12*n]:

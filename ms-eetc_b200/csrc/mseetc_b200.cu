@@ -296,6 +296,7 @@ struct mseetc_solver {
     int launches[NCLS];
     long long cells[NCLS];
     std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
+    std::vector<int> ev_class;     // class of every event pair of the last solve (timeline)
     cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
     int sweep_lanes;               // 1: sequential sweeps; 8 / 32: lanes per instance of the parallel-in-time sweeps
     long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
@@ -585,9 +586,23 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]);
         h->ms[evClass[i]] += ms;
     }
+    h->ev_class = evClass;
     h->last_ticks = tick;
     h->last_launches = launches;
     return 0;
+}
+
+int mseetc_last_timeline(mseetc_handle h, mseetc_handle origin, double* out, int32_t max_entries) {
+    if (!h || !origin || !out) return fail(-1, "mseetc_last_timeline: null argument");
+    if (origin->ev_class.empty()) return 0;
+    int n = 0;
+    for (size_t i = 0; i < h->ev_class.size() && n < max_entries; ++i, ++n) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, origin->ev[0], h->ev[2 * i]) != cudaSuccess) { cudaGetLastError(); break; }
+        if (cudaEventElapsedTime(&b, origin->ev[0], h->ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); break; }
+        out[3 * n] = (double)h->ev_class[i]; out[3 * n + 1] = (double)a; out[3 * n + 2] = (double)b;
+    }
+    return n;
 }
 
 int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out, void* cuda_stream) {

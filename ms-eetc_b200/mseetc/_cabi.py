@@ -58,6 +58,7 @@ def lib():
     L.mseetc_set_profiling.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_profile.argtypes = [vp, vp, vp, vp]
     L.mseetc_bytes_per_cell.argtypes = [vp, ctypes.c_int]
+    L.mseetc_last_timeline.argtypes = [vp, vp, vp, i32]
     L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
     L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
@@ -176,7 +177,10 @@ class StreamPool:
     def __init__(self, make_handle, k, device):
         torch = _torch_cuda()
         self.handles = [make_handle() for _ in range(k)]
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(k)]
+        # graded priorities: sub-batches of equal size would otherwise march in phase (all in their bandwidth-bound interval
+        # kernels together, then all in their latency-bound sweeps together); with priorities the first stream runs as if alone
+        # and the others fill the gaps its sweeps leave
+        self.streams = [torch.cuda.Stream(device=device, priority=max(-4, -(k - 1 - i))) for i in range(k)]
         self.device = device
 
     @staticmethod
@@ -187,7 +191,29 @@ class StreamPool:
         cuts[-1] = n
         return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
-    def solve(self, params, nint, trk_of, trk_off, ds, c0, bmax, tmin=None, out=None, want_lam=False):
+    @staticmethod
+    def interleave(n, k, tile=32):
+        """Order of the instances that balances the sub-batches: 32-instance tiles are dealt round-robin to the k streams, so a
+        contiguous run of cheap instances (a sorted sweep whose short trip times are screened as infeasible) is shared by all
+        streams while screened tiles stay whole (their warps exit at once).  Returns (perm, parts): sub-batch i is
+        perm[parts[i][0]:parts[i][1]] of the caller's order."""
+        tiles = [np.arange(t, min(t + tile, n)) for t in range(0, n, tile)]
+        groups = [[] for _ in range(k)]
+        for j, t in enumerate(tiles[:-1] if len(tiles[-1]) < tile else tiles):
+            groups[j % k].append(t)
+        if len(tiles[-1]) < tile:
+            groups[-1].append(tiles[-1])              # the ragged tile goes last so that every sub-batch starts on a tile
+        perm, parts, pos = [], [], 0
+        for g in groups:
+            if not g:
+                continue
+            idx = np.concatenate(g)
+            perm.append(idx)
+            parts.append((pos, pos + len(idx)))
+            pos += len(idx)
+        return np.concatenate(perm), parts
+
+    def solve(self, params, nint, trk_of, trk_off, ds, c0, bmax, tmin=None, out=None, want_lam=False, parts=None):
         import threading
         torch = _torch_cuda()
         n = int(nint.numel())
@@ -200,7 +226,7 @@ class StreamPool:
                        obj=torch.empty(n, dtype=torch.float64, device=dev), kkt=torch.empty(n, dtype=torch.float64, device=dev),
                        iters=torch.empty(n, dtype=torch.int32, device=dev), status=torch.empty(n, dtype=torch.int32, device=dev))
         main = torch.cuda.current_stream(dev)
-        parts = self.bounds(n, len(self.handles))
+        parts = parts if parts is not None else self.bounds(n, len(self.handles))
         info, errors = [None] * len(parts), []
 
         def work(i, a, b):
@@ -246,6 +272,15 @@ def last_profile(handle):
     _check(lib().mseetc_last_profile(handle._h, ms, la, ce), 'mseetc_last_profile')
     return {name: dict(ms=ms[i], launches=la[i], cells=ce[i], bytes_per_cell=lib().mseetc_bytes_per_cell(handle._h, i))
             for i, name in enumerate(KERNEL_CLASSES)}
+
+
+def last_timeline(handle, origin=None, max_entries=4096):
+    "Launches of the last solve on `handle` as rows (class index, start ms, end ms), relative to the first launch on `origin`."
+    buf = np.zeros((max_entries, 3))
+    n = lib().mseetc_last_timeline(handle._h, (origin or handle)._h, buf.ctypes.data_as(ctypes.c_void_p), int(max_entries))
+    if n < 0:
+        _check(n, 'mseetc_last_timeline')
+    return buf[:n]
 
 
 def eval_interval(inp, num_steps, num_approx):

@@ -110,7 +110,7 @@ class _Presolve:
         import torch
         try:
             torch.cuda.set_device(self.dev)
-            side = torch.cuda.Stream(device=self.dev)
+            side = torch.cuda.Stream(device=self.dev, priority=-5)      # tiny, latency-critical kernels: ahead of the batch
             with torch.cuda.stream(side):
                 t0, vN, v0, sub, device = self.args
                 dur, st = self.solver.minimum_time(t0, vN, v0, overrides=sub, device=device)
@@ -270,6 +270,21 @@ class casadiSolver():
             slot['bufs'][i] = buf
         return buf
 
+    def _device_out(self, tag, n, dev, want_lam):
+        "Device result buffers are kept per solver and batch size as well (no cudaMalloc of 50 MB blocks inside a solve)."
+        import torch
+        h = self._ensure_handle()
+        N, stp = h.problem.n_intervals_max, 3 + h.nu
+        key = (tag, n, str(dev), bool(want_lam))
+        cache = self._dev.setdefault('out', {})
+        if key not in cache:
+            for k in [k for k in cache if k[0] == tag]:
+                del cache[k]
+            f64, i32 = dict(dtype=torch.float64, device=dev), dict(dtype=torch.int32, device=dev)
+            cache[key] = dict(z=torch.zeros((n, N * stp + 2), **f64), lam=torch.zeros((n, N * h.rows), **f64) if want_lam else None,
+                              obj=torch.empty(n, **f64), kkt=torch.empty(n, **f64), iters=torch.empty(n, **i32), status=torch.empty(n, **i32))
+        return dict(cache[key])
+
     def _ensure_handle(self):
         if self._handle is None:
             self._handle = self._make_handle()
@@ -350,6 +365,12 @@ class casadiSolver():
             lossT, lossR = (1 - etaT) / etaT, 1 - etaR
         t_begin = _time.perf_counter()
         P, M = self._planes(n, T, t0, v0, vN, overrides, lossT, lossR)
+        # several streams: the instances are dealt to the sub-batches tile by tile (balanced work, see StreamPool.interleave);
+        # everything below works in that order and the results are put back in the caller's order on the device
+        pooled = int(self.streams) > 1 and n >= 2 * MIN_INSTANCES_PER_STREAM
+        perm, parts = _cabi.StreamPool.interleave(n, int(self.streams)) if pooled else (None, None)
+        if perm is not None:
+            P = np.ascontiguousarray(P[:, perm])
         dev = torch.device(device if device is not None else 'cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         tmin = None
         presolve = None
@@ -364,6 +385,7 @@ class casadiSolver():
             else:
                 _, first, inverse = np.unique(key, axis=1, return_index=True, return_inverse=True)
                 inverse = np.asarray(inverse).reshape(-1)
+            first = perm[first] if perm is not None else first          # indices into the caller's arrays
             sub = {k: np.broadcast_to(np.asarray(v, dtype=float), (n,))[first] for k, v in overrides.items()}
             tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)      # 0 = "not known yet"
             presolve = _Presolve(self, dev, tmin_dev, (t0[first], vN[first], v0[first], sub, device), inverse)
@@ -376,7 +398,7 @@ class casadiSolver():
             vmx = np.broadcast_to(np.asarray(overrides.get('velocityMax', self._base['velocityMax']), dtype=float), (n,))
             tabs = [self._tables(rho[i], self._base['g'], vmx[i]) for i in range(n)]
             ds = np.concatenate([t[0] for t in tabs]); c0 = np.concatenate([t[1] for t in tabs]); bmax = np.concatenate([t[2] for t in tabs])
-            trk_of = np.arange(n, dtype=np.int32)
+            trk_of = np.arange(n, dtype=np.int32) if perm is None else perm.astype(np.int32)
             trk_off = (np.arange(n + 1) * N).astype(np.int32)
         else:
             ds, c0, bmax = self._tables(self._base['rho'], self._base['g'], self._base['velocityMax'])
@@ -388,13 +410,22 @@ class casadiSolver():
                 up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64))
         tm = presolve.tmin_dev if presolve is not None else None
         t_up = _time.perf_counter() - t_begin
-        if int(self.streams) > 1 and n >= 2 * MIN_INSTANCES_PER_STREAM:
-            out = self._ensure_pool(dev).solve(*args, tmin=tm, want_lam=want_multipliers)
+        buf = self._device_out('solve', n, dev, want_multipliers)
+        if pooled:
+            out = self._ensure_pool(dev).solve(*args, tmin=tm, want_lam=want_multipliers, parts=parts, out=buf)
+            back = torch.from_numpy(np.argsort(perm)).to(dev)
+            ordered = self._device_out('ordered', n, dev, want_multipliers)
+            for k, v in ordered.items():
+                if v is not None:
+                    torch.index_select(out[k], 0, back, out=v)
+            out = dict(out, **{k: v for k, v in ordered.items() if v is not None})
         else:
-            out = self._ensure_handle().solve_device(*args, want_z=True, want_lam=want_multipliers, tmin=tm)
+            out = self._ensure_handle().solve_device(*args, want_z=True, want_lam=want_multipliers, tmin=tm, out=buf)
         t_solve = _time.perf_counter() - t_begin
         if presolve is not None:
             tmin = presolve.join()
+            if perm is not None:
+                tmin = tmin[np.argsort(perm)]
         t_join = _time.perf_counter() - t_begin
         # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
         out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))

@@ -45,6 +45,8 @@ print('tmin', tmin, 'status', st)
 
 zero = np.zeros(n)
 P, M = solver._planes(n, T, zero, zero + 1.0, zero + 1.0, {}, (1 - train.etaTraction) / train.etaTraction, 1 - train.etaRgBrake)
+perm, parts = _cabi.StreamPool.interleave(n, streams) if streams > 1 else (np.arange(n), None)
+P = np.ascontiguousarray(P[:, perm])
 ds, c0, bmax = solver._tables(solver._base['rho'], solver._base['g'], solver._base['velocityMax'])
 up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
 args = (up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(np.zeros(n, np.int32), torch.int32),
@@ -58,7 +60,7 @@ for tag, tm in (('sweep, tmin known', tm_known), ('sweep, no screening', None)):
             _cabi.set_profiling(hh, prof)
         for rep in range(3):
             torch.cuda.synchronize(); t0 = time.perf_counter()
-            out = pool.solve(*args, tmin=tm)
+            out = pool.solve(*args, tmin=tm, parts=parts)
             torch.cuda.synchronize(); w = 1e3 * (time.perf_counter() - t0)
         if prof:
             show(tag + ' (events on)', pool.handles, w)
