@@ -109,120 +109,204 @@ MS_HD double init_t(const Ctx& c, int j, int s, int N) {
 // spent on it.  The exact certificate is the minimum trip time (time-optimal solve, running concurrently); the host
 // layer checks every early flag against it and re-solves an instance without screening should a flag ever be wrong.
 #define MS_SCREEN_MARGIN 0.02
+// Both per-instance set-up routines below walk the track sequentially (one thread per instance).  Their loops work on chunks
+// of MS_PCH intervals -- all loads of a chunk are issued before the first dependent operation and the results are stored after
+// the last one -- so a pass costs one memory latency per chunk instead of one per interval.
+#define MS_PCH 8
+struct TrainLimits {
+    double sr0, sr1, sr2, felU, felL, fpbL, pUp, pLo, aLo, aUp, b0, bN, bmin;
+};
+MS_HD TrainLimits load_limits(const Ctx& c, int s) {
+    const Config& g = c.cfg;
+    TrainLimits q;
+    q.sr0 = c.P(P_SR0, s); q.sr1 = c.P(P_SR1, s); q.sr2 = c.P(P_SR2, s);
+    q.felU = c.P(P_FEL_U, s); q.felL = c.P(P_FEL_L, s); q.fpbL = g.withPn ? c.P(P_FPB_L, s) : 0.0;
+    q.pUp = g.withPower ? c.P(P_P_UP, s) : 1e30; q.pLo = g.withPower ? c.P(P_P_LO, s) : -1e30;
+    q.aLo = c.P(P_A_LO, s); q.aUp = c.P(P_A_UP, s);
+    q.b0 = c.P(P_B0, s); q.bN = c.P(P_BN, s); q.bmin = c.P(P_BMIN, s);
+    return q;
+}
+// speed envelope: fastest acceleration from b_0 (forward), latest braking into b_N (backward), with the fraction `frac` of the
+// force, power and acceleration limits and the speed limits scaled by `flim`; the node values go to plane `dst`.
+// Returns the trip time of the envelope (trapezoidal in 1/v, exact for b linear in s).
+MS_HD double speed_envelope(const Ctx& c, int s, int N, const TrainLimits& q, double frac, double flim, double vfloor, int brakeIters, int dst,
+                             double* bmaxAll) {
+    double b = q.b0;
+    c.W(dst, 0, s) = q.b0;
+    for (int k0 = 0; k0 < N; k0 += MS_PCH) {
+        double ds[MS_PCH], c0[MS_PCH], lim[MS_PCH], out[MS_PCH];
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            const int k = k0 + i;
+            if (k < N) {
+                ds[i] = c.W(WS_TRK + TRK_DS, k, s); c0[i] = c.W(WS_TRK + TRK_C0, k, s);
+                lim[i] = (k + 1 < N) ? flim * c.W(WS_TRK + TRK_BMAX, k + 1, s) : q.bN;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            if (k0 + i < N) {
+                const double v = sqrt(b);
+                const double r = q.sr0 + q.sr1 * v + q.sr2 * b + c0[i];
+                const double a = fmin(frac * (fmin(q.felU, q.pUp * rcp(fmax(v, vfloor))) - r), frac * q.aUp);
+                b = fmax(q.bmin, fmin(lim[i], b + 2.0 * ds[i] * a));
+                out[i] = b;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) if (k0 + i < N) c.W(dst, k0 + i + 1, s) = out[i];
+    }
+    b = q.bN;
+    c.W(dst, N, s) = q.bN;
+    double vn = sqrt(q.bN), tt = 0.0, bmx = 0.0;
+    for (int k1 = N - 1; k1 >= 0; k1 -= MS_PCH) {
+        double ds[MS_PCH], c0[MS_PCH], fw[MS_PCH], out[MS_PCH];
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            const int k = k1 - i;
+            if (k >= 0) { ds[i] = c.W(WS_TRK + TRK_DS, k, s); c0[i] = c.W(WS_TRK + TRK_C0, k, s); fw[i] = c.W(dst, k, s); }
+        }
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            const int k = k1 - i;
+            if (k >= 0) {
+                double bk = q.b0;
+                if (k >= 1) {
+                    bk = b;
+                    for (int it = 0; it < brakeIters; ++it) {   // the braking deceleration depends on the speed at the start of the interval
+                        const double v = sqrt(bk);
+                        const double r = q.sr0 + q.sr1 * v + q.sr2 * bk + c0[i];
+                        const double a = fmax(frac * (fmax(q.felL, q.pLo * rcp(fmax(v, vfloor))) + q.fpbL - r), frac * q.aLo);      // negative
+                        bk = b - 2.0 * ds[i] * a;
+                    }
+                    bk = fmin(fw[i], bk);
+                    bmx = fmax(bmx, bk);
+                }
+                const double vk = sqrt(bk);
+                tt += 2.0 * ds[i] * rcp(vk + vn);
+                b = bk; vn = vk;
+                out[i] = bk;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) if (k1 - i >= 1) c.W(dst, k1 - i, s) = out[i];
+    }
+    if (bmaxAll) *bmaxAll = bmx;
+    return tt;
+}
+
 MS_HD void inst_screen(const Ctx& c, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || !g.energy || !c.tmin || c.I(SI_PHASE, s) == PH_DONE) return;
     const int N = c.I(SI_N_INT, s);
-    const int P = WS_IT1;                       // scratch plane, overwritten by inst_profile / the first trial point
-    const double sr0 = c.P(P_SR0, s), sr1 = c.P(P_SR1, s), sr2 = c.P(P_SR2, s);
-    const double felU = c.P(P_FEL_U, s), felL = c.P(P_FEL_L, s), fpbL = g.withPn ? c.P(P_FPB_L, s) : 0.0;
-    const double pUp = g.withPower ? c.P(P_P_UP, s) : 1e30, pLo = g.withPower ? c.P(P_P_LO, s) : -1e30;
-    const double aLo = c.P(P_A_LO, s), aUp = c.P(P_A_UP, s);
-    const double b0 = c.P(P_B0, s), bN = c.P(P_BN, s), bmin = c.P(P_BMIN, s);
-    double b = b0;
-    c.W(P + IT_B, 0, s) = b0;
-    for (int k = 0; k < N; ++k) {
-        const double v = sqrt(b), ds = c.W(WS_TRK + TRK_DS, k, s);
-        const double r = sr0 + sr1 * v + sr2 * b + c.W(WS_TRK + TRK_C0, k, s);
-        const double a = fmin(fmin(felU, pUp / fmax(v, 1e-3)) - r, aUp);
-        const double lim = (k + 1 < N) ? c.W(WS_TRK + TRK_BMAX, k + 1, s) : bN;
-        b = fmax(bmin, fmin(lim, b + 2.0 * ds * a));
-        c.W(P + IT_B, k + 1, s) = b;
-    }
-    b = bN;
-    double vn = sqrt(bN), tLow = 0.0;
-    for (int k = N - 1; k >= 0; --k) {
-        const double ds = c.W(WS_TRK + TRK_DS, k, s);
-        double bk = b0;
-        if (k >= 1) {
-            bk = b;
-            for (int it = 0; it < 3; ++it) {        // the braking deceleration depends on the speed at the start of the interval
-                const double v = sqrt(bk);
-                const double r = sr0 + sr1 * v + sr2 * bk + c.W(WS_TRK + TRK_C0, k, s);
-                const double a = fmax(fmax(felL, pLo / fmax(v, 1e-3)) + fpbL - r, aLo);      // negative
-                bk = b - 2.0 * ds * a;
-            }
-            bk = fmin(c.W(P + IT_B, k, s), bk);
-        }
-        const double vk = sqrt(bk);
-        tLow += 2.0 * ds / (vk + vn);
-        b = bk; vn = vk;
-    }
+    const TrainLimits q = load_limits(c, s);
+    // scratch plane: overwritten by inst_profile / the first trial point
+    const double tLow = speed_envelope(c, s, N, q, 1.0, 1.0, 1e-3, 2, WS_IT1 + IT_B, nullptr);
     if (isfinite(tLow) && (c.P(P_T, s) - c.P(P_T0, s)) < (1.0 - MS_SCREEN_MARGIN) * tLow) finish(c, s, ST_INFEASIBLE);
 }
 
 // Dynamically consistent starting profile (initMode 1): speed envelope from the limits with bounded acceleration and
 // braking, cruise speed capped so that the trip takes the available time, times and forces from the ODE.  It replaces
 // the constant-speed guess of the reference only as a starting point; the NLP and its optimum are unchanged.
-MS_HD void inst_profile(const Ctx& c, int s) {
+// `smv`, `smd` (optional, stride `sms` doubles between consecutive k): shared-memory columns for the node speeds and the
+// interval lengths, which the cruise-cap search reads once per evaluation.
+MS_HD void inst_profile(const Ctx& c, int s, double* smv = nullptr, double* smd = nullptr, int sms = 0) {
     const Config& g = c.cfg;
     if (s >= g.nInst || !g.initMode || c.I(SI_PHASE, s) == PH_DONE) return;
     const int N = c.I(SI_N_INT, s);
     const int P = WS_IT1;                       // scratch: buffer 1 holds the profile until cell_init has consumed it
-    const double sr0 = c.P(P_SR0, s), sr1 = c.P(P_SR1, s), sr2 = c.P(P_SR2, s);
-    const double felU = c.P(P_FEL_U, s), felL = c.P(P_FEL_L, s), fpbL = g.withPn ? c.P(P_FPB_L, s) : 0.0;
-    const double pUp = g.withPower ? c.P(P_P_UP, s) : 1e30, pLo = g.withPower ? c.P(P_P_LO, s) : -1e30;
-    const double aLo = c.P(P_A_LO, s), aUp = c.P(P_A_UP, s);
-    const double b0 = c.P(P_B0, s), bN = c.P(P_BN, s), bmin = c.P(P_BMIN, s);
+    const TrainLimits q = load_limits(c, s);
     const double Tav = c.P(P_T, s) - c.P(P_T0, s);
     // ---- fastest admissible profile: accelerate / brake with 80 % of what the force, power and acceleration limits allow
-    double b = b0, bmaxAll = 0.0;
-    c.W(P + IT_B, 0, s) = b0;
-    for (int k = 0; k < N; ++k) {
-        const double v = sqrt(b), ds = c.W(WS_TRK + TRK_DS, k, s);
-        const double r = sr0 + sr1 * v + sr2 * b + c.W(WS_TRK + TRK_C0, k, s);
-        const double a = fmin(0.8 * (fmin(felU, pUp / fmax(v, 1.0)) - r), 0.8 * aUp);
-        const double lim = (k + 1 < N) ? 0.97 * c.W(WS_TRK + TRK_BMAX, k + 1, s) : bN;
-        b = fmax(bmin, fmin(lim, b + 2.0 * ds * a));
-        c.W(P + IT_B, k + 1, s) = b;
-    }
-    b = bN;
-    c.W(P + IT_B, N, s) = bN;
-    for (int k = N - 1; k >= 1; --k) {
-        const double v = sqrt(b), ds = c.W(WS_TRK + TRK_DS, k, s);
-        const double r = sr0 + sr1 * v + sr2 * b + c.W(WS_TRK + TRK_C0, k, s);
-        const double a = fmax(0.8 * (fmax(felL, pLo / fmax(v, 1.0)) + fpbL - r), 0.8 * aLo);      // negative
-        b = fmin(c.W(P + IT_B, k, s), b - 2.0 * ds * a);
-        c.W(P + IT_B, k, s) = b;
-        bmaxAll = fmax(bmaxAll, b);
-    }
-    // ---- energy mode: cap the cruise speed so that the trip uses (almost all of) the available time
+    double bmaxAll = 0.0;
+    const double tFast = speed_envelope(c, s, N, q, 0.8, 0.97, 1.0, 1, P + IT_B, &bmaxAll);
+    // ---- energy mode: cap the cruise speed so that the trip uses (almost all of) the available time.  The trip time is a
+    // decreasing function of the cap: bracketing + regula falsi (Illinois) on the speed
     double cap = 1e30;
-    if (g.energy) {
-        double lo = bmin, hi = bmaxAll;
-        for (int it = 0; it < 22; ++it) {
-            const double trial = (it == 0) ? 1e30 : 0.5 * (lo + hi);
-            double tt = 0.0, vp = sqrt(fmin(b0, fmax(trial, b0)));
+    const double target = 0.995 * Tav;
+    if (g.energy && tFast < target) {
+        const int V = P + IT_SL;                  // scratch when no shared memory is given (IT_SL is written last, below)
+        if (!smv) { smv = &c.W(V, 0, s); smd = &c.W(WS_TRK + TRK_DS, 0, s); sms = WS_FIELDS * 32; }
+        const bool copyDs = (smd != &c.W(WS_TRK + TRK_DS, 0, s));
+        for (int k0 = 0; k0 <= N; k0 += MS_PCH) {
+            double bb[MS_PCH], dd[MS_PCH];
+#pragma unroll
+            for (int i = 0; i < MS_PCH; ++i)
+                if (k0 + i <= N) { bb[i] = c.W(P + IT_B, k0 + i, s); dd[i] = (copyDs && k0 + i < N) ? c.W(WS_TRK + TRK_DS, k0 + i, s) : 0.0; }
+#pragma unroll
+            for (int i = 0; i < MS_PCH; ++i)
+                if (k0 + i <= N) { smv[(size_t)(k0 + i) * sms] = sqrt(bb[i]); if (copyDs && k0 + i < N) smd[(size_t)(k0 + i) * sms] = dd[i]; }
+        }
+        auto trip = [&](double vcap) {            // interior nodes capped, boundary speeds kept
+            double tt = 0.0, vp = smv[0];
+#pragma unroll 8
             for (int k = 0; k < N; ++k) {
-                const double bn = c.W(P + IT_B, k + 1, s);
-                const double vn = sqrt((k + 1 < N) ? fmin(bn, trial) : bn);
-                tt += 2.0 * c.W(WS_TRK + TRK_DS, k, s) / (vp + vn);
+                const double vk = smv[(size_t)(k + 1) * sms];
+                const double vn = (k + 1 < N) ? fmin(vk, vcap) : vk;
+                tt += 2.0 * smd[(size_t)k * sms] * rcp(vp + vn);
                 vp = vn;
             }
-            if (it == 0) { if (tt >= 0.995 * Tav) break; continue; }    // no slack in the timetable: keep the fastest profile
-            if (tt > 0.995 * Tav) lo = trial; else hi = trial;
-            cap = hi;
-            if (hi - lo < 1e-3 * hi) break;
+            return tt;
+        };
+        double lo = sqrt(q.bmin), hi = sqrt(bmaxAll);
+        double fhi = tFast - target;              // fastest profile: negative, there is slack in the timetable
+        if (hi > lo) {
+            double flo = trip(lo) - target;       // slowest cap: positive unless even crawling is too fast
+            if (flo > 0.0) {
+                double vc = hi;
+                int side = 0;
+                for (int it = 0; it < 40 && hi - lo > 5e-4 * hi; ++it) {
+                    const double x = fmin(fmax((lo * fhi - hi * flo) / (fhi - flo), lo + 1e-3 * (hi - lo)), hi - 1e-3 * (hi - lo));
+                    const double fx = trip(x) - target;
+                    if (fabs(fx) <= 2e-4 * target) { vc = x; break; }      // within 0.02 % of the target time: good enough for a start
+                    if (fx > 0.0) { lo = x; flo = fx; if (side < 0) fhi *= 0.5; side = -1; }
+                    else { hi = x; fhi = fx; if (side > 0) flo *= 0.5; side = 1; }
+                    vc = hi;
+                }
+                cap = vc * vc;
+            } else cap = lo * lo;
         }
     }
     // ---- times, forces and epigraph variable of the profile
     double t = c.P(P_T0, s);
     c.W(P + IT_T, 0, s) = t;
-    b = b0;
-    for (int k = 0; k < N; ++k) {
-        double bn = c.W(P + IT_B, k + 1, s);
-        if (k + 1 < N) { bn = fmin(bn, cap); c.W(P + IT_B, k + 1, s) = bn; }
-        const double ds = c.W(WS_TRK + TRK_DS, k, s);
-        t += 2.0 * ds / (sqrt(b) + sqrt(bn));
-        c.W(P + IT_T, k + 1, s) = t;
-        const double bm = 0.5 * (b + bn);
-        const double F = (bn - b) / (2.0 * ds) + sr0 + sr1 * sqrt(bm) + sr2 * bm + c.W(WS_TRK + TRK_C0, k, s);
-        const double vmx = fmax(sqrt(fmax(b, bn)), 1.0);
-        const double fel = fmin(fmax(F, fmax(0.97 * felL, 0.97 * pLo / vmx)), fmin(0.97 * felU, 0.97 * pUp / vmx));
-        c.W(P + IT_FEL, k, s) = fel;
-        c.W(P + IT_FPB, k, s) = g.withPn ? fmin(0.0, fmax(0.97 * fpbL, F - fel)) : 0.0;
-        c.W(P + IT_SL, k, s) = 0.5 * fabs(fel) + 0.02;
-        b = bn;
+    double b = q.b0, vb = sqrt(q.b0);
+    for (int k0 = 0; k0 < N; k0 += MS_PCH) {
+        double bnx[MS_PCH], ds[MS_PCH], c0[MS_PCH], ot[MS_PCH], of[MS_PCH], op[MS_PCH];
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            const int k = k0 + i;
+            if (k < N) { bnx[i] = c.W(P + IT_B, k + 1, s); ds[i] = c.W(WS_TRK + TRK_DS, k, s); c0[i] = c.W(WS_TRK + TRK_C0, k, s); }
+        }
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            const int k = k0 + i;
+            if (k < N) {
+                const double bn = (k + 1 < N) ? fmin(bnx[i], cap) : bnx[i];
+                bnx[i] = bn;
+                const double vbn = sqrt(bn);
+                t += 2.0 * ds[i] * rcp(vb + vbn);
+                ot[i] = t;
+                const double bm = 0.5 * (b + bn);
+                const double F = (bn - b) * rcp(2.0 * ds[i]) + q.sr0 + q.sr1 * sqrt(bm) + q.sr2 * bm + c0[i];
+                const double ivmx = 0.97 * rcp(fmax(fmax(vb, vbn), 1.0));
+                const double fel = fmin(fmax(F, fmax(0.97 * q.felL, q.pLo * ivmx)), fmin(0.97 * q.felU, q.pUp * ivmx));
+                of[i] = fel;
+                op[i] = g.withPn ? fmin(0.0, fmax(0.97 * q.fpbL, F - fel)) : 0.0;
+                b = bn; vb = vbn;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MS_PCH; ++i) {
+            const int k = k0 + i;
+            if (k < N) {
+                if (k + 1 < N) c.W(P + IT_B, k + 1, s) = bnx[i];
+                c.W(P + IT_T, k + 1, s) = ot[i];
+                c.W(P + IT_FEL, k, s) = of[i];
+                c.W(P + IT_FPB, k, s) = op[i];
+                c.W(P + IT_SL, k, s) = 0.5 * fabs(of[i]) + 0.02;
+            }
+        }
     }
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -24,14 +25,19 @@ namespace {
 
 thread_local std::string g_err;
 
-// ---- interval-parallel kernels: one thread per (interval k, instance), warp = 32 instances at one k ---------
+// ---- interval-parallel kernels: one thread per (interval k, instance), warp = 32 instances at one k.  The kernels stride over
+// the cells, so any grid works; the default is one block per 128 cells (measured faster than a persistent grid of a few blocks
+// per SM, MSEETC_CELL_WAVES=w selects the latter for experiments: 110.9k / 115.5k / 118.6k / 122.0k solves/s at w = 1/2/4/8
+// against 122.6k with the full grid on the bench workload).
 #define MS_CELL_KERNEL(NAME, MINB, CALL)                                        \
     __global__ void __launch_bounds__(128, MINB) NAME(Ctx c, BatchIO io) {      \
-        const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       \
-        const int s = (int)(idx % c.cfg.S);                                     \
-        const int k = (int)(idx / c.cfg.S);                                     \
-        if (k >= c.cfg.NK) return;                                              \
-        CALL;                                                                   \
+        const size_t total = (size_t)c.cfg.NK * c.cfg.S;                        \
+        const size_t stride = (size_t)gridDim.x * 128;                          \
+        for (size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x; idx < total; idx += stride) { \
+            const int s = (int)(idx % c.cfg.S);                                 \
+            const int k = (int)(idx / c.cfg.S);                                 \
+            CALL;                                                               \
+        }                                                                       \
     }
 #ifndef MS_MINB_TRIAL
 #define MS_MINB_TRIAL 3
@@ -56,9 +62,14 @@ __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < c.cfg.S) inst_setup(c, io, s);
 }
-__global__ void __launch_bounds__(64) k_inst_profile(Ctx c) {
+// useSmem: dynamic shared memory holds two columns per thread (node speeds, interval lengths: 2 * NK * blockDim doubles)
+__global__ void __launch_bounds__(64) k_inst_profile(Ctx c, int useSmem) {
+    extern __shared__ double prof_sm[];
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < c.cfg.S) { inst_screen(c, s); inst_profile(c, s); }
+    if (s >= c.cfg.S) return;
+    inst_screen(c, s);
+    if (useSmem) inst_profile(c, s, prof_sm + threadIdx.x, prof_sm + (size_t)c.cfg.NK * blockDim.x + threadIdx.x, (int)blockDim.x);
+    else inst_profile(c, s);
 }
 
 // ---- per-instance reductions: block = 32 instances x RED_W warps; warp w sums the intervals k = w, w+RED_W, ...
@@ -475,7 +486,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
     const size_t cellThreads = (size_t)g.NK * g.S;
-    const unsigned cgrid = (unsigned)((cellThreads + 127) / 128);
+    const unsigned cgridFull = (unsigned)((cellThreads + 127) / 128);
     const int ib = (g.S >= 148 * 64 * 2) ? 64 : 32;
     const unsigned igrid = (unsigned)((g.S + ib - 1) / ib);
     // prefetch depth of the Riccati ring: as deep as shared memory allows for the blocks resident on one SM
@@ -485,6 +496,14 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         cudaGetDevice(&devId);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devId);
     }
+    // grids of the interval kernels (see MS_CELL_KERNEL)
+    static const int cellWaves = []() { const char* e = getenv("MSEETC_CELL_WAVES"); return e ? atoi(e) : 0; }();
+    auto pgrid = [&](int minb) {
+        if (cellWaves < 1) return cgridFull;
+        const unsigned want = (unsigned)(nsm * minb * cellWaves) | 1u;
+        return want < cgridFull ? want : cgridFull;
+    };
+    const unsigned cgrid = pgrid(4), gridTrial = pgrid(dyn ? 2 : MS_MINB_TRIAL), gridEval = pgrid(dyn ? 2 : MS_MINB_EVAL), gridStep = pgrid(MS_MINB_STEP);
     const int blocksPerSm = (int)((igrid + nsm - 1) / nsm);
     const size_t slotBytes = sizeof(double) * RING_NF_MAX * ib;
     int depth = (int)((size_t)200 * 1024 / ((size_t)(blocksPerSm < 1 ? 1 : blocksPerSm) * slotBytes)) - 1;
@@ -523,7 +542,12 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     const unsigned rgrid = (unsigned)(g.S / 32);
     begin(CLS_MISC); k_inst_setup<<<igrid, ib, 0, st>>>(c, io); end(CLS_MISC);
     begin(CLS_MISC); k_cell_setup<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
-    if (g.initMode || (tmin && g.energy)) { begin(CLS_MISC); k_inst_profile<<<igrid, ib, 0, st>>>(c); end(CLS_MISC); }
+    if (g.initMode || (tmin && g.energy)) {
+        size_t profBytes = (size_t)2 * g.NK * ib * sizeof(double);
+        if (profBytes > (size_t)200 * 1024 / (blocksPerSm < 1 ? 1 : blocksPerSm)) profBytes = 0;      // long horizons: scratch stays in HBM
+        if (profBytes) cudaFuncSetAttribute(k_inst_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)profBytes);
+        begin(CLS_MISC); k_inst_profile<<<igrid, ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
+    }
     begin(CLS_MISC);
     if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
     end(CLS_MISC);
@@ -531,7 +555,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     int tick = 0;
     for (;;) {
         begin(CLS_EVAL);
-        if (dyn) k_cell_eval_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_eval<<<cgrid, 128, 0, st>>>(c, io);
+        if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
         end(CLS_EVAL);
         begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
         begin(CLS_STEP);
@@ -539,7 +563,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         else if (h->sweep_lanes == 32) k_step_pit<32><<<(unsigned)(((size_t)g.S * 32 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
         else stepKernel<<<igrid, ib, ringBytes, st>>>(c);
         end(CLS_STEP);
-        begin(CLS_CSTEP); k_cell_step<<<cgrid, 128, 0, st>>>(c, io); end(CLS_CSTEP);
+        begin(CLS_CSTEP); k_cell_step<<<gridStep, 128, 0, st>>>(c, io); end(CLS_CSTEP);
         begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);
         if (tick >= maxTicks) break;
         // completion polling without draining the queue: the counter is copied every tick into a small pinned ring and the
@@ -557,7 +581,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             }
         }
         begin(CLS_TRIAL);
-        if (dyn) k_cell_trial_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_trial<<<cgrid, 128, 0, st>>>(c, io);
+        if (dyn) k_cell_trial_dyn<<<gridTrial, 128, 0, st>>>(c, io); else k_cell_trial<<<gridTrial, 128, 0, st>>>(c, io);
         end(CLS_TRIAL);
         begin(CLS_DECIDE); k_inst_decide<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_DECIDE);
         ++tick;
