@@ -218,7 +218,8 @@ def run_gpu(args):
     outbuf = dict(z=torch.zeros((n, N_INT * stp + 2), dtype=torch.float64, device=dev), lam=None,
                   obj=torch.empty(n, dtype=torch.float64, device=dev), kkt=torch.empty(n, dtype=torch.float64, device=dev),
                   iters=torch.empty(n, dtype=torch.int32, device=dev), status=torch.empty(n, dtype=torch.int32, device=dev))
-    prof = {k: dict(ms=0.0, launches=0, cells=0) for k in _cabi.KERNEL_CLASSES}
+    prof = {k: dict(ms=0.0, launches=0, cells=0) for k in _cabi.KERNEL_CLASSES}          # the sweep (all pool streams)
+    prof_pre = {k: dict(ms=0.0, launches=0, cells=0) for k in _cabi.KERNEL_CLASSES}      # the concurrent time-optimal presolve
     launches = [0]
 
     tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -248,9 +249,10 @@ def run_gpu(args):
         if accumulate:
             launches[0] += tr['launches'] + out['launches']
             for hh in pool.handles + [ht]:
+                acc = prof_pre if hh is ht else prof
                 for k, v in _cabi.last_profile(hh).items():
-                    prof[k]['ms'] += v['ms']; prof[k]['launches'] += v['launches']; prof[k]['cells'] += v['cells']
-                    prof[k]['bytes_per_cell'] = v['bytes_per_cell'] if hh is h else prof[k].get('bytes_per_cell', v['bytes_per_cell'])
+                    acc[k]['ms'] += v['ms']; acc[k]['launches'] += v['launches']; acc[k]['cells'] += v['cells']
+                    acc[k]['bytes_per_cell'] = v['bytes_per_cell']
         return out, tr
 
     for _ in range(args.warmup):
@@ -293,6 +295,8 @@ def run_gpu(args):
         ts = time.perf_counter()
         res = solver.solve_batch(T)
         e2e_steps.append(round(1e3 * (time.perf_counter() - ts), 2))
+        if e2e_steps[-1] >= max(e2e_steps):
+            slowest = {k: round(1e3 * v, 2) for k, v in res['timing'].items()}
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -321,14 +325,18 @@ def run_gpu(args):
     if not kern:
         kern = {'inst_step': dict(ms_total=1.0, launches=1, avg_us=0.0, bytes_per_cell=0.0, cells=0, achieved_gbs=0.0, frac_hbm=0.0)}
     top = max(kern, key=lambda k: kern[k]['ms_total'])
-    ncu_traffic = None
+    ncu_traffic, capture = None, None
     tfile = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tfile):
-        ncu_traffic = json.load(open(tfile)).get(top)
+        tj = json.load(open(tfile))
+        ncu_traffic = tj.get(top)
+        capture = (tj.get('captures_r01_q') or {}).get(top)
     roofline = {'bound': 'hbm', 'kernel': top, 'achieved': kern[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-                'frac': kern[top]['achieved_gbs'] / peak, 'traffic': ncu_traffic, 'peak_source': peak_src,
+                'frac': kern[top]['achieved_gbs'] / peak, 'traffic': ncu_traffic, 'traffic_capture': capture, 'peak_source': peak_src,
                 'share_of_device_time': kern[top]['ms_total'] / max(1e-12, sum(v['ms_total'] for v in kern.values())),
-                'bytes_per_launch': kern[top]['cells'] * kern[top]['bytes_per_cell'] / kern[top]['launches'], 'kernels': kern}
+                'bytes_per_launch': kern[top]['cells'] * kern[top]['bytes_per_cell'] / kern[top]['launches'], 'kernels': kern,
+                'presolve': {'ms_total': sum(v['ms'] for v in prof_pre.values()), 'launches': sum(v['launches'] for v in prof_pre.values()),
+                             'note': 'single-instance time-optimal solve on its own stream, concurrent with the sweep (not in `kernels`)'}}
 
     # ---------------- CPU baseline beside it (bounded sample, rank 0, N = 1 only)
     cpu = None
@@ -352,7 +360,8 @@ def run_gpu(args):
             'feasible_solves_per_s': int(feas.sum()) * world * args.steps / (ms * 1e-3),
             'e2e': {'value': total * args.steps / e2e_s, 'unit': 'solves/s', 'h2d_bytes_per_step': res['h2d_bytes'],
                     'last_call_breakdown_s': res.get('timing'),
-                    'd2h_bytes_per_step': res['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s / args.steps, 'steps_ms': e2e_steps},
+                    'd2h_bytes_per_step': res['d2h_bytes'], 'ms_per_step': 1e3 * e2e_s / args.steps, 'steps_ms': e2e_steps,
+                    'slowest_step_breakdown_ms': slowest},
             'gpu_launches': launches[0], 'clocks': clocks, 'roofline': roofline}
     if cpu is not None:
         line['cpu_baseline'] = cpu

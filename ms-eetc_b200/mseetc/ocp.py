@@ -285,6 +285,20 @@ class casadiSolver():
                               obj=torch.empty(n, **f64), kkt=torch.empty(n, **f64), iters=torch.empty(n, **i32), status=torch.empty(n, **i32))
         return dict(cache[key])
 
+    def _upload(self, name, array, dtype, dev):
+        """Host array -> persistent page-locked staging buffer -> persistent device tensor, asynchronously on the current stream
+        (a pageable cudaMemcpy can stall behind unrelated work of the context, and allocates on every call)."""
+        import torch
+        a = np.ascontiguousarray(array)
+        cache = self._dev.setdefault('in', {})
+        slot = cache.get(name)
+        if slot is None or slot[0].shape != a.shape or slot[1].device != dev or slot[0].dtype != dtype:
+            slot = (torch.empty(a.shape, dtype=dtype, pin_memory=True), torch.empty(a.shape, dtype=dtype, device=dev))
+            cache[name] = slot
+        slot[0].copy_(torch.from_numpy(a))
+        slot[1].copy_(slot[0], non_blocking=True)
+        return slot[1]
+
     def _ensure_handle(self):
         if self._handle is None:
             self._handle = self._make_handle()
@@ -300,6 +314,8 @@ class casadiSolver():
             sib._lossKind = 'none'
             sib._handle = None
             sib._sibling = None
+            sib._pool = None
+            sib._dev = {}             # own staging / result buffers: the sibling runs concurrently on a second host thread
             sib.scalingFactorObjective = self.trackLength / self._base['velocityMax']
             if self.initialGuess == 'profile':
                 # the speed-envelope starting profile is close to the time-optimal run: a small initial barrier parameter keeps
@@ -404,10 +420,11 @@ class casadiSolver():
             ds, c0, bmax = self._tables(self._base['rho'], self._base['g'], self._base['velocityMax'])
             trk_of = np.zeros(n, dtype=np.int32)
             trk_off = np.array([0, N], dtype=np.int32)
-        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt, non_blocking=False)
         t_pack = _time.perf_counter() - t_begin
-        args = (up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(trk_of, torch.int32),
-                up(trk_off, torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64))
+        f64, i32 = torch.float64, torch.int32
+        args = (self._upload('P', P, f64, dev), self._upload('nint', np.full(n, N, np.int32), i32, dev), self._upload('trk_of', trk_of, i32, dev),
+                self._upload('trk_off', trk_off, i32, dev), self._upload('ds', ds, f64, dev), self._upload('c0', c0, f64, dev),
+                self._upload('bmax', bmax, f64, dev))
         tm = presolve.tmin_dev if presolve is not None else None
         t_up = _time.perf_counter() - t_begin
         buf = self._device_out('solve', n, dev, want_multipliers)

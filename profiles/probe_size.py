@@ -20,13 +20,15 @@ h = solver._make_handle()
 _cabi.set_profiling(h, True)
 ds, c0, bmax = solver._tables(solver._base['rho'], solver._base['g'], solver._base['velocityMax'])
 up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
-for n in (32, 256, 512, 1024, 2048, 4096, 8192):
+sizes = [int(a) for a in sys.argv[1:]] or [32, 256, 512, 1024, 2048, 4096, 8192]
+reps = 1 if len(sys.argv) > 1 else 3      # one solve per size when a size list is given (ncu captures)
+for n in sizes:
     T = np.linspace(1040.0, 1243.0, n)
     zero = np.zeros(n)
     P, M = solver._planes(n, T, zero, zero + 1.0, zero + 1.0, {}, (1 - train.etaTraction) / train.etaTraction, 1 - train.etaRgBrake)
     args = (up(P, torch.float64), up(np.full(n, N, np.int32), torch.int32), up(np.zeros(n, np.int32), torch.int32),
             up(np.array([0, N], np.int32), torch.int32), up(ds, torch.float64), up(c0, torch.float64), up(bmax, torch.float64))
-    for rep in range(3):
+    for rep in range(reps):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         out = h.solve_device(*args)
         torch.cuda.synchronize(); w = 1e3 * (time.perf_counter() - t0)
