@@ -297,6 +297,7 @@ def run_gpu(args):
         e2e_steps.append(round(1e3 * (time.perf_counter() - ts), 2))
         if e2e_steps[-1] >= max(e2e_steps):
             slowest = {k: round(1e3 * v, 2) for k, v in res['timing'].items()}
+            slowest['stream_threads_ms'] = res.get('spans_ms')
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     if dist is not None:

@@ -213,7 +213,7 @@ class StreamPool:
             pos += len(idx)
         return np.concatenate(perm), parts
 
-    def solve(self, params, nint, trk_of, trk_off, ds, c0, bmax, tmin=None, out=None, want_lam=False, parts=None):
+    def solve(self, params, nint, trk_of, trk_off, ds, c0, bmax, tmin=None, out=None, want_lam=False, parts=None, on_started=None):
         import threading
         torch = _torch_cuda()
         n = int(nint.numel())
@@ -229,8 +229,13 @@ class StreamPool:
         parts = parts if parts is not None else self.bounds(n, len(self.handles))
         info, errors = [None] * len(parts), []
 
+        import time as _t
+        t_ref = _t.perf_counter()
+        spans = [None] * len(parts)
+
         def work(i, a, b):
             try:
+                t_in = _t.perf_counter() - t_ref
                 torch.cuda.set_device(dev)
                 st = self.streams[i]
                 st.wait_stream(main)
@@ -239,12 +244,15 @@ class StreamPool:
                     r = self.handles[i].solve_device(params[:, a:b].contiguous(), nint[a:b], trk_of[a:b], trk_off, ds, c0, bmax,
                                                      tmin=tmin[a:b] if tmin is not None else None, out=sub)
                     info[i] = (r['ticks'], r['launches'])
+                spans[i] = (round(1e3 * t_in, 2), round(1e3 * (_t.perf_counter() - t_ref), 2))
             except Exception as exc:
                 errors.append(exc)
 
         threads = [threading.Thread(target=work, args=(i, a, b)) for i, (a, b) in enumerate(parts)]
         for t in threads:
             t.start()
+        if on_started is not None:
+            on_started()                 # e.g. start the presolve thread once the stream threads are on their way into the library
         for t in threads:
             t.join()
         if errors:
@@ -254,6 +262,7 @@ class StreamPool:
         out = dict(out)
         out['ticks'] = max(i[0] for i in info if i)
         out['launches'] = sum(i[1] for i in info if i)
+        out['spans_ms'] = spans                  # (entered, left) the library per stream thread, relative to the call
         return out
 
 

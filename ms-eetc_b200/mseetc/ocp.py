@@ -108,19 +108,50 @@ class _Presolve:
 
     def _run(self):
         import torch
+        self.t_start = _time.perf_counter()
         try:
             torch.cuda.set_device(self.dev)
             side = torch.cuda.Stream(device=self.dev, priority=-5)      # tiny, latency-critical kernels: ahead of the batch
+            solver, dev = self.solver, self.dev
+            sib = solver._time_sibling()
+            t0, vN, v0, sub, device = self.args
+            m = len(t0)
+            f64 = torch.float64
             with torch.cuda.stream(side):
-                t0, vN, v0, sub, device = self.args
-                dur, st = self.solver.minimum_time(t0, vN, v0, overrides=sub, device=device)
-                dur = np.where(st == 0, dur, 0.0)        # no certificate when the time-optimal solve did not converge
-                full = np.ascontiguousarray(dur[self.inverse])
-                self.tmin_dev.copy_(torch.from_numpy(full).to(self.tmin_dev.device, non_blocking=False))
+                # lean path: everything up to the moment the certificate is in device memory avoids host round trips and
+                # allocations (persistent staging / result buffers of the sibling, in-place device arithmetic)
+                lim = np.minimum(solver.points['Speed limit [m/s]'].values[:-1], solver._base['velocityMax'])
+                horizon = t0 + 1.5 * float(np.sum(solver.steps / lim))          # same bound as minimum_time
+                P, _ = sib._planes(m, horizon, t0, v0, vN, dict(sub), 0.0, 0.0)
+                ds, c0, bmax, trk_of, trk_off = sib._track_tables(m, sub)
+                i32 = torch.int32
+                args = (sib._upload('P', P, f64, dev), sib._upload('nint', np.full(m, sib.numIntervals, np.int32), i32, dev),
+                        sib._upload('trk_of', trk_of, i32, dev), sib._upload('trk_off', trk_off, i32, dev),
+                        sib._upload('ds', ds, f64, dev), sib._upload('c0', c0, f64, dev), sib._upload('bmax', bmax, f64, dev))
+                inv = sib._upload('inverse', np.asarray(self.inverse, dtype=np.int64), torch.int64, dev)
+                t0_dev = sib._upload('t0', np.ascontiguousarray(t0, dtype=float), f64, dev)
+                out = sib._ensure_handle().solve_device(*args, want_z=True, out=sib._device_out('solve', m, dev, False))
+                pre = sib._dev.setdefault('pre', {})
+                if pre.get('m') != m or pre['dur'].device != dev:
+                    pre.update(m=m, dur=torch.empty(m, dtype=f64, device=dev), ok=torch.empty(m, dtype=torch.bool, device=dev))
+                torch.sub(out['z'][:, -2], t0_dev, out=pre['dur'])
+                torch.eq(out['status'], 0, out=pre['ok'])
+                pre['dur'].mul_(pre['ok'])                   # no certificate where the time-optimal solve did not converge
+                torch.index_select(pre['dur'], 0, inv, out=self.tmin_dev)
                 side.synchronize()
-            self.tmin = full
+                t_pub = _time.perf_counter()
+                dur = pre['dur'].cpu().numpy()
+                if np.any(dur <= 0.0):
+                    # rare: retry the instances that did not converge with longer horizons (host path), publish again
+                    dur2, st2 = solver.minimum_time(t0, vN, v0, overrides=sub, device=device)
+                    dur = np.where(st2 == 0, dur2, 0.0)
+                    self.tmin_dev.copy_(torch.from_numpy(np.ascontiguousarray(dur[self.inverse])).to(dev))
+                    side.synchronize()
+            self.tmin = np.ascontiguousarray(dur[self.inverse])
+            self.detail = dict(publish_at=t_pub - self.t_start)
         except Exception as exc:      # surfaced by join()
             self.error = exc
+        self.t_end = _time.perf_counter()
 
     def join(self):
         self.thread.join()
@@ -299,6 +330,22 @@ class casadiSolver():
         slot[1].copy_(slot[0], non_blocking=True)
         return slot[1]
 
+    def _track_tables(self, n, overrides, perm=None):
+        "Track tables of a batch: shared unless rho / velocityMax vary per instance (then one table per instance, in the caller's order)."
+        N = self.numIntervals
+        if any(k in overrides for k in ('rho', 'velocityMax')):
+            rho = np.broadcast_to(np.asarray(overrides.get('rho', self._base['rho']), dtype=float), (n,))
+            vmx = np.broadcast_to(np.asarray(overrides.get('velocityMax', self._base['velocityMax']), dtype=float), (n,))
+            tabs = [self._tables(rho[i], self._base['g'], vmx[i]) for i in range(n)]
+            ds = np.concatenate([t[0] for t in tabs]); c0 = np.concatenate([t[1] for t in tabs]); bmax = np.concatenate([t[2] for t in tabs])
+            trk_of = np.arange(n, dtype=np.int32) if perm is None else perm.astype(np.int32)
+            trk_off = (np.arange(n + 1) * N).astype(np.int32)
+        else:
+            ds, c0, bmax = self._tables(self._base['rho'], self._base['g'], self._base['velocityMax'])
+            trk_of = np.zeros(n, dtype=np.int32)
+            trk_off = np.array([0, N], dtype=np.int32)
+        return ds, c0, bmax, trk_of, trk_off
+
     def _ensure_handle(self):
         if self._handle is None:
             self._handle = self._make_handle()
@@ -405,21 +452,8 @@ class casadiSolver():
             sub = {k: np.broadcast_to(np.asarray(v, dtype=float), (n,))[first] for k, v in overrides.items()}
             tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)      # 0 = "not known yet"
             presolve = _Presolve(self, dev, tmin_dev, (t0[first], vN[first], v0[first], sub, device), inverse)
-            presolve.start()
-        # ---- track tables: shared unless rho / g / velocityMax vary per instance
-        per_inst_track = any(k in overrides for k in ('rho', 'velocityMax'))
         N = self.numIntervals
-        if per_inst_track:
-            rho = np.broadcast_to(np.asarray(overrides.get('rho', self._base['rho']), dtype=float), (n,))
-            vmx = np.broadcast_to(np.asarray(overrides.get('velocityMax', self._base['velocityMax']), dtype=float), (n,))
-            tabs = [self._tables(rho[i], self._base['g'], vmx[i]) for i in range(n)]
-            ds = np.concatenate([t[0] for t in tabs]); c0 = np.concatenate([t[1] for t in tabs]); bmax = np.concatenate([t[2] for t in tabs])
-            trk_of = np.arange(n, dtype=np.int32) if perm is None else perm.astype(np.int32)
-            trk_off = (np.arange(n + 1) * N).astype(np.int32)
-        else:
-            ds, c0, bmax = self._tables(self._base['rho'], self._base['g'], self._base['velocityMax'])
-            trk_of = np.zeros(n, dtype=np.int32)
-            trk_off = np.array([0, N], dtype=np.int32)
+        ds, c0, bmax, trk_of, trk_off = self._track_tables(n, overrides, perm)
         t_pack = _time.perf_counter() - t_begin
         f64, i32 = torch.float64, torch.int32
         args = (self._upload('P', P, f64, dev), self._upload('nint', np.full(n, N, np.int32), i32, dev), self._upload('trk_of', trk_of, i32, dev),
@@ -428,21 +462,33 @@ class casadiSolver():
         tm = presolve.tmin_dev if presolve is not None else None
         t_up = _time.perf_counter() - t_begin
         buf = self._device_out('solve', n, dev, want_multipliers)
-        if pooled:
-            out = self._ensure_pool(dev).solve(*args, tmin=tm, want_lam=want_multipliers, parts=parts, out=buf)
-            back = torch.from_numpy(np.argsort(perm)).to(dev)
-            ordered = self._device_out('ordered', n, dev, want_multipliers)
-            for k, v in ordered.items():
-                if v is not None:
-                    torch.index_select(out[k], 0, back, out=v)
-            out = dict(out, **{k: v for k, v in ordered.items() if v is not None})
-        else:
-            out = self._ensure_handle().solve_device(*args, want_z=True, want_lam=want_multipliers, tmin=tm, out=buf)
-        t_solve = _time.perf_counter() - t_begin
-        if presolve is not None:
-            tmin = presolve.join()
-            if perm is not None:
-                tmin = tmin[np.argsort(perm)]
+        back = self._upload('back', np.argsort(perm), torch.int64, dev) if pooled else None
+        ordered = self._device_out('ordered', n, dev, want_multipliers) if pooled else None
+        # ---- concurrent part: the presolve thread and the stream threads of the pool spend their time inside the library (GIL
+        # released), but each needs the GIL for a moment to get there; with the interpreter's default 5 ms switch interval those
+        # hand-overs can cost more than the solve, so it is shortened for the duration of the call
+        import sys
+        interval = sys.getswitchinterval()
+        sys.setswitchinterval(1e-4)
+        try:
+            if presolve is not None and not pooled:
+                presolve.start()
+            if pooled:
+                out = self._ensure_pool(dev).solve(*args, tmin=tm, want_lam=want_multipliers, parts=parts, out=buf,
+                                                   on_started=presolve.start if presolve is not None else None)
+                for k, v in ordered.items():
+                    if v is not None:
+                        torch.index_select(out[k], 0, back, out=v)
+                out = dict(out, **{k: v for k, v in ordered.items() if v is not None})
+            else:
+                out = self._ensure_handle().solve_device(*args, want_z=True, want_lam=want_multipliers, tmin=tm, out=buf)
+            t_solve = _time.perf_counter() - t_begin
+            if presolve is not None:
+                tmin = presolve.join()
+                if perm is not None:
+                    tmin = tmin[np.argsort(perm)]
+        finally:
+            sys.setswitchinterval(interval)
         t_join = _time.perf_counter() - t_begin
         # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
         out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
@@ -478,6 +524,13 @@ class casadiSolver():
         res['tmin'] = tmin
         res['timing'] = dict(pack=t_pack, upload=t_up - t_pack, solve=t_solve - t_up, presolve_join=t_join - t_solve,
                              d2h=_time.perf_counter() - t_begin - t_join)
+        self._last_timing = dict(res['timing'])
+        if presolve is not None:
+            res['timing']['presolve_thread'] = presolve.t_end - presolve.t_start
+            for k, v in getattr(presolve, 'detail', {}).items():
+                res['timing']['presolve_' + k] = v
+        if isinstance(out.get('spans_ms'), list):
+            res['spans_ms'] = out['spans_ms']
         res['wall'] = _time.perf_counter() - t_begin
         scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
         # reference ocp.py:361: cost in kWh (energy) or s (time)
