@@ -844,20 +844,31 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
             g1[i] += gp1 * av[i];
         }
     }
+    // ---- static condensation of s (its pivot H_ss is a sum of barrier terms, > 0, and independent of the value function):
+    // the sweep works on the Schur complement; the column of s is stored next to it for cell_step and the delta_w != 0 path
+    const double hb = H[sidx(V_B, V_SL)], hF = H[sidx(V_FEL, V_SL)], hQ = H[sidx(V_FPB, V_SL)], hss = H[sidx(V_SL, V_SL)];
+    {
+        const double is = rcp(hss);
+        const double eb = hb * is, eF = hF * is, eQ = hQ * is;
+        H[sidx(V_B, V_B)] -= eb * hb; H[sidx(V_B, V_FEL)] -= eb * hF; H[sidx(V_B, V_FPB)] -= eb * hQ;
+        H[sidx(V_FEL, V_FEL)] -= eF * hF; H[sidx(V_FEL, V_FPB)] -= eF * hQ; H[sidx(V_FPB, V_FPB)] -= eQ * hQ;
+        g0[V_B] -= eb * g0[V_SL]; g0[V_FEL] -= eF * g0[V_SL]; g0[V_FPB] -= eQ * g0[V_SL];
+        g1[V_B] -= eb * g1[V_SL]; g1[V_FEL] -= eF * g1[V_SL]; g1[V_FPB] -= eQ * g1[V_SL];
+    }
     // ---- store
     c.W(WS_QP + QP_H_TT, k, s) = H[sidx(V_T, V_T)];
     c.W(WS_QP + QP_H_BB, k, s) = H[sidx(V_B, V_B)];
     c.W(WS_QP + QP_H_BFEL, k, s) = H[sidx(V_B, V_FEL)];
     c.W(WS_QP + QP_H_BFPB, k, s) = H[sidx(V_B, V_FPB)];
-    c.W(WS_QP + QP_H_BSL, k, s) = H[sidx(V_B, V_SL)];
+    c.W(WS_QP + QP_H_BSL, k, s) = hb;
     c.W(WS_QP + QP_H_FF, k, s) = H[sidx(V_F, V_F)];
     c.W(WS_QP + QP_H_FFEL, k, s) = H[sidx(V_F, V_FEL)];
     c.W(WS_QP + QP_H_FELFEL, k, s) = H[sidx(V_FEL, V_FEL)];
     c.W(WS_QP + QP_H_FELFPB, k, s) = H[sidx(V_FEL, V_FPB)];
-    c.W(WS_QP + QP_H_FELSL, k, s) = H[sidx(V_FEL, V_SL)];
+    c.W(WS_QP + QP_H_FELSL, k, s) = hF;
     c.W(WS_QP + QP_H_FPBFPB, k, s) = H[sidx(V_FPB, V_FPB)];
-    c.W(WS_QP + QP_H_FPBSL, k, s) = H[sidx(V_FPB, V_SL)];
-    c.W(WS_QP + QP_H_SLSL, k, s) = H[sidx(V_SL, V_SL)];
+    c.W(WS_QP + QP_H_FPBSL, k, s) = hQ;
+    c.W(WS_QP + QP_H_SLSL, k, s) = hss;
     c.W(WS_QP + QP_TAU_B, k, s) = tau.g0;
     c.W(WS_QP + QP_TAU_F, k, s) = tau.g1;
     c.W(WS_QP + QP_PHI_B, k, s) = phi.g0;

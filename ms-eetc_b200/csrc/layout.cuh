@@ -35,12 +35,17 @@ enum ItField {
 enum StField { ST_FEL = 0, ST_FPB, ST_SL, ST_T, ST_B, ST_W, ST_YT = ST_W + NROW, ST_YB, ST_YD, ST_N = ST_YD + NROW };
 // ---- stage QP produced by the interval kernel, consumed by the Riccati sweeps
 enum QpField {
-    // folded stage Hessian over (t,b,f | Fel,Fpb,sl); only structurally non-zero entries
-    QP_H_TT = 0, QP_H_BB, QP_H_BFEL, QP_H_BFPB, QP_H_BSL, QP_H_FF, QP_H_FFEL, QP_H_FELFEL, QP_H_FELFPB,
-    QP_H_FELSL, QP_H_FPBFPB, QP_H_FPBSL, QP_H_SLSL,
+    // folded stage Hessian over (t,b,f | Fel,Fpb), structurally non-zero entries only, with the loss-epigraph variable s already
+    // eliminated (static condensation in cell_eval: s couples to nothing across intervals and its pivot does not depend on
+    // the value function, so the sweep carries two controls instead of three)
+    QP_H_TT = 0, QP_H_BB, QP_H_BFEL, QP_H_BFPB, QP_H_FF, QP_H_FFEL, QP_H_FELFEL, QP_H_FELFPB, QP_H_FPBFPB,
     QP_TAU_B, QP_TAU_F, QP_PHI_B, QP_PHI_F, QP_RT, QP_RB,          // linearised coupling rows
-    QP_G0_B, QP_G0_F, QP_G0_FEL, QP_G0_FPB, QP_G0_SL,              // gradient, mu-independent part
-    QP_G1_T, QP_G1_B, QP_G1_FEL, QP_G1_FPB, QP_G1_SL,              // gradient, coefficient of mu
+    QP_G0_B, QP_G0_F, QP_G0_FEL, QP_G0_FPB,                        // condensed gradient, mu-independent part
+    QP_G1_T, QP_G1_B, QP_G1_FEL, QP_G1_FPB,                        // condensed gradient, coefficient of mu
+    QP_SWEEP_N,                                                     // the backward sweep reads the fields above
+    // column of s: Hessian entries (b,s), (Fel,s), (Fpb,s), (s,s) and its gradient parts; needed to recover d s (cell_step),
+    // when the regularisation delta_w is non-zero, and by the dense algebra of the last interval
+    QP_H_BSL = QP_SWEEP_N, QP_H_FELSL, QP_H_FPBSL, QP_H_SLSL, QP_G0_SL, QP_G1_SL,
     QP_HC_B, QP_HC_FEL, QP_HC_FPB, QP_HC_SL, QP_HPP, QP_GP0, QP_GP1,   // terms in b_{k+1} (for multiplier recovery)
     QP_J_P0_B, QP_J_P0_FEL, QP_J_P1_FEL, QP_J_P1_BN, QP_J_ACC_B,   // inequality row gradients
     QP_J_LTR_FEL, QP_J_LTR_B, QP_J_LTR_BN, QP_J_LRG_FEL, QP_J_LRG_B, QP_J_LRG_BN,

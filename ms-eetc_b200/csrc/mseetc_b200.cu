@@ -440,8 +440,8 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
         case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
         case CLS_DECIDE: return 8.0 * 4;
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13));
-        case CLS_STEP:   return 8.0 * (BwdFields::NF + RIC_N + FwdFields::NF + 5);
-        case CLS_CSTEP:  return 8.0 * ((7 + 3 + iter + 11 + rows + 2 + 7 + 9) + (2 * rows + 2 + 3));
+        case CLS_STEP:   return 8.0 * (BwdFields::NF + 17 + FwdFields::NF + 4);      // factors written: K 6, kf 2, P 6, p 3
+        case CLS_CSTEP:  return 8.0 * ((6 + 3 + iter + 11 + rows + 2 + 7 + 6 + 9) + (2 * rows + 3 + 3));
         case CLS_ALPHA:  return 8.0 * 3;
         case CLS_KKT:    return 8.0 * 14;
         default:         return 0.0;

@@ -180,7 +180,9 @@ MS_HD bool pit_phase_a(const Ctx& c, int s, int kLo, int kHi, double mu, double 
         double v[BwdFields::NF];
         fetch.get(c, k, s, v);
         StageQP q;
-        stage_build(v, mu, delta, pn, false, q);
+        double vs[6];
+        load_scol(c, k, s, vs);
+        stage_build(v, vs, mu, delta, pn, false, q);
         Elem e;
         if (!elem_from_stage(q, e)) return false;
         if (!have) { E = e; have = true; }

@@ -23,15 +23,17 @@ namespace mseetc {
 // With the tiled layout every field of interval k of one instance is  record(k) + compile-time offset, and the record
 // of k+1 follows at a compile-time stride, so the address arithmetic of a sweep is one pointer bump per interval.
 enum { REC_STRIDE = WS_FIELDS * 32 };
-struct BwdFields {   // folded stage Hessian (13), linearised coupling rows (6), gradient parts (5 + 5)
-    enum { NF = 29 };
+struct BwdFields {   // condensed stage Hessian (9), linearised coupling rows (6), condensed gradient parts (4 + 4)
+    enum { NF = QP_SWEEP_N };
     static MS_HD constexpr int off(int f) { return (WS_QP + f) * 32; }
 };
-struct FwdFields {   // K, k (12) | linearised coupling rows (6)
-    enum { NF = 18 };
-    static MS_HD constexpr int off(int f) { return f < 12 ? (WS_RIC + f) * 32 : (WS_QP + QP_TAU_B + (f - 12)) * 32; }
+struct FwdFields {   // feedback rows of Fel, Fpb (6 + 2) | linearised coupling rows (6)
+    enum { NF = 14 };
+    static MS_HD constexpr int off(int f) {
+        return f < 6 ? (WS_RIC + RIC_K + f) * 32 : f < 8 ? (WS_RIC + RIC_KF + (f - 6)) * 32 : (WS_QP + QP_TAU_B + (f - 8)) * 32;
+    }
 };
-enum { RING_NF_MAX = 29 };
+enum { RING_NF_MAX = QP_SWEEP_N };
 
 // direct loads (host emulation, and the device when no ring is configured)
 template <class FL>
@@ -92,27 +94,36 @@ struct StageQP {
     double pb, pF, rb;        // Phi_b, Phi_F, b residual (needed by the terminal-speed elimination)
 };
 
-MS_HD void stage_build(const double* v, double mu, double delta, double pn, bool last, StageQP& q) {
+// column of s of interval k (see QpField)
+MS_HD void load_scol(const Ctx& c, int k, int s, double* vs) {
+    const double* q = &c.W(WS_QP + QP_H_BSL, k, s);
+    for (int i = 0; i < 6; ++i) vs[i] = q[i * 32];
+}
+
+// dense stage QP over (t,b,f | Fel,Fpb,s): the condensation of s is undone (v holds the condensed entries, vs the column of s)
+MS_HD void stage_build(const double* v, const double* vs, double mu, double delta, double pn, bool last, StageQP& q) {
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) q.M[i][j] = 0.0;
+    const double hb = vs[0], hF = vs[1], hQ = vs[2], hss = vs[3], mS = vs[4] + mu * vs[5];
+    const double is = rcp(hss);
     q.M[0][0] = v[QP_H_TT] + delta;
-    q.M[1][1] = v[QP_H_BB] + delta;
-    q.M[1][3] = q.M[3][1] = v[QP_H_BFEL];
-    q.M[1][4] = q.M[4][1] = v[QP_H_BFPB];
-    q.M[1][5] = q.M[5][1] = v[QP_H_BSL];
+    q.M[1][1] = v[QP_H_BB] + hb * hb * is + delta;
+    q.M[1][3] = q.M[3][1] = v[QP_H_BFEL] + hb * hF * is;
+    q.M[1][4] = q.M[4][1] = v[QP_H_BFPB] + hb * hQ * is;
+    q.M[1][5] = q.M[5][1] = hb;
     q.M[2][2] = v[QP_H_FF];
     q.M[2][3] = q.M[3][2] = v[QP_H_FFEL];
-    q.M[3][3] = v[QP_H_FELFEL] + delta;
-    q.M[3][4] = q.M[4][3] = v[QP_H_FELFPB];
-    q.M[3][5] = q.M[5][3] = v[QP_H_FELSL];
-    q.M[4][4] = v[QP_H_FPBFPB] + delta;
-    q.M[4][5] = q.M[5][4] = v[QP_H_FPBSL];
-    q.M[5][5] = v[QP_H_SLSL] + delta;
+    q.M[3][3] = v[QP_H_FELFEL] + hF * hF * is + delta;
+    q.M[3][4] = q.M[4][3] = v[QP_H_FELFPB] + hF * hQ * is;
+    q.M[3][5] = q.M[5][3] = hF;
+    q.M[4][4] = v[QP_H_FPBFPB] + hQ * hQ * is + delta;
+    q.M[4][5] = q.M[5][4] = hQ;
+    q.M[5][5] = hss + delta;
     q.m[0] = mu * v[QP_G1_T];
-    q.m[1] = v[QP_G0_B] + mu * v[QP_G1_B];
+    q.m[1] = v[QP_G0_B] + mu * v[QP_G1_B] + hb * is * mS;
     q.m[2] = v[QP_G0_F];
-    q.m[3] = v[QP_G0_FEL] + mu * v[QP_G1_FEL];
-    q.m[4] = v[QP_G0_FPB] + mu * v[QP_G1_FPB];
-    q.m[5] = v[QP_G0_SL] + mu * v[QP_G1_SL];
+    q.m[3] = v[QP_G0_FEL] + mu * v[QP_G1_FEL] + hF * is * mS;
+    q.m[4] = v[QP_G0_FPB] + mu * v[QP_G1_FPB] + hQ * is * mS;
+    q.m[5] = mS;
     const double tb = v[QP_TAU_B], tF = v[QP_TAU_F];
     q.pb = v[QP_PHI_B]; q.pF = v[QP_PHI_F]; q.rb = v[QP_RB];
     // G = [A B]: rows t, b, f of the next state
@@ -195,93 +206,92 @@ MS_HD bool stage_riccati(StageQP& q, bool last, double pn, double P[3][3], doubl
 
 // Backward Riccati step of a regular interval (k < N-1), exploiting the structure of the stage QP:
 //   t+ = t + tau_b b + tau_F w + rt,   b+ = phi_b b + phi_F w + rb,   f+ = Fel,     w = Fel + pn Fpb
-// and the sparsity of the folded Hessian (QpField lists its non-zero entries).  The control block is factorised as
-// L D L' (no square roots); its pivots are the inertia test.  Same mathematics as stage_build + stage_riccati, about a
-// third of the arithmetic; the sequential sweeps spend most of their time here.
-MS_HD void ldl3_solve(double l10, double l20, double l21, double i0, double i1, double i2,
-                      double r0, double r1, double r2, double& x0, double& x1, double& x2) {
-    const double y1 = r1 - l10 * r0, y2 = r2 - l20 * r0 - l21 * y1;
-    x2 = y2 * i2;
-    x1 = y1 * i1 - l21 * x2;
-    x0 = r0 * i0 - l10 * x1 - l20 * x2;
+// the sparsity of the folded Hessian (QpField lists its non-zero entries) and the condensation of s.  The 2x2 control block
+// is factorised as L D L' (no square roots); its pivots -- together with the pivot of s, H_ss + delta > 0 -- are the inertia
+// test.  `vs` (column of s) is only needed when delta_w != 0: the condensed entries were formed with delta = 0 and are corrected
+// by (1/H_ss - 1/(H_ss + delta)) h h', which keeps IPOPT's "delta on every primal variable" exact.
+MS_HD void ldl2_solve(double l10, double i0, double i1, double r0, double r1, double& x0, double& x1) {
+    x1 = (r1 - l10 * r0) * i1;
+    x0 = r0 * i0 - l10 * x1;
 }
 
-MS_HD bool stage_riccati_sparse(const double* v, double mu, double delta, double pn,
+MS_HD bool stage_riccati_sparse(const double* v, const double* vs, double mu, double delta, double pn,
                                 double P[3][3], double p[3], double K[3][3], double kf[3]) {
     const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F], rt = v[QP_RT], rb = v[QP_RB];
     const double P00 = P[0][0], P01 = P[0][1], P02 = P[0][2], P11 = P[1][1], P12 = P[1][2], P22 = P[2][2];
+    double Hbb = v[QP_H_BB], HbF = v[QP_H_BFEL], HbQ = v[QP_H_BFPB], HFF = v[QP_H_FELFEL], HFQ = v[QP_H_FELFPB], HQQ = v[QP_H_FPBFPB];
+    double gb = v[QP_G0_B] + mu * v[QP_G1_B], gF = v[QP_G0_FEL] + mu * v[QP_G1_FEL], gQ = v[QP_G0_FPB] + mu * v[QP_G1_FPB];
+    if (vs) {
+        const double hb = vs[0], hF = vs[1], hQ = vs[2], hss = vs[3], mS = vs[4] + mu * vs[5];
+        if (!(hss + delta > 0.0)) return false;
+        const double cf = rcp(hss) - rcp(hss + delta);
+        Hbb += hb * hb * cf; HbF += hb * hF * cf; HbQ += hb * hQ * cf;
+        HFF += hF * hF * cf; HFQ += hF * hQ * cf; HQQ += hQ * hQ * cf;
+        gb += hb * mS * cf; gF += hF * mS * cf; gQ += hQ * mS * cf;
+    }
     // P times the b- and w-columns of the transition
     const double y0b = P00 * tb + P01 * pb, y1b = P01 * tb + P11 * pb, y2b = P02 * tb + P12 * pb;
     const double y0w = P00 * tF + P01 * pF, y1w = P01 * tF + P11 * pF, y2w = P02 * tF + P12 * pF;
     const double ww = tF * y0w + pF * y1w, bw = tb * y0w + pb * y1w;
-    // stage Hessian + G' P G, non-zero entries only (t, b, f | F = Fel, Q = Fpb, S = slack)
+    // stage Hessian + G' P G, non-zero entries only (t, b, f | F = Fel, Q = Fpb)
     const double Mtt = v[QP_H_TT] + delta + P00;
     const double Mtb = y0b;
     const double MtF = y0w + P02;
     const double MtQ = pn * y0w;
-    const double Mbb = v[QP_H_BB] + delta + (tb * y0b + pb * y1b);
-    const double MbF = v[QP_H_BFEL] + (bw + y2b);
-    const double MbQ = v[QP_H_BFPB] + pn * bw;
-    const double MbS = v[QP_H_BSL];
+    const double Mbb = Hbb + delta + (tb * y0b + pb * y1b);
+    const double MbF = HbF + (bw + y2b);
+    const double MbQ = HbQ + pn * bw;
     const double Mff = v[QP_H_FF];
     const double MfF = v[QP_H_FFEL];
-    const double MFF = v[QP_H_FELFEL] + delta + (ww + 2.0 * y2w + P22);
-    const double MFQ = v[QP_H_FELFPB] + pn * (ww + y2w);
-    const double MFS = v[QP_H_FELSL];
-    const double MQQ = v[QP_H_FPBFPB] + delta + pn * (pn * ww);
-    const double MQS = v[QP_H_FPBSL];
-    const double MSS = v[QP_H_SLSL] + delta;
+    const double MFF = HFF + delta + (ww + 2.0 * y2w + P22);
+    const double MFQ = HFQ + pn * (ww + y2w);
+    const double MQQ = HQQ + delta + pn * (pn * ww);
     // gradient + G' (P r + p)
     const double pr0 = p[0] + P00 * rt + P01 * rb, pr1 = p[1] + P01 * rt + P11 * rb, pr2 = p[2] + P02 * rt + P12 * rb;
     const double gw = tF * pr0 + pF * pr1;
     const double mt = mu * v[QP_G1_T] + pr0;
-    const double mb = v[QP_G0_B] + mu * v[QP_G1_B] + (tb * pr0 + pb * pr1);
+    const double mb = gb + (tb * pr0 + pb * pr1);
     const double mf = v[QP_G0_F];
-    const double mF = v[QP_G0_FEL] + mu * v[QP_G1_FEL] + (gw + pr2);
-    const double mQ = v[QP_G0_FPB] + mu * v[QP_G1_FPB] + pn * gw;
-    const double mS = v[QP_G0_SL] + mu * v[QP_G1_SL];
+    const double mF = gF + (gw + pr2);
+    const double mQ = gQ + pn * gw;
     // L D L' of the control block
     if (!(MFF > 0.0) || !isfinite(MFF)) return false;
     const double i0 = rcp(MFF);
-    const double l10 = MFQ * i0, l20 = MFS * i0;
+    const double l10 = MFQ * i0;
     const double d1 = MQQ - l10 * MFQ;
     if (!(d1 > 0.0) || !isfinite(d1)) return false;
     const double i1 = rcp(d1);
-    const double u21 = MQS - l20 * MFQ;
-    const double l21 = u21 * i1;
-    const double d2 = MSS - l20 * MFS - l21 * u21;
-    if (!(d2 > 0.0) || !isfinite(d2)) return false;
-    const double i2 = rcp(d2);
     // feedback: Muu [K kf] = -[Mux mu]
-    double x0, x1, x2;
-    ldl3_solve(l10, l20, l21, i0, i1, i2, MtF, MtQ, 0.0, x0, x1, x2);
-    K[0][0] = -x0; K[1][0] = -x1; K[2][0] = -x2;
-    ldl3_solve(l10, l20, l21, i0, i1, i2, MbF, MbQ, MbS, x0, x1, x2);
-    K[0][1] = -x0; K[1][1] = -x1; K[2][1] = -x2;
-    ldl3_solve(l10, l20, l21, i0, i1, i2, MfF, 0.0, 0.0, x0, x1, x2);
-    K[0][2] = -x0; K[1][2] = -x1; K[2][2] = -x2;
-    ldl3_solve(l10, l20, l21, i0, i1, i2, mF, mQ, mS, x0, x1, x2);
-    kf[0] = -x0; kf[1] = -x1; kf[2] = -x2;
+    double x0, x1;
+    ldl2_solve(l10, i0, i1, MtF, MtQ, x0, x1);
+    K[0][0] = -x0; K[1][0] = -x1;
+    ldl2_solve(l10, i0, i1, MbF, MbQ, x0, x1);
+    K[0][1] = -x0; K[1][1] = -x1;
+    ldl2_solve(l10, i0, i1, MfF, 0.0, x0, x1);
+    K[0][2] = -x0; K[1][2] = -x1;
+    ldl2_solve(l10, i0, i1, mF, mQ, x0, x1);
+    kf[0] = -x0; kf[1] = -x1;
+    K[2][0] = K[2][1] = K[2][2] = 0.0; kf[2] = 0.0;     // d s is recovered interval-parallel (cell_step)
     // value function of this node (upper triangle, mirrored)
     P[0][0] = Mtt + MtF * K[0][0] + MtQ * K[1][0];
     P[0][1] = P[1][0] = Mtb + MtF * K[0][1] + MtQ * K[1][1];
     P[0][2] = P[2][0] = MtF * K[0][2] + MtQ * K[1][2];
-    P[1][1] = Mbb + MbF * K[0][1] + MbQ * K[1][1] + MbS * K[2][1];
-    P[1][2] = P[2][1] = MbF * K[0][2] + MbQ * K[1][2] + MbS * K[2][2];
+    P[1][1] = Mbb + MbF * K[0][1] + MbQ * K[1][1];
+    P[1][2] = P[2][1] = MbF * K[0][2] + MbQ * K[1][2];
     P[2][2] = Mff + MfF * K[0][2];
     p[0] = mt + MtF * kf[0] + MtQ * kf[1];
-    p[1] = mb + MbF * kf[0] + MbQ * kf[1] + MbS * kf[2];
+    p[1] = mb + MbF * kf[0] + MbQ * kf[1];
     p[2] = mf + MfF * kf[0];
     return true;
 }
 
 MS_HD void stage_store(const Ctx& c, int k, int s, const double K[3][3], const double kf[3], const double P[3][3], const double p[3]) {
     double* r = &c.W(WS_RIC, k, s);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 2; ++i) {      // feedback rows of Fel and Fpb
         for (int j = 0; j < 3; ++j) r[(RIC_K + 3 * i + j) * 32] = K[i][j];
         r[(RIC_KF + i) * 32] = kf[i];
-        r[(RIC_PV + i) * 32] = p[i];
     }
+    for (int i = 0; i < 3; ++i) r[(RIC_PV + i) * 32] = p[i];
     r[(RIC_P + 0) * 32] = P[0][0]; r[(RIC_P + 1) * 32] = P[0][1]; r[(RIC_P + 2) * 32] = P[0][2];
     r[(RIC_P + 3) * 32] = P[1][1]; r[(RIC_P + 4) * 32] = P[1][2]; r[(RIC_P + 5) * 32] = P[2][2];
 }
@@ -322,8 +332,10 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
     if (k == N - 1) {
         // last interval: terminal speed fixed, Fel eliminated (dense algebra, once per sweep)
         fetch.get(c, k, s, v);
+        double vs[6];
+        load_scol(c, k, s, vs);
         StageQP q;
-        stage_build(v, mu, delta, pn, true, q);
+        stage_build(v, vs, mu, delta, pn, true, q);
         if (!stage_riccati(q, true, pn, P, p, K, kf)) return false;
         if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
@@ -338,7 +350,9 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
     }
     for (; k >= kLo; --k) {
         fetch.get(c, k, s, v);
-        if (!stage_riccati_sparse(v, mu, delta, pn, P, p, K, kf)) return false;
+        double vs[6];
+        if (delta > 0.0) load_scol(c, k, s, vs);
+        if (!stage_riccati_sparse(v, delta > 0.0 ? vs : nullptr, mu, delta, pn, P, p, K, kf)) return false;
         if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
             const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
@@ -365,7 +379,7 @@ MS_HD bool riccati_backward(const Ctx& c, int s, int N, double mu, double delta,
 }
 
 // ---- forward sweep over the intervals kLo .. kHi-1 from d x_{kLo}: primal step ---------------------------------
-// Writes d Fel, d Fpb, d s of interval k and d t, d b of node k+1 into the step planes.  The new coupling-row multipliers
+// Writes d Fel, d Fpb of interval k and d t, d b of node k+1 into the step planes.  d s and the new coupling-row multipliers
 // (costates of the stepped state) need nothing sequential and are evaluated by the interval-parallel cell_step.
 template <class Fetch>
 MS_HD void riccati_forward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch, double dx[3]) {
@@ -377,19 +391,17 @@ MS_HD void riccati_forward_range(const Ctx& c, int s, int N, int kLo, int kHi, d
     for (int k = kLo; k < kHi; ++k, st += REC_STRIDE) {
         double v[FwdFields::NF];
         fetch.get(c, k, s, v);
-        double du[3];
-        for (int i = 0; i < 3; ++i) du[i] = v[9 + i] + v[3 * i + 0] * dx[0] + v[3 * i + 1] * dx[1] + v[3 * i + 2] * dx[2];
-        if (!g.withPn) du[1] = 0.0;
-        const double tb = v[12], tF = v[13], pb = v[14], pF = v[15], rt = v[16], rb = v[17];
-        const double dF = du[0] + du[1];
+        const double du0 = v[6] + v[0] * dx[0] + v[1] * dx[1] + v[2] * dx[2];
+        const double du1 = g.withPn ? v[7] + v[3] * dx[0] + v[4] * dx[1] + v[5] * dx[2] : 0.0;
+        const double tb = v[8], tF = v[9], pb = v[10], pF = v[11], rt = v[12], rb = v[13];
+        const double dF = du0 + du1;
         const double dtn = dx[0] + tb * dx[1] + tF * dF + rt;
         const double dbn = (k + 1 < N) ? pb * dx[1] + pF * dF + rb : 0.0;
-        st[ST_FEL * 32] = du[0];
-        st[ST_FPB * 32] = du[1];
-        st[ST_SL * 32] = du[2];
+        st[ST_FEL * 32] = du0;
+        st[ST_FPB * 32] = du1;
         st[ST_T * 32 + REC_STRIDE] = dtn;
         st[ST_B * 32 + REC_STRIDE] = dbn;
-        dx[0] = dtn; dx[1] = dbn; dx[2] = du[0];
+        dx[0] = dtn; dx[1] = dbn; dx[2] = du0;
     }
 }
 
@@ -533,37 +545,36 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
     // ---- all loads first, then arithmetic, then all stores (loads must not queue behind stores through the same base)
     const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
-    double CI[IT_N], CS[ST_N], QJ[QP_N - QP_HC_B], RP[9];
+    double CI[IT_N], CS[ST_N], QJ[QP_N - QP_H_BSL], RP[9];
     {
         const double* ip = &c.W(it, k, s);
         const double* sp = &c.W(WS_ST, k, s);
-        const double* qp = &c.W(WS_QP + QP_HC_B, k, s);
+        const double* qp = &c.W(WS_QP + QP_H_BSL, k, s);
         const double* rp = &c.W(WS_RIC + RIC_P, kn, s);       // value function of the next node: P (tt,tb,tf,bb,bf,ff), p
 #pragma unroll
         for (int f = 0; f < IT_N; ++f) CI[f] = ip[f * 32];
 #pragma unroll
         for (int f = 0; f < ST_N; ++f) CS[f] = sp[f * 32];
 #pragma unroll
-        for (int f = 0; f < QP_N - QP_HC_B; ++f) QJ[f] = qp[f * 32];
+        for (int f = 0; f < QP_N - QP_H_BSL; ++f) QJ[f] = qp[f * 32];
 #pragma unroll
         for (int f = 0; f < 9; ++f) RP[f] = rp[f * 32];
     }
     const double dbn = c.W(WS_ST + ST_B, kn, s), dtn = c.W(WS_ST + ST_T, kn, s);
     // last interval only: b_N is fixed, the multiplier of its row follows from stationarity w.r.t. Fel (see below)
-    double LQ[9] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0};
+    double LQ[8] = {0, 0, 0, 0, 0, 0, 0, 1.0};
     if (k == N - 1) {
         const double* q = &c.W(WS_QP, k, s);
         LQ[0] = q[QP_G0_FEL * 32]; LQ[1] = q[QP_G1_FEL * 32]; LQ[2] = q[QP_H_BFEL * 32]; LQ[3] = q[QP_H_FFEL * 32];
-        LQ[4] = q[QP_H_FELFEL * 32]; LQ[5] = q[QP_H_FELFPB * 32]; LQ[6] = q[QP_H_FELSL * 32]; LQ[7] = q[QP_TAU_F * 32];
-        LQ[8] = q[QP_PHI_F * 32];
+        LQ[4] = q[QP_H_FELFEL * 32]; LQ[5] = q[QP_H_FELFPB * 32]; LQ[6] = q[QP_TAU_F * 32]; LQ[7] = q[QP_PHI_F * 32];
     }
     const double pFel = c.W(it + IT_FEL, km, s), pDFel = c.W(WS_ST + ST_FEL, km, s);
     const double dsk = c.W(WS_TRK + TRK_DS, k, s);
     const Bnd B = load_bounds(c, k, s);
     const double mu = c.D(SD_MU, s), tauF = c.D(SD_TAU, s), scale = c.P(P_SCALE, s);
-#define MS_QJ(F) QJ[(F) - QP_HC_B]
+#define MS_QJ(F) QJ[(F) - QP_H_BSL]
     Ftb f{1.0, 1.0, 0.0};
-    double OW[NROW], OYD[NROW], oyt = 0.0, oyb = 0.0;
+    double OW[NROW], OYD[NROW], oyt = 0.0, oyb = 0.0, ods = 0.0;
 #pragma unroll
     for (int j = 0; j < NROW; ++j) { OW[j] = 0.0; OYD[j] = 0.0; }
     const double dt = CS[ST_T], db = CS[ST_B];
@@ -578,7 +589,14 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
         }
     }
     if (k < N) {
-        const double du0 = CS[ST_FEL], du1 = CS[ST_FPB], du2 = CS[ST_SL];
+        const double du0 = CS[ST_FEL], du1 = CS[ST_FPB];
+        // d s from its own stationarity row (s was eliminated from the stage QP before the sweep):
+        //   (H_ss + delta) ds + H_bs db + H_Fs dFel + H_Qs dFpb + g_s = 0
+        const double delta = c.D(SD_DELTA, s);
+        const double sX = MS_QJ(QP_G0_SL) + mu * MS_QJ(QP_G1_SL) + MS_QJ(QP_H_BSL) * db + MS_QJ(QP_H_FELSL) * du0 + MS_QJ(QP_H_FPBSL) * du1;
+        const double isd = rcp(MS_QJ(QP_H_SLSL) + delta);
+        const double du2 = -sX * isd;
+        ods = du2;
         const double fel = CI[IT_FEL], fpb = CI[IT_FPB], sl = CI[IT_SL];
         // new coupling-row multipliers = minus the costates of the stepped state: gradient of the value function of the
         // backward sweep at node k+1, plus the terms of this interval that depend on b_{k+1} directly
@@ -590,8 +608,10 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
                 + MS_QJ(QP_HPP) * dbn + MS_QJ(QP_GP0) + mu * MS_QJ(QP_GP1);
         } else {
             const double dfk = (k >= 1) ? pDFel : 0.0;        // d f_k = d Fel_{k-1}
-            const double gF = LQ[0] + mu * LQ[1] + LQ[2] * db + LQ[3] * dfk + (LQ[4] + c.D(SD_DELTA, s)) * du0 + LQ[5] * du1 + LQ[6] * du2;
-            pib = -(gF + LQ[7] * pit) / LQ[8];
+            // stationarity w.r.t. Fel in the condensed entries; the last term vanishes unless delta_w != 0
+            const double gF = LQ[0] + mu * LQ[1] + LQ[2] * db + LQ[3] * dfk + (LQ[4] + delta) * du0 + LQ[5] * du1
+                            + MS_QJ(QP_H_FELSL) * sX * (rcp(MS_QJ(QP_H_SLSL)) - isd);
+            pib = -(gF + LQ[6] * pit) / LQ[7];
         }
         oyt = -pit - CI[IT_YT];
         oyb = -pib - CI[IT_YB];
@@ -642,6 +662,7 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     }
 #undef MS_QJ
     if (k < N) {
+        c.W(WS_ST + ST_SL, k, s) = ods;
         c.W(WS_ST + ST_YT, k, s) = oyt;
         c.W(WS_ST + ST_YB, k, s) = oyb;
 #pragma unroll
