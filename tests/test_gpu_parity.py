@@ -312,6 +312,35 @@ def test_stream_pool_is_bitwise_identical_to_single_stream(cabi):
         assert np.array_equal(a[key], b[key]), key
 
 
+def test_pooled_batch_with_overrides_and_screening_matches_single_stream(cabi):
+    """Per-instance parameters, per-instance track tables (rho) and screening through the tile-interleaved two-stream path give
+    the same results, in the caller's order, as one stream; trips below their own minimum time are reported infeasible."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    opts = {'numIntervals': 200, 'maxIterations': 500, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    rng = np.random.default_rng(5)
+    n = 1100
+    ov = dict(mass=391000 * rng.uniform(0.85, 1.15, n), r0=train.r0 * rng.uniform(0.8, 1.2, n), rho=rng.uniform(1.04, 1.08, n),
+              etaTraction=rng.uniform(0.80, 0.92, n))
+    T = rng.uniform(1300.0, 1700.0, n)            # the minimum time on this track is about 1470 s: a third is infeasible
+    res = {}
+    for streams in (1, 2):
+        solver = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), opts)
+        solver.streams = streams
+        res[streams] = solver.solve_batch(T, overrides=ov)
+    a, b = res[1], res[2]
+    assert np.array_equal(a['status'], b['status']) and np.array_equal(a['tmin'], b['tmin'])
+    ok = a['status'] == 0
+    assert ok.sum() > 500 and (a['status'] == 4).sum() > 200
+    for key in ('z', 'obj', 'kkt', 'iters'):
+        assert np.array_equal(a[key][ok], b[key][ok]), key
+    assert np.all(a['kkt'][ok] <= 1e-8)
+    feasible = T >= a['tmin'] * (1 - 1e-9)
+    assert np.all(ok[feasible]) and np.all(a['status'][~feasible] == 4)
+
+
 def test_solve_instances_mixed_tracks_and_interval_counts(cabi):
     "BASELINE config 5 in miniature: random tracks, mixed numIntervals, one device call; oracle spot check."
     from mseetc.ocp import casadiSolver, solve_instances
