@@ -332,10 +332,22 @@ def run_gpu(args):
         tj = json.load(open(tfile))
         ncu_traffic = tj.get(top)
         capture = (tj.get('captures_r01_q') or {}).get(top)
+    # FP64 view (report both candidates): static FP64 operation counts per cell (profiles/fp64_ops.json, from the SASS
+    # of this build) against the DFMA throughput measured on this device
+    fp64 = None
+    ofile = os.path.join(ROOT, 'profiles', 'fp64_ops.json')
+    if os.path.exists(ofile):
+        ops = json.load(open(ofile))
+        peak64 = _cabi.measure_fp64_peak()
+        fp64 = {'peak_gflops': peak64, 'peak_source': 'measured here (k_fp64_peak: independent DFMA chains, CUDA events)', 'kernels': {}}
+        for k, v in kern.items():
+            if k in ops and v['ms_total'] > 0:
+                gf = v['cells'] * ops[k]['flop_per_cell'] / (v['ms_total'] * 1e-3) / 1e9
+                fp64['kernels'][k] = {'flop_per_cell': ops[k]['flop_per_cell'], 'achieved_gflops': gf, 'frac_fp64': gf / peak64}
     roofline = {'bound': 'hbm', 'kernel': top, 'achieved': kern[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
                 'frac': kern[top]['achieved_gbs'] / peak, 'traffic': ncu_traffic, 'traffic_capture': capture, 'peak_source': peak_src,
                 'share_of_device_time': kern[top]['ms_total'] / max(1e-12, sum(v['ms_total'] for v in kern.values())),
-                'bytes_per_launch': kern[top]['cells'] * kern[top]['bytes_per_cell'] / kern[top]['launches'], 'kernels': kern,
+                'bytes_per_launch': kern[top]['cells'] * kern[top]['bytes_per_cell'] / kern[top]['launches'], 'kernels': kern, 'fp64': fp64,
                 'presolve': {'ms_total': sum(v['ms'] for v in prof_pre.values()), 'launches': sum(v['launches'] for v in prof_pre.values()),
                              'note': 'single-instance time-optimal solve on its own stream, concurrent with the sweep (not in `kernels`)'}}
 

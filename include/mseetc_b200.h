@@ -161,6 +161,10 @@ double mseetc_bytes_per_cell(mseetc_handle h, int kernel_class);
  * e.g. the first stream of a pool, or `h` itself).  Returns the number of entries written; needs profiling switched on. */
 int mseetc_last_timeline(mseetc_handle h, mseetc_handle origin, double* out, int32_t max_entries);
 
+/* Measurement aid (the FP64 roofline denominator is not in MEASURED_PEAKS.json): sustained DFMA throughput of the
+ * current device in GFLOP/s (FMA = 2), from a kernel of independent FMA chains timed with CUDA events on the given stream. */
+int mseetc_measure_fp64_peak(double* gflops_out, void* cuda_stream);
+
 /* One shooting interval for n points (train.py:347-364): tau = t1 - t0 and b1, with first and second
  * sensitivities w.r.t. (b0, F).  in_dev planes [7*n]: b0, F, ds, c0, sr0, sr1, sr2; out_dev planes [12*n]:
  * tau, dtau/db, dtau/dF, d2tau/dbb, d2tau/dbF, d2tau/dFF, then the same six for b1. */

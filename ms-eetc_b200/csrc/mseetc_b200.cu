@@ -288,6 +288,21 @@ __global__ void k_eval_loss_rows(LossMapDev lm, int n, const double* in, const d
     eval_loss_rows_point(lm, i, n, in, par, out);
 }
 
+// FP64 roofline denominator: 16 independent DFMA chains per thread, enough resident warps to keep the pipe full
+__global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = a + 1e-3 * (threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fma(x[i], b, a);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc += x[i];
+    if (acc == 12345.678) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;      // never true: keeps the chains alive
+}
+
 __global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     eval_interval_point(i, n, numSteps, numApprox, in, out);
@@ -627,6 +642,37 @@ int mseetc_last_timeline(mseetc_handle h, mseetc_handle origin, double* out, int
         out[3 * n] = (double)h->ev_class[i]; out[3 * n + 1] = (double)a; out[3 * n + 2] = (double)b;
     }
     return n;
+}
+
+int mseetc_measure_fp64_peak(double* gflops_out, void* cuda_stream) {
+    if (!gflops_out) return fail(-1, "mseetc_measure_fp64_peak: null argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = nsm * 8, threads = 256, iters = 20000;
+    double* sink = nullptr;
+    cudaError_t e = cudaMalloc((void**)&sink, sizeof(double) * (size_t)blocks * threads);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {        // first pass is the warm-up
+        cudaEventRecord(a, st);
+        k_fp64_peak<<<blocks, threads, 0, st>>>(sink, iters, 1.0000001, 0.9999999);
+        cudaEventRecord(b, st);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double gf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e9;
+        if (rep > 0 && gf > best) best = gf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(sink);
+    if (e != cudaSuccess) return cuda_fail(e, "k_fp64_peak");
+    *gflops_out = best;
+    return 0;
 }
 
 int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out, void* cuda_stream) {

@@ -59,6 +59,7 @@ def lib():
     L.mseetc_last_profile.argtypes = [vp, vp, vp, vp]
     L.mseetc_bytes_per_cell.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_timeline.argtypes = [vp, vp, vp, i32]
+    L.mseetc_measure_fp64_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
     L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
@@ -281,6 +282,14 @@ def last_profile(handle):
     _check(lib().mseetc_last_profile(handle._h, ms, la, ce), 'mseetc_last_profile')
     return {name: dict(ms=ms[i], launches=la[i], cells=ce[i], bytes_per_cell=lib().mseetc_bytes_per_cell(handle._h, i))
             for i, name in enumerate(KERNEL_CLASSES)}
+
+
+def measure_fp64_peak():
+    "Sustained DFMA throughput of the current device in GFLOP/s (roofline denominator of the FP64 pipe)."
+    torch = _torch_cuda()
+    out = ctypes.c_double(0.0)
+    _check(lib().mseetc_measure_fp64_peak(ctypes.byref(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'mseetc_measure_fp64_peak')
+    return out.value
 
 
 def last_timeline(handle, origin=None, max_entries=4096):
