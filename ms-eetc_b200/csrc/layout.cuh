@@ -52,8 +52,8 @@ enum QpField {
     QP_RES,                                                         // QP_RES + Row : d_j(x) - w_j
     QP_N = QP_RES + NROW
 };
-// ---- Riccati factors
-enum RicField { RIC_K = 0, RIC_KF = 9, RIC_P = 12, RIC_PV = 18, RIC_N = 21 };
+// ---- Riccati factors: feedback rows of Fel and Fpb (2 x 3), their constant parts (2), value function P (6, upper triangle), p (3)
+enum RicField { RIC_K = 0, RIC_KF = 6, RIC_P = 8, RIC_PV = 14, RIC_N = 17 };
 // ---- per-interval partial sums (reduced sequentially per instance: deterministic)
 enum PartField {
     PT_TH = 0, PT_F, PT_SLOG, PT_SDAMP,          // trial point: constraint violation, objective, barrier sums

@@ -126,15 +126,39 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
 
 // Riccati sweeps: one thread per instance, stage data prefetched `depth` intervals ahead through a cp.async ring
 // in dynamic shared memory ((depth+1) * RING_NF_MAX * blockDim doubles).
-template <int BS, int DEPTH>
+// BULK = true (experiment, MSEETC_STEP_BULK=1): tiles whose running instances share one interval count fetch their stage data
+// with bulk copies of the TMA unit (cp.async.bulk + mbarrier, BulkRing) instead of per-lane cp.async.  Measured on B200:
+// 244 us per launch against 178 us -- in this one-warp, latency-bound recursion the mbarrier wait and the warp barrier per
+// interval cost more than the 23 + 14 LDGSTS they replace -- so the per-lane ring is the default.
+template <int BS, int DEPTH, bool BULK>
 __global__ void __launch_bounds__(BS) k_step(Ctx c) {
-    extern __shared__ double ring[];
+    extern __shared__ __align__(128) double ring[];
     const int s = blockIdx.x * BS + threadIdx.x;
     if (s >= c.cfg.S) return;
-    RingFetch<BwdFields, BS, DEPTH> fb;
-    fb.sm = ring + threadIdx.x;
-    RingFetch<FwdFields, BS, DEPTH> ff;
-    ff.sm = ring + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool active = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_FACTOR;
+    double* wring = ring + (size_t)warp * ((DEPTH + 1) * RING_NF_MAX * 32);
+    if (BULK) {
+        const unsigned mask = __ballot_sync(0xffffffffu, active);
+        if (!active) return;
+        const int N = c.I(SI_N_INT, s);
+        if (__all_sync(mask, N == __shfl_sync(mask, N, __ffs((int)mask) - 1))) {
+            unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring + (size_t)(BS / 32) * ((DEPTH + 1) * RING_NF_MAX * 32))
+                                       + (size_t)warp * 2 * (DEPTH + 1);
+            BulkRing<BwdFields, DEPTH> fb;
+            BulkRing<FwdFields, DEPTH> ff;
+            fb.setup(wring, bars, mask, lane);
+            ff.setup(wring, bars + (DEPTH + 1), mask, lane);
+            inst_step_warp(c, s, mask, fb, ff);
+            return;
+        }
+    }
+    if (!active) return;
+    // every lane prefetches its own intervals (cp.async, one column per lane): works for mixed interval counts inside a tile
+    RingFetch<BwdFields, 32, DEPTH> fb;
+    fb.sm = wring + lane;
+    RingFetch<FwdFields, 32, DEPTH> ff;
+    ff.sm = wring + lane;
     inst_step(c, s, fb, ff);
 }
 
@@ -524,14 +548,16 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     int depth = (int)((size_t)200 * 1024 / ((size_t)(blocksPerSm < 1 ? 1 : blocksPerSm) * slotBytes)) - 1;
     // the depth is a compile-time constant of the kernel: largest instantiated value that fits
     void (*stepKernel)(Ctx);
+    static const bool stepBulk = []() { const char* e = getenv("MSEETC_STEP_BULK"); return e && atoi(e) != 0; }();
     if (ib == 32) {
-        if (depth >= 8) { depth = 8; stepKernel = k_step<32, 8>; } else { depth = 4; stepKernel = k_step<32, 4>; }
+        if (depth >= 8) { depth = 8; stepKernel = stepBulk ? k_step<32, 8, true> : k_step<32, 8, false>; }
+        else { depth = 4; stepKernel = k_step<32, 4, false>; }
     } else {
-        if (depth >= 4) { depth = 4; stepKernel = k_step<64, 4>; }
-        else if (depth >= 2) { depth = 2; stepKernel = k_step<64, 2>; }
-        else { depth = 1; stepKernel = k_step<64, 1>; }
+        if (depth >= 4) { depth = 4; stepKernel = k_step<64, 4, false>; }
+        else if (depth >= 2) { depth = 2; stepKernel = k_step<64, 2, false>; }
+        else { depth = 1; stepKernel = k_step<64, 1, false>; }
     }
-    const size_t ringBytes = (size_t)(depth + 1) * slotBytes;
+    const size_t ringBytes = (size_t)(depth + 1) * slotBytes + (size_t)(ib / 32) * 2 * (depth + 1) * sizeof(unsigned long long);
     cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
     int launches = 0;
     cudaError_t e;
