@@ -550,10 +550,27 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
 // filter acceptance                                                         (IPOPT sec. 2.3, eqs. 18-20)
 // ------------------------------------------------------------------------------------------------
 // partial sums of the trial-point quantities over the intervals k = w, w+W, w+2W, ... (ascending)
+// The per-instance reductions read their partial planes MS_RED_U intervals at a time (all loads of a group in flight, then
+// summed in the original order: same bits as a one-by-one loop).
+#define MS_RED_U 4
 MS_HD void trial_partials(const Ctx& c, int s, int N, int w, int W, double* acc) {
     acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
-    for (int k = w; k <= N; k += W)
-        for (int f = 0; f < 4; ++f) acc[f] += c.W(WS_PART + PT_TH + f, k, s);
+    for (int k0 = w; k0 <= N; k0 += MS_RED_U * W) {
+        double v[MS_RED_U][4];
+#pragma unroll
+        for (int u = 0; u < MS_RED_U; ++u) {
+            const int k = k0 + u * W;
+            if (k <= N) {
+                const double* q = &c.W(WS_PART + PT_TH, k, s);
+#pragma unroll
+                for (int f = 0; f < 4; ++f) v[u][f] = q[f * 32];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MS_RED_U; ++u)
+            if (k0 + u * W <= N)
+                for (int f = 0; f < 4; ++f) acc[f] += v[u][f];
+    }
 }
 
 MS_HD void inst_decide(const Ctx& c, int s, const double* sums) {

@@ -41,6 +41,7 @@ enum { RING_NF_MAX = QP_SWEEP_N };
 // direct loads (host emulation, and the device when no ring is configured)
 template <class FL>
 struct DirectFetch {
+    enum { COLLECTIVE = 0 };
     MS_HD void start(const Ctx&, int, int, int, int) {}
     MS_HD void get(const Ctx& c, int k, int s, double* v) {
         const double* rec = &c.W(0, k, s);
@@ -55,6 +56,7 @@ struct DirectFetch {
 // global record pointer are running counters (no division, one pointer bump per interval).
 template <class FL, int BS, int DEPTH>
 struct RingFetch {
+    enum { COLLECTIVE = 0 };
     double* sm;          // this thread's column of slot 0
     const double* next;  // record of the next interval to request
     int left;            // intervals not yet requested
@@ -117,6 +119,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 template <class FL, int DEPTH>
 struct BulkRing {
+    enum { COLLECTIVE = 1 };    // all running lanes of the warp must consume every requested interval
     double* sm;                 // ring of this warp: slot stride FL::NF * 32 doubles, field-major, lane-minor
     unsigned long long* bar;    // DEPTH + 1 mbarriers of this warp and this field list
     const double* next;         // (tile, k) record of the next interval to request
@@ -295,12 +298,14 @@ MS_HD bool stage_riccati(StageQP& q, bool last, double pn, double P[3][3], doubl
 // Backward Riccati step of a regular interval (k < N-1), exploiting the structure of the stage QP:
 //   t+ = t + tau_b b + tau_F w + rt,   b+ = phi_b b + phi_F w + rb,   f+ = Fel,     w = Fel + pn Fpb
 // the sparsity of the folded Hessian (QpField lists its non-zero entries) and the condensation of s.  The 2x2 control block
-// is factorised as L D L' (no square roots); its pivots -- together with the pivot of s, H_ss + delta > 0 -- are the inertia
-// test.  `vs` (column of s) is only needed when delta_w != 0: the condensed entries were formed with delta = 0 and are corrected
+// is inverted through its leading entry and its determinant (no square roots); their signs -- together with the pivot of s,
+// H_ss + delta > 0 -- are the inertia test.  `vs` (column of s) is only needed when delta_w != 0: the condensed entries were formed with delta = 0 and are corrected
 // by (1/H_ss - 1/(H_ss + delta)) h h', which keeps IPOPT's "delta on every primal variable" exact.
-MS_HD void ldl2_solve(double l10, double i0, double i1, double r0, double r1, double& x0, double& x1) {
-    x1 = (r1 - l10 * r0) * i1;
-    x0 = r0 * i0 - l10 * x1;
+// x = C^{-1} r for the 2x2 control block C = [[a, b], [b, d]] with i0 = 1/a and idet = 1/(a d - b^2): the two reciprocals do
+// not depend on each other (shorter dependent chain than pivot-after-pivot), a > 0 and det > 0 are the inertia test
+MS_HD void sym2_solve(double a, double b, double i0, double idet, double r0, double r1, double& x0, double& x1) {
+    x1 = (a * r1 - b * r0) * idet;
+    x0 = (r0 - b * x1) * i0;
 }
 
 MS_HD bool stage_riccati_sparse(const double* v, const double* vs, double mu, double delta, double pn,
@@ -331,7 +336,7 @@ MS_HD bool stage_riccati_sparse(const double* v, const double* vs, double mu, do
     const double MbQ = HbQ + pn * bw;
     const double Mff = v[QP_H_FF];
     const double MfF = v[QP_H_FFEL];
-    const double MFF = HFF + delta + (ww + 2.0 * y2w + P22);
+    const double MFF = ww + (2.0 * y2w + (P22 + (HFF + delta)));
     const double MFQ = HFQ + pn * (ww + y2w);
     const double MQQ = HQQ + delta + pn * (pn * ww);
     // gradient + G' (P r + p)
@@ -342,22 +347,19 @@ MS_HD bool stage_riccati_sparse(const double* v, const double* vs, double mu, do
     const double mf = v[QP_G0_F];
     const double mF = gF + (gw + pr2);
     const double mQ = gQ + pn * gw;
-    // L D L' of the control block
-    if (!(MFF > 0.0) || !isfinite(MFF)) return false;
-    const double i0 = rcp(MFF);
-    const double l10 = MFQ * i0;
-    const double d1 = MQQ - l10 * MFQ;
-    if (!(d1 > 0.0) || !isfinite(d1)) return false;
-    const double i1 = rcp(d1);
+    // control block: positive definite <=> MFF > 0 and det > 0 (the second pivot of L D L' is det / MFF)
+    const double det = MFF * MQQ - MFQ * MFQ;
+    if (!(MFF > 0.0) || !(det > 0.0) || !isfinite(MFF) || !isfinite(det)) return false;
+    const double i0 = rcp(MFF), idet = rcp(det);
     // feedback: Muu [K kf] = -[Mux mu]
     double x0, x1;
-    ldl2_solve(l10, i0, i1, MtF, MtQ, x0, x1);
+    sym2_solve(MFF, MFQ, i0, idet, MtF, MtQ, x0, x1);
     K[0][0] = -x0; K[1][0] = -x1;
-    ldl2_solve(l10, i0, i1, MbF, MbQ, x0, x1);
+    sym2_solve(MFF, MFQ, i0, idet, MbF, MbQ, x0, x1);
     K[0][1] = -x0; K[1][1] = -x1;
-    ldl2_solve(l10, i0, i1, MfF, 0.0, x0, x1);
+    sym2_solve(MFF, MFQ, i0, idet, MfF, 0.0, x0, x1);
     K[0][2] = -x0; K[1][2] = -x1;
-    ldl2_solve(l10, i0, i1, mF, mQ, x0, x1);
+    sym2_solve(MFF, MFQ, i0, idet, mF, mQ, x0, x1);
     kf[0] = -x0; kf[1] = -x1;
     K[2][0] = K[2][1] = K[2][2] = 0.0; kf[2] = 0.0;     // d s is recovered interval-parallel (cell_step)
     // value function of this node (upper triangle, mirrored)
@@ -416,10 +418,11 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
     if (kHi <= kLo) return true;
     fetch.start(c, s, kHi - 1, kLo, -1);
     int k = kHi - 1;
-    // a failed inertia test does not leave the loop: the prefetch ring may be collective over the warp and every requested
-    // interval has to be consumed; the remaining (discarded) stages cost one sweep in the rare regularisation case
+    // with a ring that is collective over the warp a failed inertia test does not leave the loop (every requested interval has
+    // to be consumed; the remaining, discarded stages cost one sweep in the rare regularisation case); otherwise it returns at once
     bool ok = true;
-    double v[BwdFields::NF], K[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, kf[3] = {0, 0, 0};
+    double v[BwdFields::NF], K[3][3], kf[3];
+    if (Fetch::COLLECTIVE) for (int i = 0; i < 3; ++i) { kf[i] = 0.0; for (int j = 0; j < 3; ++j) K[i][j] = 0.0; }
     if (k == N - 1) {
         // last interval: terminal speed fixed, Fel eliminated (dense algebra, once per sweep)
         fetch.get(c, k, s, v);
@@ -427,7 +430,7 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
         load_scol(c, k, s, vs);
         StageQP q;
         stage_build(v, vs, mu, delta, pn, true, q);
-        if (!stage_riccati(q, true, pn, P, p, K, kf)) ok = false;
+        if (!stage_riccati(q, true, pn, P, p, K, kf)) { if (!Fetch::COLLECTIVE) return false; ok = false; }
         if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
             double Mk[9], mk[3];
@@ -443,7 +446,7 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
         fetch.get(c, k, s, v);
         double vs[6];
         if (delta > 0.0) load_scol(c, k, s, vs);
-        if (!stage_riccati_sparse(v, delta > 0.0 ? vs : nullptr, mu, delta, pn, P, p, K, kf)) ok = false;
+        if (!stage_riccati_sparse(v, delta > 0.0 ? vs : nullptr, mu, delta, pn, P, p, K, kf)) { if (!Fetch::COLLECTIVE) return false; ok = false; }
         if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
             const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
@@ -515,20 +518,36 @@ MS_HD void kkt_init(KktAcc& a) {
 }
 MS_HD void kkt_partials(const Ctx& c, int s, int N, int it, int w, int W, KktAcc& a) {
     kkt_init(a);
-    for (int k = w; k <= N; k += W) {
-        a.th += c.W(WS_PART + PC_TH, k, s);
-        a.fo += c.W(WS_PART + PC_F, k, s);
-        a.slog += c.W(WS_PART + PC_SLOG, k, s);
-        a.sdamp += c.W(WS_PART + PC_SDAMP, k, s);
-        a.zsum += c.W(WS_PART + PC_ZSUM, k, s);
-        a.ysum += c.W(WS_PART + PC_YSUM, k, s);
-        a.dinf = fmax(a.dinf, c.W(WS_PART + PC_DINF, k, s));
-        a.pinf = fmax(a.pinf, c.W(WS_PART + PC_PINF, k, s));
-        a.cmin = fmin(a.cmin, c.W(WS_PART + PC_CMIN, k, s));
-        a.cmax = fmax(a.cmax, c.W(WS_PART + PC_CMAX, k, s));
-        if (k >= 1) {   // stationarity w.r.t. the node variables couples interval k-1 and k
-            a.dinf = fmax(a.dinf, fabs(c.W(WS_PART + PC_OWN_T, k, s) + c.W(it + IT_YT, k - 1, s)));
-            if (k < N) a.dinf = fmax(a.dinf, fabs(c.W(WS_PART + PC_OWN_B, k, s) + c.W(WS_PART + PC_CN_B, k - 1, s)));
+    for (int k0 = w; k0 <= N; k0 += MS_RED_U * W) {
+        double v[MS_RED_U][14];
+#pragma unroll
+        for (int u = 0; u < MS_RED_U; ++u) {
+            const int k = k0 + u * W;
+            if (k <= N) {
+                const double* q = &c.W(WS_PART, k, s);
+                v[u][0] = q[PC_TH * 32]; v[u][1] = q[PC_F * 32]; v[u][2] = q[PC_SLOG * 32]; v[u][3] = q[PC_SDAMP * 32];
+                v[u][4] = q[PC_ZSUM * 32]; v[u][5] = q[PC_YSUM * 32]; v[u][6] = q[PC_DINF * 32]; v[u][7] = q[PC_PINF * 32];
+                v[u][8] = q[PC_CMIN * 32]; v[u][9] = q[PC_CMAX * 32];
+                if (k >= 1) {   // stationarity w.r.t. the node variables couples interval k-1 and k
+                    v[u][10] = q[PC_OWN_T * 32]; v[u][11] = c.W(it + IT_YT, k - 1, s);
+                    if (k < N) { v[u][12] = q[PC_OWN_B * 32]; v[u][13] = c.W(WS_PART + PC_CN_B, k - 1, s); }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MS_RED_U; ++u) {
+            const int k = k0 + u * W;
+            if (k <= N) {
+                a.th += v[u][0]; a.fo += v[u][1]; a.slog += v[u][2]; a.sdamp += v[u][3]; a.zsum += v[u][4]; a.ysum += v[u][5];
+                a.dinf = fmax(a.dinf, v[u][6]);
+                a.pinf = fmax(a.pinf, v[u][7]);
+                a.cmin = fmin(a.cmin, v[u][8]);
+                a.cmax = fmax(a.cmax, v[u][9]);
+                if (k >= 1) {
+                    a.dinf = fmax(a.dinf, fabs(v[u][10] + v[u][11]));
+                    if (k < N) a.dinf = fmax(a.dinf, fabs(v[u][12] + v[u][13]));
+                }
+            }
         }
     }
 }
@@ -803,10 +822,19 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
 // ---- step-size limits of one instance and the first trial step size ----------------------------------------
 MS_HD void alpha_partials(const Ctx& c, int s, int N, int w, int W, double* acc) {
     acc[0] = 1.0; acc[1] = 1.0; acc[2] = 0.0;
-    for (int k = w; k <= N; k += W) {
-        acc[0] = fmin(acc[0], c.W(WS_PART + PS_AP, k, s));
-        acc[1] = fmin(acc[1], c.W(WS_PART + PS_AZ, k, s));
-        acc[2] += c.W(WS_PART + PS_GPHID, k, s);
+    for (int k0 = w; k0 <= N; k0 += MS_RED_U * W) {
+        double v[MS_RED_U][3];
+#pragma unroll
+        for (int u = 0; u < MS_RED_U; ++u) {
+            const int k = k0 + u * W;
+            if (k <= N) {
+                const double* q = &c.W(WS_PART + PS_AP, k, s);
+                v[u][0] = q[0]; v[u][1] = q[32]; v[u][2] = q[64];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MS_RED_U; ++u)
+            if (k0 + u * W <= N) { acc[0] = fmin(acc[0], v[u][0]); acc[1] = fmin(acc[1], v[u][1]); acc[2] += v[u][2]; }
     }
 }
 

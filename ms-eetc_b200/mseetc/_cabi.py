@@ -59,7 +59,8 @@ def lib():
     L.mseetc_last_profile.argtypes = [vp, vp, vp, vp]
     L.mseetc_bytes_per_cell.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_timeline.argtypes = [vp, vp, vp, i32]
-    L.mseetc_measure_fp64_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
+    if hasattr(L, 'mseetc_measure_fp64_peak'):      # absent from older builds loaded through MSEETC_B200_LIB (tuning experiments)
+        L.mseetc_measure_fp64_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
     L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
