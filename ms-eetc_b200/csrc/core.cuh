@@ -104,11 +104,14 @@ MS_HD double init_t(const Ctx& c, int j, int s, int N) {
 // Early infeasibility screening (only when the caller asked for screening by passing a tmin plane): a lower bound on the
 // trip duration from the speed envelope at 100 % of the force, power, acceleration and speed limits -- fastest
 // acceleration from b_0, latest braking into b_N, never above the limits.  No admissible run is faster, up to
-// discretisation effects that MS_SCREEN_MARGIN covers, and terminalTime is an upper bound on t_N (ocp.py:260-261): an
+// discretisation effects that MS_SCREEN_MARGIN covers (with piecewise-constant forces b is monotone inside an interval, so
+// the discrete run respects the limits between the nodes too and is a restriction of the continuous problem; what remains
+// are the Euler steps of the envelope and the RK4 / quadrature errors of the NLP, O(1e-4) relative at the usual grids),
+// and terminalTime is an upper bound on t_N (ocp.py:260-261): an
 // instance whose available time is below (1 - margin) * bound is reported infeasible before a single iteration is
 // spent on it.  The exact certificate is the minimum trip time (time-optimal solve, running concurrently); the host
 // layer checks every early flag against it and re-solves an instance without screening should a flag ever be wrong.
-#define MS_SCREEN_MARGIN 0.02
+#define MS_SCREEN_MARGIN 0.01
 // Both per-instance set-up routines below walk the track sequentially (one thread per instance).  Their loops work on chunks
 // of MS_PCH intervals -- all loads of a chunk are issued before the first dependent operation and the results are stored after
 // the last one -- so a pass costs one memory latency per chunk instead of one per interval.
