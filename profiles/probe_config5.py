@@ -30,3 +30,6 @@ for rep in range(2):
     print('energy   wall %.3f ticks %d launches %d status hist %s iters max %d' % (dt, res['ticks'], res['launches'], np.bincount(res['status'], minlength=6).tolist(), res['iters'].max()))
 bad = np.where((res['status'] != 0) & (tres['status'] == 0))[0]
 print('failed energy: iters', res['iters'][bad][:20].tolist(), 'kkt', ['%.1e' % x for x in res['kkt'][bad][:20]])
+tbad = np.where(tres['status'] != 0)[0]
+print('failed time-opt idx', tbad.tolist(), 'N', nint[tbad].tolist(), 'iters', tres['iters'][tbad].tolist(), 'kkt', ['%.1e' % x for x in tres['kkt'][tbad]])
+print('failed energy idx', bad.tolist(), 'status', res['status'][bad].tolist(), 'N', nint[bad].tolist())
