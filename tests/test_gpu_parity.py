@@ -341,6 +341,25 @@ def test_pooled_batch_with_overrides_and_screening_matches_single_stream(cabi):
     assert np.all(ok[feasible]) and np.all(a['status'][~feasible] == 4)
 
 
+def test_early_screening_flags_are_checked_against_the_certificate(cabi, monkeypatch):
+    """The envelope screening of the device (before the first iteration) is only trusted when the exact minimum time confirms
+    it: with a (faked) certificate that calls those trips feasible, the flagged instances are solved again without
+    screening -- they then end as the plain iteration ends on an infeasible problem, not as 'Infeasible_Problem_Detected'."""
+    from mseetc import ocp
+    from mseetc.train import Train
+    from mseetc.track import Track
+    opts = {'numIntervals': 300, 'maxIterations': 120, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    solver = ocp.casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), Track(config={'id': 'CH_StGallen_Wil'}), opts)
+    T = np.array([900.0, 950.0, 1100.0, 1242.0])
+    plain = solver.solve_batch(T)
+    assert list(plain['status']) == [4, 4, 0, 0] and list(plain['iters'][:2]) == [0, 0]
+    real_join = ocp._Presolve.join
+    monkeypatch.setattr(ocp._Presolve, 'join', lambda self: 0.5 * real_join(self))
+    faked = solver.solve_batch(T)
+    assert list(faked['status'][2:]) == [0, 0] and np.array_equal(faked['z'][2:], plain['z'][2:])
+    assert all(st not in (0, 4) for st in faked['status'][:2]) and np.all(faked['iters'][:2] > 0)
+
+
 def test_solve_instances_mixed_tracks_and_interval_counts(cabi):
     "BASELINE config 5 in miniature: random tracks, mixed numIntervals, one device call; oracle spot check."
     from mseetc.ocp import casadiSolver, solve_instances
