@@ -557,7 +557,17 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         else if (depth >= 2) { depth = 2; stepKernel = k_step<64, 2, false>; }
         else { depth = 1; stepKernel = k_step<64, 1, false>; }
     }
-    const size_t ringBytes = (size_t)(depth + 1) * slotBytes + (size_t)(ib / 32) * 2 * (depth + 1) * sizeof(unsigned long long);
+    size_t ringBytes = (size_t)(depth + 1) * slotBytes + (size_t)(ib / 32) * 2 * (depth + 1) * sizeof(unsigned long long);
+    // The sweep blocks are spread over the SMs: the request is padded so that no more than blocksPerSm of them fit on one SM
+    // (otherwise the block scheduler packs several of these one-warp, latency-bound blocks onto whatever SM has room while a
+    // concurrent stream's interval kernels occupy the others, and they slow each other down: 243 -> 196 us per launch and
+    // 129 k -> 137 k solves/s on the bench workload).  MSEETC_STEP_SMEM_KB overrides the padding (0 = none).
+    static const int stepSmemKb = []() { const char* e = getenv("MSEETC_STEP_SMEM_KB"); return e ? atoi(e) : -1; }();
+    {
+        const int bps = blocksPerSm < 1 ? 1 : blocksPerSm;
+        const size_t pad = stepSmemKb >= 0 ? (size_t)stepSmemKb * 1024 : (size_t)228 * 1024 / (bps + 1) + 1024;
+        if (pad > ringBytes && pad <= (size_t)227 * 1024) ringBytes = pad;
+    }
     cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
     int launches = 0;
     cudaError_t e;
