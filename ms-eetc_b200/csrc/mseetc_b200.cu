@@ -348,6 +348,8 @@ struct mseetc_solver {
     std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
     std::vector<int> ev_class;     // class of every event pair of the last solve (timeline)
     cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
+    cudaStream_t hp;               // experiment MSEETC_TWO_LEVEL: library-owned highest-priority stream for the small kernels
+    cudaEvent_t xev[16];           // hand-over events between the caller's stream and hp
     int sweep_lanes;               // 1: sequential sweeps; 8 / 32: lanes per instance of the parallel-in-time sweeps
     long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
     double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
@@ -389,6 +391,8 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     cudaError_t e = cudaHostAlloc((void**)&h->done_host, 256, cudaHostAllocDefault);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
     for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming);
+    h->hp = nullptr;
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->xev[i], cudaEventDisableTiming);
     *out = h;
     return 0;
 }
@@ -573,17 +577,37 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
     std::vector<int> evClass;   // class of each recorded event pair
+    static const bool twoLevel = []() { const char* e = getenv("MSEETC_TWO_LEVEL"); return e && atoi(e) != 0; }();
+    if (twoLevel && !h->hp) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        cudaStreamCreateWithPriority(&h->hp, cudaStreamNonBlocking, greatest);
+    }
+    cudaStream_t cur = st;
+    int xev = 0;
+    // experiment: the small latency-critical kernels (reductions, sweeps) go to a highest-priority stream, the interval kernels
+    // stay on the caller's stream; hand-over by events
+    auto use = [&](bool high) -> cudaStream_t {
+        cudaStream_t want = (twoLevel && high) ? h->hp : st;
+        if (want != cur) {
+            cudaEvent_t ev = h->xev[xev++ % 16];
+            cudaEventRecord(ev, cur);
+            cudaStreamWaitEvent(want, ev, 0);
+            cur = want;
+        }
+        return want;
+    };
     auto begin = [&](int cls) {
         h->launches[cls] += 1;
         ++launches;
         if (!h->profiling) return;
         const size_t need = 2 * (evClass.size() + 1);
         while (h->ev.size() < need) { cudaEvent_t x; cudaEventCreate(&x); h->ev.push_back(x); }
-        cudaEventRecord(h->ev[2 * evClass.size()], st);
+        cudaEventRecord(h->ev[2 * evClass.size()], cur);
     };
     auto end = [&](int cls) {
         if (!h->profiling) return;
-        cudaEventRecord(h->ev[2 * evClass.size() + 1], st);
+        cudaEventRecord(h->ev[2 * evClass.size() + 1], cur);
         evClass.push_back(cls);
     };
     e = cudaMemsetAsync(c.done, 0, 256, st);
@@ -608,14 +632,18 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_EVAL);
         if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
         end(CLS_EVAL);
-        begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
+        use(true);
+        begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_KKT);
         begin(CLS_STEP);
-        if (h->sweep_lanes == 8) k_step_pit<8><<<(unsigned)(((size_t)g.S * 8 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
-        else if (h->sweep_lanes == 32) k_step_pit<32><<<(unsigned)(((size_t)g.S * 32 + 63) / 64), 64, 0, st>>>(c, c.done + 48);
-        else stepKernel<<<igrid, ib, ringBytes, st>>>(c);
+        if (h->sweep_lanes == 8) k_step_pit<8><<<(unsigned)(((size_t)g.S * 8 + 63) / 64), 64, 0, cur>>>(c, c.done + 48);
+        else if (h->sweep_lanes == 32) k_step_pit<32><<<(unsigned)(((size_t)g.S * 32 + 63) / 64), 64, 0, cur>>>(c, c.done + 48);
+        else stepKernel<<<igrid, ib, ringBytes, cur>>>(c);
         end(CLS_STEP);
+        use(false);
         begin(CLS_CSTEP); k_cell_step<<<gridStep, 128, 0, st>>>(c, io); end(CLS_CSTEP);
-        begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_ALPHA);
+        use(true);
+        begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_ALPHA);
+        use(false);
         if (tick >= maxTicks) break;
         // completion polling without draining the queue: the counter is copied every tick into a small pinned ring and the
         // copy made two ticks ago is tested (its event has normally completed), so kernels of the next ticks are already queued
@@ -634,7 +662,9 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_TRIAL);
         if (dyn) k_cell_trial_dyn<<<gridTrial, 128, 0, st>>>(c, io); else k_cell_trial<<<gridTrial, 128, 0, st>>>(c, io);
         end(CLS_TRIAL);
-        begin(CLS_DECIDE); k_inst_decide<<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_DECIDE);
+        use(true);
+        begin(CLS_DECIDE); k_inst_decide<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_DECIDE);
+        use(false);
         ++tick;
     }
     begin(CLS_MISC); k_cell_extract<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
