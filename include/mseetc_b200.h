@@ -121,7 +121,11 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);
  *                     (terminalTime is an upper bound on t_N, ocp.py:260-261) and are reported as
  *                     MSEETC_INFEASIBLE_PROBLEM_DETECTED without iterating.  An entry of 0 means "not known yet": the
  *                     array is re-read once per iteration, so the minimum times may be produced concurrently (another
- *                     stream / thread) while this call is running.
+ *                     stream / thread) while this call is running.  Passing the array (even all zeros) also switches on
+ *                     the envelope screening: an instance whose available time is more than 1 % below a speed-envelope
+ *                     lower bound on the trip duration gets the same status before its first iteration (iterations 0).
+ *                     The caller is expected to confirm such flags with the exact minimum time once it is known (the
+ *                     Python layer does, and re-solves with tmin_dev = NULL should one not be confirmed).
  * outputs (device, caller-owned; each may be NULL except status_out):
  *   z_out_dev    [n_instances * (n_intervals_max*(3+nu)+2)]  reference variable order (ocp.py:166-181,248-249)
  *   lam_g_out_dev[n_instances * n_intervals_max*rows]        multipliers of g in reference row order
