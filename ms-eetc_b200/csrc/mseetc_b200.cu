@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_decide(Ctx c) {
     }
 }
 
-__global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c) {
+// `mirror` (mapped pinned host memory): the completion counter as it stands when this kernel runs, for the host's polling --
+// a store from the kernel instead of a 4-byte cudaMemcpyAsync between two kernels of every tick (which cost ~10 us of stream time)
+__global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c, int* mirror) {
+    if (mirror && blockIdx.x == 0 && threadIdx.x == 0) *mirror = *(volatile int*)c.done;
     __shared__ double sm[RED_W][3][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + lane;
@@ -338,7 +341,8 @@ enum { CLS_TRIAL = 0, CLS_DECIDE, CLS_EVAL, CLS_STEP, CLS_MISC, CLS_CSTEP, CLS_A
 
 struct mseetc_solver {
     mseetc_problem prob;
-    int* done_host;     // pinned: [0] done counter, [16..] 4 x uint64 cell counters
+    int* done_host;     // pinned + mapped: [0] done counter, [16..] 4 x uint64 cell counters, [32..35] polling mirrors
+    int* done_host_dev; // device alias of done_host
     int last_ticks;
     int last_launches;
     int profiling;
@@ -388,8 +392,10 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->lm_dev = nullptr;
     memset(&h->lm, 0, sizeof h->lm);
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
-    cudaError_t e = cudaHostAlloc((void**)&h->done_host, 256, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void**)&h->done_host, 256, cudaHostAllocMapped);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
+    e = cudaHostGetDevicePointer((void**)&h->done_host_dev, h->done_host, 0);
+    if (e != cudaSuccess) { cudaFreeHost(h->done_host); delete h; return cuda_fail(e, "cudaHostGetDevicePointer"); }
     for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming);
     h->hp = nullptr;
     for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->xev[i], cudaEventDisableTiming);
@@ -642,15 +648,14 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         use(false);
         begin(CLS_CSTEP); k_cell_step<<<gridStep, 128, 0, st>>>(c, io); end(CLS_CSTEP);
         use(true);
-        begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_ALPHA);
+        begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, cur>>>(c, h->done_host_dev + 32 + tick % 4); end(CLS_ALPHA);
         use(false);
         if (tick >= maxTicks) break;
-        // completion polling without draining the queue: the counter is copied every tick into a small pinned ring and the
-        // copy made two ticks ago is tested (its event has normally completed), so kernels of the next ticks are already queued
+        // completion polling without draining the queue: k_inst_alpha mirrors the counter every tick into a small mapped pinned
+        // ring and the mirror written two ticks ago is tested (its event has normally completed), so kernels of the next ticks
+        // are already queued
         {
             const int slot = tick % 4;
-            e = cudaMemcpyAsync(h->done_host + 32 + slot, c.done, sizeof(int), cudaMemcpyDeviceToHost, st);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(done)");
             cudaEventRecord(h->poll_ev[slot], st);
             if (tick >= 2) {
                 const int old = (tick - 2) % 4;
