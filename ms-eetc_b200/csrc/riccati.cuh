@@ -411,9 +411,11 @@ MS_HD void closed_loop_compose(double* Mc, double* mc, const double* Mk, const d
     for (int i = 0; i < 3; ++i) mc[i] = mn[i];
 }
 
-template <class Fetch>
-MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch,
-                                  double P[3][3], double p[3], double* Mc, double* mc, bool storeAll = true) {
+// REG: the regularised variant (delta_w != 0: the column of s is loaded and the condensed entries corrected); the plain
+// variant keeps that rarely needed code out of the hot loop
+template <bool REG, class Fetch>
+MS_HD bool riccati_backward_range_t(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch,
+                                    double P[3][3], double p[3], double* Mc, double* mc, bool storeAll) {
     const double pn = c.cfg.withPn ? 1.0 : 0.0;
     if (kHi <= kLo) return true;
     fetch.start(c, s, kHi - 1, kLo, -1);
@@ -445,8 +447,8 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
     for (; k >= kLo; --k) {
         fetch.get(c, k, s, v);
         double vs[6];
-        if (delta > 0.0) load_scol(c, k, s, vs);
-        if (!stage_riccati_sparse(v, delta > 0.0 ? vs : nullptr, mu, delta, pn, P, p, K, kf)) { if (!Fetch::COLLECTIVE) return false; ok = false; }
+        if (REG) load_scol(c, k, s, vs);
+        if (!stage_riccati_sparse(v, REG ? vs : nullptr, mu, delta, pn, P, p, K, kf)) { if (!Fetch::COLLECTIVE) return false; ok = false; }
         if (storeAll || k == kLo) stage_store(c, k, s, K, kf, P, p);
         if (Mc) {
             const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
@@ -463,6 +465,14 @@ MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, 
         }
     }
     return ok;
+}
+
+template <class Fetch>
+MS_HD bool riccati_backward_range(const Ctx& c, int s, int N, int kLo, int kHi, double mu, double delta, Fetch& fetch,
+                                  double P[3][3], double p[3], double* Mc, double* mc, bool storeAll = true) {
+    // a collective ring keeps all lanes of the warp in one variant (the correction terms vanish for delta = 0)
+    if (Fetch::COLLECTIVE || delta > 0.0) return riccati_backward_range_t<true>(c, s, N, kLo, kHi, mu, delta, fetch, P, p, Mc, mc, storeAll);
+    return riccati_backward_range_t<false>(c, s, N, kLo, kHi, mu, delta, fetch, P, p, Mc, mc, storeAll);
 }
 
 template <class Fetch>
