@@ -526,12 +526,15 @@ MS_HD void kkt_init(KktAcc& a) {
     a.th = a.fo = a.slog = a.sdamp = a.zsum = a.ysum = 0.0;
     a.dinf = a.pinf = a.cmax = 0.0; a.cmin = 1e300;
 }
+// 14 planes per interval: two intervals per group keep the loaded values in registers (four spill under the 128-register
+// limit of a 512-thread block, and a spilled load is waited for at once)
+#define MS_KKT_U 2
 MS_HD void kkt_partials(const Ctx& c, int s, int N, int it, int w, int W, KktAcc& a) {
     kkt_init(a);
-    for (int k0 = w; k0 <= N; k0 += MS_RED_U * W) {
-        double v[MS_RED_U][14];
+    for (int k0 = w; k0 <= N; k0 += MS_KKT_U * W) {
+        double v[MS_KKT_U][14];
 #pragma unroll
-        for (int u = 0; u < MS_RED_U; ++u) {
+        for (int u = 0; u < MS_KKT_U; ++u) {
             const int k = k0 + u * W;
             if (k <= N) {
                 const double* q = &c.W(WS_PART, k, s);
@@ -545,7 +548,7 @@ MS_HD void kkt_partials(const Ctx& c, int s, int N, int it, int w, int W, KktAcc
             }
         }
 #pragma unroll
-        for (int u = 0; u < MS_RED_U; ++u) {
+        for (int u = 0; u < MS_KKT_U; ++u) {
             const int k = k0 + u * W;
             if (k <= N) {
                 a.th += v[u][0]; a.fo += v[u][1]; a.slog += v[u][2]; a.sdamp += v[u][3]; a.zsum += v[u][4]; a.ysum += v[u][5];
