@@ -203,8 +203,9 @@ MS_HD void inst_screen(const Ctx& c, int s) {
     if (s >= g.nInst || !g.energy || !c.tmin || c.I(SI_PHASE, s) == PH_DONE) return;
     const int N = c.I(SI_N_INT, s);
     const TrainLimits q = load_limits(c, s);
-    // scratch plane: overwritten by inst_profile / the first trial point
-    const double tLow = speed_envelope(c, s, N, q, 1.0, 1.0, 1e-3, 2, WS_IT1 + IT_B, nullptr);
+    // scratch plane: a step plane (zeroed by cell_init afterwards); inst_profile, which may run concurrently in another block,
+    // works in the planes of iterate buffer 1
+    const double tLow = speed_envelope(c, s, N, q, 1.0, 1.0, 1e-3, 2, WS_ST + ST_B, nullptr);
     if (isfinite(tLow) && (c.P(P_T, s) - c.P(P_T0, s)) < (1.0 - MS_SCREEN_MARGIN) * tLow) finish(c, s, ST_INFEASIBLE);
 }
 

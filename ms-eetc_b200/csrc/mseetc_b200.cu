@@ -63,12 +63,17 @@ __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
     if (s < c.cfg.S) inst_setup(c, io, s);
 }
 // useSmem: dynamic shared memory holds two columns per thread (node speeds, interval lengths: 2 * NK * blockDim doubles)
-__global__ void __launch_bounds__(64) k_inst_profile(Ctx c, int useSmem) {
+__global__ void __launch_bounds__(128) k_inst_profile(Ctx c, int useSmem) {
     extern __shared__ double prof_sm[];
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    // the first half of the block screens, the second half builds the starting profile of the same instances: the two walks
+    // over the track are independent, so they run side by side (an instance that the screening flags gets a profile nobody reads)
+    const int half = blockDim.x >> 1;
+    const bool profileRole = (int)threadIdx.x >= half;
+    const int col = profileRole ? (int)threadIdx.x - half : (int)threadIdx.x;
+    const int s = blockIdx.x * half + col;
     if (s >= c.cfg.S) return;
-    inst_screen(c, s);
-    if (useSmem) inst_profile(c, s, prof_sm + threadIdx.x, prof_sm + (size_t)c.cfg.NK * blockDim.x + threadIdx.x, (int)blockDim.x);
+    if (!profileRole) { inst_screen(c, s); return; }
+    if (useSmem) inst_profile(c, s, prof_sm + col, prof_sm + (size_t)c.cfg.NK * half + col, half);
     else inst_profile(c, s);
 }
 
@@ -627,7 +632,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         size_t profBytes = (size_t)2 * g.NK * ib * sizeof(double);
         if (profBytes > (size_t)200 * 1024 / (blocksPerSm < 1 ? 1 : blocksPerSm)) profBytes = 0;      // long horizons: scratch stays in HBM
         if (profBytes) cudaFuncSetAttribute(k_inst_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)profBytes);
-        begin(CLS_MISC); k_inst_profile<<<igrid, ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
+        begin(CLS_MISC); k_inst_profile<<<igrid, 2 * ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
     }
     begin(CLS_MISC);
     if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
