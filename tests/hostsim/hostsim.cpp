@@ -36,7 +36,11 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     g.lossKind = pr->loss_kind; g.numSteps = pr->num_steps; g.numApprox = pr->num_approx_steps;
     g.maxIter = pr->max_iterations; g.tol = pr->tol; g.muInit = pr->mu_init; g.initMode = init_mode;
     WsPlan plan = plan_workspace(g.S, g.NK);
-    std::vector<char> buf(plan.total, 0);
+    // the device workspace is uninitialised memory: poison it here (0xFF bytes = NaN doubles, -1 ints) so that a read of a plane
+    // nobody has written shows up in the emulation too; the library clears the integer state and the counters itself
+    std::vector<char> buf(plan.total, (char)0xFF);
+    std::memset(buf.data() + plan.off_si, 0, sizeof(int) * (size_t)SI_N * g.S);
+    std::memset(buf.data() + plan.off_done, 0, 256);
     Ctx c;
     c.cfg = g;
     c.ws = (double*)(buf.data() + plan.off_ws);
