@@ -326,17 +326,18 @@ MS_HD LossPar load_losspar(const Ctx& c, int s) {
 template <bool DYN>
 MS_HD void ineq_values(const Ctx& c, int s, double fel, double fpb, double sl, double b0, double b1,
                        const IntervalCoef& q, double* d) {
-    d[R_P0] = fel * sqrt(b0);
-    d[R_P1] = fel * sqrt(b1);
-    d[R_ACC] = accel(b0, fel + fpb, q);
+    // every operation individually rounded (see mul_rn): cell_eval and cell_step both evaluate these rows
+    d[R_P0] = mul_rn(fel, sqrt(b0));
+    d[R_P1] = mul_rn(fel, sqrt(b1));
+    d[R_ACC] = sub_rn(sub_rn(add_rn(fel, fpb), fma(q.sr1, sqrt(b0), mul_rn(q.sr2, b0))), add_rn(q.sr0, q.c0));
     if (DYN) {
         LossRow tr, rg;
         loss_rows_dynamic(c.lm, load_losspar(c, s), fel, b0, b1, tr, rg);
         d[R_LTR] = sl - tr.v;
         d[R_LRG] = sl - rg.v;
     } else {
-        d[R_LTR] = sl - c.P(P_CT, s) * fel;
-        d[R_LRG] = sl + c.P(P_CR, s) * fel;
+        d[R_LTR] = fma(-c.P(P_CT, s), fel, sl);
+        d[R_LRG] = fma(c.P(P_CR, s), fel, sl);
     }
 }
 
@@ -807,7 +808,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     double cn_b = yb;
     #pragma unroll
     for (int j = 0; j < NROW; ++j) {
-        c.W(WS_QP + QP_RES + j, k, s) = 0.0;
+        if (DYN) c.W(WS_QP + QP_RES + j, k, s) = 0.0;
         if (!row_on(g, j)) continue;
         double L, U; bool hasU;
         row_bounds(B, j, L, U, hasU);
@@ -828,8 +829,8 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
             cmin = fmin(cmin, pr); cmax = fmax(cmax, pr); zsum += vU;
             bar_add(bar, sU, false);
         }
-        const double res = d[j] - w;
-        c.W(WS_QP + QP_RES + j, k, s) = res;
+        const double res = sub_rn(d[j], w);
+        if (DYN) c.W(WS_QP + QP_RES + j, k, s) = res;      // otherwise cell_step recomputes it (bit for bit)
         th += fabs(res); pinf = fmax(pinf, fabs(res)); ysum += fabs(ydv[j]);
         dinf = fmax(dinf, fabs(rw));
         #pragma unroll
@@ -913,6 +914,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     c.W(WS_QP + QP_HPP, k, s) = hpp;
     c.W(WS_QP + QP_GP0, k, s) = gp0;
     c.W(WS_QP + QP_GP1, k, s) = gp1;
+    if (DYN) {      // constant-efficiency rows: cell_step recomputes the row gradients
     c.W(WS_QP + QP_J_P0_B, k, s) = J[R_P0][V_B];
     c.W(WS_QP + QP_J_P0_FEL, k, s) = J[R_P0][V_FEL];
     c.W(WS_QP + QP_J_P1_FEL, k, s) = J[R_P1][V_FEL];
@@ -924,6 +926,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     c.W(WS_QP + QP_J_LRG_FEL, k, s) = J[R_LRG][V_FEL];
     c.W(WS_QP + QP_J_LRG_B, k, s) = J[R_LRG][V_B];
     c.W(WS_QP + QP_J_LRG_BN, k, s) = J[R_LRG][V_BN];
+    }
     c.W(WS_PART + PC_TH, k, s) = th;
     c.W(WS_PART + PC_F, k, s) = fo;
     c.W(WS_PART + PC_SLOG, k, s) = bar_finish(bar);

@@ -22,6 +22,32 @@ MS_HD double rcp(double x) {
 #endif
 }
 
+// individually rounded operations that the compiler may not contract into an FMA: used where two kernels must reproduce the
+// same value bit for bit (the residual d(x) - w of an active row is a difference of nearly equal numbers that is later
+// multiplied by z/s ~ 1e12; a last-bit difference between the kernel that condenses it and the one that recovers the step
+// would show up in the multipliers)
+MS_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+MS_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+MS_HD double sub_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+
 // variables: x0 (= b at interval start), x1 (= total specific force F)
 struct Jet2 {
     double v, g0, g1, h00, h01, h11;

@@ -55,7 +55,8 @@ MS_CELL_KERNEL(k_cell_trial, MS_MINB_TRIAL, cell_trial<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_trial_dyn, 2, cell_trial<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_eval, MS_MINB_EVAL, cell_eval<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_eval_dyn, 2, cell_eval<true>(c, k, s))
-MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step(c, k, s))
+MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step<false>(c, k, s))
+MS_CELL_KERNEL(k_cell_step_dyn, MS_MINB_STEP, cell_step<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
 
 __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
@@ -490,12 +491,13 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
     const int prim = 4 + (p.with_pn_brake ? 1 : 0);
     const int iter = prim + rows + 2 + rows + nz;           // x, w, y, yd, z
     const int step = prim + rows + 2 + rows;
+    const bool dynMap = (p.loss_kind == 2 && p.energy_optimal);
     switch (cls) {
         case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
         case CLS_DECIDE: return 8.0 * 4;
-        case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13));
+        case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13)) - (dynMap ? 0.0 : 8.0 * 16);     // row gradients / residuals not stored
         case CLS_STEP:   return 8.0 * (BwdFields::NF + 17 + FwdFields::NF + 4);      // factors written: K 6, kf 2, P 6, p 3
-        case CLS_CSTEP:  return 8.0 * ((6 + 3 + iter + 11 + rows + 2 + 7 + 6 + 9) + (2 * rows + 3 + 3));
+        case CLS_CSTEP:  return 8.0 * ((6 + 3 + iter + 11 + rows + 2 + 7 + 6 + 9) + (2 * rows + 3 + 3)) - (dynMap ? 0.0 : 8.0 * 14);      // ... recomputed (+ b_{k+1}, c0)
         case CLS_ALPHA:  return 8.0 * 3;
         case CLS_KKT:    return 8.0 * 14;
         default:         return 0.0;
@@ -651,7 +653,9 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         else stepKernel<<<igrid, ib, ringBytes, cur>>>(c);
         end(CLS_STEP);
         use(false);
-        begin(CLS_CSTEP); k_cell_step<<<gridStep, 128, 0, st>>>(c, io); end(CLS_CSTEP);
+        begin(CLS_CSTEP);
+        if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, st>>>(c, io); else k_cell_step<<<gridStep, 128, 0, st>>>(c, io);
+        end(CLS_CSTEP);
         use(true);
         begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, cur>>>(c, h->done_host_dev + 32 + tick % 4); end(CLS_ALPHA);
         use(false);

@@ -696,6 +696,11 @@ MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, doub
     f.gphid += (-mu * r + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
 }
 
+// DYN = false (no or constant-efficiency loss rows): the gradients and residuals of the inequality rows are cheap functions
+// of the iterate this kernel loads anyway, so they are recomputed here -- bit for bit, see mul_rn -- instead of being stored
+// by cell_eval and read back (16 planes less traffic in each of the two kernels); with the spline loss map they come from
+// the stage-QP record.
+template <bool DYN>
 MS_HD void cell_step(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_STEPPED) return;
@@ -704,7 +709,9 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
     // ---- all loads first, then arithmetic, then all stores (loads must not queue behind stores through the same base)
     const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
-    double CI[IT_N], CS[ST_N], QJ[QP_N - QP_H_BSL], RP[9];
+    double CI[IT_N], CS[ST_N], RP[9];
+    constexpr int NQJ = DYN ? (QP_N - QP_H_BSL) : (QP_J_P0_B - QP_H_BSL);      // planes read from the stage-QP record
+    double QJ[NQJ];
     {
         const double* ip = &c.W(it, k, s);
         const double* sp = &c.W(WS_ST, k, s);
@@ -715,11 +722,14 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
 #pragma unroll
         for (int f = 0; f < ST_N; ++f) CS[f] = sp[f * 32];
 #pragma unroll
-        for (int f = 0; f < QP_N - QP_H_BSL; ++f) QJ[f] = qp[f * 32];
+        for (int f = 0; f < NQJ; ++f) QJ[f] = qp[f * 32];
 #pragma unroll
         for (int f = 0; f < 9; ++f) RP[f] = rp[f * 32];
     }
     const double dbn = c.W(WS_ST + ST_B, kn, s), dtn = c.W(WS_ST + ST_T, kn, s);
+    const double bNext = DYN ? 0.0 : c.W(it + IT_B, kn, s);
+    IntervalCoef q;
+    if (!DYN) q = load_coef(c, (k < N) ? k : km, s);
     // last interval only: b_N is fixed, the multiplier of its row follows from stationarity w.r.t. Fel (see below)
     double LQ[8] = {0, 0, 0, 0, 0, 0, 0, 1.0};
     if (k == N - 1) {
@@ -757,6 +767,28 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
         const double du2 = -sX * isd;
         ods = du2;
         const double fel = CI[IT_FEL], fpb = CI[IT_FPB], sl = CI[IT_SL];
+        // gradients and residuals of the inequality rows: from the stage-QP record (DYN) or recomputed with the expressions of
+        // cell_eval (ocp.py:189,199,225-226 with constant efficiencies)
+        double jP0b, jP0f, jP1f, jP1n, jAccb, jLtrF, jLtrB, jLtrN, jLrgF, jLrgB, jLrgN, rres[NROW];
+        if (DYN) {
+            jP0b = MS_QJ(QP_J_P0_B); jP0f = MS_QJ(QP_J_P0_FEL); jP1f = MS_QJ(QP_J_P1_FEL); jP1n = MS_QJ(QP_J_P1_BN);
+            jAccb = MS_QJ(QP_J_ACC_B);
+            jLtrF = MS_QJ(QP_J_LTR_FEL); jLtrB = MS_QJ(QP_J_LTR_B); jLtrN = MS_QJ(QP_J_LTR_BN);
+            jLrgF = MS_QJ(QP_J_LRG_FEL); jLrgB = MS_QJ(QP_J_LRG_B); jLrgN = MS_QJ(QP_J_LRG_BN);
+#pragma unroll
+            for (int j = 0; j < NROW; ++j) rres[j] = MS_QJ(QP_RES + j);
+        } else {
+            const double bk = CI[IT_B], v0 = sqrt(bk), v1 = sqrt(bNext);
+            const double iv0 = rcp(v0), iv1 = rcp(v1);
+            double dval[NROW];
+            ineq_values<false>(c, s, fel, fpb, sl, bk, bNext, q, dval);
+            jP0b = 0.5 * fel * iv0; jP0f = v0; jP1f = v1; jP1n = 0.5 * fel * iv1;
+            jAccb = -(0.5 * q.sr1 * iv0 + q.sr2);
+            jLtrF = -c.P(P_CT, s); jLtrB = 0.0; jLtrN = 0.0;
+            jLrgF = c.P(P_CR, s); jLrgB = 0.0; jLrgN = 0.0;
+#pragma unroll
+            for (int j = 0; j < NROW; ++j) rres[j] = row_on(g, j) ? sub_rn(dval[j], CI[IT_W + j]) : 0.0;
+        }
         // new coupling-row multipliers = minus the costates of the stepped state: gradient of the value function of the
         // backward sweep at node k+1, plus the terms of this interval that depend on b_{k+1} directly
         const double pit = RP[6] + RP[0] * dtn + RP[1] * dbn + RP[2] * du0;
@@ -793,12 +825,12 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
         for (int j = 0; j < NROW; ++j) {
             if (!row_on(g, j)) continue;
             double jd;
-            if (j == R_P0) jd = MS_QJ(QP_J_P0_B) * db + MS_QJ(QP_J_P0_FEL) * du0;
-            else if (j == R_P1) jd = MS_QJ(QP_J_P1_FEL) * du0 + MS_QJ(QP_J_P1_BN) * dbn;
-            else if (j == R_ACC) jd = MS_QJ(QP_J_ACC_B) * db + du0 + du1;
-            else if (j == R_LTR) jd = du2 + MS_QJ(QP_J_LTR_FEL) * du0 + MS_QJ(QP_J_LTR_B) * db + MS_QJ(QP_J_LTR_BN) * dbn;
-            else jd = du2 + MS_QJ(QP_J_LRG_FEL) * du0 + MS_QJ(QP_J_LRG_B) * db + MS_QJ(QP_J_LRG_BN) * dbn;
-            const double dw = jd + MS_QJ(QP_RES + j);
+            if (j == R_P0) jd = jP0b * db + jP0f * du0;
+            else if (j == R_P1) jd = jP1f * du0 + jP1n * dbn;
+            else if (j == R_ACC) jd = jAccb * db + du0 + du1;
+            else if (j == R_LTR) jd = du2 + jLtrF * du0 + jLtrB * db + jLtrN * dbn;
+            else jd = du2 + jLrgF * du0 + jLrgB * db + jLrgN * dbn;
+            const double dw = jd + rres[j];
             double L, U; bool hasU;
             row_bounds(B, j, L, U, hasU);
             const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;

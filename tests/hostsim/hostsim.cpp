@@ -81,7 +81,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
             if (pit_lanes > 1) inst_step_pit_emulated(c, s, pit_lanes, fb, ff);   // lanes-per-instance (parallel-in-time) variant
             else inst_step(c, s, fb, ff);
         }
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_step(c, k, s);
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_step<true>(c, k, s); else cell_step<false>(c, k, s); }
         for (int s = 0; s < g.nInst; ++s) {
             if (c.I(SI_PHASE, s) != PH_STEPPED) continue;
             const int N = c.I(SI_N_INT, s);
