@@ -585,7 +585,9 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         const size_t pad = stepSmemKb >= 0 ? (size_t)stepSmemKb * 1024 : (size_t)228 * 1024 / (bps + 1) + 1024;
         if (pad > ringBytes && pad <= (size_t)227 * 1024) ringBytes = pad;
     }
-    cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ringBytes);
+    // the attribute belongs to the kernel, not to this call: handles on other host threads launch the same kernel with other
+    // sizes, so it is set to the hardware maximum rather than to this call's request
+    cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     int launches = 0;
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -633,7 +635,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     if (g.initMode || (tmin && g.energy)) {
         size_t profBytes = (size_t)2 * g.NK * ib * sizeof(double);
         if (profBytes > (size_t)200 * 1024 / (blocksPerSm < 1 ? 1 : blocksPerSm)) profBytes = 0;      // long horizons: scratch stays in HBM
-        if (profBytes) cudaFuncSetAttribute(k_inst_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)profBytes);
+        if (profBytes) cudaFuncSetAttribute(k_inst_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         begin(CLS_MISC); k_inst_profile<<<igrid, 2 * ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
     }
     begin(CLS_MISC);

@@ -360,6 +360,24 @@ def test_early_screening_flags_are_checked_against_the_certificate(cabi, monkeyp
     assert all(st not in (0, 4) for st in faked['status'][:2]) and np.all(faked['iters'][:2] > 0)
 
 
+def test_concurrent_handles_of_different_batch_sizes(cabi):
+    """Regression: the sweep kernel's shared-memory request depends on the batch size of a handle, and handles of different
+    sizes run concurrently on several host threads (two sub-batches of 4096 and a presolve batch of 8192 distinct problems
+    here) -- the kernel attribute that admits the request is process-wide and must not be lowered by another handle."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    opts = {'numIntervals': 300, 'maxIterations': 500, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    solver = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), opts)
+    solver.streams = 2
+    rng = np.random.default_rng(3)
+    n = 8192
+    ov = dict(mass=391000 * rng.uniform(0.85, 1.15, n), r0=train.r0 * rng.uniform(0.8, 1.2, n), etaTraction=rng.uniform(0.80, 0.92, n))
+    res = solver.solve_batch(1541.0, overrides=ov)
+    assert np.all(res['status'] == 0) and np.all(res['kkt'] <= 1e-8)
+
+
 def test_solve_instances_mixed_tracks_and_interval_counts(cabi):
     "BASELINE config 5 in miniature: random tracks, mixed numIntervals, one device call; oracle spot check."
     from mseetc.ocp import casadiSolver, solve_instances
