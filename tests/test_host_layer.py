@@ -273,3 +273,20 @@ def test_postprocess_integrated_losses_and_rolling_resistance():
             rel = np.nanmax(np.abs(df['Losses [kWh]'] - mid['Losses [kWh]'])) / np.nanmax(mid['Losses [kWh]'])
             assert rel < 2e-2
         assert abs(np.nansum(df['Energy [kWh]']) - np.nansum(mid['Energy [kWh]'])) / np.nansum(mid['Energy [kWh]']) < 2e-2
+
+
+def test_stream_pool_interleave_is_a_tile_aligned_permutation():
+    "Sub-batches of the two-stream solve: every instance once, tiles of 32 dealt round-robin, every sub-batch starts on a tile."
+    from mseetc._cabi import StreamPool
+    for n, k in ((4096, 2), (4100, 2), (1030, 3), (64, 2), (33, 2), (5000, 4)):
+        perm, parts = StreamPool.interleave(n, k)
+        assert sorted(perm.tolist()) == list(range(n))
+        assert parts[0][0] == 0 and parts[-1][1] == n and all(a % 32 == 0 for a, _ in parts)
+        assert all(b == a2 for (_, b), (a2, _) in zip(parts[:-1], parts[1:]))
+        first = perm[parts[0][0]:parts[0][1]]
+        assert first[:32].tolist() == list(range(32))                      # tile 0 -> sub-batch 0
+        if len(parts) > 1 and n >= 64:
+            second = perm[parts[1][0]:parts[1][1]]
+            assert second[0] == 32                                          # tile 1 -> sub-batch 1
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 64                                # balanced up to the ragged tile
