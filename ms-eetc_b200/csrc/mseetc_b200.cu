@@ -116,19 +116,27 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c, int* mirror) {
 }
 
 __global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
-    __shared__ KktAcc sm[RED_W][32];
+    __shared__ double sm[RED_W][10][32];      // field-major: conflict-free columns (one lane = one instance)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + lane;
     const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_EVAL;
     KktAcc acc;
     kkt_init(acc);
     if (on) kkt_partials(c, s, c.I(SI_N_INT, s), c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0, w, RED_W, acc);
-    sm[w][lane] = acc;
+    sm[w][0][lane] = acc.th; sm[w][1][lane] = acc.fo; sm[w][2][lane] = acc.slog; sm[w][3][lane] = acc.sdamp;
+    sm[w][4][lane] = acc.zsum; sm[w][5][lane] = acc.ysum; sm[w][6][lane] = acc.dinf; sm[w][7][lane] = acc.pinf;
+    sm[w][8][lane] = acc.cmin; sm[w][9][lane] = acc.cmax;
     __syncthreads();
     if (w == 0 && on) {
         KktAcc tot;
         kkt_init(tot);
-        for (int ww = 0; ww < RED_W; ++ww) kkt_combine(tot, sm[ww][lane]);
+        for (int ww = 0; ww < RED_W; ++ww) {
+            KktAcc o;
+            o.th = sm[ww][0][lane]; o.fo = sm[ww][1][lane]; o.slog = sm[ww][2][lane]; o.sdamp = sm[ww][3][lane];
+            o.zsum = sm[ww][4][lane]; o.ysum = sm[ww][5][lane]; o.dinf = sm[ww][6][lane]; o.pinf = sm[ww][7][lane];
+            o.cmin = sm[ww][8][lane]; o.cmax = sm[ww][9][lane];
+            kkt_combine(tot, o);
+        }
         inst_kkt(c, s, tot);
     }
 }
