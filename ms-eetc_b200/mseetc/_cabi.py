@@ -5,6 +5,7 @@ pointers.  There is no CPU fallback: without the shared library or without a CUD
 raises RuntimeError.
 """
 import ctypes
+import functools
 import os
 
 import numpy as np
@@ -195,6 +196,22 @@ class StreamPool:
 
     @staticmethod
     def interleave(n, k, tile=32):
+        "Cached front end of _interleave (pure function of its arguments; the arrays are shared, do not modify them)."
+        return StreamPool._interleave(int(n), int(k), int(tile))[:2]
+
+    @staticmethod
+    def interleave_inverse(n, k, tile=32):
+        "argsort of the permutation: position of every instance of the caller's order in the dealt order."
+        return StreamPool._interleave(int(n), int(k), int(tile))[2]
+
+    @staticmethod
+    @functools.lru_cache(maxsize=16)
+    def _interleave(n, k, tile):
+        perm, parts = StreamPool._interleave_build(n, k, tile)
+        return perm, parts, np.argsort(perm)
+
+    @staticmethod
+    def _interleave_build(n, k, tile=32):
         """Order of the instances that balances the sub-batches: 32-instance tiles are dealt round-robin to the k streams, so a
         contiguous run of cheap instances (a sorted sweep whose short trip times are screened as infeasible) is shared by all
         streams while screened tiles stay whole (their warps exit at once).  Returns (perm, parts): sub-batch i is

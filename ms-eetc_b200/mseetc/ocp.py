@@ -256,7 +256,16 @@ class casadiSolver():
         return P, M
 
     def _tables(self, rho, g, vmax):
-        "Per-interval tables ds, c0 and node table bmax for one (rho, g, vmax)."
+        "Per-interval tables ds, c0 and node table bmax for one (rho, g, vmax); the last result is kept (the grid is fixed at construction)."
+        key = (float(rho), float(g), float(vmax))
+        cached = self._dev.get('tables')
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        out = self._tables_build(rho, g, vmax)
+        self._dev['tables'] = (key, out)
+        return out
+
+    def _tables_build(self, rho, g, vmax):
         pts = self.points
         N = self.numIntervals
         grad = pts['Gradient [permil]'].values[:N] / 1e3
@@ -440,10 +449,12 @@ class casadiSolver():
         if screen and self.energyOptimal:
             # minimum trip time of every distinct problem, computed CONCURRENTLY (second host thread + second stream) with
             # the energy-optimal batch; the kernels pick the values up as soon as they are in device memory
-            key = np.delete(P, [_cabi.PARAM_INDEX['T_END'], _cabi.PARAM_INDEX['LOSS_TR'], _cabi.PARAM_INDEX['LOSS_RG'],
-                                _cabi.PARAM_INDEX['OBJ_SCALE'], _cabi.PARAM_INDEX['DYN_AUX'], _cabi.PARAM_INDEX['DYN_ETAG'],
-                                _cabi.PARAM_INDEX['DYN_SCALE']], axis=0)
-            if n == 1 or np.all(key == key[:, :1]):
+            # a pure trip-time sweep (no overrides, scalar boundary data) is one problem: no need to compare the columns
+            same_problem = not overrides_in and all(len(a) == 1 for a in arrs[1:])
+            key = None if same_problem else np.delete(P, [_cabi.PARAM_INDEX['T_END'], _cabi.PARAM_INDEX['LOSS_TR'], _cabi.PARAM_INDEX['LOSS_RG'],
+                                                         _cabi.PARAM_INDEX['OBJ_SCALE'], _cabi.PARAM_INDEX['DYN_AUX'], _cabi.PARAM_INDEX['DYN_ETAG'],
+                                                         _cabi.PARAM_INDEX['DYN_SCALE']], axis=0)
+            if n == 1 or same_problem or np.all(key == key[:, :1]):
                 first, inverse = np.array([0]), np.zeros(n, dtype=np.intp)
             else:
                 _, first, inverse = np.unique(key, axis=1, return_index=True, return_inverse=True)
@@ -462,7 +473,7 @@ class casadiSolver():
         tm = presolve.tmin_dev if presolve is not None else None
         t_up = _time.perf_counter() - t_begin
         buf = self._device_out('solve', n, dev, want_multipliers)
-        back = self._upload('back', np.argsort(perm), torch.int64, dev) if pooled else None
+        back = self._upload('back', _cabi.StreamPool.interleave_inverse(n, int(self.streams)), torch.int64, dev) if pooled else None
         ordered = self._device_out('ordered', n, dev, want_multipliers) if pooled else None
         # ---- concurrent part: the presolve thread and the stream threads of the pool spend their time inside the library (GIL
         # released), but each needs the GIL for a moment to get there; with the interpreter's default 5 ms switch interval those
@@ -486,7 +497,7 @@ class casadiSolver():
             if presolve is not None:
                 tmin = presolve.join()
                 if perm is not None:
-                    tmin = tmin[np.argsort(perm)]
+                    tmin = tmin[_cabi.StreamPool.interleave_inverse(n, int(self.streams))]
         finally:
             sys.setswitchinterval(interval)
         t_join = _time.perf_counter() - t_begin
