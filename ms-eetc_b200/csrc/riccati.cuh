@@ -1,15 +1,18 @@
 // Search direction of one interior-point iteration: Riccati recursion over the shooting intervals.
 //
 // The Newton system of the reference NLP (all rows of ocp.py:183-241 linearised, bound and slack multipliers
-// condensed by cell_eval) is a linear-quadratic OCP in (d t, d b, d Fel_{k-1} | d Fel, d Fpb, d s).  It replaces
+// condensed by cell_eval) is a linear-quadratic OCP in (d t, d b, d Fel_{k-1} | d Fel, d Fpb, d s); cell_eval also
+// eliminates d s, whose pivot does not depend on the value function, so the sweeps carry two controls.  It replaces
 // IPOPT's sparse LDL^T (MUMPS) behind ocp.py:359:
 //   riccati_backward   value functions P_k, p_k and feedback K_k, k_k; positive-definiteness of every reduced
-//                      control Hessian is the inertia test (IPOPT Alg. IC regularises when it fails)
-//   riccati_forward    d x_k, d u_k and the new coupling-row multipliers (costates)
-//   cell_step          (interval-parallel) slack and inequality-multiplier steps, fraction-to-boundary limits,
-//                      directional derivative of the barrier function
+//                      control Hessian is the inertia test (IPOPT Alg. IC regularises when it fails); a plain variant
+//                      and one for delta_w != 0 so that the rarely needed correction stays out of the hot loop
+//   riccati_forward    d Fel, d Fpb, d t, d b -- nothing else is sequential
+//   cell_step          (interval-parallel) d s, the new coupling-row multipliers (costates of the stepped state), slack
+//                      and inequality-multiplier steps, fraction-to-boundary limits, directional derivative of the barrier
+//                      function; recomputes the row gradients / residuals bit for bit instead of reading them back
 //   inst_alpha         deterministic per-instance reduction of those limits -> first trial step size
-// The two sweeps are sequential in k for one instance; their stage data are prefetched `depth` intervals ahead
+// The two sweeps are sequential in k for one instance; their stage data are prefetched DEPTH intervals ahead
 // into a shared-memory ring with cp.async (one column per lane: no block-level synchronisation needed).
 #pragma once
 #include "core.cuh"
