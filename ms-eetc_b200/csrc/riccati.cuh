@@ -85,7 +85,7 @@ struct RingFetch {
         for (int d = 0; d < DEPTH; ++d) issue();
     }
     __device__ void get(const Ctx&, int, int, double* v) {
-        __pipeline_wait_prior(DEPTH - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");      // (__pipeline_wait_prior caps its argument at 8)
         const double* src = sm + head * (FL::NF * BS);
 #pragma unroll
         for (int f = 0; f < FL::NF; ++f) v[f] = src[f * BS];
