@@ -31,9 +31,9 @@ class Train():
     def __init__(self, config, pathJSON=Path(__file__).parent.parent / 'trains') -> None:
         self.g = 9.81   # [m/s^2]
         if not isinstance(config, dict):
-            raise ValueError("the train configuration must be a dict")
+            raise ValueError("Train configuration should be provided as a dictionary!")
         if 'id' not in config:
-            raise ValueError("the train configuration needs an 'id'")
+            raise ValueError("Train ID must be specified in configuration!")
         with open(Path(pathJSON) / (config['id'] + '.json')) as fh:
             data = json.load(fh)
         checkTTOBenchVersion(data, ['1.1', '1.2', '1.3'])
@@ -49,12 +49,12 @@ class Train():
                 accepted.add(key)
                 continue
             if not isinstance(val, dict) or val.keys() != {'unit', 'value'}:
-                raise ValueError("configuration entry '{}' must be a dict with the keys 'unit' and 'value'".format(key))
+                raise ValueError("Configuration field '{}' should be specified as a dictionary with 'unit' and 'value' keys!".format(key))
             if key in data or key in mayBeAdded:
                 data[key] = val
                 accepted.add(key)
         if set(config) != accepted:
-            raise ValueError("unknown entries in the train configuration: {}".format(', '.join(set(config) - accepted)))
+            raise ValueError("Redundant fields in train configuration: {}!".format(', '.join(set(config) - accepted)))
 
         quantity = lambda key, sign=1.0: convertUnit(sign * abs(data[key]['value']) if sign < 0 else data[key]['value'], data[key]['unit'])
         self.mass = quantity('mass')                       # [kg]
@@ -71,7 +71,7 @@ class Train():
         hasT, hasR = 'efficiency traction' in data, 'efficiency reg brake' in data
         if hasT or hasR:
             if not (hasT and hasR):
-                raise ValueError("the json file has to give both efficiencies (traction and regenerative brake) or none")
+                raise ValueError("Both efficiencies need to be specified in json file!")
             self.etaTraction = quantity('efficiency traction')
             self.etaRgBrake = quantity('efficiency reg brake')
         self.checkFields()
@@ -79,33 +79,33 @@ class Train():
     def checkFields(self):
         finitePos = lambda x: x is not None and x > 0 and not np.isinf(x)
         if self.mass is None or self.mass < 0 or np.isinf(self.mass):
-            raise ValueError("mass {} is not a positive number".format(self.mass))
+            raise ValueError("Train mass must be a positive number, not {}!".format(self.mass))
         if self.g is None or not 9 <= self.g <= 10:
-            raise ValueError("g = {} is outside [9, 10] m/s^2".format(self.g))
+            raise ValueError("Acceleration of gravity must be between 9 and 10 m/s^2, not {}!".format(self.g))
         if self.rho is None or not 1 <= self.rho <= 1.5:
-            raise ValueError("rotating-mass factor {} is outside [1, 1.5]".format(self.rho))
+            raise ValueError("Rotation mass factor must be between 1 and 1.5, not {}!".format(self.rho))
         if not finitePos(self.velocityMax):
-            raise ValueError("maximum velocity {} is not a positive number".format(self.velocityMax))
+            raise ValueError("Maximum velocity must be a strictly positive number, not {}!".format(self.velocityMax))
         if self.forceMax is not None and not finitePos(self.forceMax):
-            raise ValueError("forceMax = {}: must be > 0 or None".format(self.forceMax))
+            raise ValueError("Maximum traction force must be strictly positive or free (None), not {}!".format(self.forceMax))
         if self.forceMinPn is not None and (self.forceMinPn > 0 or np.isinf(self.forceMinPn)):
-            raise ValueError("forceMinPn = {}: must be <= 0 or None".format(self.forceMinPn))
+            raise ValueError("Maximum pneumatic braking force must be negative, zero or free (None), not {}!".format(self.forceMinPn))
         if self.forceMin is not None and (self.forceMin > 0 or np.isinf(self.forceMin)):
-            raise ValueError("forceMin = {}: must be <= 0 or None".format(self.forceMin))
+            raise ValueError("Maximum regenerative braking force must be negative, zero or free (None), not {}!".format(self.forceMin))
         if self.forceMin == 0 and self.forceMinPn == 0:
-            raise ValueError("at least one of the two brakes has to be available")
+            raise ValueError("Both brakes cannot be deactivated simultaneously!")
         if self.powerMax is not None and not finitePos(self.powerMax):
-            raise ValueError("powerMax = {}: must be > 0 or None".format(self.powerMax))
+            raise ValueError("Maximum traction power must be strictly positive or free (None), not {}!".format(self.powerMax))
         if self.powerMin is not None and (self.powerMin >= 0 or np.isinf(self.powerMin)):
-            raise ValueError("powerMin = {}: must be < 0 or None".format(self.powerMin))
+            raise ValueError("Maximum regenerative brake power must be strictly negative or free (None), not {}!".format(self.powerMin))
         if self.accMax is not None and not finitePos(self.accMax):
-            raise ValueError("accMax = {}: must be > 0 or None".format(self.accMax))
+            raise ValueError("Maximum acceleration must be strictly positive or free (None), not {}!".format(self.accMax))
         if self.accMin is not None and (self.accMin >= 0 or np.isinf(self.accMin)):
-            raise ValueError("accMin = {}: must be < 0 or None".format(self.accMin))
+            raise ValueError("Maximum deceleration must be strictly negative or free (None), not {}!".format(self.accMin))
         for name in ('r0', 'r1', 'r2'):
             coef = getattr(self, name)
             if coef is None or coef < 0:
-                raise ValueError("Davis coefficient {} = {} is negative".format(name, coef))
+                raise ValueError("Rolling resistance coefficient {} must be positive, not {}!".format(name, coef))
 
     def exportModel(self):
         "Specific (per kg of rotating mass) model data for the integrator."
@@ -123,7 +123,7 @@ class Train():
             etaT, etaR = self.etaTraction, self.etaRgBrake
             absolute = lambda f, v: f * v * (f > 0) * (1 - etaT) / etaT - (1 - etaR) * f * v * (f < 0)
         else:
-            raise ValueError("the train has neither a powerLosses callable nor the two efficiencies")
+            raise ValueError("Power losses function of train must by either explicitly or implicitly defined!")
         M = self.mass * self.rho
 
         def specific(f, v):
@@ -167,7 +167,7 @@ class TrainIntegrator():
 
     def __init__(self, model, solver, optsDict={}) -> None:
         if solver not in {'RK', 'IRK', 'CVODES'}:
-            raise ValueError("integration method not recognised")
+            raise ValueError("Unknown integration method!")
         if solver != 'RK':
             raise NotImplementedError("Only the explicit Runge-Kutta branch is implemented on the device")
         self.model = model
@@ -175,7 +175,7 @@ class TrainIntegrator():
 
     def solve(self, time, velocitySquared, ds, traction=0, pnBrake=0, gradient=0, curvature=0):
         if not self.model.withPnBrake and pnBrake != 0:
-            raise ValueError("a pneumatic brake force was given although that brake is switched off")
+            raise ValueError("Cannot define value for pneumatic braking when this brake is deactivated!")
         from mseetc import _cabi
         m = self.model
         F = traction + (pnBrake if m.withPnBrake else 0)
@@ -194,7 +194,7 @@ class OptionsRK(Options):
 
     def checkValues(self):
         if self.order != 4:
-            raise ValueError("only the explicit Runge-Kutta method of order 4 is available")
+            raise ValueError("Only explicit Runge-Kutta of order 4 is currently implemented in casadi!")
         self.checkPositiveInteger(self.numSteps, 'Number of integration steps', allowZero=False)
         self.checkPositiveInteger(self.numApproxSteps, 'Number of time approximation steps', allowZero=True)
 
@@ -212,14 +212,14 @@ class OptionsIRK(Options):
 
     def checkValues(self):
         if int(self.order) != self.order or not 1 <= self.order <= 9:
-            raise ValueError("the order of the implicit Runge-Kutta method must be an integer in 1..9")
+            raise ValueError("Order of implicit Runge-Kutta should be a positive integer between 1 and 9!")
         self.checkPositiveInteger(self.numSteps, 'Number of integration steps', allowZero=False)
         self.checkPositiveInteger(self.numApproxSteps, 'Number of time approximation steps', allowZero=True)
         if self.collMethod not in {'radau', 'legendre'}:
-            raise ValueError("collocation method {} not recognised".format(self.collMethod))
+            raise ValueError("Unknown collocation method: {}!".format(self.collMethod))
         self.checkPositiveInteger(self.maxIter, 'Maximum number of iterations', allowZero=False)
         if not isinstance(self.jit, bool):
-            raise ValueError("the JIT switch must be True or False")
+            raise ValueError("JIT option must be a boolean!")
 
 
 class OptionsCVODES(Options):
