@@ -24,26 +24,26 @@ def importTuples(tuples, xLabel, yLabels):
     if not isinstance(yLabels, list):
         yLabels = [yLabels]
     if not isinstance(tuples, list):
-        raise ValueError("sections must be given as a list of tuples / lists")
+        raise ValueError("Input must be a list (of tuples or lists)!")
     width = 1 + len(yLabels)
     if not all(isinstance(row, (tuple, list)) and len(row) == width for row in tuples):
-        raise ValueError("malformed section list")
+        raise ValueError("Error in list!")
     position = np.array([row[0] for row in tuples])
     if (position < 0).any():
-        raise ValueError("section positions must be >= 0")
+        raise ValueError("Position data cannot be negative!")
     if np.isinf(position).any():
-        raise ValueError("section positions must be finite")
+        raise ValueError("Position data cannot be infinite!")
     if (np.diff(position) <= 0).any():
-        raise ValueError("section positions must increase strictly")
+        raise ValueError("Position data must monotonically increase!")
     data = {label: [float(row[1 + j]) for row in tuples] for j, label in enumerate(yLabels)}
     return pd.DataFrame(data, index=pd.Index(position, name=xLabel))
 
 
 def checkDataFrame(df, trackLength):
     if df.index[0] != 0:
-        raise ValueError("'{}': the first section has to start at position 0".format(df.columns[0]))
+        raise ValueError("Error in '{}': First track section must start at 0 m (beginning of track)!".format(df.columns[0]))
     if df.index[-1] > trackLength:
-        raise ValueError("'{}': the last section starts at or beyond the end of the track ({} m)".format(df.columns[0], trackLength))
+        raise ValueError("Error in '{}': Last track section must start before {} m (end of track)!".format(df.columns[0], trackLength))
     return True
 
 
@@ -74,7 +74,7 @@ def computeDiscretizationPoints(track, numIntervals):
     uniform = np.linspace(0, track.length, numIntervals + 1 - (len(merged) - 1))
     grid = np.union1d(uniform, merged.index.values.astype(float))
     if len(grid) != numIntervals + 1:
-        raise ValueError("the grid does not have numIntervals + 1 points (too few intervals for the track sections, or a grid point on a section boundary)")
+        raise ValueError("Wrong number of computed discretization intervals!")
     cols = _sample_steps([merged], grid)
     return pd.DataFrame({name: cols[name] for name in merged.columns}, index=pd.Index(grid, name='position [m]'))
 
@@ -85,17 +85,16 @@ class Track():
 
     def __init__(self, config, pathJSON=Path(__file__).parent.parent / 'tracks'):
         if not isinstance(config, dict):
-            raise ValueError("the track configuration must be a dict")
+            raise ValueError("Track configuration should be provided as a dictionary!")
         if 'id' not in config:
-            raise ValueError("the track configuration needs an 'id'")
+            raise ValueError("Track ID must be specified in configuration!")
         with open(Path(pathJSON) / (config['id'] + '.json')) as fh:
             data = json.load(fh)
         checkTTOBenchVersion(data, ['1.1', '1.2', '1.3'])
 
         stops = data['stops']
-        alt = data.get('altitude')
         self.length = convertUnit(stops['values'][-1], stops['unit'])
-        self.altitude = 0 if alt is None else convertUnit(alt['value'], alt['unit'])
+        self.altitude = convertUnit(data['altitude']['value'], data['altitude']['unit']) if 'altitude' in data else 0
         self.title = data['metadata']['id']
 
         self.importSpeedLimitTuples(data['speed limits']['values'], data['speed limits']['units']['velocity'])
@@ -114,9 +113,9 @@ class Track():
         iFrom = config.get('from', 0)
         iTo = config.get('to', nStops - 1)
         if not 0 <= iFrom < nStops - 1:
-            raise ValueError("'from' is not a valid stop index")
+            raise ValueError("Index of departure is out of bounds!")
         if not iFrom < iTo < nStops:
-            raise ValueError("'to' is not a valid stop index after 'from'")
+            raise ValueError("Index of destination is out of bounds!")
         self.updateLimits(convertUnit(stops['values'][iFrom], stops['unit']), convertUnit(stops['values'][iTo], stops['unit']))
         self.checkFields()
 
@@ -152,38 +151,38 @@ class Track():
 
     def checkFields(self):
         if not self.lengthOk():
-            raise ValueError("track length {} is not a positive number".format(self.length))
+            raise ValueError("Track length must be a strictly positive number, not {}!".format(self.length))
         if self.altitude is None or np.isinf(self.altitude):
-            raise ValueError("altitude {} is not a number".format(self.altitude))
+            raise ValueError("Altitude must be a number, not {}!".format(self.altitude))
         if not self.gradientsOk():
-            raise ValueError("inconsistent gradient sections")
+            raise ValueError("Issue with track gradients!")
         if not self.speedLimitsOk():
-            raise ValueError("inconsistent speed-limit sections")
+            raise ValueError("Issue with track speed limits!")
         if not self.curvaturesOk():
-            raise ValueError("inconsistent curvature sections")
+            raise ValueError("Issue with track curvatures!")
 
     # ------------------------------------------------------------------ import
     def importGradientTuples(self, tuples, unit='permil'):
         if not self.lengthOk():
-            raise ValueError("set a valid track length before importing gradients")
+            raise ValueError("Cannot import gradients without a valid track length!")
         if unit not in {'permil'}:
-            raise ValueError("unsupported gradient unit")
+            raise ValueError("Specified gradient unit not supported!")
         self.gradients = importTuples(tuples, _POS, 'Gradient [permil]')
         checkDataFrame(self.gradients, self.length)
 
     def importSpeedLimitTuples(self, tuples, unit='km/h'):
         if not self.lengthOk():
-            raise ValueError("set a valid track length before importing speed limits")
+            raise ValueError("Cannot import speed limits without a valid track length!")
         if unit not in {'km/h', 'm/s'}:
-            raise ValueError("unsupported speed unit")
+            raise ValueError("Specified speed unit not supported!")
         self.speedLimits = importTuples([(p, convertUnit(v, unit)) for p, v in tuples], _POS, 'Speed limit [m/s]')
         checkDataFrame(self.speedLimits, self.length)
 
     def importCurvatureTuples(self, tuples, unitRadiusStart='m', unitRadiusEnd='m', clothoidSamplingInterval=None):
         if not self.lengthOk():
-            raise ValueError("set a valid track length before importing curvatures")
+            raise ValueError("Cannot import curvature without a valid track length!")
         if unitRadiusStart not in {'m', 'km'} or unitRadiusEnd not in {'m', 'km'}:
-            raise ValueError("unsupported radius unit")
+            raise ValueError("Specified curvature radius unit not supported!")
         # float("infinity") -> inf, i.e. straight track
         sections = [(p, convertUnit(float(r0), unitRadiusStart), convertUnit(float(r1), unitRadiusEnd)) for p, r0, r1 in tuples]
         self.curvatures = importTuples(self.sampleClothoid(sections, clothoidSamplingInterval), _POS, ['Curvature [1/m]'])
@@ -199,13 +198,13 @@ class Track():
         """
         radii = [sec[j] for sec in tuples for j in (1, 2)]
         if any(r == 0 for r in radii):
-            raise ValueError("a curve radius of 0 is not admissible")
+            raise ValueError("Curvature radius cannot be 0!")
         if any(sec[0] < 0 for sec in tuples):
-            raise ValueError("clothoid positions must be >= 0")
+            raise ValueError("Positions cannot be negative!")
         if any(a[0] == b[0] for a, b in zip(tuples[:-1], tuples[1:])):
-            raise ValueError("clothoid positions must increase strictly")
+            raise ValueError("Positions must be monotonically increasing")
         if ds is not None and ds <= 0:
-            raise ValueError("the clothoid sampling interval must be positive (or None)")
+            raise ValueError("Discretization step must be greater than zero or None!")
 
         out = []
         for n, (start, rStart, rEnd) in enumerate(tuples):
@@ -231,7 +230,7 @@ class Track():
         try:
             self.checkFields()
         except ValueError as e:
-            raise ValueError("reversing the track failed: {}".format(e))
+            raise ValueError("Track cannot be reversed due to error: {}".format(str(e)))
 
         def mirrored(df, sign):
             ends = np.append(df.index.values[1:], self.length)
@@ -275,7 +274,7 @@ class Track():
         a = 0 if positionStart is None else positionStart
         b = self.length if positionEnd is None else positionEnd
         if (not 0 <= a < self.length) or (not 0 < b <= self.length):
-            raise ValueError("the new limits must lie inside the track")
+            raise ValueError("Given positions must be between limits of track!")
         a, b = convertUnit(a, unit), convertUnit(b, unit)
 
         def cropped(df):
