@@ -112,6 +112,10 @@ MS_HD double init_t(const Ctx& c, int j, int s, int N) {
 // spent on it.  The exact certificate is the minimum trip time (time-optimal solve, running concurrently); the host
 // layer checks every early flag against it and re-solves an instance without screening should a flag ever be wrong.
 #define MS_SCREEN_MARGIN 0.01
+// Relative margin of the exact certificate (minimum trip time from the time-optimal solve): that solve minimises
+// t_N + 1e-4 * sum(F^2) (ocp.py:146-150), so its t_N can sit slightly above the true minimum; trips within the margin below
+// it are left to the iteration instead of being reported infeasible.
+#define MS_TMIN_MARGIN 1e-6
 // Both per-instance set-up routines below walk the track sequentially (one thread per instance).  Their loops work on chunks
 // of MS_PCH intervals -- all loads of a chunk are issued before the first dependent operation and the results are stored after
 // the last one -- so a pass costs one memory latency per chunk instead of one per interval.

@@ -29,7 +29,7 @@ MS_HD void inst_setup(const Ctx& c, const BatchIO& io, int s) {
     c.I(SI_N_INT, s) = io.nint[s];
     inst_init(c, s);
     // screening with a known minimum trip duration: terminalTime is an upper bound on t_N (ocp.py:260-261)
-    if (io.tmin && io.tmin[s] > 0.0 && (c.P(P_T, s) - c.P(P_T0, s)) < io.tmin[s] * (1.0 - 1e-9)) finish(c, s, ST_INFEASIBLE);
+    if (io.tmin && io.tmin[s] > 0.0 && (c.P(P_T, s) - c.P(P_T0, s)) < io.tmin[s] * (1.0 - MS_TMIN_MARGIN)) finish(c, s, ST_INFEASIBLE);
 }
 
 MS_HD void cell_setup(const Ctx& c, const BatchIO& io, int k, int s) {

@@ -410,9 +410,10 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
     e = cudaHostGetDevicePointer((void**)&h->done_host_dev, h->done_host, 0);
     if (e != cudaSuccess) { cudaFreeHost(h->done_host); delete h; return cuda_fail(e, "cudaHostGetDevicePointer"); }
-    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming);
     h->hp = nullptr;
-    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&h->xev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->xev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFreeHost(h->done_host); delete h; return cuda_fail(e, "cudaEventCreateWithFlags"); }
     *out = h;
     return 0;
 }
@@ -422,6 +423,8 @@ int mseetc_destroy(mseetc_handle h) {
     cudaFreeHost(h->done_host);
     if (h->lm_dev) cudaFree(h->lm_dev);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->poll_ev[i]);
+    for (int i = 0; i < 16; ++i) cudaEventDestroy(h->xev[i]);
+    if (h->hp) cudaStreamDestroy(h->hp);
     for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
     delete h;
     return 0;

@@ -77,6 +77,9 @@ struct RingFetch {
         tail = (tail == DEPTH) ? 0 : tail + 1;
     }
     __device__ void start(const Ctx& c, int s, int kFirst, int kLast, int direction) {
+        // a sweep that was left early (failed inertia test) still has copies in flight into these slots: drain them before the
+        // slots are requested again, otherwise a stale copy can land after the new one
+        asm volatile("cp.async.wait_all;" ::: "memory");
         next = &c.W(0, kFirst, s);
         step = (long)direction * REC_STRIDE;
         left = (direction < 0 ? kFirst - kLast : kLast - kFirst) + 1;
@@ -582,7 +585,7 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     // time-optimal solve on another stream): terminalTime is an upper bound on t_N (ocp.py:260-261)
     if (c.tmin) {
         const double tm = c.tmin[s];
-        if (tm > 0.0 && (c.P(P_T, s) - c.P(P_T0, s)) < tm * (1.0 - 1e-9)) { finish(c, s, ST_INFEASIBLE); return; }
+        if (tm > 0.0 && (c.P(P_T, s) - c.P(P_T0, s)) < tm * (1.0 - MS_TMIN_MARGIN)) { finish(c, s, ST_INFEASIBLE); return; }
     }
     const double th = a.th, fo = a.fo, dinf = a.dinf, pinf = a.pinf, cmin = a.cmin, cmax = a.cmax, zsum = a.zsum, ysum = a.ysum;
     // counts for the IPOPT error scaling s_d, s_c (eq. 6)

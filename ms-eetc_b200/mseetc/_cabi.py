@@ -18,6 +18,9 @@ PARAMS = ['SR0', 'SR1', 'SR2', 'FEL_LO', 'FEL_UP', 'FPB_LO', 'POW_LO', 'POW_UP',
           'DYN_SCALE']
 PARAM_INDEX = {name: i for i, name in enumerate(PARAMS)}
 
+# relative margin below the minimum trip time inside which an instance is still iterated (MS_TMIN_MARGIN, core.cuh)
+TMIN_MARGIN = 1e-6
+
 STATUS_STRINGS = {   # IPOPT's return_status vocabulary (what stats['Solver status'] holds in the reference, ocp.py:362)
     0: 'Solve_Succeeded',
     1: 'Maximum_Iterations_Exceeded',

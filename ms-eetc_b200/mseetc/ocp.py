@@ -297,13 +297,14 @@ class casadiSolver():
         return self._pool
 
     def _pinned(self, key, like):
-        """Page-locked staging buffers are kept per solver in a ring of two per output (allocating 50 MB of pinned memory per call
-        costs more than the solve): a returned array stays valid until the second-next solve_batch call on this solver."""
+        """Page-locked staging buffers are kept per solver in a ring of three per output (allocating 50 MB of pinned memory per call
+        costs more than the solve): a returned array stays valid until the second-next solve_batch call on this solver (a call
+        may use two slots: its own and the one of the nested re-solve of wrongly screened instances)."""
         import torch
         ring = self._dev.setdefault('pinned', {})
-        slot = ring.setdefault(key, {'bufs': [None, None], 'next': 0})
+        slot = ring.setdefault(key, {'bufs': [None, None, None], 'next': 0})
         i = slot['next']
-        slot['next'] = 1 - i
+        slot['next'] = (i + 1) % 3
         buf = slot['bufs'][i]
         if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
             buf = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
@@ -394,7 +395,8 @@ class casadiSolver():
             cur = sib.solve_batch(t0 + factor * running, initialTime, terminalVelocity, initialVelocity, overrides=overrides,
                                   screen=False, device=device)
             if res is None:
-                res = cur
+                # own copies: `cur` are views of a two-deep ring of pinned buffers that the next passes reuse
+                res = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in cur.items()}
             else:
                 redo = res['status'] != 0
                 for key in ('z', 'status', 'obj', 'kkt', 'iters'):
@@ -517,7 +519,7 @@ class casadiSolver():
         res = {k: (v.numpy() if hasattr(v, 'numpy') else v) for k, v in res.items()}
         if tmin is not None:
             # an instance below its minimum trip time is infeasible whatever the iteration did before the certificate arrived
-            short = (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
+            short = (tmin > 0) & ((T - t0) < tmin * (1 - _cabi.TMIN_MARGIN))
             res['status'][(res['status'] != 0) & short] = 4
             # the device also screens with a speed-envelope bound before the first iteration (inst_screen, core.cuh); every such
             # flag is checked against the exact certificate and an instance flagged wrongly is solved again without screening
@@ -561,7 +563,7 @@ class casadiSolver():
             # classify the failure: below the minimum trip time the problem is infeasible (what IPOPT's restoration
             # phase would report); the time-optimal solve is only paid for on failure
             dur, st = self.minimum_time(initialTime, terminalVelocity, initialVelocity)
-            if st[0] == 0 and (terminalTime - initialTime) < dur[0] * (1 - 1e-9):
+            if st[0] == 0 and (terminalTime - initialTime) < dur[0] * (1 - _cabi.TMIN_MARGIN):
                 status = 4
         stats = {'Solver status': _cabi.STATUS_STRINGS.get(status, 'Internal_Error'), 'IP iterations': int(res['iters'][0]),
                  'CPU time [s]': res['wall'], 'Cost': float(res['cost'][0])}
@@ -657,7 +659,7 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
     out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
     res = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
     if tmin is not None:
-        short = (tmin > 0) & ((T - t0) < tmin * (1 - 1e-9))
+        short = (tmin > 0) & ((T - t0) < tmin * (1 - _cabi.TMIN_MARGIN))
         res['status'][(res['status'] != 0) & short] = 4
         wrong = np.flatnonzero((res['status'] == 4) & ~short)      # early envelope flag without an exact certificate: solve again
         if len(wrong):
