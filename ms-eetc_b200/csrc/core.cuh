@@ -415,6 +415,7 @@ MS_HD void inst_init(const Ctx& c, int s) {
     c.I(SI_NREG, s) = 0;
     c.I(SI_TICKS, s) = 0;
     c.I(SI_LAST_GAIN, s) = 0;
+    c.I(SI_FACT, s) = 0;
 }
 
 // slack of a bound and the matching barrier pieces

@@ -89,7 +89,9 @@ enum SdField {
     SD_FILTER,                                   // SD_FILTER + 2*i : (theta_i, phi_i)
     SD_N = SD_FILTER + 2 * 12
 };
-enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_LAST_GAIN, SI_N };
+enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_LAST_GAIN,
+               SI_FACT,     // a factorisation has been stored (its chunk-end value functions are the references of pit.cuh)
+               SI_N };
 
 enum Phase { PH_EVAL = 0, PH_TRIAL = 1, PH_DONE = 2, PH_STEPPED = 3, PH_FACTOR = 4 };
 enum { RED_W = 16 };   // interleave factor of the per-instance reductions (fixed -> bitwise reproducible sums)

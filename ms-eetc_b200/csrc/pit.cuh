@@ -306,4 +306,312 @@ inline void inst_step_pit_emulated(const Ctx& c, int s, int G, FetchB& fb, Fetch
     c.I(SI_PHASE, s) = PH_STEPPED;
 }
 
+
+// =====================================================================================================================
+// Chunked parallel-in-time sweeps, second formulation (used for short and long horizons alike).
+//
+// A chunk of consecutive intervals [kLo, kHi) maps the value function (Pi, pi) at its end node to the value function at its
+// start node by a linear-fractional transformation.  Its coefficients are what a Riccati recursion with ZERO terminal value
+// produces anyway -- value function (Pbar, pbar) at the chunk start, closed-loop transition x_e = Phi x_a + phi under the
+// zero-terminal gains -- plus the closed-loop controllability Gramian  W = sum_j Phi_{e<-j+1} B Rt_j^{-1} B' Phi_{e<-j+1}':
+//     P_a = Pbar + Phi' T Phi,                 T = Pi (I + W Pi)^{-1} = (Pi^{-1} + W)^{-1}   (symmetric)
+//     p_a = pbar + Phi' (pi + T (phi - W pi))
+// (same element as in Sarkka & Garcia-Fernandez, but accumulated by the stable, structure-exploiting stage recursion of
+// riccati.cuh instead of by repeated generic combinations, and only ever applied to a genuine value function.)
+//   phase A   every chunk but the last: zero-terminal recursion -> element (27 numbers); the last chunk runs the ordinary
+//             recursion from the terminal node (exact) and keeps its factors
+//   chain     the value functions at the chunk ends follow one after the other, last chunk first: G - 2 applications of an
+//             element to a value function (3x3 Cholesky factorisations, no ill-conditioned unsymmetric inverse)
+//   phase C   ordinary recursion inside every chunk from its end value: gains, value functions, exact inertia test; closed-loop
+//             transition of the chunk
+//   chain     state step at the chunk starts (G affine maps applied one after the other)
+//   phase F   forward sweep inside every chunk
+struct ChunkElem {
+    double P[6], p[3], Phi[9], phi[3], W[6];      // P, W symmetric: (00,01,02,11,12,22)
+};
+
+template <bool REG, class Fetch>
+MS_HD bool chunk_element_t(const Ctx& c, int s, int kLo, int kHi, double mu, double delta, Fetch& fetch, const double* refP, const double* refp,
+                           ChunkElem& E) {
+    const double pn = c.cfg.withPn ? 1.0 : 0.0;
+    double P[3][3], p[3];
+    sym_to_full(refP, P);
+    for (int i = 0; i < 3; ++i) p[i] = refp[i];
+    for (int i = 0; i < 9; ++i) E.Phi[i] = 0.0;
+    E.Phi[0] = E.Phi[4] = E.Phi[8] = 1.0;
+    for (int i = 0; i < 3; ++i) E.phi[i] = 0.0;
+    for (int i = 0; i < 6; ++i) E.W[i] = 0.0;
+    bool ok = true;
+    if (kHi > kLo) {
+        fetch.start(c, s, kHi - 1, kLo, -1);
+        for (int k = kHi - 1; k >= kLo; --k) {
+            double v[BwdFields::NF], vs[6], K[3][3], kf[3], cb[4];
+            fetch.get(c, k, s, v);
+            if (REG) load_scol(c, k, s, vs);
+            if (!stage_riccati_sparse(v, REG ? vs : nullptr, mu, delta, pn, P, p, K, kf, cb)) { ok = false; if (!Fetch::COLLECTIVE) return false; }
+            const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F];
+            // Gramian: W += Y Rt^{-1} Y',  Y = Phi_{e<-k+1} B,  B = [(tF, pF, 1)  pn (tF, pF, 0)]
+            double yF[3], yQ[3], xF[3], xQ[3];
+            for (int i = 0; i < 3; ++i) {
+                const double g = E.Phi[3 * i] * tF + E.Phi[3 * i + 1] * pF;
+                yF[i] = g + E.Phi[3 * i + 2]; yQ[i] = pn * g;
+                sym2_solve(cb[0], cb[1], cb[2], cb[3], yF[i], yQ[i], xF[i], xQ[i]);
+            }
+            E.W[0] += yF[0] * xF[0] + yQ[0] * xQ[0]; E.W[1] += yF[0] * xF[1] + yQ[0] * xQ[1]; E.W[2] += yF[0] * xF[2] + yQ[0] * xQ[2];
+            E.W[3] += yF[1] * xF[1] + yQ[1] * xQ[1]; E.W[4] += yF[1] * xF[2] + yQ[1] * xQ[2]; E.W[5] += yF[2] * xF[2] + yQ[2] * xQ[2];
+            // closed loop of this interval under the zero-terminal gains, composed onto the transition of the intervals behind it
+            const double kfw = kf[0] + pn * kf[1];
+            double Mk[9], mk[3];
+            mk[0] = v[QP_RT] + tF * kfw; mk[1] = v[QP_RB] + pF * kfw; mk[2] = kf[0];
+            for (int j = 0; j < 3; ++j) {
+                const double kw = K[0][j] + pn * K[1][j];
+                Mk[j] = (j == 0 ? 1.0 : j == 1 ? tb : 0.0) + tF * kw;
+                Mk[3 + j] = (j == 1 ? pb : 0.0) + pF * kw;
+                Mk[6 + j] = K[0][j];
+            }
+            closed_loop_compose(E.Phi, E.phi, Mk, mk);
+        }
+    }
+    full_to_sym(P, E.P);
+    for (int i = 0; i < 3; ++i) E.p[i] = p[i];
+    return ok;
+}
+template <class Fetch>
+MS_HD bool chunk_element(const Ctx& c, int s, int kLo, int kHi, double mu, double delta, Fetch& fetch, const double* refP, const double* refp,
+                         ChunkElem& E) {
+    if (delta > 0.0) return chunk_element_t<true>(c, s, kLo, kHi, mu, delta, fetch, refP, refp, E);
+    return chunk_element_t<false>(c, s, kLo, kHi, mu, delta, fetch, refP, refp, E);
+}
+
+// The same for a terminal value given as a difference to the reference value the element was accumulated with:
+//     T = (I + dPi W)^{-1} dPi     (dPi symmetric, not necessarily definite; 3x3 elimination with row pivoting, then symmetrised)
+// The closer the reference is to the value function (the chunk-end values of the previous interior-point iteration are used),
+// the smaller the correction and the better conditioned the recursion that produced the element.
+MS_HD bool chunk_apply_diff(const ChunkElem& E, const double dPi[3][3], const double dpi[3], double P[3][3], double p[3]) {
+    double W[3][3];
+    sym_to_full(E.W, W);
+    // augmented rows [I + dPi W | dPi]
+    double a0[6], a1[6], a2[6];
+    {
+        double* rows[3] = {a0, a1, a2};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                rows[i][j] = (i == j ? 1.0 : 0.0) + dPi[i][0] * W[0][j] + dPi[i][1] * W[1][j] + dPi[i][2] * W[2][j];
+                rows[i][3 + j] = dPi[i][j];
+            }
+    }
+#define MS_ROWSWAP(x, y) { for (int q = 0; q < 6; ++q) { const double t_ = x[q]; x[q] = y[q]; y[q] = t_; } }
+    // column 0
+    if (fabs(a1[0]) > fabs(a0[0])) MS_ROWSWAP(a0, a1)
+    if (fabs(a2[0]) > fabs(a0[0])) MS_ROWSWAP(a0, a2)
+    if (!(fabs(a0[0]) > 1e-300) || !isfinite(a0[0])) return false;
+    { const double r = rcp(a0[0]); const double f1 = a1[0] * r, f2 = a2[0] * r;
+      for (int q = 1; q < 6; ++q) { a1[q] -= f1 * a0[q]; a2[q] -= f2 * a0[q]; } }
+    // column 1
+    if (fabs(a2[1]) > fabs(a1[1])) MS_ROWSWAP(a1, a2)
+    if (!(fabs(a1[1]) > 1e-300) || !isfinite(a1[1])) return false;
+    { const double r = rcp(a1[1]); const double f2 = a2[1] * r;
+      for (int q = 2; q < 6; ++q) a2[q] -= f2 * a1[q]; }
+    if (!(fabs(a2[2]) > 1e-300) || !isfinite(a2[2])) return false;
+#undef MS_ROWSWAP
+    // back substitution for the three right-hand sides
+    double T[3][3];
+    {
+        const double r2 = rcp(a2[2]), r1 = rcp(a1[1]), r0 = rcp(a0[0]);
+        for (int j = 0; j < 3; ++j) {
+            const double x2 = a2[3 + j] * r2;
+            const double x1 = (a1[3 + j] - a1[2] * x2) * r1;
+            const double x0 = (a0[3 + j] - a0[1] * x1 - a0[2] * x2) * r0;
+            T[0][j] = x0; T[1][j] = x1; T[2][j] = x2;
+        }
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j) { const double x = 0.5 * (T[i][j] + T[j][i]); T[i][j] = x; T[j][i] = x; }
+    // P = Pbar + Phi' T Phi ;  p = pbar + Phi' (dpi + T (phi - W dpi))
+    double TP[3][3], w[3], u[3];
+    for (int i = 0; i < 3; ++i) {
+        w[i] = E.phi[i] - (W[i][0] * dpi[0] + W[i][1] * dpi[1] + W[i][2] * dpi[2]);
+        for (int j = 0; j < 3; ++j) TP[i][j] = T[i][0] * E.Phi[j] + T[i][1] * E.Phi[3 + j] + T[i][2] * E.Phi[6 + j];
+    }
+    for (int i = 0; i < 3; ++i) u[i] = dpi[i] + T[i][0] * w[0] + T[i][1] * w[1] + T[i][2] * w[2];
+    double Pb[3][3];
+    sym_to_full(E.P, Pb);
+    for (int i = 0; i < 3; ++i) {
+        p[i] = E.p[i] + (E.Phi[i] * u[0] + E.Phi[3 + i] * u[1] + E.Phi[6 + i] * u[2]);
+        for (int j = i; j < 3; ++j) {
+            const double x = Pb[i][j] + (E.Phi[i] * TP[0][j] + E.Phi[3 + i] * TP[1][j] + E.Phi[6 + i] * TP[2][j]);
+            P[i][j] = x; P[j][i] = x;
+        }
+    }
+    for (int i = 0; i < 3; ++i) { if (!isfinite(p[i])) return false; for (int j = 0; j < 3; ++j) if (!isfinite(P[i][j])) return false; }
+    return true;
+}
+
+// Value function at the start of a chunk from the one at its end.  Pi = L L' (Cholesky, semi-definite tolerant: a pivot that is
+// zero or negative within rounding gives a zero column), T = L (I + L' W L)^{-1} L' with a second Cholesky factorisation of
+// the 3x3 matrix I + L' W L >= I.  Returns false when Pi is clearly not positive semi-definite (or not finite).
+MS_HD bool chunk_apply(const ChunkElem& E, const double Pi[3][3], const double pi[3], double P[3][3], double p[3]) {
+    const double big = fmax(fmax(fabs(Pi[0][0]), fabs(Pi[1][1])), fabs(Pi[2][2]));
+    if (!isfinite(big)) return false;
+    const double tiny = 1e-13 * big, neg = -1e-7 * big;
+    double L[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    {
+        const double d0 = Pi[0][0];
+        if (d0 < neg) return false;
+        if (d0 > tiny) { const double r = rcp(sqrt(d0)); L[0][0] = d0 * r; L[1][0] = Pi[1][0] * r; L[2][0] = Pi[2][0] * r; }
+        const double d1 = Pi[1][1] - L[1][0] * L[1][0];
+        if (d1 < neg) return false;
+        if (d1 > tiny) { const double r = rcp(sqrt(d1)); L[1][1] = d1 * r; L[2][1] = (Pi[2][1] - L[2][0] * L[1][0]) * r; }
+        const double d2 = Pi[2][2] - L[2][0] * L[2][0] - L[2][1] * L[2][1];
+        if (d2 < neg) return false;
+        if (d2 > tiny) L[2][2] = sqrt(d2);
+    }
+    double W[3][3];
+    sym_to_full(E.W, W);
+    // G = I + L' W L
+    double WL[3][3], G[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) WL[i][j] = W[i][0] * L[0][j] + W[i][1] * L[1][j] + W[i][2] * L[2][j];
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) G[i][j] = (i == j ? 1.0 : 0.0) + L[0][i] * WL[0][j] + L[1][i] * WL[1][j] + L[2][i] * WL[2][j];
+    // G = C C' (lower), reciprocals of the diagonal
+    const double c00 = sqrt(G[0][0]), i00 = rcp(c00);
+    const double c10 = G[0][1] * i00, c20 = G[0][2] * i00;
+    const double e1 = G[1][1] - c10 * c10;
+    if (!(e1 > 0.0)) return false;
+    const double c11 = sqrt(e1), i11 = rcp(c11);
+    const double c21 = (G[1][2] - c20 * c10) * i11;
+    const double e2 = G[2][2] - c20 * c20 - c21 * c21;
+    if (!(e2 > 0.0)) return false;
+    const double i22 = rcp(sqrt(e2));
+    // U = C^{-1} L'  (column j of L' is row j of L)
+    double U[3][3];
+    for (int j = 0; j < 3; ++j) {
+        const double r0 = L[j][0], r1 = L[j][1], r2 = L[j][2];
+        const double y0 = r0 * i00, y1 = (r1 - c10 * y0) * i11, y2 = (r2 - c20 * y0 - c21 * y1) * i22;
+        U[0][j] = y0; U[1][j] = y1; U[2][j] = y2;
+    }
+    // V = U Phi ;  P = Pbar + V'V ;  p = pbar + Phi' pi + V' U (phi - W pi)
+    double V[3][3], w[3], u[3];
+    for (int i = 0; i < 3; ++i) {
+        w[i] = E.phi[i] - (W[i][0] * pi[0] + W[i][1] * pi[1] + W[i][2] * pi[2]);
+        for (int j = 0; j < 3; ++j) V[i][j] = U[i][0] * E.Phi[j] + U[i][1] * E.Phi[3 + j] + U[i][2] * E.Phi[6 + j];
+    }
+    for (int i = 0; i < 3; ++i) u[i] = U[i][0] * w[0] + U[i][1] * w[1] + U[i][2] * w[2];
+    double Pb[3][3];
+    sym_to_full(E.P, Pb);
+    for (int i = 0; i < 3; ++i) {
+        p[i] = E.p[i] + (E.Phi[i] * pi[0] + E.Phi[3 + i] * pi[1] + E.Phi[6 + i] * pi[2]) + (V[0][i] * u[0] + V[1][i] * u[1] + V[2][i] * u[2]);
+        for (int j = i; j < 3; ++j) {
+            const double x = Pb[i][j] + (V[0][i] * V[0][j] + V[1][i] * V[1][j] + V[2][i] * V[2][j]);
+            P[i][j] = x; P[j][i] = x;
+        }
+    }
+    return true;
+}
+
+// ---- host emulation of the chunked driver (tests/hostsim): the lanes of one instance in a loop ----------------------------
+#if !defined(__CUDACC__)
+struct PitDiag { double devP, devp; long applies, applyFails, elemFails; };
+inline PitDiag& pit_diag() { static PitDiag d{0, 0, 0, 0, 0}; return d; }
+#endif
+template <class FetchB, class FetchF>
+inline bool pit_chunks_direction_emulated(const Ctx& c, int s, int N, int G, double mu, double delta, FetchB& fb, FetchF& ff, bool& scanFailed) {
+    scanFailed = false;
+    ChunkElem E[64];
+    double Pe[64][3][3], pe[64][3];
+    Aff T[64];
+    int kLo[64], kHi[64];
+    for (int l = 0; l < G; ++l) pit_chunk(N, G, l, kLo[l], kHi[l]);
+    // reference terminal values: what the previous factorisation left at the chunk-end nodes (zero before the first one)
+    double refP[64][6], refp[64][3];
+    const bool haveRef = c.I(SI_FACT, s) != 0;
+    for (int l = 1; l < G - 1; ++l) {
+        for (int i = 0; i < 6; ++i) refP[l][i] = haveRef ? c.W(WS_RIC + RIC_P + i, kHi[l], s) : 0.0;
+        for (int i = 0; i < 3; ++i) refp[l][i] = haveRef ? c.W(WS_RIC + RIC_PV + i, kHi[l], s) : 0.0;
+    }
+    // phase A
+    for (int l = 1; l < G - 1; ++l)
+        if (!chunk_element(c, s, kLo[l], kHi[l], mu, delta, fb, refP[l], refp[l], E[l])) { scanFailed = true; return false; }
+    {   // last chunk: ordinary recursion from the terminal node, factors kept
+        double P[3][3], p[3];
+        terminal_value(c, s, N, mu, delta, P, p);
+        aff_identity(T[G - 1]);
+        if (!riccati_backward_range(c, s, N, kLo[G - 1], N, mu, delta, fb, P, p, T[G - 1].M, T[G - 1].m)) return false;
+        if (G >= 2) { for (int i = 0; i < 3; ++i) { pe[G - 2][i] = p[i]; for (int j = 0; j < 3; ++j) Pe[G - 2][i][j] = P[i][j]; } }
+    }
+    // chain of value functions at the chunk ends
+    for (int l = G - 3; l >= 0; --l) {
+        double dP[3][3], dp[3], R[3][3];
+        sym_to_full(refP[l + 1], R);
+        for (int i = 0; i < 3; ++i) { dp[i] = pe[l + 1][i] - refp[l + 1][i]; for (int j = 0; j < 3; ++j) dP[i][j] = Pe[l + 1][i][j] - R[i][j]; }
+        if (!chunk_apply_diff(E[l + 1], dP, dp, Pe[l], pe[l])) { scanFailed = true; return false; }
+    }
+    // phase C
+    for (int l = 0; l < G - 1; ++l) {
+        aff_identity(T[l]);
+        double P[3][3], p[3];
+        for (int i = 0; i < 3; ++i) { p[i] = pe[l][i]; for (int j = 0; j < 3; ++j) P[i][j] = Pe[l][i][j]; }
+        if (!riccati_backward_range(c, s, N, kLo[l], kHi[l], mu, delta, fb, P, p, T[l].M, T[l].m)) return false;
+    }
+#if !defined(__CUDACC__)
+    if (getenv("HOSTSIM_PIT_DIAG") && atoi(getenv("HOSTSIM_PIT_DIAG")) >= 3) {
+        for (int l = 0; l < G - 1; ++l) {
+            const int k = kHi[l];
+            printf("   chunk %2d end node %3d  P chain/rec:", l, k);
+            const int ij[6][2] = {{0,0},{0,1},{0,2},{1,1},{1,2},{2,2}};
+            for (int i = 0; i < 6; ++i) printf(" %.3e|%.1e", Pe[l][ij[i][0]][ij[i][1]], Pe[l][ij[i][0]][ij[i][1]] - c.W(WS_RIC + RIC_P + i, k, s));
+            printf("   p:");
+            for (int i = 0; i < 3; ++i) printf(" %.3e|%.1e", pe[l][i], pe[l][i] - c.W(WS_RIC + RIC_PV + i, k, s));
+            printf("\n");
+        }
+    }
+#endif
+    // chain of chunk-start states, forward sweeps
+    c.W(WS_ST + ST_T, 0, s) = 0.0;
+    c.W(WS_ST + ST_B, 0, s) = 0.0;
+    double dx[3] = {0.0, 0.0, 0.0};
+    for (int l = 0; l < G; ++l) {
+        double d[3] = {dx[0], dx[1], dx[2]};
+        riccati_forward_range(c, s, N, kLo[l], (l == G - 1) ? N : kHi[l], mu, delta, ff, d);
+        double nx[3];
+        for (int i = 0; i < 3; ++i) nx[i] = T[l].m[i] + T[l].M[3 * i] * dx[0] + T[l].M[3 * i + 1] * dx[1] + T[l].M[3 * i + 2] * dx[2];
+#if !defined(__CUDACC__)
+        if (getenv("HOSTSIM_PIT_DIAG") && atoi(getenv("HOSTSIM_PIT_DIAG")) >= 3 && l < G - 1)
+            printf("   fwd chunk %2d: chain (%.3e %.3e %.3e) in-chunk-minus-chain (%.1e %.1e %.1e)  m (%.2e %.2e %.2e)\n", l, nx[0], nx[1], nx[2], d[0]-nx[0], d[1]-nx[1], d[2]-nx[2], T[l].m[0], T[l].m[1], T[l].m[2]);
+#endif
+        for (int i = 0; i < 3; ++i) dx[i] = nx[i];
+    }
+    return true;
+}
+
+// per-instance driver with the inertia-correction ladder (host emulation).  A failure of the element algebra (zero-terminal
+// recursion not positive definite, value function not positive semi-definite) sends the instance to the sequential sweeps.
+template <class FetchB, class FetchF>
+inline void inst_step_pit_chunks_emulated(const Ctx& c, int s, int G, FetchB& fb, FetchF& ff, long* fallbacks) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_FACTOR) return;
+    const int N = c.I(SI_N_INT, s);
+    const double mu = c.D(SD_MU, s);
+    double delta = 0.0;
+    const double dlast = c.D(SD_DELTA_LAST, s);
+    bool ok = false;
+    for (int tries = 0; tries < 40; ++tries) {
+        count_cells(c, 2, N);
+        bool scanFailed = false;
+        if (pit_chunks_direction_emulated(c, s, N, G, mu, delta, fb, ff, scanFailed)) { ok = true; break; }
+        if (scanFailed) { if (fallbacks) *fallbacks += 1; inst_step(c, s, fb, ff); return; }
+        c.I(SI_NREG, s) += 1;
+        if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
+        else delta *= (dlast == 0.0) ? 100.0 : 8.0;
+        if (delta > 1e40) break;
+    }
+    if (!ok) { finish(c, s, ST_STEP_FAILED); return; }
+    if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
+    c.D(SD_DELTA, s) = delta;
+    count_cells(c, 3, N);
+    c.I(SI_FACT, s) = 1;
+    c.I(SI_PHASE, s) = PH_STEPPED;
+}
+
 }  // namespace mseetc

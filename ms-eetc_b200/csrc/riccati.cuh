@@ -314,8 +314,9 @@ MS_HD void sym2_solve(double a, double b, double i0, double idet, double r0, dou
     x0 = (r0 - b * x1) * i0;
 }
 
+// `cb` (optional): reduced control block of this stage, (M_FF, M_FQ, 1/M_FF, 1/det), for the chunk elements of pit.cuh
 MS_HD bool stage_riccati_sparse(const double* v, const double* vs, double mu, double delta, double pn,
-                                double P[3][3], double p[3], double K[3][3], double kf[3]) {
+                                double P[3][3], double p[3], double K[3][3], double kf[3], double* cb = nullptr) {
     const double tb = v[QP_TAU_B], tF = v[QP_TAU_F], pb = v[QP_PHI_B], pF = v[QP_PHI_F], rt = v[QP_RT], rb = v[QP_RB];
     const double P00 = P[0][0], P01 = P[0][1], P02 = P[0][2], P11 = P[1][1], P12 = P[1][2], P22 = P[2][2];
     double Hbb = v[QP_H_BB], HbF = v[QP_H_BFEL], HbQ = v[QP_H_BFPB], HFF = v[QP_H_FELFEL], HFQ = v[QP_H_FELFPB], HQQ = v[QP_H_FPBFPB];
@@ -357,6 +358,7 @@ MS_HD bool stage_riccati_sparse(const double* v, const double* vs, double mu, do
     const double det = MFF * MQQ - MFQ * MFQ;
     if (!(MFF > 0.0) || !(det > 0.0) || !isfinite(MFF) || !isfinite(det)) return false;
     const double i0 = rcp(MFF), idet = rcp(det);
+    if (cb) { cb[0] = MFF; cb[1] = MFQ; cb[2] = i0; cb[3] = idet; }
     // feedback: Muu [K kf] = -[Mux mu]
     double x0, x1;
     sym2_solve(MFF, MFQ, i0, idet, MtF, MtQ, x0, x1);
@@ -650,6 +652,7 @@ MS_HD void inst_step(const Ctx& c, int s, FetchB& fb, FetchF& ff) {
     c.D(SD_DELTA, s) = delta;
     count_cells(c, 3, N);
     riccati_forward(c, s, N, mu, delta, ff);
+    c.I(SI_FACT, s) = 1;
     c.I(SI_PHASE, s) = PH_STEPPED;
 }
 
