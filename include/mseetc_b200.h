@@ -125,7 +125,8 @@ size_t mseetc_workspace_bytes(mseetc_handle h, int32_t n_instances);
  *                     the envelope screening: an instance whose available time is more than 1 % below a speed-envelope
  *                     lower bound on the trip duration gets the same status before its first iteration (iterations 0).
  *                     The caller is expected to confirm such flags with the exact minimum time once it is known (the
- *                     Python layer does, and re-solves with tmin_dev = NULL should one not be confirmed).
+ *                     Python layer does, and re-solves with tmin_dev = NULL should one not be confirmed).  A negative entry
+ *                     exempts an instance from both screenings (the caller asserts that it is feasible).
  * outputs (device, caller-owned; each may be NULL except status_out):
  *   z_out_dev    [n_instances * (n_intervals_max*(3+nu)+2)]  reference variable order (ocp.py:166-181,248-249)
  *   lam_g_out_dev[n_instances * n_intervals_max*rows]        multipliers of g in reference row order

@@ -25,6 +25,8 @@ namespace {
 
 thread_local std::string g_err;
 
+enum { PIT_SL = 8 };      // instances per block of the parallel-in-time sweep kernel (pad_slots keeps S a multiple of 32)
+
 // ---- interval-parallel kernels: one thread per (interval k, instance), warp = 32 instances at one k.  The kernels stride over
 // the cells, so any grid works; the default is one block per 128 cells (measured faster than a persistent grid of a few blocks
 // per SM, MSEETC_CELL_WAVES=w selects the latter for experiments: 110.9k / 115.5k / 118.6k / 122.0k solves/s at w = 1/2/4/8
@@ -179,149 +181,83 @@ __global__ void __launch_bounds__(BS) k_step(Ctx c) {
     inst_step(c, s, fb, ff);
 }
 
-// ---- parallel-in-time sweeps: G lanes per instance (pit.cuh).  Chunk elements -> suffix scan (warp shuffles) -> exact
-// Riccati inside every chunk (twice: the second pass takes its end value from the neighbour's first pass, a block-Jacobi
-// refinement) -> prefix scan of the closed-loop chunk transitions -> chunk-local forward sweeps.  An a-posteriori check of
-// the chunk-end value functions decides per instance whether the result is trusted; otherwise lane 0 redoes the
-// sequential sweeps (same kernel), so accuracy never depends on the scan.
-template <int G>
-__device__ __forceinline__ void shfl_down_arr(const double* src, double* dst, int n, int d) {
-    for (int i = 0; i < n; ++i) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d, G);
-}
-template <int G>
-__device__ __forceinline__ void shfl_up_arr(const double* src, double* dst, int n, int d) {
-    for (int i = 0; i < n; ++i) dst[i] = __shfl_up_sync(0xffffffffu, src[i], d, G);
-}
-
-template <int G>
-__global__ void __launch_bounds__(64) k_step_pit(Ctx c, int* fallbackCount) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = gtid / G, cl = gtid % G;
-    const int lane = threadIdx.x & 31;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-    const Config& g = c.cfg;
-    const bool active = s < g.nInst && c.I(SI_PHASE, s) == PH_FACTOR;
-    const int N = active ? c.I(SI_N_INT, s) : 2;
-    const double mu = active ? c.D(SD_MU, s) : 0.1;
+// ---- parallel-in-time sweeps (pit.cuh): a block = SL consecutive instances x G chunk lanes, thread = (chunk l, instance).
+// The lanes of a warp that work on the same chunk sit next to each other, so a warp touches 32/SL segments of SL * 8 bytes per
+// field (whole 32-byte sectors for SL >= 4).  Elements, chunk-end values, chunk transitions and chunk-start states go through
+// shared memory; the two short sequential chains over the chunks are run by the lane of chunk 0.  Stage data are prefetched
+// through the same per-thread cp.async ring as in k_step.  An instance whose element algebra fails, or whose chain and recursion
+// disagree, is redone by the sequential sweeps (lane of chunk 0, same kernel), so accuracy never rests on the chain.
+template <int SL, int G, int DEPTH>
+__global__ void __launch_bounds__(SL * G) k_step_pit(Ctx c, int* fallbackCount) {
+    extern __shared__ __align__(128) double pit_sm[];
+    constexpr int BS = SL * G;
+    double* ring = pit_sm;
+    double* shbase = pit_sm + (size_t)(DEPTH + 1) * RING_NF_MAX * BS;
+    int* flags = reinterpret_cast<int*>(shbase + (size_t)G * SH_N * SL);
+    const int col = threadIdx.x % SL, l = threadIdx.x / SL;
+    const int s = blockIdx.x * SL + col;
+    const bool active = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_FACTOR;
+    if (!__syncthreads_or(active)) return;
+    PitShare sh{shbase, flags, SL};
+    PitLane t;
+    t.s = s; t.col = col; t.l = l; t.G = G;
+    t.N = active ? c.I(SI_N_INT, s) : 2;
+    t.mu = active ? c.D(SD_MU, s) : 0.1;
+    t.delta = 0.0;
     const double dlast = active ? c.D(SD_DELTA_LAST, s) : 0.0;
-    int kLo, kHi;
-    pit_chunk(N, G, cl, kLo, kHi);
-    DirectFetch<BwdFields> fb;
-    DirectFetch<FwdFields> ff;
+    pit_chunk(t.N, G, l, t.kLo, t.kHi);
+    if (active) pit_read_reference(c, t);
+    if (l == 0) flags[col] = 0;
+    RingFetch<BwdFields, BS, DEPTH> fb;
+    fb.sm = ring + threadIdx.x;
+    RingFetch<FwdFields, BS, DEPTH> ff;
+    ff.sm = ring + threadIdx.x;
     double delta = 0.0;
-    bool pending = active, failedForGood = false, fallback = false;
-    Aff T;
-    aff_identity(T);
+    bool pending = active, failed = false, fallback = false;
     for (int tries = 0; tries < 40; ++tries) {
-        if (!__any_sync(0xffffffffu, pending)) break;
-        bool ok = true;
-        Elem E;
-        elem_identity(E);
-        double Pl[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, pl[3] = {0, 0, 0};
+        // (this barrier also puts the reference reads and the flag reset before the first store of the pass)
+        if (!__syncthreads_or(pending)) break;
+        t.delta = delta;
         if (pending) {
-            if (cl == 0) count_cells(c, 2, N);
-            if (cl == G - 1) {      // interval N-1 (terminal-speed elimination): value function of node N-1
-                terminal_value(c, s, N, mu, delta, Pl, pl);
-                ok = riccati_backward_range(c, s, N, N - 1, N, mu, delta, fb, Pl, pl, nullptr, nullptr);
-                if (ok) elem_from_value(E, Pl, pl);
-            }
-            if (ok) ok = pit_phase_a(c, s, kLo, kHi, mu, delta, fb, cl == G - 1, E);
+            if (l == 0) count_cells(c, 2, t.N);
+            pit_phase_a(c, t, sh, fb);
         }
-        // suffix scan of the chunk elements (all lanes take part in the shuffles)
-        for (int d = 1; d < G; d <<= 1) {
-            Elem O;
-            shfl_down_arr<G>((const double*)&E, (double*)&O, sizeof(Elem) / sizeof(double), d);
-            const bool okO = __shfl_down_sync(0xffffffffu, ok ? 1 : 0, d, G) != 0;
-            if (cl + d < G) {
-                Elem R;
-                ok = ok && okO && elem_combine(E, O, R);
-                E = R;
-            }
-        }
-        Elem En;
-        shfl_down_arr<G>((const double*)&E, (double*)&En, sizeof(Elem) / sizeof(double), 1);
-        const bool okN = __shfl_down_sync(0xffffffffu, ok ? 1 : 0, 1, G) != 0;
-        double P[3][3], p[3];
-        if (cl == G - 1) { for (int i = 0; i < 3; ++i) { p[i] = pl[i]; for (int j = 0; j < 3; ++j) P[i][j] = Pl[i][j]; } }
-        else { sym_to_full(En.J, P); for (int i = 0; i < 3; ++i) p[i] = -En.eta[i]; ok = ok && okN; }
-        double P0[3][3], p0[3];
-        for (int i = 0; i < 3; ++i) { p0[i] = p[i]; for (int j = 0; j < 3; ++j) P0[i][j] = P[i][j]; }
-        // pass 0: in-chunk recursion from the scan's end value (only (P,p) at the chunk start is kept)
-        if (pending && ok) ok = riccati_backward_range(c, s, N, kLo, kHi, mu, delta, fb, P, p, nullptr, nullptr, false);
-        __syncwarp();
-        // pass 1: end value = what the next lane's stable recursion produced at that node
-        double dev = 0.0;
-        if (pending && ok && cl < G - 1 && kHi > kLo) {
-            double sy[6];
-            for (int i = 0; i < 6; ++i) sy[i] = c.W(WS_RIC + RIC_P + i, kHi, s);
-            sym_to_full(sy, P);
-            for (int i = 0; i < 3; ++i) p[i] = c.W(WS_RIC + RIC_PV + i, kHi, s);
-            double num = 0.0, den = 1e-300;
-            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { num = fmax(num, fabs(P[i][j] - P0[i][j])); den = fmax(den, fabs(P[i][j])); }
-            dev = num / den;
-        } else if (cl == G - 1) {
-            for (int i = 0; i < 3; ++i) { p[i] = pl[i]; for (int j = 0; j < 3; ++j) P[i][j] = Pl[i][j]; }
-        } else {
-            for (int i = 0; i < 3; ++i) { p[i] = p0[i]; for (int j = 0; j < 3; ++j) P[i][j] = P0[i][j]; }
-        }
-        __syncwarp();
-        aff_identity(T);
-        if (pending && ok) ok = riccati_backward_range(c, s, N, kLo, kHi, mu, delta, fb, P, p, T.M, T.m, true);
-        // group decisions: wrong inertia -> regularise and retry; scan not trustworthy -> sequential fallback
-        const unsigned bad = __ballot_sync(0xffffffffu, pending && !ok);
-        const unsigned sus = __ballot_sync(0xffffffffu, pending && ok && dev > 1e-6);
+        __syncthreads();
+        if (pending && l == 0) pit_value_chain(sh, col, G);
+        __syncthreads();
+        if (pending) pit_phase_c(c, t, sh, fb);
+        __syncthreads();
+        const int f = flags[col];
+        __syncthreads();
+        if (l == 0) flags[col] = 0;
         if (pending) {
-            if (bad & gmask) {
-                if (cl == 0) c.I(SI_NREG, s) += 1;
-                if (delta == 0.0) delta = (dlast == 0.0) ? 1e-4 : fmax(1e-20, dlast / 3.0);
-                else delta *= (dlast == 0.0) ? 100.0 : 8.0;
-                if (delta > 1e40) { failedForGood = true; pending = false; }
-            } else {
-                fallback = (sus & gmask) != 0;
-                pending = false;
-            }
+            if (f & PIT_SCAN_FAILED) { fallback = true; pending = false; }
+            else if (f & PIT_BAD_INERTIA) {
+                if (l == 0) c.I(SI_NREG, s) += 1;
+                delta = pit_next_delta(delta, dlast);
+                if (delta > 1e40) { failed = true; pending = false; }
+            } else pending = false;
         }
     }
-    if (pending) failedForGood = true;
-    // ---- sequential fallback for the instances whose scan was not accurate enough (lane 0 of the group works)
-    if (__any_sync(0xffffffffu, fallback)) {
-        if (fallback && cl == 0) {
+    if (pending) failed = true;
+    if (__syncthreads_or(fallback)) {
+        if (fallback && l == 0) {
             atomicAdd(fallbackCount, 1);
             inst_step(c, s, fb, ff);            // complete sequential direction incl. its own inertia ladder and phase change
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (fallback || !active) return;
-    if (failedForGood) { if (cl == 0) finish(c, s, ST_STEP_FAILED); return; }
-    // ---- prefix scan of the closed-loop chunk transitions -> state step at every chunk start
-    // (lanes of finished groups left above; the shuffles below use the group mask)
-    for (int d = 1; d < G; d <<= 1) {
-        Aff O;
-        for (int i = 0; i < 12; ++i) ((double*)&O)[i] = __shfl_up_sync(gmask, ((const double*)&T)[i], d, G);
-        if (cl >= d) { Aff R; aff_compose(O, T, R); T = R; }
+    const bool go = active && !fallback && !failed;
+    if (failed && l == 0) finish(c, s, ST_STEP_FAILED);
+    if (go && l == 0) {
+        pit_state_chain(sh, col, G);
+        count_cells(c, 3, t.N);
+        if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta;
+        c.D(SD_DELTA, s) = delta;
     }
-    double dx[3];
-    for (int i = 0; i < 3; ++i) { const double v = __shfl_up_sync(gmask, T.m[i], 1, G); dx[i] = (cl > 0) ? v : 0.0; }
-    if (cl == 0) { c.W(WS_ST + ST_T, 0, s) = 0.0; c.W(WS_ST + ST_B, 0, s) = 0.0; count_cells(c, 3, N); if (delta > 0.0) c.D(SD_DELTA_LAST, s) = delta; c.D(SD_DELTA, s) = delta; }
-    __syncwarp(gmask);
-    double dxs[3] = {dx[0], dx[1], dx[2]};
-    riccati_forward_range(c, s, N, kLo, kHi, mu, delta, ff, dx);
-    // consistency of the scan with the exact in-chunk recursion: the state step at my chunk end must equal the next lane's start
-    double nxt[3];
-    for (int i = 0; i < 3; ++i) nxt[i] = __shfl_down_sync(gmask, dxs[i], 1, G);
-    double mism = 0.0, mag = 1e-300;
-    if (cl < G - 1) for (int i = 0; i < 3; ++i) { mism = fmax(mism, fabs(dx[i] - nxt[i])); mag = fmax(mag, fmax(fabs(dx[i]), fabs(nxt[i]))); }
-    const bool offF = __ballot_sync(gmask, mism > 1e-9 * mag + 1e-14) & gmask;
-    if (offF) {
-        // the feedback gains are exact (stable in-chunk recursions); only the chunk start states were off: lane 0 redoes the
-        // forward sweep sequentially
-        __syncwarp(gmask);
-        if (cl == 0) { atomicAdd(fallbackCount + 1, 1); riccati_forward(c, s, N, mu, delta, ff); }
-    } else if (cl == G - 1) {
-        riccati_forward_range(c, s, N, N - 1, N, mu, delta, ff, dx);
-    }
-    __syncwarp(gmask);
-    if (cl == 0) c.I(SI_PHASE, s) = PH_STEPPED;
+    __syncthreads();
+    if (go) pit_phase_f(c, t, sh, ff);
+    if (go && l == 0) { c.I(SI_FACT, s) = 1; c.I(SI_PHASE, s) = PH_STEPPED; }
 }
 
 __global__ void k_eval_loss_rows(LossMapDev lm, int n, const double* in, const double* par, double* out) {
@@ -470,7 +406,7 @@ int mseetc_eval_loss_rows(mseetc_handle h, int32_t n, const double* in, const do
 
 int mseetc_set_sweep_lanes(mseetc_handle h, int lanes) {
     if (!h) return fail(-1, "mseetc_set_sweep_lanes: null handle");
-    if (lanes != 1 && lanes != 8 && lanes != 32) return fail(-2, "mseetc_set_sweep_lanes: lanes must be 1, 8 or 32");
+    if (lanes != 1 && lanes != 8 && lanes != 16 && lanes != 32) return fail(-2, "mseetc_set_sweep_lanes: lanes must be 1, 8, 16 or 32");
     h->sweep_lanes = lanes;
     return 0;
 }
@@ -507,7 +443,9 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
         case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
         case CLS_DECIDE: return 8.0 * 4;
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13)) - (dynMap ? 0.0 : 8.0 * 16);     // row gradients / residuals not stored
-        case CLS_STEP:   return 8.0 * (BwdFields::NF + 17 + FwdFields::NF + 4);      // factors written: K 6, kf 2, P 6, p 3
+        // factors written: K 6, kf 2, P 6, p 3; the parallel-in-time sweeps read the condensed stage QP twice (element pass and
+        // in-chunk recursion) -- the second read is counted: it is issued and, beyond L2, served by HBM
+        case CLS_STEP:   return 8.0 * ((h->sweep_lanes > 1 ? 2 : 1) * BwdFields::NF + 17 + FwdFields::NF + 4);
         case CLS_CSTEP:  return 8.0 * ((6 + 3 + iter + 11 + rows + 2 + 7 + 6 + 9) + (2 * rows + 3 + 3)) - (dynMap ? 0.0 : 8.0 * 14);      // ... recomputed (+ b_{k+1}, c0)
         case CLS_ALPHA:  return 8.0 * 3;
         case CLS_KKT:    return 8.0 * 14;
@@ -603,6 +541,21 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     // the attribute belongs to the kernel, not to this call: handles on other host threads launch the same kernel with other
     // sizes, so it is set to the hardware maximum rather than to this call's request
     cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // parallel-in-time sweeps: SL = 8 instances per block, G = sweep_lanes chunk lanes per instance
+    void (*pitKernel)(Ctx, int*) = nullptr;
+    int pitThreads = 0;
+    size_t pitBytes = 0;
+    if (h->sweep_lanes > 1) {
+        static const int pitDepth = []() { const char* e = getenv("MSEETC_PIT_DEPTH"); return e ? atoi(e) : 1; }();
+        const int G = h->sweep_lanes;
+        const bool deep = pitDepth >= 2 && G <= 16;
+        if (G == 8) pitKernel = deep ? k_step_pit<PIT_SL, 8, 2> : k_step_pit<PIT_SL, 8, 1>;
+        else if (G == 16) pitKernel = deep ? k_step_pit<PIT_SL, 16, 2> : k_step_pit<PIT_SL, 16, 1>;
+        else pitKernel = k_step_pit<PIT_SL, 32, 1>;
+        pitThreads = PIT_SL * G;
+        pitBytes = sizeof(double) * ((size_t)((deep ? 2 : 1) + 1) * RING_NF_MAX * pitThreads + (size_t)G * SH_N * PIT_SL) + sizeof(int) * PIT_SL;
+        cudaFuncSetAttribute(pitKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
     int launches = 0;
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -665,8 +618,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         use(true);
         begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_KKT);
         begin(CLS_STEP);
-        if (h->sweep_lanes == 8) k_step_pit<8><<<(unsigned)(((size_t)g.S * 8 + 63) / 64), 64, 0, cur>>>(c, c.done + 48);
-        else if (h->sweep_lanes == 32) k_step_pit<32><<<(unsigned)(((size_t)g.S * 32 + 63) / 64), 64, 0, cur>>>(c, c.done + 48);
+        if (pitKernel) pitKernel<<<(unsigned)(g.S / PIT_SL), pitThreads, pitBytes, cur>>>(c, c.done + 48);
         else stepKernel<<<igrid, ib, ringBytes, cur>>>(c);
         end(CLS_STEP);
         use(false);

@@ -114,8 +114,12 @@ class Handle:
             pass
 
     def set_sweep_lanes(self, lanes):
-        "1 = sequential Riccati sweeps; 8 / 32 = parallel-in-time sweeps with that many lanes per instance."
+        "1 = sequential Riccati sweeps; 8 / 16 / 32 = parallel-in-time sweeps with that many chunk lanes per instance."
         _check(lib().mseetc_set_sweep_lanes(self._h, int(lanes)), 'mseetc_set_sweep_lanes')
+        self._lanes = int(lanes)
+
+    def sweep_lanes(self):
+        return getattr(self, '_lanes', 1)
 
     def last_sweep_fallbacks(self):
         return int(lib().mseetc_last_sweep_fallbacks(self._h))

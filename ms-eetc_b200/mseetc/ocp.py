@@ -65,6 +65,19 @@ class OptionsCasadiSolver(Options):
             raise ValueError("'integrateLosses' flag must be a boolean!")
 
 
+def auto_sweep_lanes(numIntervals):
+    """Chunk lanes per instance of the Riccati sweeps (pit.cuh).  The sequential sweep is a dependent chain of numIntervals
+    stages that takes the same time for 1 and for 4096 instances; with G lanes the chain is ~2 numIntervals / G stages plus
+    G - 2 short chain steps, at about 2.5 times the arithmetic and 1.4 times the bytes."""
+    if numIntervals >= 1024:
+        return 32
+    if numIntervals >= 96:
+        return 16
+    if numIntervals >= 48:
+        return 8
+    return 1
+
+
 def classify_losses(train):
     """Recognise the loss model of a train: ('none'|'static', cT, cR) with
     PLtr/v = cT*f and PLrgb/v = -cR*f (reference train.py:204 + utils.py:197-220).
@@ -97,9 +110,10 @@ def classify_losses(train):
 class _Presolve:
     "Time-optimal solve of the distinct problems of a batch on a side stream, in a second host thread."
 
-    def __init__(self, solver, dev, tmin_dev, args, inverse):
+    def __init__(self, solver, dev, tmin_dev, args, inverse, mask=None):
         import threading
         self.solver, self.dev, self.tmin_dev, self.args, self.inverse = solver, dev, tmin_dev, args, inverse
+        self.mask = mask          # None, or boolean [n]: False = instance the caller asserted feasible (never screened, plane value -1)
         self.tmin, self.error = None, None
         self.thread = threading.Thread(target=self._run, daemon=True)
 
@@ -137,7 +151,13 @@ class _Presolve:
                 torch.sub(out['z'][:, -2], t0_dev, out=pre['dur'])
                 torch.eq(out['status'], 0, out=pre['ok'])
                 pre['dur'].mul_(pre['ok'])                   # no certificate where the time-optimal solve did not converge
-                torch.index_select(pre['dur'], 0, inv, out=self.tmin_dev)
+                if self.mask is None:
+                    torch.index_select(pre['dur'], 0, inv, out=self.tmin_dev)
+                else:
+                    keep = sib._upload('mask', np.asarray(self.mask, dtype=np.bool_), torch.bool, dev)
+                    tmp = torch.index_select(pre['dur'], 0, inv)
+                    tmp.masked_fill_(~keep, -1.0)
+                    self.tmin_dev.copy_(tmp)
                 side.synchronize()
                 t_pub = _time.perf_counter()
                 dur = pre['dur'].cpu().numpy()
@@ -145,9 +165,14 @@ class _Presolve:
                     # rare: retry the instances that did not converge with longer horizons (host path), publish again
                     dur2, st2 = solver.minimum_time(t0, vN, v0, overrides=sub, device=device)
                     dur = np.where(st2 == 0, dur2, 0.0)
-                    self.tmin_dev.copy_(torch.from_numpy(np.ascontiguousarray(dur[self.inverse])).to(dev))
+                    full = np.ascontiguousarray(dur[self.inverse])
+                    if self.mask is not None:
+                        full[~np.asarray(self.mask)] = -1.0
+                    self.tmin_dev.copy_(torch.from_numpy(full).to(dev))
                     side.synchronize()
             self.tmin = np.ascontiguousarray(dur[self.inverse])
+            if self.mask is not None:
+                self.tmin[~np.asarray(self.mask)] = 0.0        # not computed for instances the caller asserted feasible
             self.detail = dict(publish_at=t_pub - self.t_start)
         except Exception as exc:      # surfaced by join()
             self.error = exc
@@ -204,7 +229,7 @@ class casadiSolver():
         self.muInit = 0.1             # IPOPT's mu_init (the reference leaves the default)
         self.streams = DEFAULT_STREAMS
         self._pool = None
-        self.sweepLanes = 'auto'      # 1 sequential sweeps | 8 | 32 lanes per instance (parallel in time) | 'auto'
+        self.sweepLanes = 'auto'      # 1 sequential sweeps | 8 | 16 | 32 chunk lanes per instance (parallel in time) | 'auto'
 
     # ------------------------------------------------------------------ packing
     @staticmethod
@@ -287,7 +312,7 @@ class casadiSolver():
             h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
         lanes = self.sweepLanes
         if lanes == 'auto':
-            lanes = 32 if self.numIntervals >= 2048 else 1     # long horizons: chunks of >= 64 intervals per lane
+            lanes = auto_sweep_lanes(self.numIntervals)
         h.set_sweep_lanes(int(lanes))
         return h
 
@@ -406,7 +431,7 @@ class casadiSolver():
         return res['z'][:, -2] - np.broadcast_to(t0, res['z'][:, -2].shape), res['status']
 
     def solve_batch(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None,
-                    want_multipliers=False, device=None, screen=True):
+                    want_multipliers=False, device=None, screen=True, to_host=True):
         """Solve n instances that share this solver's track, options and problem structure.
 
         terminalTime / initialTime / terminalVelocity / initialVelocity: scalars or arrays of length n.
@@ -420,7 +445,12 @@ class casadiSolver():
         screen=True (energy-optimal mode only): terminalTime is an upper bound on t_N, so an instance is infeasible
         exactly when it is below the minimum trip time.  The minimum time of every distinct
         (train, boundary speeds) combination in the batch is computed first by a time-optimal solve and instances
-        below it are reported as 'Infeasible_Problem_Detected' without iterating."""
+        below it are reported as 'Infeasible_Problem_Detected' without iterating.  `screen` may also be a boolean array of
+        length n: False marks instances the caller knows to be feasible (e.g. a Monte Carlo at a timetable value with
+        slack) -- they take no part in the minimum-time presolve and are never screened.
+
+        to_host=False leaves z / lam / obj / kkt / iters / status as torch tensors on the device (used by
+        mseetc.sharding.solve_batch_sharded, which gathers them over NVLink before one device-to-host copy)."""
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -428,6 +458,12 @@ class casadiSolver():
         overrides_in = dict(overrides)
         arrs = [np.atleast_1d(np.asarray(a, dtype=float)) for a in (terminalTime, initialTime, terminalVelocity, initialVelocity)]
         n = max([len(a) for a in arrs] + [len(np.atleast_1d(v)) for v in overrides.values()])
+        screen_mask = None
+        if not isinstance(screen, (bool, np.bool_)):
+            screen_mask = np.broadcast_to(np.asarray(screen, dtype=bool), (n,))
+            screen = bool(screen_mask.any())
+            if screen_mask.all():
+                screen_mask = None
         T, t0, vN, v0 = [np.broadcast_to(a, (n,)) for a in arrs]
         etaT = np.asarray(overrides.pop('etaTraction', getattr(self.train, 'etaTraction', 1.0)), dtype=float)
         etaR = np.asarray(overrides.pop('etaRgBrake', getattr(self.train, 'etaRgBrake', 1.0)), dtype=float)
@@ -456,15 +492,27 @@ class casadiSolver():
             key = None if same_problem else np.delete(P, [_cabi.PARAM_INDEX['T_END'], _cabi.PARAM_INDEX['LOSS_TR'], _cabi.PARAM_INDEX['LOSS_RG'],
                                                          _cabi.PARAM_INDEX['OBJ_SCALE'], _cabi.PARAM_INDEX['DYN_AUX'], _cabi.PARAM_INDEX['DYN_ETAG'],
                                                          _cabi.PARAM_INDEX['DYN_SCALE']], axis=0)
+            mask_dealt = None
+            if screen_mask is not None:
+                mask_dealt = screen_mask[perm] if perm is not None else screen_mask
             if n == 1 or same_problem or np.all(key == key[:, :1]):
                 first, inverse = np.array([0]), np.zeros(n, dtype=np.intp)
-            else:
+            elif mask_dealt is None:
                 _, first, inverse = np.unique(key, axis=1, return_index=True, return_inverse=True)
                 inverse = np.asarray(inverse).reshape(-1)
+            else:
+                # only the instances that are to be screened take part in the presolve
+                sel = np.flatnonzero(mask_dealt)
+                _, f_sel, inv_sel = np.unique(key[:, sel], axis=1, return_index=True, return_inverse=True)
+                first = sel[f_sel]
+                inverse = np.zeros(n, dtype=np.intp)
+                inverse[sel] = np.asarray(inv_sel).reshape(-1)
             first = perm[first] if perm is not None else first          # indices into the caller's arrays
             sub = {k: np.broadcast_to(np.asarray(v, dtype=float), (n,))[first] for k, v in overrides.items()}
-            tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)      # 0 = "not known yet"
-            presolve = _Presolve(self, dev, tmin_dev, (t0[first], vN[first], v0[first], sub, device), inverse)
+            tmin_dev = torch.zeros(n, dtype=torch.float64, device=dev)      # 0 = "not known yet", -1 = "never screen this instance"
+            if mask_dealt is not None:
+                tmin_dev.masked_fill_(torch.from_numpy(np.ascontiguousarray(~mask_dealt)).to(dev), -1.0)
+            presolve = _Presolve(self, dev, tmin_dev, (t0[first], vN[first], v0[first], sub, device), inverse, mask_dealt)
         N = self.numIntervals
         ds, c0, bmax, trk_of, trk_off = self._track_tables(n, overrides, perm)
         t_pack = _time.perf_counter() - t_begin
@@ -506,6 +554,20 @@ class casadiSolver():
         # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
         out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
         res = {}
+        if not to_host:
+            # results stay on the device; the certificate is applied there as well
+            if tmin is not None:
+                tmin_t = torch.from_numpy(np.ascontiguousarray(tmin)).to(dev)
+                short_t = (tmin_t > 0) & (torch.from_numpy(np.ascontiguousarray(T - t0)).to(dev) < tmin_t * (1 - _cabi.TMIN_MARGIN))
+                out['status'][(out['status'] != 0) & short_t] = 4
+            res = {k: v for k, v in out.items() if v is not None}
+            torch.cuda.current_stream(dev).synchronize()
+            res['tmin'] = tmin
+            res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
+            res['wall'] = _time.perf_counter() - t_begin
+            res['totalMass'] = M
+            res['scale'] = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
+            return res
         for k, v in out.items():                          # device -> pinned host buffers -> numpy
             if v is None:
                 continue
@@ -627,9 +689,12 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
     trk_off = np.concatenate([[0], np.cumsum(nint)]).astype(np.int32)
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
     io = ref.opts.integrationOptions
-    mk = lambda energy, loss: _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
-                                           int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess],
-                                           stall_iterations=int(ref.stallIterations))
+    def mk(energy, loss):
+        hd = _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
+                          int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess],
+                          stall_iterations=int(ref.stallIterations))
+        hd.set_sweep_lanes(auto_sweep_lanes(int(nint.min())) if ref.sweepLanes == 'auto' else int(ref.sweepLanes))
+        return hd
     dev_tabs = dict(nint=up(nint, torch.int32), trk_of=up(np.arange(n, dtype=np.int32), torch.int32), trk_off=up(trk_off, torch.int32),
                     ds=up(np.concatenate([t[0] for t in tabs]), torch.float64), c0=up(np.concatenate([t[1] for t in tabs]), torch.float64),
                     bmax=up(np.concatenate([t[2] for t in tabs]), torch.float64))

@@ -151,7 +151,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
                 if (c.I(SI_PHASE, s) == PH_STEPPED) {
                     if (diag >= 3) lin_residual(c, s, N, "seq");
                     c.I(SI_PHASE, s) = PH_FACTOR;
-                    inst_step_pit_chunks_emulated(c, s, pit_lanes, fb, ff, &fallbacks);
+                    inst_step_pit_emulated(c, s, pit_lanes, fb, ff, &fallbacks);
                     double num[4] = {0,0,0,0}, den[4] = {1e-300,1e-300,1e-300,1e-300};
                     const int fld[4] = {ST_FEL, ST_FPB, ST_T, ST_B};
                     for (int k = 0; k <= N; ++k) for (int i = 0; i < 4; ++i) { num[i] = fmax(num[i], fabs(c.W(WS_ST+fld[i],k,s) - ref[4*k+i])); den[i] = fmax(den[i], fabs(ref[4*k+i])); }
@@ -171,8 +171,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
                 }
                 continue;
             }
-            if (pit_lanes > 1 && (s >= g.nInst || c.I(SI_ITERS, s) < pit_until)) inst_step_pit_chunks_emulated(c, s, pit_lanes, fb, ff, &fallbacks);   // chunked parallel-in-time variant
-            else if (pit_lanes < -1) inst_step_pit_emulated(c, s, -pit_lanes, fb, ff);               // first (scan) formulation
+            if (pit_lanes > 1 && (s >= g.nInst || c.I(SI_ITERS, s) < pit_until)) inst_step_pit_emulated(c, s, pit_lanes, fb, ff, &fallbacks);   // chunked parallel-in-time variant
             else inst_step(c, s, fb, ff);
         }
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_step<true>(c, k, s); else cell_step<false>(c, k, s); }

@@ -18,7 +18,7 @@ def cabi(built_lib):
     return _cabi
 
 
-def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True, initial_guess=0):
+def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True, initial_guess=0, lanes=1):
     "Raw C-ABI call with arrays packed from oracle NLP objects (same packing as the CPU emulation harness)."
     import torch
     import harness
@@ -32,6 +32,7 @@ def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True, in
     cu = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to('cuda', dtype=dt)
     h = cabi.Handle(Nmax, ref.withPn, ref.withPower, ref.energy, {'none': 0, 'static': 1}[ref.lossKind],
                     ref.opts['numSteps'], ref.opts['numApproxSteps'], max_iter, initial_guess=initial_guess)
+    h.set_sweep_lanes(lanes)
     out = h.solve_device(cu(params, torch.float64), cu(nint, torch.int32), cu(np.arange(n, dtype=np.int32), torch.int32),
                          cu(trk_off, torch.int32), cu(np.concatenate([p[1] for p in packs]), torch.float64),
                          cu(np.concatenate([p[2] for p in packs]), torch.float64),
@@ -87,19 +88,33 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('guess', [0, 1], ids=['reference-guess', 'profile-guess'])
-@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
-def test_cuda_solver_matches_oracle(cabi, case, guess):
-    """north_star bar: optimal energy 1e-6 relative, trajectories 1e-4 relative, same active set, KKT <= 1e-8."""
+_ORACLE = {}
+
+
+def oracle_case(case):
+    "Oracle NLP and optimum of one parity case (solved once per session)."
     from oracle.problem import load_track
     name, mk, path, crop, N, T, energy, v0, vN, rk = case
-    track = load_track(path)
-    if crop:
-        track.crop(positionEnd=crop)
-    nlp = oracle_nlp(mk(), track, N, energy=energy, **rk)
-    ref = oracle_solve(nlp, T, v0=v0, vN=vN)
+    if name not in _ORACLE:
+        track = load_track(path)
+        if crop:
+            track.crop(positionEnd=crop)
+        nlp = oracle_nlp(mk(), track, N, energy=energy, **rk)
+        _ORACLE[name] = (nlp, oracle_solve(nlp, T, v0=v0, vN=vN))
+    return _ORACLE[name]
+
+
+# sweeps: 1 = sequential Riccati sweeps, 8 / 16 / 32 = parallel-in-time sweeps with that many chunk lanes per instance
+@pytest.mark.parametrize('lanes', [1, 8, 16, 32], ids=['seq', 'pit8', 'pit16', 'pit32'])
+@pytest.mark.parametrize('guess', [0, 1], ids=['reference-guess', 'profile-guess'])
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_cuda_solver_matches_oracle(cabi, case, guess, lanes):
+    """north_star bar: optimal energy 1e-6 relative, trajectories 1e-4 relative, same active set, KKT <= 1e-8 -- with the
+    sequential and with the parallel-in-time sweeps, each against the oracle."""
+    name, mk, path, crop, N, T, energy, v0, vN, rk = case
+    nlp, ref = oracle_case(case)
     assert ref.success, ref.status
-    out = device_solve(cabi, [nlp], [T], v0=v0, vN=vN, initial_guess=guess)
+    out = device_solve(cabi, [nlp], [T], v0=v0, vN=vN, initial_guess=guess, lanes=lanes)
     assert out['status'][0] == 0
     assert out['kkt'][0] <= 1e-8
     if guess == 0:
