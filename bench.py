@@ -604,7 +604,7 @@ def main():
     ap.add_argument('--instances', type=int, default=N_INST, help='instances per GPU of the sweep workload')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline leg')
     ap.add_argument('--no-latency', action='store_true', help='skip the config-1 single-solve latency leg')
-    ap.add_argument('--streams', type=int, default=2, help='concurrent sub-batches (CUDA streams / host threads) per GPU')
+    ap.add_argument('--streams', type=int, default=1, help='concurrent sub-batches (CUDA streams / host threads) per GPU')
     ap.add_argument('--sweep-lanes', default='auto', help="Riccati sweeps: 1 sequential, 8/16/32 parallel in time, 'auto'")
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -140,11 +140,17 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
                        int32_t* iters_out_dev, int32_t* status_out_dev,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
 
-/* Sweep variant: 1 = sequential Riccati sweeps, one thread per instance (default); 8 or 32 = parallel-in-time sweeps with that
- * many lanes per instance (associative scan over chunk elements + exact in-chunk recursions + a-posteriori check with
- * sequential fallback per instance).  Pays for long horizons and small batches. */
+/* Sweep variant (replaces MUMPS behind mseetc/ocp.py:359): 1 = sequential Riccati sweeps, one thread per instance (default of
+ * a new handle); 8, 16 or 32 = parallel-in-time sweeps with that many chunk lanes per instance (chunk elements from reference
+ * Riccati recursions, sequential chain of the chunk-end value functions, exact in-chunk recursions, a-posteriori consistency
+ * check with sequential fallback per instance; see csrc/pit.cuh); 0 = chosen per call from n_intervals_max and the batch size
+ * (what the Python layer sets): 16 lanes from 96 intervals, 32 from 1024, sequential sweeps beyond 4096 instances per call. */
 int mseetc_set_sweep_lanes(mseetc_handle h, int lanes);
+int mseetc_last_sweep_lanes(mseetc_handle h);          /* lanes the last mseetc_solve_batch on h ran with */
+/* instances x iterations of the last solve that fell back to the sequential sweeps; reasons (out3): reference recursion of a
+ * chunk not positive definite / chain step numerically singular / chain and recursion disagreed */
 long long mseetc_last_sweep_fallbacks(mseetc_handle h);
+int mseetc_last_sweep_fallback_reasons(mseetc_handle h, int32_t* out3);
 
 /* number of solver ticks (lock-step rounds) and kernel launches of the last mseetc_solve_batch on h */
 int mseetc_last_ticks(mseetc_handle h);

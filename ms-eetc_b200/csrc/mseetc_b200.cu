@@ -25,7 +25,6 @@ namespace {
 
 thread_local std::string g_err;
 
-enum { PIT_SL = 8 };      // instances per block of the parallel-in-time sweep kernel (pad_slots keeps S a multiple of 32)
 
 // ---- interval-parallel kernels: one thread per (interval k, instance), warp = 32 instances at one k.  The kernels stride over
 // the cells, so any grid works; the default is one block per 128 cells (measured faster than a persistent grid of a few blocks
@@ -187,6 +186,10 @@ __global__ void __launch_bounds__(BS) k_step(Ctx c) {
 // shared memory; the two short sequential chains over the chunks are run by the lane of chunk 0.  Stage data are prefetched
 // through the same per-thread cp.async ring as in k_step.  An instance whose element algebra fails, or whose chain and recursion
 // disagree, is redone by the sequential sweeps (lane of chunk 0, same kernel), so accuracy never rests on the chain.
+// L2 prefetch distance of the sweep rings, in intervals beyond the ring's own look-ahead (0 = off; 104 -> 95 us with 3)
+#ifndef MS_PIT_PF
+#define MS_PIT_PF 3
+#endif
 template <int SL, int G, int DEPTH>
 __global__ void __launch_bounds__(SL * G) k_step_pit(Ctx c, int* fallbackCount) {
     extern __shared__ __align__(128) double pit_sm[];
@@ -208,12 +211,16 @@ __global__ void __launch_bounds__(SL * G) k_step_pit(Ctx c, int* fallbackCount) 
     pit_chunk(t.N, G, l, t.kLo, t.kHi);
     if (active) pit_read_reference(c, t);
     if (l == 0) flags[col] = 0;
-    RingFetch<BwdFields, BS, DEPTH> fb;
+    RingFetch<BwdFields, BS, DEPTH, MS_PIT_PF> fb;
     fb.sm = ring + threadIdx.x;
-    RingFetch<FwdFields, BS, DEPTH> ff;
+    // the forward sweep spends next to no arithmetic per interval: it needs the deeper look-ahead, and its 14 planes per interval
+    // leave room for it in the same ring
+    constexpr int FDEPTH = ((DEPTH + 1) * BwdFields::NF) / FwdFields::NF - 1;
+    RingFetch<FwdFields, BS, FDEPTH, 2 * MS_PIT_PF> ff;
     ff.sm = ring + threadIdx.x;
     double delta = 0.0;
     bool pending = active, failed = false, fallback = false;
+    int why = 0;
     for (int tries = 0; tries < 40; ++tries) {
         // (this barrier also puts the reference reads and the flag reset before the first store of the pass)
         if (!__syncthreads_or(pending)) break;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(SL * G) k_step_pit(Ctx c, int* fallbackCount) 
         __syncthreads();
         if (l == 0) flags[col] = 0;
         if (pending) {
-            if (f & PIT_SCAN_FAILED) { fallback = true; pending = false; }
+            if (f & PIT_SCAN_FAILED) { fallback = true; pending = false; why = f; }
             else if (f & PIT_BAD_INERTIA) {
                 if (l == 0) c.I(SI_NREG, s) += 1;
                 delta = pit_next_delta(delta, dlast);
@@ -243,6 +250,9 @@ __global__ void __launch_bounds__(SL * G) k_step_pit(Ctx c, int* fallbackCount) 
     if (__syncthreads_or(fallback)) {
         if (fallback && l == 0) {
             atomicAdd(fallbackCount, 1);
+            if (why & PIT_ELEM_FAILED) atomicAdd(fallbackCount + 1, 1);
+            if (why & PIT_APPLY_FAILED) atomicAdd(fallbackCount + 2, 1);
+            if (why & PIT_INCONSISTENT) atomicAdd(fallbackCount + 3, 1);
             inst_step(c, s, fb, ff);            // complete sequential direction incl. its own inertia ladder and phase change
         }
         __syncthreads();
@@ -304,8 +314,10 @@ struct mseetc_solver {
     cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
     cudaStream_t hp;               // experiment MSEETC_TWO_LEVEL: library-owned highest-priority stream for the small kernels
     cudaEvent_t xev[16];           // hand-over events between the caller's stream and hp
-    int sweep_lanes;               // 1: sequential sweeps; 8 / 32: lanes per instance of the parallel-in-time sweeps
+    int sweep_lanes;               // 0: chosen per call; 1: sequential sweeps; 8 / 16 / 32: chunk lanes per instance of the parallel-in-time sweeps
+    int last_lanes;                // what the last solve used
     long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
+    int fallback_why[3];           // of those: reference recursion failed / chain step singular / chain and recursion disagreed
     double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
     LossMapDev lm;
 };
@@ -338,7 +350,9 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->last_launches = 0;
     h->profiling = 0;
     h->sweep_lanes = 1;
+    h->last_lanes = 1;
     h->last_fallbacks = 0;
+    h->fallback_why[0] = h->fallback_why[1] = h->fallback_why[2] = 0;
     h->lm_dev = nullptr;
     memset(&h->lm, 0, sizeof h->lm);
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
@@ -406,11 +420,17 @@ int mseetc_eval_loss_rows(mseetc_handle h, int32_t n, const double* in, const do
 
 int mseetc_set_sweep_lanes(mseetc_handle h, int lanes) {
     if (!h) return fail(-1, "mseetc_set_sweep_lanes: null handle");
-    if (lanes != 1 && lanes != 8 && lanes != 16 && lanes != 32) return fail(-2, "mseetc_set_sweep_lanes: lanes must be 1, 8, 16 or 32");
+    if (lanes != 0 && lanes != 1 && lanes != 8 && lanes != 16 && lanes != 32) return fail(-2, "mseetc_set_sweep_lanes: lanes must be 0 (auto), 1, 8, 16 or 32");
     h->sweep_lanes = lanes;
     return 0;
 }
 long long mseetc_last_sweep_fallbacks(mseetc_handle h) { return h ? h->last_fallbacks : -1; }
+int mseetc_last_sweep_lanes(mseetc_handle h) { return h ? h->last_lanes : -1; }
+int mseetc_last_sweep_fallback_reasons(mseetc_handle h, int32_t* out3) {
+    if (!h || !out3) return fail(-1, "mseetc_last_sweep_fallback_reasons: null argument");
+    for (int i = 0; i < 3; ++i) out3[i] = h->fallback_why[i];
+    return 0;
+}
 
 int mseetc_set_profiling(mseetc_handle h, int on) {
     if (!h) return fail(-1, "mseetc_set_profiling: null handle");
@@ -445,7 +465,7 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13)) - (dynMap ? 0.0 : 8.0 * 16);     // row gradients / residuals not stored
         // factors written: K 6, kf 2, P 6, p 3; the parallel-in-time sweeps read the condensed stage QP twice (element pass and
         // in-chunk recursion) -- the second read is counted: it is issued and, beyond L2, served by HBM
-        case CLS_STEP:   return 8.0 * ((h->sweep_lanes > 1 ? 2 : 1) * BwdFields::NF + 17 + FwdFields::NF + 4);
+        case CLS_STEP:   return 8.0 * ((h->last_lanes > 1 ? 2 : 1) * BwdFields::NF + 17 + FwdFields::NF + 4);
         case CLS_CSTEP:  return 8.0 * ((6 + 3 + iter + 11 + rows + 2 + 7 + 6 + 9) + (2 * rows + 3 + 3)) - (dynMap ? 0.0 : 8.0 * 14);      // ... recomputed (+ b_{k+1}, c0)
         case CLS_ALPHA:  return 8.0 * 3;
         case CLS_KKT:    return 8.0 * 14;
@@ -541,19 +561,33 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     // the attribute belongs to the kernel, not to this call: handles on other host threads launch the same kernel with other
     // sizes, so it is set to the hardware maximum rather than to this call's request
     cudaFuncSetAttribute(stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    // parallel-in-time sweeps: SL = 8 instances per block, G = sweep_lanes chunk lanes per instance
+    // parallel-in-time sweeps: G = sweep_lanes chunk lanes per instance, SL instances per block.  Wider groups read longer
+    // contiguous pieces of every plane (SL * 8 bytes): measured at 2048 active instances, 16 lanes: SL = 8 104 us, SL = 16 89 us
+    // (4096 instances: 211 vs 148 us; 512 instances: 67 vs 76 us).  One instantiation per lane count, so that an instance gets
+    // bit for bit the same direction whatever the size of the batch it is solved in.  Prefetch: one interval ahead through the
+    // cp.async ring plus L2 prefetches three further on (a ring of depth 2 costs a resident block per SM: 124 vs 104 us).
     void (*pitKernel)(Ctx, int*) = nullptr;
-    int pitThreads = 0;
+    int pitThreads = 0, pitSL = 8;
     size_t pitBytes = 0;
-    if (h->sweep_lanes > 1) {
-        static const int pitDepth = []() { const char* e = getenv("MSEETC_PIT_DEPTH"); return e ? atoi(e) : 1; }();
-        const int G = h->sweep_lanes;
-        const bool deep = pitDepth >= 2 && G <= 16;
-        if (G == 8) pitKernel = deep ? k_step_pit<PIT_SL, 8, 2> : k_step_pit<PIT_SL, 8, 1>;
-        else if (G == 16) pitKernel = deep ? k_step_pit<PIT_SL, 16, 2> : k_step_pit<PIT_SL, 16, 1>;
-        else pitKernel = k_step_pit<PIT_SL, 32, 1>;
-        pitThreads = PIT_SL * G;
-        pitBytes = sizeof(double) * ((size_t)((deep ? 2 : 1) + 1) * RING_NF_MAX * pitThreads + (size_t)G * SH_N * PIT_SL) + sizeof(int) * PIT_SL;
+    // 0 = auto: the sequential sweep is a dependent chain of n_intervals stages that takes the same time for 1 and for 4096
+    // instances (153 us at 300 intervals); with G lanes the chain is ~2 n_intervals / G stages plus G - 2 short chain steps, at
+    // 2.5 times the arithmetic and 1.4 times the bytes -- faster up to ~4096 instances per call (55 / 67 / 89 / 148 us at 32 /
+    // 512 / 2048 / 4096 instances), slower beyond, where the sweeps are bandwidth-bound
+    int lanesNow = h->sweep_lanes;
+    if (lanesNow == 0) {
+        const int Nmax = p.n_intervals_max;
+        lanesNow = Nmax >= 1024 ? 32 : Nmax >= 96 ? 16 : Nmax >= 48 ? 8 : 1;
+        if (lanesNow > 1 && lanesNow < 32 && g.S > 4096) lanesNow = 1;
+    }
+    h->last_lanes = lanesNow;
+    if (lanesNow > 1) {
+        const int G = lanesNow;
+        pitSL = (G == 32) ? 8 : 16;
+        if (G == 8) pitKernel = k_step_pit<16, 8, 1>;
+        else if (G == 16) pitKernel = k_step_pit<16, 16, 1>;
+        else pitKernel = k_step_pit<8, 32, 1>;
+        pitThreads = pitSL * G;
+        pitBytes = sizeof(double) * ((size_t)2 * RING_NF_MAX * pitThreads + (size_t)G * SH_N * pitSL) + sizeof(int) * pitSL;
         cudaFuncSetAttribute(pitKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     int launches = 0;
@@ -618,7 +652,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         use(true);
         begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_KKT);
         begin(CLS_STEP);
-        if (pitKernel) pitKernel<<<(unsigned)(g.S / PIT_SL), pitThreads, pitBytes, cur>>>(c, c.done + 48);
+        if (pitKernel) pitKernel<<<(unsigned)(g.S / pitSL), pitThreads, pitBytes, cur>>>(c, c.done + 48);
         else stepKernel<<<igrid, ib, ringBytes, cur>>>(c);
         end(CLS_STEP);
         use(false);
@@ -668,6 +702,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         h->cells[CLS_KKT] = (long long)cnt[1];
         h->cells[CLS_MISC] = 0;
         h->last_fallbacks = (long long)h->done_host[48];
+        for (int i = 0; i < 3; ++i) h->fallback_why[i] = h->done_host[49 + i];
     }
     for (size_t i = 0; i < evClass.size(); ++i) {
         float ms = 0.f;

@@ -118,48 +118,34 @@ MS_HD bool chunk_element(const Ctx& c, int s, int kLo, int kHi, double mu, doubl
     return chunk_element_t<false>(c, s, kLo, kHi, mu, delta, fetch, refP, refp, E);
 }
 
-// The same for a terminal value given as a difference to the reference value the element was accumulated with:
-//     T = (I + dPi W)^{-1} dPi     (dPi symmetric, not necessarily definite; 3x3 elimination with row pivoting, then symmetrised)
-// The closer the reference is to the value function (the chunk-end values of the previous interior-point iteration are used),
-// the smaller the correction and the better conditioned the recursion that produced the element.
+// Value function at the start of a chunk from the one at its end, given as a difference to the reference value the element was
+// accumulated with:   T = (I + dPi W)^{-1} dPi   (dPi symmetric, not necessarily definite; T symmetrised).
 MS_HD bool chunk_apply_diff(const ChunkElem& E, const double dPi[3][3], const double dpi[3], double P[3][3], double p[3]) {
     double W[3][3];
     sym_to_full(E.W, W);
-    // augmented rows [I + dPi W | dPi]
-    double a0[6], a1[6], a2[6];
-    {
-        double* rows[3] = {a0, a1, a2};
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) {
-                rows[i][j] = (i == j ? 1.0 : 0.0) + dPi[i][0] * W[0][j] + dPi[i][1] * W[1][j] + dPi[i][2] * W[2][j];
-                rows[i][3 + j] = dPi[i][j];
-            }
+    // X = I + dPi W, equilibrated and inverted through its adjugate: four independent reciprocals and a short dependent chain --
+    // this routine is the step of a sequential chain over the chunks.  The equilibrated X is moderately conditioned whenever the
+    // reference and the true terminal value both give the right inertia; a tiny determinant fails the instance over to the
+    // sequential sweeps.
+    double X[3][3], D[3][3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) X[i][j] = (i == j ? 1.0 : 0.0) + dPi[i][0] * W[0][j] + dPi[i][1] * W[1][j] + dPi[i][2] * W[2][j];
+        // rows of very different size (a barrier term of 1e9 next to O(1) entries): equilibrate X T = dPi row by row
+        const double big = fmax(fmax(fabs(X[i][0]), fabs(X[i][1])), fabs(X[i][2]));
+        if (!(big > 0.0) || !isfinite(big)) return false;
+        const double r = rcp(big);
+        for (int j = 0; j < 3; ++j) { X[i][j] *= r; D[i][j] = dPi[i][j] * r; }
     }
-#define MS_ROWSWAP(x, y) { for (int q = 0; q < 6; ++q) { const double t_ = x[q]; x[q] = y[q]; y[q] = t_; } }
-    // column 0
-    if (fabs(a1[0]) > fabs(a0[0])) MS_ROWSWAP(a0, a1)
-    if (fabs(a2[0]) > fabs(a0[0])) MS_ROWSWAP(a0, a2)
-    if (!(fabs(a0[0]) > 1e-300) || !isfinite(a0[0])) return false;
-    { const double r = rcp(a0[0]); const double f1 = a1[0] * r, f2 = a2[0] * r;
-      for (int q = 1; q < 6; ++q) { a1[q] -= f1 * a0[q]; a2[q] -= f2 * a0[q]; } }
-    // column 1
-    if (fabs(a2[1]) > fabs(a1[1])) MS_ROWSWAP(a1, a2)
-    if (!(fabs(a1[1]) > 1e-300) || !isfinite(a1[1])) return false;
-    { const double r = rcp(a1[1]); const double f2 = a2[1] * r;
-      for (int q = 2; q < 6; ++q) a2[q] -= f2 * a1[q]; }
-    if (!(fabs(a2[2]) > 1e-300) || !isfinite(a2[2])) return false;
-#undef MS_ROWSWAP
-    // back substitution for the three right-hand sides
+    double A[3][3];
+    A[0][0] = X[1][1] * X[2][2] - X[1][2] * X[2][1]; A[0][1] = X[0][2] * X[2][1] - X[0][1] * X[2][2]; A[0][2] = X[0][1] * X[1][2] - X[0][2] * X[1][1];
+    A[1][0] = X[1][2] * X[2][0] - X[1][0] * X[2][2]; A[1][1] = X[0][0] * X[2][2] - X[0][2] * X[2][0]; A[1][2] = X[0][2] * X[1][0] - X[0][0] * X[1][2];
+    A[2][0] = X[1][0] * X[2][1] - X[1][1] * X[2][0]; A[2][1] = X[0][1] * X[2][0] - X[0][0] * X[2][1]; A[2][2] = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+    const double det = X[0][0] * A[0][0] + X[0][1] * A[1][0] + X[0][2] * A[2][0];
+    if (!(fabs(det) > 1e-9) || !isfinite(det)) return false;
+    const double idet = rcp(det);
     double T[3][3];
-    {
-        const double r2 = rcp(a2[2]), r1 = rcp(a1[1]), r0 = rcp(a0[0]);
-        for (int j = 0; j < 3; ++j) {
-            const double x2 = a2[3 + j] * r2;
-            const double x1 = (a1[3 + j] - a1[2] * x2) * r1;
-            const double x0 = (a0[3 + j] - a0[1] * x1 - a0[2] * x2) * r0;
-            T[0][j] = x0; T[1][j] = x1; T[2][j] = x2;
-        }
-    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T[i][j] = (A[i][0] * D[0][j] + A[i][1] * D[1][j] + A[i][2] * D[2][j]) * idet;
     for (int i = 0; i < 3; ++i)
         for (int j = i + 1; j < 3; ++j) { const double x = 0.5 * (T[i][j] + T[j][i]); T[i][j] = x; T[j][i] = x; }
     // P = Pbar + Phi' T Phi ;  p = pbar + Phi' (dpi + T (phi - W dpi))
@@ -185,12 +171,21 @@ MS_HD bool chunk_apply_diff(const ChunkElem& E, const double dPi[3][3], const do
 // ---- the lanes of one instance exchange elements, chunk-end values, chunk transitions and chunk-start states through a small
 // buffer (shared memory on the device, a plain array in the host emulation): SH_N doubles per (chunk, instance)
 enum PitShareField {
-    SH_E = 0,                 // element of the chunk (27); later the closed-loop transition of the chunk (12)
+    SH_E = 0,                 // element of the chunk (27 numbers)
+    SH_TR = SH_E + 12,        // later, in the same slot: closed-loop transition of the chunk (12)
     SH_REF = SH_E + 27,       // reference terminal value of the chunk (P 6, p 3); later the state step at the chunk start (3)
-    SH_PE = SH_REF + 9,       // value function at the chunk END (P 6, p 3)
-    SH_N = SH_PE + 9
+    SH_N = SH_REF + 9
 };
-enum { PIT_BAD_INERTIA = 1, PIT_SCAN_FAILED = 2 };
+// The value function at the END of chunk l (P 6, p 3) lives in the first 9 numbers of the element slot of chunk l + 1: the chain
+// writes it there when it has consumed that element (the last chunk has no element: its slot takes the exact value of its start).
+#define SH_PE_AT(sh, i, l, col) (sh).at(SH_E + (i), (l) + 1, col)
+enum {
+    PIT_BAD_INERTIA = 1,       // exact inertia test of an in-chunk recursion failed: regularise (delta_w ladder) and retry
+    PIT_ELEM_FAILED = 2,       // reference recursion of a chunk not positive definite
+    PIT_APPLY_FAILED = 4,      // I + dPi W numerically singular
+    PIT_INCONSISTENT = 8,      // chain and recursion disagree on a chunk-end value function
+    PIT_SCAN_FAILED = PIT_ELEM_FAILED | PIT_APPLY_FAILED | PIT_INCONSISTENT      // any of them: sequential sweeps
+};
 struct PitShare {
     double* base;      // [chunk][SH_N][width]
     int* flags;        // [width]: PIT_BAD_INERTIA | PIT_SCAN_FAILED
@@ -224,7 +219,7 @@ template <class Fetch>
 MS_HD void pit_phase_a(const Ctx& c, const PitLane& t, const PitShare& sh, Fetch& fb) {
     if (t.l >= 1 && t.l <= t.G - 2) {
         ChunkElem E;
-        if (!chunk_element(c, t.s, t.kLo, t.kHi, t.mu, t.delta, fb, t.refP, t.refp, E)) { sh.raise(t.col, PIT_SCAN_FAILED); return; }
+        if (!chunk_element(c, t.s, t.kLo, t.kHi, t.mu, t.delta, fb, t.refP, t.refp, E)) { sh.raise(t.col, PIT_ELEM_FAILED); return; }
         const double* e = (const double*)&E;
         for (int i = 0; i < 27; ++i) sh.at(SH_E + i, t.l, t.col) = e[i];
         for (int i = 0; i < 6; ++i) sh.at(SH_REF + i, t.l, t.col) = t.refP[i];
@@ -238,8 +233,8 @@ MS_HD void pit_phase_a(const Ctx& c, const PitLane& t, const PitShare& sh, Fetch
         if (t.G >= 2) {
             double sy[6];
             full_to_sym(P, sy);
-            for (int i = 0; i < 6; ++i) sh.at(SH_PE + i, t.G - 2, t.col) = sy[i];
-            for (int i = 0; i < 3; ++i) sh.at(SH_PE + 6 + i, t.G - 2, t.col) = p[i];
+            for (int i = 0; i < 6; ++i) SH_PE_AT(sh, i, t.G - 2, t.col) = sy[i];
+            for (int i = 0; i < 3; ++i) SH_PE_AT(sh, 6 + i, t.G - 2, t.col) = p[i];
         }
     }
 }
@@ -250,9 +245,9 @@ MS_HD void pit_value_chain(const PitShare& sh, int col, int G) {
     double Pn[3][3], pn[3];
     {
         double sy[6];
-        for (int i = 0; i < 6; ++i) sy[i] = sh.at(SH_PE + i, G - 2, col);
+        for (int i = 0; i < 6; ++i) sy[i] = SH_PE_AT(sh, i, G - 2, col);
         sym_to_full(sy, Pn);
-        for (int i = 0; i < 3; ++i) pn[i] = sh.at(SH_PE + 6 + i, G - 2, col);
+        for (int i = 0; i < 3; ++i) pn[i] = SH_PE_AT(sh, 6 + i, G - 2, col);
     }
     for (int l = G - 3; l >= 0; --l) {
         ChunkElem E;
@@ -263,10 +258,10 @@ MS_HD void pit_value_chain(const PitShare& sh, int col, int G) {
         sym_to_full(sy, R);
         for (int i = 0; i < 3; ++i) { dp[i] = pn[i] - sh.at(SH_REF + 6 + i, l + 1, col); for (int j = 0; j < 3; ++j) dP[i][j] = Pn[i][j] - R[i][j]; }
         double P[3][3], p[3];
-        if (!chunk_apply_diff(E, dP, dp, P, p)) { sh.raise(col, PIT_SCAN_FAILED); return; }
+        if (!chunk_apply_diff(E, dP, dp, P, p)) { sh.raise(col, PIT_APPLY_FAILED); return; }
         full_to_sym(P, sy);
-        for (int i = 0; i < 6; ++i) sh.at(SH_PE + i, l, col) = sy[i];
-        for (int i = 0; i < 3; ++i) { sh.at(SH_PE + 6 + i, l, col) = p[i]; pn[i] = p[i]; for (int j = 0; j < 3; ++j) Pn[i][j] = P[i][j]; }
+        for (int i = 0; i < 6; ++i) SH_PE_AT(sh, i, l, col) = sy[i];
+        for (int i = 0; i < 3; ++i) { SH_PE_AT(sh, 6 + i, l, col) = p[i]; pn[i] = p[i]; for (int j = 0; j < 3; ++j) Pn[i][j] = P[i][j]; }
     }
 }
 
@@ -276,20 +271,20 @@ template <class Fetch>
 MS_HD void pit_phase_c(const Ctx& c, const PitLane& t, const PitShare& sh, Fetch& fb) {
     if (t.l > t.G - 2 || sh.flags[t.col]) return;
     double P[3][3], p[3], sy[6];
-    for (int i = 0; i < 6; ++i) sy[i] = sh.at(SH_PE + i, t.l, t.col);
+    for (int i = 0; i < 6; ++i) sy[i] = SH_PE_AT(sh, i, t.l, t.col);
     sym_to_full(sy, P);
-    for (int i = 0; i < 3; ++i) p[i] = sh.at(SH_PE + 6 + i, t.l, t.col);
+    for (int i = 0; i < 3; ++i) p[i] = SH_PE_AT(sh, 6 + i, t.l, t.col);
     Aff T;
     aff_identity(T);
     if (!riccati_backward_range(c, t.s, t.N, t.kLo, t.kHi, t.mu, t.delta, fb, P, p, T.M, T.m)) { sh.raise(t.col, PIT_BAD_INERTIA); return; }
-    for (int i = 0; i < 9; ++i) sh.at(SH_E + i, t.l, t.col) = T.M[i];
-    for (int i = 0; i < 3; ++i) sh.at(SH_E + 9 + i, t.l, t.col) = T.m[i];
+    for (int i = 0; i < 9; ++i) sh.at(SH_TR + i, t.l, t.col) = T.M[i];
+    for (int i = 0; i < 3; ++i) sh.at(SH_TR + 9 + i, t.l, t.col) = T.m[i];
     if (t.l >= 1 && t.kHi > t.kLo) {
         double num = 0.0, den = 1e-300, pnum = 0.0, pden = 1e-300;
         full_to_sym(P, sy);
-        for (int i = 0; i < 6; ++i) { const double q = sh.at(SH_PE + i, t.l - 1, t.col); num = fmax(num, fabs(sy[i] - q)); den = fmax(den, fabs(q)); }
-        for (int i = 0; i < 3; ++i) { const double q = sh.at(SH_PE + 6 + i, t.l - 1, t.col); pnum = fmax(pnum, fabs(p[i] - q)); pden = fmax(pden, fabs(q)); }
-        if (!(num <= PIT_CONSISTENCY_TOL * den) || !(pnum <= PIT_CONSISTENCY_TOL * pden + 1e-12)) sh.raise(t.col, PIT_SCAN_FAILED);
+        for (int i = 0; i < 6; ++i) { const double q = SH_PE_AT(sh, i, t.l - 1, t.col); num = fmax(num, fabs(sy[i] - q)); den = fmax(den, fabs(q)); }
+        for (int i = 0; i < 3; ++i) { const double q = SH_PE_AT(sh, 6 + i, t.l - 1, t.col); pnum = fmax(pnum, fabs(p[i] - q)); pden = fmax(pden, fabs(q)); }
+        if (!(num <= PIT_CONSISTENCY_TOL * den) || !(pnum <= PIT_CONSISTENCY_TOL * pden + 1e-12)) sh.raise(t.col, PIT_INCONSISTENT);
     }
 }
 
@@ -301,7 +296,7 @@ MS_HD void pit_state_chain(const PitShare& sh, int col, int G) {
         if (l == G - 1) break;
         double nx[3];
         for (int i = 0; i < 3; ++i)
-            nx[i] = sh.at(SH_E + 9 + i, l, col) + sh.at(SH_E + 3 * i, l, col) * dx[0] + sh.at(SH_E + 3 * i + 1, l, col) * dx[1] + sh.at(SH_E + 3 * i + 2, l, col) * dx[2];
+            nx[i] = sh.at(SH_TR + 9 + i, l, col) + sh.at(SH_TR + 3 * i, l, col) * dx[0] + sh.at(SH_TR + 3 * i + 1, l, col) * dx[1] + sh.at(SH_TR + 3 * i + 2, l, col) * dx[2];
         for (int i = 0; i < 3; ++i) dx[i] = nx[i];
     }
 }

@@ -57,7 +57,9 @@ struct DirectFetch {
 // cp.async ring in shared memory with DEPTH + 1 slots, column = thread: stage k + DEPTH*dir is requested as soon as
 // stage k has been copied to registers, into the slot that was consumed one iteration earlier.  Slot indices and the
 // global record pointer are running counters (no division, one pointer bump per interval).
-template <class FL, int BS, int DEPTH>
+// PF > 0: the record PF intervals further on is pulled into L2 at the same time (prefetch.global.L2: no shared memory, no
+// registers), so that a shallow ring sees L2 latency instead of DRAM latency
+template <class FL, int BS, int DEPTH, int PF = 0>
 struct RingFetch {
     enum { COLLECTIVE = 0 };
     double* sm;          // this thread's column of slot 0
@@ -70,6 +72,11 @@ struct RingFetch {
             double* dst = sm + tail * (FL::NF * BS);
 #pragma unroll
             for (int f = 0; f < FL::NF; ++f) __pipeline_memcpy_async(dst + f * BS, next + FL::off(f), 8);
+            if (PF > 0 && left > PF) {
+                const double* far = next + PF * step;
+#pragma unroll
+                for (int f = 0; f < FL::NF; ++f) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + FL::off(f)));
+            }
             next += step;
             --left;
         }

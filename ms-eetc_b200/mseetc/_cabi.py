@@ -71,6 +71,8 @@ def lib():
     L.mseetc_set_sweep_lanes.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_sweep_fallbacks.argtypes = [vp]
     L.mseetc_last_sweep_fallbacks.restype = ctypes.c_longlong
+    L.mseetc_last_sweep_lanes.argtypes = [vp]
+    L.mseetc_last_sweep_fallback_reasons.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     L.mseetc_eval_loss_rows.argtypes = [vp, i32, vp, vp, vp, vp]
     _lib = L
     return L
@@ -114,15 +116,23 @@ class Handle:
             pass
 
     def set_sweep_lanes(self, lanes):
-        "1 = sequential Riccati sweeps; 8 / 16 / 32 = parallel-in-time sweeps with that many chunk lanes per instance."
+        "0 = chosen per call; 1 = sequential Riccati sweeps; 8 / 16 / 32 = parallel-in-time sweeps with that many chunk lanes per instance."
         _check(lib().mseetc_set_sweep_lanes(self._h, int(lanes)), 'mseetc_set_sweep_lanes')
         self._lanes = int(lanes)
 
     def sweep_lanes(self):
-        return getattr(self, '_lanes', 1)
+        "lanes the last solve on this handle ran with (the setting, before the first solve)"
+        n = int(lib().mseetc_last_sweep_lanes(self._h))
+        return n if getattr(self, '_solved', False) else getattr(self, '_lanes', 1)
 
     def last_sweep_fallbacks(self):
         return int(lib().mseetc_last_sweep_fallbacks(self._h))
+
+    def last_sweep_fallback_reasons(self):
+        "(reference recursion failed, chain step singular, chain and recursion disagreed) of the last solve"
+        out = (ctypes.c_int32 * 3)()
+        _check(lib().mseetc_last_sweep_fallback_reasons(self._h, out), 'mseetc_last_sweep_fallback_reasons')
+        return tuple(int(x) for x in out)
 
     def set_loss_map(self, knots_load, knots_speed, coef):
         "Upload the motor-loss spline (efficiency.createSpline) used by loss_kind 2."
@@ -172,6 +182,7 @@ class Handle:
                                       _ptr(bmax), _ptr(tmin), _ptr(out['z']), _ptr(out['lam']), _ptr(out['obj']), _ptr(out['kkt']),
                                       _ptr(out['iters']), _ptr(out['status']), _ptr(ws), need, ctypes.c_void_p(stream))
         _check(rc, 'mseetc_solve_batch')
+        self._solved = True
         out['ticks'] = lib().mseetc_last_ticks(self._h)
         out['launches'] = lib().mseetc_last_launches(self._h)
         return out

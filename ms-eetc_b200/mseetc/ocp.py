@@ -28,8 +28,10 @@ DEFAULT_INITIAL_GUESS = 'profile'
 # anyway (Maximum_Iterations_Exceeded); otherwise one instance cycling around a kink of a non-smooth loss map holds the whole
 # lock-step batch until maxIterations.  0 disables the watchdog (`solver.stallIterations = 0`).
 DEFAULT_STALL_ITERATIONS = 80
-# Sub-batches solved concurrently on separate CUDA streams (one host thread each); see _cabi.StreamPool.
-DEFAULT_STREAMS = 2
+# Sub-batches solved concurrently on separate CUDA streams (one host thread each); see _cabi.StreamPool.  With the sequential
+# sweeps (a 150 us dependent chain per iteration whatever the batch size) a second stream filled the gaps (+10 %); with the
+# parallel-in-time sweeps one stream is as fast (23.7 vs 23.6 ms per 4096-instance sweep) and every kernel runs alone.
+DEFAULT_STREAMS = 1
 MIN_INSTANCES_PER_STREAM = 512
 
 
@@ -63,19 +65,6 @@ class OptionsCasadiSolver(Options):
             raise ValueError("Unknown integration method!")
         if not isinstance(self.integrateLosses, bool):
             raise ValueError("'integrateLosses' flag must be a boolean!")
-
-
-def auto_sweep_lanes(numIntervals):
-    """Chunk lanes per instance of the Riccati sweeps (pit.cuh).  The sequential sweep is a dependent chain of numIntervals
-    stages that takes the same time for 1 and for 4096 instances; with G lanes the chain is ~2 numIntervals / G stages plus
-    G - 2 short chain steps, at about 2.5 times the arithmetic and 1.4 times the bytes."""
-    if numIntervals >= 1024:
-        return 32
-    if numIntervals >= 96:
-        return 16
-    if numIntervals >= 48:
-        return 8
-    return 1
 
 
 def classify_losses(train):
@@ -310,10 +299,7 @@ class casadiSolver():
         if self._lossKind == 'dynamic' and self.energyOptimal:
             dp = self.train.powerLosses.device_params
             h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
-        lanes = self.sweepLanes
-        if lanes == 'auto':
-            lanes = auto_sweep_lanes(self.numIntervals)
-        h.set_sweep_lanes(int(lanes))
+        h.set_sweep_lanes(0 if self.sweepLanes == 'auto' else int(self.sweepLanes))      # 0: the library picks per call
         return h
 
     def _ensure_pool(self, dev):
@@ -693,7 +679,7 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
         hd = _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
                           int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess],
                           stall_iterations=int(ref.stallIterations))
-        hd.set_sweep_lanes(auto_sweep_lanes(int(nint.min())) if ref.sweepLanes == 'auto' else int(ref.sweepLanes))
+        hd.set_sweep_lanes(0 if ref.sweepLanes == 'auto' else int(ref.sweepLanes))
         return hd
     dev_tabs = dict(nint=up(nint, torch.int32), trk_of=up(np.arange(n, dtype=np.int32), torch.int32), trk_off=up(trk_off, torch.int32),
                     ds=up(np.concatenate([t[0] for t in tabs]), torch.float64), c0=up(np.concatenate([t[1] for t in tabs]), torch.float64),

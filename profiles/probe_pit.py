@@ -17,7 +17,7 @@ rows = []
 for n in sizes:
     T = np.linspace(1040.0, 1240.0, n)
     ref = None
-    for lanes in (1, 8, 16, 32):
+    for lanes in [int(x) for x in os.environ.get('PROBE_LANES', '1,8,16,32').split(',')]:
         s = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), opts)
         s.streams = 1; s.sweepLanes = lanes
         h = s._ensure_handle(); _cabi.set_profiling(h, True)
@@ -29,7 +29,7 @@ for n in sizes:
         if ref is None: ref = {k: np.array(v) for k, v in res.items() if isinstance(v, np.ndarray)}
         row = dict(n=n, lanes=lanes, converged=int((res['status'] == 0).sum()), iters_mean=float(res['iters'].mean()), iters_max=int(res['iters'].max()),
                    same_iters=bool(np.array_equal(res['iters'], ref['iters'])), k_step_us=1e3 * p['ms'] / max(1, p['launches']), launches=p['launches'],
-                   device_ms=tot, wall_ms=1e3 * dt, fallbacks=int(h.last_sweep_fallbacks()),
+                   device_ms=tot, wall_ms=1e3 * dt, fallbacks=int(h.last_sweep_fallbacks()), fallback_reasons=h.last_sweep_fallback_reasons(),
                    obj_rel=float(np.max(np.abs(res['obj'] - ref['obj']) / np.abs(ref['obj']))), dz=float(np.abs(res['z'] - ref['z']).max()))
         rows.append(row)
         print(json.dumps(row), flush=True)

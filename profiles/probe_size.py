@@ -16,6 +16,8 @@ train = Train(config={'id': 'NL_Intercity_VIRM6'})
 solver = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), bench.OPTS)
 dev = torch.device('cuda', 0)
 N = bench.N_INT
+if os.environ.get('MSEETC_LANES'):
+    solver.sweepLanes = int(os.environ['MSEETC_LANES'])      # 1 sequential, 8 / 16 / 32 parallel in time (default: auto)
 h = solver._make_handle()
 _cabi.set_profiling(h, True)
 ds, c0, bmax = solver._tables(solver._base['rho'], solver._base['g'], solver._base['velocityMax'])
