@@ -65,7 +65,8 @@ enum mseetc_status {
     MSEETC_RESTORATION_FAILED = 2,
     MSEETC_ERROR_IN_STEP_COMPUTATION = 3,
     MSEETC_INFEASIBLE_PROBLEM_DETECTED = 4,
-    MSEETC_INVALID_NUMBER_DETECTED = 5
+    MSEETC_INVALID_NUMBER_DETECTED = 5,
+    MSEETC_SOLVED_TO_ACCEPTABLE_LEVEL = 6   /* IPOPT's acceptable_tol 1e-6 for 15 iterations: success in CasADi's stats() */
 };
 
 typedef struct mseetc_problem {
@@ -139,6 +140,20 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
                        double* z_out_dev, double* lam_g_out_dev, double* obj_out_dev, double* kkt_out_dev,
                        int32_t* iters_out_dev, int32_t* status_out_dev,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
+
+/* Trajectory tables of a batch: what utils.postProcessDataFrame (mseetc/utils.py:223-336, called at ocp.py:407) adds to every
+ * returned solution, for all instances at once, incl. the time-domain re-simulation columns (utils.py:164-194; RK4 with
+ * Richardson extrapolation in place of CVODES).  table_out_dev: [n_instances][n_intervals_max+1][mseetc_table_columns()],
+ * row-major, columns in the reference's order with the index column 'Time [s]' first; rows beyond an instance's last node and
+ * all rows of failed instances (status_dev, may be NULL) are NaN.  node_tables_dev: four planes (position [m], speed limit
+ * [m/s], gradient [permil], curvature [1/m]) of [sum (N_j+1)] doubles, node_plane_stride doubles apart, indexed like bmax_dev;
+ * mass_dev [n_instances]: train.mass without the rotating-mass factor (utils.py:294).  The other arguments are those of
+ * mseetc_solve_batch.  Synchronises the stream. */
+int mseetc_table_columns(void);
+int mseetc_postprocess_batch(mseetc_handle h, int32_t n_instances, const double* z_dev, const double* params_dev,
+                             const int32_t* n_intervals_dev, const int32_t* track_of_inst_dev, const int32_t* track_offset_dev,
+                             const double* ds_dev, const double* c0_dev, const double* node_tables_dev, size_t node_plane_stride,
+                             const double* mass_dev, const int32_t* status_dev, double* table_out_dev, void* cuda_stream);
 
 /* Sweep variant (replaces MUMPS behind mseetc/ocp.py:359): 1 = sequential Riccati sweeps, one thread per instance (default of
  * a new handle); 8, 16 or 32 = parallel-in-time sweeps with that many chunk lanes per instance (chunk elements from reference

@@ -417,6 +417,7 @@ MS_HD void inst_init(const Ctx& c, int s) {
     c.I(SI_TICKS, s) = 0;
     c.I(SI_LAST_GAIN, s) = 0;
     c.I(SI_FACT, s) = 0;
+    c.I(SI_NACC, s) = 0;
 }
 
 // slack of a bound and the matching barrier pieces
@@ -584,6 +585,15 @@ MS_HD void trial_partials(const Ctx& c, int s, int N, int w, int W, double* acc)
     }
 }
 
+// IPOPT's second termination test with its default thresholds (acceptable_tol 1e-6, acceptable_constr_viol_tol 1e-2,
+// acceptable_compl_inf_tol 1e-2, acceptable_dual_inf_tol 1e10) on the errors of the current iterate (set by inst_kkt); CasADi
+// counts "Solved_To_Acceptable_Level" as success (reference ocp.py:364 reads stats()['success'])
+#define MS_ACCEPTABLE_TOL 1e-6
+#define MS_ACCEPTABLE_ITER 15
+MS_HD bool acceptable_point(const Ctx& c, int s) {
+    return c.D(SD_KKT, s) <= MS_ACCEPTABLE_TOL && c.D(SD_DINF, s) <= 1e10 && c.D(SD_PINF, s) <= 1e-2 && c.D(SD_CINF, s) <= 1e-2;
+}
+
 MS_HD void inst_decide(const Ctx& c, int s, const double* sums) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_TRIAL) return;
@@ -627,7 +637,8 @@ MS_HD void inst_decide(const Ctx& c, int s, const double* sums) {
         double a2 = 0.5 * alpha;
         c.I(SI_NLS, s) += 1;
         if (a2 < c.D(SD_ALPHA_MIN, s)) {
-            finish(c, s, ST_RESTORATION_FAILED);   // no restoration phase: report like IPOPT would
+            // no restoration phase: report like IPOPT would -- which, at a point of "acceptable" quality, is success
+            finish(c, s, acceptable_point(c, s) ? ST_ACCEPTABLE : ST_RESTORATION_FAILED);
         } else {
             c.D(SD_ALPHA, s) = a2;
         }

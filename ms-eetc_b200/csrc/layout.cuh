@@ -90,6 +90,7 @@ enum SdField {
     SD_N = SD_FILTER + 2 * 12
 };
 enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_LAST_GAIN,
+               SI_NACC,     // consecutive iterations at IPOPT's "acceptable" level
                SI_FACT,     // a factorisation has been stored (its chunk-end value functions are the references of pit.cuh)
                SI_N };
 
@@ -98,7 +99,7 @@ enum { RED_W = 16 };   // interleave factor of the per-instance reductions (fixe
 // status codes (mapped to IPOPT's vocabulary by the host shim, ocp.py:362)
 enum Status {
     ST_RUNNING = -1, ST_SOLVE_SUCCEEDED = 0, ST_MAXITER = 1, ST_RESTORATION_FAILED = 2, ST_STEP_FAILED = 3,
-    ST_INFEASIBLE = 4, ST_INVALID_NUMBER = 5
+    ST_INFEASIBLE = 4, ST_INVALID_NUMBER = 5, ST_ACCEPTABLE = 6
 };
 
 struct Config {

@@ -15,6 +15,7 @@
 
 #include "../../include/mseetc_b200.h"
 #include "io.cuh"
+#include "table.cuh"
 
 using namespace mseetc;
 
@@ -268,6 +269,15 @@ __global__ void __launch_bounds__(SL * G) k_step_pit(Ctx c, int* fallbackCount) 
     __syncthreads();
     if (go) pit_phase_f(c, t, sh, ff);
     if (go && l == 0) { c.I(SI_FACT, s) = 1; c.I(SI_PHASE, s) = PH_STEPPED; }
+}
+
+__global__ void __launch_bounds__(128) k_cell_table(TableIO io, LossMapDev lm) {
+    const size_t total = (size_t)(io.Nmax + 1) * io.n;
+    for (size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 128)
+        cell_table(io, lm, (int)(idx % (io.Nmax + 1)), (int)(idx / (io.Nmax + 1)));
+}
+__global__ void __launch_bounds__(32) k_inst_resim(TableIO io) {
+    inst_resim(io, blockIdx.x * 32 + threadIdx.x);
 }
 
 __global__ void k_eval_loss_rows(LossMapDev lm, int n, const double* in, const double* par, double* out) {
@@ -712,6 +722,30 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     h->ev_class = evClass;
     h->last_ticks = tick;
     h->last_launches = launches;
+    return 0;
+}
+
+int mseetc_table_columns(void) { return (int)TAB_NCOL; }
+
+int mseetc_postprocess_batch(mseetc_handle h, int32_t n, const double* z, const double* params, const int32_t* nint, const int32_t* trk_of,
+                             const int32_t* trk_off, const double* ds, const double* c0, const double* nodes, size_t node_stride,
+                             const double* mass, const int32_t* status, double* table_out, void* cuda_stream) {
+    if (!h) return fail(-1, "mseetc_postprocess_batch: null handle");
+    if (n < 1) return fail(-2, "mseetc_postprocess_batch: n_instances must be >= 1");
+    if (!z || !params || !nint || !trk_of || !trk_off || !ds || !c0 || !nodes || !mass || !table_out)
+        return fail(-3, "mseetc_postprocess_batch: null device pointer");
+    const mseetc_problem& p = h->prob;
+    if (p.loss_kind == 2 && p.energy_optimal && !h->lm_dev) return fail(-6, "mseetc_postprocess_batch: loss_kind 2 needs mseetc_set_loss_map first");
+    TableIO io{z, params, nint, trk_of, trk_off, ds, c0, nodes, node_stride, mass, status, table_out, n, p.n_intervals_max, p.with_pn_brake,
+               p.energy_optimal ? p.loss_kind : 0};
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t total = (size_t)(io.Nmax + 1) * n;
+    k_cell_table<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(io, h->lm);
+    k_inst_resim<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(io);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "table kernels launch");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "table kernels");
     return 0;
 }
 

@@ -613,6 +613,10 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     }
     if (!isfinite(E0) || !isfinite(fo)) { finish(c, s, ST_INVALID_NUMBER); return; }
     if (E0 <= g.tol) { finish(c, s, ST_SOLVE_SUCCEEDED); return; }
+    // acceptable level for MS_ACCEPTABLE_ITER consecutive iterations (IPOPT default acceptable_iter 15)
+    if (acceptable_point(c, s)) {
+        if (++c.I(SI_NACC, s) >= MS_ACCEPTABLE_ITER) { finish(c, s, ST_ACCEPTABLE); return; }
+    } else c.I(SI_NACC, s) = 0;
     if (c.I(SI_ITERS, s) >= g.maxIter) { finish(c, s, ST_MAXITER); return; }
     // stall watchdog (batch throughput): an instance that cycles around a kink of a non-smooth loss map would otherwise hold
     // the whole lock-step batch until max_iter; it ends with the status it would end with anyway
@@ -620,7 +624,7 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
         const double best = c.D(SD_KKT_BEST, s);
         // counted in trial evaluations (lock-step ticks), which is what a straggler costs the batch
         if (best <= 0.0 || E0 < 0.9 * best) { c.D(SD_KKT_BEST, s) = E0; c.I(SI_LAST_GAIN, s) = c.I(SI_TICKS, s); }
-        else if (c.I(SI_TICKS, s) - c.I(SI_LAST_GAIN, s) > g.stallIters) { finish(c, s, ST_MAXITER); return; }
+        else if (c.I(SI_TICKS, s) - c.I(SI_LAST_GAIN, s) > g.stallIters) { finish(c, s, acceptable_point(c, s) ? ST_ACCEPTABLE : ST_MAXITER); return; }
     }
     // ---- monotone barrier update (eq. 7), filter reset
     double mu = c.D(SD_MU, s);

@@ -28,7 +28,9 @@ STATUS_STRINGS = {   # IPOPT's return_status vocabulary (what stats['Solver stat
     3: 'Error_In_Step_Computation',
     4: 'Infeasible_Problem_Detected',
     5: 'Invalid_Number_Detected',
+    6: 'Solved_To_Acceptable_Level',
 }
+SUCCESS_CODES = (0, 6)      # what CasADi's stats()['success'] is true for (reference ocp.py:364)
 
 
 class Problem(ctypes.Structure):
@@ -57,6 +59,8 @@ def lib():
     L.mseetc_workspace_bytes.argtypes = [vp, i32]
     L.mseetc_workspace_bytes.restype = sz
     L.mseetc_solve_batch.argtypes = [vp, i32] + [vp] * 14 + [vp, sz, vp]
+    L.mseetc_table_columns.restype = ctypes.c_int
+    L.mseetc_postprocess_batch.argtypes = [vp, i32] + [vp] * 8 + [sz] + [vp] * 4
     L.mseetc_last_ticks.argtypes = [vp]
     L.mseetc_last_launches.argtypes = [vp]
     L.mseetc_set_profiling.argtypes = [vp, ctypes.c_int]
@@ -186,6 +190,28 @@ class Handle:
         out['ticks'] = lib().mseetc_last_ticks(self._h)
         out['launches'] = lib().mseetc_last_launches(self._h)
         return out
+
+
+TABLE_COLUMNS = ('Time [s]', 'Position [m]', 'Velocity [m/s]', 'Force (el) [N]', 'Force (pnb) [N]', 'Slacks', 'Speed limit [m/s]',
+                 'Gradient [permil]', 'Curvature [1/m]', 'Force (acc) [N]', 'Force (rgb) [N]', 'Force [N]', 'Max. Power [kW]', 'Min. Power [kW]',
+                 'Losses [kWh]', 'Energy [kWh]', 'Energy (pnb) [kWh]', 'Energy (kin) [kWh]', 'Acceleration [m/s^2]', 'Position - cvodes [m]',
+                 'Velocity - cvodes [m/s]', 'Error position [m]', 'Error velocity [m/s]')      # reference ocp.py:401-405, utils.py:230-334,188-192
+
+
+def postprocess_device(handle, z, params, nint, trk_of, trk_off, ds, c0, nodes, mass, status, out=None):
+    "Batched trajectory tables on the device (mseetc_postprocess_batch); all arguments torch CUDA tensors; returns [n, Nmax+1, columns]."
+    torch = _torch_cuda()
+    n = int(nint.numel())
+    ncol = lib().mseetc_table_columns()
+    assert ncol == len(TABLE_COLUMNS)
+    Nmax = handle.problem.n_intervals_max
+    if out is None:
+        out = torch.empty((n, Nmax + 1, ncol), dtype=torch.float64, device=z.device)
+    stream = torch.cuda.current_stream(z.device).cuda_stream
+    _check(lib().mseetc_postprocess_batch(handle._h, n, _ptr(z), _ptr(params), _ptr(nint), _ptr(trk_of), _ptr(trk_off), _ptr(ds), _ptr(c0),
+                                          _ptr(nodes), int(nodes.shape[1]), _ptr(mass), _ptr(status), _ptr(out), ctypes.c_void_p(stream)),
+           'mseetc_postprocess_batch')
+    return out
 
 
 class StreamPool:

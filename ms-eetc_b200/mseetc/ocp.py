@@ -382,6 +382,7 @@ class casadiSolver():
             sib._lossKind = 'none'
             sib._handle = None
             sib._sibling = None
+            sib._restart = None
             sib._pool = None
             sib._dev = {}             # own staging / result buffers: the sibling runs concurrently on a second host thread
             sib.scalingFactorObjective = self.trackLength / self._base['velocityMax']
@@ -391,6 +392,17 @@ class casadiSolver():
                 sib.muInit = 1e-4
             self._sibling = sib
         return self._sibling
+
+    def _restart_sibling(self):
+        "The same problem started from the reference's own initial guess (second attempt for instances whose iteration broke down)."
+        if getattr(self, '_restart', None) is None:
+            import copy
+            sib = copy.copy(self)
+            sib.initialGuess = 'reference'
+            sib.muInit = 0.1
+            sib._handle, sib._sibling, sib._restart, sib._pool, sib._dev = None, None, None, None, {}
+            self._restart = sib
+        return self._restart
 
     def minimum_time(self, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None, device=None):
         """Minimum trip duration t_N - t_0 of each instance (time-optimal mode of the same problem,
@@ -417,7 +429,7 @@ class casadiSolver():
         return res['z'][:, -2] - np.broadcast_to(t0, res['z'][:, -2].shape), res['status']
 
     def solve_batch(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, overrides=None,
-                    want_multipliers=False, device=None, screen=True, to_host=True):
+                    want_multipliers=False, device=None, screen=True, to_host=True, restart=True, tables=False):
         """Solve n instances that share this solver's track, options and problem structure.
 
         terminalTime / initialTime / terminalVelocity / initialVelocity: scalars or arrays of length n.
@@ -434,6 +446,17 @@ class casadiSolver():
         below it are reported as 'Infeasible_Problem_Detected' without iterating.  `screen` may also be a boolean array of
         length n: False marks instances the caller knows to be feasible (e.g. a Monte Carlo at a timetable value with
         slack) -- they take no part in the minimum-time presolve and are never screened.
+
+        restart=True: an instance whose iteration breaks down from the speed-envelope starting profile (line search or step
+        computation fails -- where IPOPT would enter its restoration phase, which this solver does not have) is solved once
+        more from the reference's own starting point (ocp.py:325-339, mu_init 0.1), from which the iteration takes the
+        reference's path.
+
+        tables=True adds the post-processed trajectory tables of all instances, computed on the device (what
+        postProcessDataFrame adds to the table that solve() returns, reference ocp.py:407 / utils.py:223-336, with the defaults
+        CVODES=True, integrateLosses=False): res['table'] is an array [n, numIntervals+1, 23] with the columns
+        res['table_columns'] (index column 'Time [s]' first); casadiSolver.table(res, i) makes the DataFrame of instance i.
+        Rows of failed instances are NaN.
 
         to_host=False leaves z / lam / obj / kkt / iters / status as torch tensors on the device (used by
         mseetc.sharding.solve_batch_sharded, which gathers them over NVLink before one device-to-host copy)."""
@@ -538,7 +561,7 @@ class casadiSolver():
             sys.setswitchinterval(interval)
         t_join = _time.perf_counter() - t_begin
         # the reference returns no trajectory for a failed solve (ocp.py:364-370): blank those rows on the device
-        out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
+        out['z'].mul_(((out['status'] == 0) | (out['status'] == 6)).to(out['z'].dtype).unsqueeze(1))
         res = {}
         if not to_host:
             # results stay on the device; the certificate is applied there as well
@@ -568,7 +591,7 @@ class casadiSolver():
         if tmin is not None:
             # an instance below its minimum trip time is infeasible whatever the iteration did before the certificate arrived
             short = (tmin > 0) & ((T - t0) < tmin * (1 - _cabi.TMIN_MARGIN))
-            res['status'][(res['status'] != 0) & short] = 4
+            res['status'][(res['status'] != 0) & (res['status'] != 6) & short] = 4
             # the device also screens with a speed-envelope bound before the first iteration (inst_screen, core.cuh); every such
             # flag is checked against the exact certificate and an instance flagged wrongly is solved again without screening
             wrong = np.flatnonzero((res['status'] == 4) & ~short)
@@ -580,6 +603,20 @@ class casadiSolver():
                     if key in res and isinstance(res[key], np.ndarray):
                         res[key][wrong] = redo[key]
 
+        if restart and self.initialGuess == 'profile':
+            broke = np.flatnonzero((res['status'] == 2) | (res['status'] == 3) | (res['status'] == 5))
+            if len(broke):
+                pick = lambda a: np.broadcast_to(np.asarray(a, dtype=float), (n,))[broke]
+                redo = self._restart_sibling().solve_batch(T[broke], t0[broke], vN[broke], v0[broke], overrides={k: pick(v) for k, v in overrides_in.items()},
+                                                           want_multipliers=want_multipliers, device=device, screen=False, restart=False)
+                better = (redo['status'] == 0) | (redo['status'] == 6)
+                for key in ('z', 'lam', 'obj', 'kkt', 'iters', 'status'):
+                    if key in res and isinstance(res[key], np.ndarray):
+                        res[key][broke[better]] = redo[key][better]
+                res['restarted'] = broke
+        if tables:
+            res['table'] = self._tables_on_device(res, P, ds, c0, trk_of, trk_off, overrides, perm, n, dev)
+            res['table_columns'] = _cabi.TABLE_COLUMNS
         res['h2d_bytes'] = int(P.nbytes + 4 * n * 2 + trk_off.nbytes + ds.nbytes + c0.nbytes + bmax.nbytes + (tmin.nbytes if tmin is not None else 0))
         res['d2h_bytes'] = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
         res['tmin'] = tmin
@@ -599,6 +636,35 @@ class casadiSolver():
         res['totalMass'] = M
         return res
 
+    def _tables_on_device(self, res, P, ds, c0, trk_of, trk_off, overrides, perm, n, dev):
+        "Post-processed tables of a solved batch (device kernels of csrc/table.cuh); P, trk_of are in the dealt order `perm`."
+        import torch
+        f64, i32 = torch.float64, torch.int32
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+        N = self.numIntervals
+        back = np.argsort(perm) if perm is not None else None
+        Pc = P[:, back] if back is not None else P                    # caller's order, like the results
+        tk = trk_of[back] if back is not None else trk_of
+        ntracks = len(trk_off) - 1
+        pts = self.points
+        one = np.stack([pts.index.values.astype(float), pts['Speed limit [m/s]'].values.astype(float),
+                        pts['Gradient [permil]'].values.astype(float), pts['Curvature [1/m]'].values.astype(float)])
+        nodes = np.tile(one, (1, ntracks))
+        mass = np.array(np.broadcast_to(np.asarray(overrides.get('mass', self._base['mass']), dtype=float), (n,)))
+        tab = _cabi.postprocess_device(self._ensure_handle(), up(res['z'], f64), up(Pc, f64), up(np.full(n, N, np.int32), i32), up(tk, i32),
+                                       up(trk_off, i32), up(ds, f64), up(c0, f64), up(nodes, f64), up(mass, f64), up(res['status'], i32))
+        host = self._pinned('table', tab)
+        host.copy_(tab, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return host.numpy()
+
+    @staticmethod
+    def table(res, i):
+        "DataFrame of instance i of a solve_batch(..., tables=True) result: the table solve() returns (reference ocp.py:401-407)."
+        cols = res['table_columns']
+        df = pd.DataFrame(res['table'][i][:, 1:], columns=list(cols[1:]), index=pd.Index(res['table'][i][:, 0], name=cols[0]))
+        return df
+
     # ------------------------------------------------------------------ reference call surface
     def solve(self, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1):
         if not isinstance(initialTime, (int, float)) or initialTime < 0:
@@ -607,7 +673,7 @@ class casadiSolver():
             raise ValueError("Terminal time must be a strictly positive number, not {}!".format(terminalTime))
         res = self.solve_batch(terminalTime, initialTime, terminalVelocity, initialVelocity, screen=False)
         status = int(res['status'][0])
-        if status != 0 and self.energyOptimal:
+        if status not in _cabi.SUCCESS_CODES and self.energyOptimal:
             # classify the failure: below the minimum trip time the problem is infeasible (what IPOPT's restoration
             # phase would report); the time-optimal solve is only paid for on failure
             dur, st = self.minimum_time(initialTime, terminalVelocity, initialVelocity)
@@ -615,7 +681,7 @@ class casadiSolver():
                 status = 4
         stats = {'Solver status': _cabi.STATUS_STRINGS.get(status, 'Internal_Error'), 'IP iterations': int(res['iters'][0]),
                  'CPU time [s]': res['wall'], 'Cost': float(res['cost'][0])}
-        if status != 0:
+        if status not in _cabi.SUCCESS_CODES:
             print("Solver failed with status '{}'".format(stats['Solver status']))
             return None, stats
         print("Solver converged in {:4d} iterations.".format(stats['IP iterations']))
@@ -641,7 +707,7 @@ class casadiSolver():
         return df
 
 
-def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, screen=True, device=None):
+def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, initialVelocity=1, screen=True, device=None, restart=True):
     """Additive API: one device call for instances that live on DIFFERENT tracks and/or interval counts
     (BASELINE config 5: random tracks, mixed numIntervals).  `solvers` is a list of casadiSolver objects with the same
     problem structure (brakes, power rows, objective, loss family, integrator options); instance i is
@@ -675,9 +741,11 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
     trk_off = np.concatenate([[0], np.cumsum(nint)]).astype(np.int32)
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
     io = ref.opts.integrationOptions
+    guess = ref.initialGuess if restart is not None else 'reference'       # restart=None: this IS the second attempt
+
     def mk(energy, loss):
         hd = _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
-                          int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[ref.initialGuess],
+                          int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[guess],
                           stall_iterations=int(ref.stallIterations))
         hd.set_sweep_lanes(0 if ref.sweepLanes == 'auto' else int(ref.sweepLanes))
         return hd
@@ -707,7 +775,7 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
         h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
     out = h.solve_device(up(P, torch.float64), dev_tabs['nint'], dev_tabs['trk_of'], dev_tabs['trk_off'], dev_tabs['ds'], dev_tabs['c0'],
                          dev_tabs['bmax'], tmin=tmin_dev)
-    out['z'].mul_((out['status'] == 0).to(out['z'].dtype).unsqueeze(1))
+    out['z'].mul_(((out['status'] == 0) | (out['status'] == 6)).to(out['z'].dtype).unsqueeze(1))
     res = {k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in out.items() if v is not None}
     if tmin is not None:
         short = (tmin > 0) & ((T - t0) < tmin * (1 - _cabi.TMIN_MARGIN))
@@ -722,6 +790,20 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
                 res[key][wrong] = redo[key]
             res['z'][wrong] = 0.0
             res['z'][wrong, :w] = redo['z']
+    if restart and guess == 'profile':
+        # instances whose iteration broke down from the speed-envelope profile: once more from the reference's starting point
+        broke = np.flatnonzero((res['status'] == 2) | (res['status'] == 3) | (res['status'] == 5))
+        if len(broke):
+            pick = lambda a: np.broadcast_to(np.asarray(a, dtype=float), (n,))[broke]
+            redo = solve_instances([solvers[i] for i in broke], pick(terminalTime), pick(initialTime), pick(terminalVelocity),
+                                   pick(initialVelocity), screen=False, device=device, restart=None)
+            w = redo['z'].shape[1]
+            better = (redo['status'] == 0) | (redo['status'] == 6)
+            for key in ('obj', 'kkt', 'iters', 'status'):
+                res[key][broke[better]] = redo[key][better]
+            res['z'][broke[better]] = 0.0
+            res['z'][broke[better], :w] = redo['z'][better]
+            res['restarted'] = broke
     res['wall'] = _time.perf_counter() - t_begin
     scale = P[_cabi.PARAM_INDEX['OBJ_SCALE']]
     M = np.array(Ms)

@@ -152,6 +152,7 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
     status = 'Maximum_Iterations_Exceeded'
     it = 0
     n_reg = 0
+    n_acc = 0
     log = []
     tau = max(0.99, 1 - mu)
     while True:
@@ -161,6 +162,13 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
         log.append((it, fval / sf, theta, dinf, mu))
         if E0 <= tol:
             status = 'Solve_Succeeded'
+            break
+        # IPOPT's second termination test (defaults: acceptable_tol 1e-6, acceptable_iter 15, acceptable_constr_viol_tol 1e-2,
+        # acceptable_compl_inf_tol 1e-2, acceptable_dual_inf_tol 1e10): CasADi reports it as success
+        acceptable = E0 <= 1e-6 and dinf <= 1e10 and pinf <= 1e-2 and cinf0 <= 1e-2
+        n_acc = n_acc + 1 if acceptable else 0
+        if n_acc >= 15:
+            status = 'Solved_To_Acceptable_Level'
             break
         if it >= max_iter:
             break
@@ -292,7 +300,8 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
             alpha *= 0.5
             nls += 1
         if not accepted:
-            status = 'Restoration_Failed'
+            # no restoration phase here; like IPOPT, a failure at an acceptable point ends as "acceptable"
+            status = 'Solved_To_Acceptable_Level' if acceptable else 'Restoration_Failed'
             break
         if not armijo:
             filt.append(((1 - 1e-5) * theta, phi - 1e-8 * theta))
@@ -317,6 +326,6 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
     lam[inr] = yd * sg[inr] / sf
     zLf = np.zeros(n_all); zUf = np.zeros(n_all)
     zLf[free] = zL / sf; zUf[free] = zU / sf
-    return Result(x=xfull.copy(), f=fval / sf, status=status, success=status == 'Solve_Succeeded', iters=it,
+    return Result(x=xfull.copy(), f=fval / sf, status=status, success=status in ('Solve_Succeeded', 'Solved_To_Acceptable_Level'), iters=it,
                   kkt=E0, dinf=dinf, pinf=pinf, mu=mu, lam=lam, zL=zLf, zU=zUf, n_reg=n_reg,
                   time=time.perf_counter() - t_start, log=log, slack=w / sg[inr])

@@ -66,3 +66,44 @@ def active_set(nlp, z, T, t0=0.0, v0=1.0, vN=1.0, rtol=1e-6):
         active = slack <= thr
         ambiguous = (slack > thr / 10) & (slack < thr * 10)
     return active, ambiguous
+
+
+def to_track_data(track):
+    "Product Track -> oracle TrackData (same step functions)."
+    from oracle.problem import TrackData
+    return TrackData(track.length, (track.speedLimits.index.values, track.speedLimits.iloc[:, 0].values),
+                     (track.gradients.index.values, track.gradients.iloc[:, 0].values),
+                     (track.curvatures.index.values, track.curvatures.iloc[:, 0].values))
+
+
+def config5_instances(n, seed=11):
+    """BASELINE configs[4] recipe: n random tracks with numIntervals drawn from {100, 200, 300, 400}; a track
+    with more sections than intervals (reference track.py:103-105) is drawn again.  Returns [(numIntervals, Track)]."""
+    import sys
+    if PKG not in sys.path:
+        sys.path.insert(0, PKG)
+    from mseetc.synthetic import random_track
+    from mseetc.track import computeDiscretizationPoints
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        N = int(rng.choice([100, 200, 300, 400]))
+        track = random_track(rng)
+        try:
+            computeDiscretizationPoints(track, N)
+        except ValueError:
+            continue
+        out.append((N, track))
+    return out
+
+
+def mc_dynamic_overrides(n, seed=20260101):
+    "Spline-loss-map half of BASELINE configs[2] (SURVEY.md 8d recipe): the draws that follow the 32768 constant-efficiency instances."
+    rng = np.random.default_rng(seed)
+    half = 32768
+    for _ in range(6):
+        rng.uniform(0, 1, half)                      # mass, r0, r1, r2, etaTraction, etaRgBrake of the first half
+    nominal = virm6()
+    ov = dict(mass=391000 * rng.uniform(0.85, 1.15, half), r0=nominal.r0 * rng.uniform(0.8, 1.2, half), r1=nominal.r1 * rng.uniform(0.8, 1.2, half),
+              r2=nominal.r2 * rng.uniform(0.8, 1.2, half), auxiliaries=rng.uniform(20e3, 35e3, half), tableScale=rng.uniform(0.9, 1.1, half))
+    return {k: v[:n] for k, v in ov.items()}
