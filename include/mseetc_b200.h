@@ -141,6 +141,19 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n_instances,
                        int32_t* iters_out_dev, int32_t* status_out_dev,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
 
+/* Host-side preprocessing of MANY tracks in one call (no device work): the grid of computeDiscretizationPoints
+ * (mseetc/track.py:91-107 with mergeDataFrames :377-383) -- per track the union of numpy.linspace(0, length, N + 1 - (M - 1)) and the
+ * M merged section starts, which must have exactly N + 1 points (error[t] = 1 otherwise, the reference raises ValueError), and
+ * the forward-filled speed limit / gradient / curvature at those points.  Step functions in CSR form (offsets [n_tracks+1],
+ * ascending positions, first position 0); node outputs indexed like bmax_dev: out_off[t] + t + k with out_off = cumsum(n_int).
+ * All pointers are HOST pointers. */
+int mseetc_discretize_tracks(int32_t n_tracks, const double* length, const int32_t* n_int,
+                             const int32_t* lim_off, const double* lim_pos, const double* lim_val,
+                             const int32_t* grd_off, const double* grd_pos, const double* grd_val,
+                             const int32_t* crv_off, const double* crv_pos, const double* crv_val,
+                             const int32_t* out_off, double* pos_nodes, double* limit_nodes, double* grad_nodes, double* curv_nodes,
+                             int32_t* error);
+
 /* Trajectory tables of a batch: what utils.postProcessDataFrame (mseetc/utils.py:223-336, called at ocp.py:407) adds to every
  * returned solution, for all instances at once, incl. the time-domain re-simulation columns (utils.py:164-194; RK4 with
  * Richardson extrapolation in place of CVODES).  table_out_dev: [n_instances][n_intervals_max+1][mseetc_table_columns()],

@@ -6,7 +6,9 @@
 // No tensor cores: the per-interval blocks are 3x3 / 6x6 FP64 and there is no dense contraction.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <limits>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -722,6 +724,55 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     h->ev_class = evClass;
     h->last_ticks = tick;
     h->last_launches = launches;
+    return 0;
+}
+
+// Host-side preprocessing for many tracks at once (no pandas frame per track): the grid of computeDiscretizationPoints.
+int mseetc_discretize_tracks(int32_t n_tracks, const double* length, const int32_t* n_int, const int32_t* lim_off, const double* lim_pos,
+                             const double* lim_val, const int32_t* grd_off, const double* grd_pos, const double* grd_val, const int32_t* crv_off,
+                             const double* crv_pos, const double* crv_val, const int32_t* out_off, double* pos_nodes, double* limit_nodes,
+                             double* grad_nodes, double* curv_nodes, int32_t* error) {
+    if (n_tracks < 1 || !length || !n_int || !lim_off || !lim_pos || !lim_val || !grd_off || !grd_pos || !grd_val || !crv_off || !crv_pos ||
+        !crv_val || !out_off || !pos_nodes || !limit_nodes || !grad_nodes || !curv_nodes || !error)
+        return fail(-1, "mseetc_discretize_tracks: bad argument");
+    std::vector<double> brk, grid;
+    for (int t = 0; t < n_tracks; ++t) {
+        const int N = n_int[t];
+        const double L = length[t];
+        error[t] = 0;
+        // merged section starts: outer join of the three step functions (track.py:377-383)
+        brk.clear();
+        brk.insert(brk.end(), lim_pos + lim_off[t], lim_pos + lim_off[t + 1]);
+        brk.insert(brk.end(), grd_pos + grd_off[t], grd_pos + grd_off[t + 1]);
+        brk.insert(brk.end(), crv_pos + crv_off[t], crv_pos + crv_off[t + 1]);
+        std::sort(brk.begin(), brk.end());
+        brk.erase(std::unique(brk.begin(), brk.end()), brk.end());
+        const int M = (int)brk.size();
+        const int nuni = N + 1 - (M - 1);                   // track.py:98
+        if (N < 1 || nuni < 2) { error[t] = 1; continue; }
+        grid.assign(brk.begin(), brk.end());
+        const double step = L / (nuni - 1);
+        for (int j = 0; j < nuni; ++j) grid.push_back(j == nuni - 1 ? L : j * step);        // numpy.linspace
+        std::sort(grid.begin(), grid.end());
+        grid.erase(std::unique(grid.begin(), grid.end()), grid.end());
+        if ((int)grid.size() != N + 1) { error[t] = 1; continue; }                           // track.py:103-105
+        double* po = pos_nodes + out_off[t] + t;
+        double* lo = limit_nodes + out_off[t] + t;
+        double* go = grad_nodes + out_off[t] + t;
+        double* co = curv_nodes + out_off[t] + t;
+        int il = lim_off[t], ig = grd_off[t], ic = crv_off[t];
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        for (int k = 0; k <= N; ++k) {                       // forward fill (track.py:101)
+            const double x = grid[k];
+            while (il + 1 < lim_off[t + 1] && lim_pos[il + 1] <= x) ++il;
+            while (ig + 1 < grd_off[t + 1] && grd_pos[ig + 1] <= x) ++ig;
+            while (ic + 1 < crv_off[t + 1] && crv_pos[ic + 1] <= x) ++ic;
+            po[k] = x;
+            lo[k] = (lim_off[t + 1] > lim_off[t] && lim_pos[il] <= x) ? lim_val[il] : nan;
+            go[k] = (grd_off[t + 1] > grd_off[t] && grd_pos[ig] <= x) ? grd_val[ig] : nan;
+            co[k] = (crv_off[t + 1] > crv_off[t] && crv_pos[ic] <= x) ? crv_val[ic] : nan;
+        }
+    }
     return 0;
 }
 

@@ -10,7 +10,7 @@ Known deviations from IPOPT proper (documented, not hidden):
   * no restoration phase: when the line search fails the solver returns ``Restoration_Failed``;
   * inertia is not available from LU: a curvature test along the step triggers the
     delta_w regularisation ladder instead;
-  * no "acceptable level" termination — only the 1e-8 scaled KKT test.
+  * "acceptable level" termination with IPOPT's defaults (1e-6 for 15 iterations), reported as success like CasADi does.
 """
 import time
 
@@ -165,8 +165,8 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
             break
         # IPOPT's second termination test (defaults: acceptable_tol 1e-6, acceptable_iter 15, acceptable_constr_viol_tol 1e-2,
         # acceptable_compl_inf_tol 1e-2, acceptable_dual_inf_tol 1e10): CasADi reports it as success
-        acceptable = E0 <= 1e-6 and dinf <= 1e10 and pinf <= 1e-2 and cinf0 <= 1e-2
-        n_acc = n_acc + 1 if acceptable else 0
+        acc_level = E0 <= 1e-6 and dinf <= 1e10 and pinf <= 1e-2 and cinf0 <= 1e-2
+        n_acc = n_acc + 1 if acc_level else 0
         if n_acc >= 15:
             status = 'Solved_To_Acceptable_Level'
             break
@@ -301,7 +301,7 @@ def solve(nlp, x0, lbz, ubz, lbg, ubg, max_iter=500, tol=1e-8, mu_init=0.1, scal
             nls += 1
         if not accepted:
             # no restoration phase here; like IPOPT, a failure at an acceptable point ends as "acceptable"
-            status = 'Solved_To_Acceptable_Level' if acceptable else 'Restoration_Failed'
+            status = 'Solved_To_Acceptable_Level' if acc_level else 'Restoration_Failed'
             break
         if not armijo:
             filt.append(((1 - 1e-5) * theta, phi - 1e-8 * theta))

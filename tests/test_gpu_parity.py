@@ -591,3 +591,30 @@ def test_batched_tables_match_post_process_data_frame(cabi, kind):
             scale = max(1.0, np.nanmax(np.abs(b)))
             tol = 1e-7 if 'cvodes' in col or 'Error' in col else 1e-11
             assert np.nanmax(np.abs(a - b)) <= tol * scale, (col, np.nanmax(np.abs(a - b)))
+
+
+def test_solve_tracks_matches_solve_instances(cabi):
+    """Batch preprocessing path (mseetc.trackbatch: native grids + vectorised tables, no casadiSolver per track) against the
+    per-track path (one casadiSolver per track, solve_instances): the same tables, hence the same results bit for bit."""
+    from mseetc.ocp import casadiSolver, solve_instances
+    from mseetc.trackbatch import TrackBatch, solve_tracks
+    from mseetc.synthetic import random_track
+    rng = np.random.default_rng(21)
+    train = _dynamic_train()
+    tracks, N = [], []
+    while len(tracks) < 48:
+        tr, n = random_track(rng), int(rng.choice([100, 200, 300, 400]))
+        try:
+            casadiSolver(train, tr, {'numIntervals': n})
+        except ValueError:
+            continue
+        tracks.append(tr); N.append(n)
+    opts = {'maxIterations': 500, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    batch = TrackBatch.from_tracks(tracks)
+    a = solve_tracks(train, batch, np.array(N), opts, timeFactor=1.15)
+    assert np.all(a['grid_error'] == 0) and (a['status'] == 0).sum() >= 44
+    solvers = [casadiSolver(train, tr, dict(opts, numIntervals=n)) for tr, n in zip(tracks, N)]
+    b = solve_instances(solvers, a['terminalTime'], screen=False)
+    assert np.array_equal(a['status'], b['status']) and np.array_equal(a['iters'], b['iters'])
+    ok = a['status'] == 0
+    assert np.array_equal(a['z'][ok], b['z'][ok]) and np.array_equal(a['cost'][ok], b['cost'][ok])

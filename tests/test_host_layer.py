@@ -290,3 +290,43 @@ def test_stream_pool_interleave_is_a_tile_aligned_permutation():
             assert second[0] == 32                                          # tile 1 -> sub-batch 1
         sizes = [b - a for a, b in parts]
         assert max(sizes) - min(sizes) <= 64                                # balanced up to the ragged tile
+
+
+def test_track_batch_grids_match_compute_discretization_points(built_lib):
+    """Native batch preprocessing (mseetc_discretize_tracks) against computeDiscretizationPoints track by track (reference
+    track.py:91-107, :377-383): the two shipped tracks, random tracks with mixed interval counts, and the ValueError case."""
+    from mseetc.track import Track, computeDiscretizationPoints
+    from mseetc.trackbatch import TrackBatch
+    from mseetc.synthetic import random_track
+    rng = np.random.default_rng(4)
+    tracks = [Track(config={'id': '00_var_speed_limit_100'}), Track(config={'id': 'CH_StGallen_Wil'})] + [random_track(rng) for _ in range(20)]
+    N = np.array([300, 300] + list(rng.choice([100, 200, 300, 400], 20)), dtype=np.int32)
+    N[5] = 3                                               # more sections than intervals: the reference raises (track.py:103-105)
+    grid = TrackBatch.from_tracks(tracks).discretize(N)
+    for i, (tr, n) in enumerate(zip(tracks, N)):
+        try:
+            ref = computeDiscretizationPoints(tr, int(n))
+        except ValueError:
+            assert grid['error'][i] == 1
+            continue
+        assert grid['error'][i] == 0
+        a = grid['off'][i] + i
+        assert np.array_equal(grid['pos'][a:a + n + 1], ref.index.values)
+        assert np.array_equal(grid['limit'][a:a + n + 1], ref['Speed limit [m/s]'].values)
+        assert np.array_equal(grid['grad'][a:a + n + 1], ref['Gradient [permil]'].values)
+        assert np.array_equal(grid['curv'][a:a + n + 1], ref['Curvature [1/m]'].values)
+    assert grid['error'][5] == 1
+
+
+def test_random_track_batch_has_the_recipe_statistics(built_lib):
+    import time
+    from mseetc.trackbatch import TrackBatch
+    t0 = time.perf_counter()
+    batch = TrackBatch.random(np.random.default_rng(11), 16384)
+    grid = batch.discretize(np.random.default_rng(1).choice([100, 200, 300, 400], 16384))
+    assert time.perf_counter() - t0 < 5.0                  # 16 384 tracks: well under the 2 s target on an idle box
+    assert batch.n == 16384 and 5e3 <= batch.length.min() and batch.length.max() <= 50e3
+    (lo, lp, lv), (go, gp, gv), (co, cp, cv) = batch.tables
+    assert set(np.round(lv * 3.6).astype(int)) <= {80, 100, 120, 140} and np.abs(gv).max() <= 25.0 and np.abs(cv).max() <= 1 / 300 + 1e-12
+    assert np.all(lp[lo[:-1]] == 0) and np.all(gp[go[:-1]] == 0)
+    assert 0.6 < (cv == 0).mean() < 0.8 and (grid['error'] == 0).mean() > 0.9
