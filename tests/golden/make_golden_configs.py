@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 CONFIG5_N = 256
 CONFIG5_SPOT = list(np.linspace(0, CONFIG5_N - 1, 10).astype(int))
-CONFIG5_ALSO = [int(x) for x in os.environ.get('CONFIG5_ALSO', '').split(',') if x]      # device failures, see the module docstring
+CONFIG5_ALSO = [int(x) for x in os.environ.get('CONFIG5_ALSO', '55,81,114').split(',') if x]      # the device's failures (profiles/probe_config5_failures.py)
 
 
 def _oracle_imports():

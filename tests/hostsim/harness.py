@@ -66,7 +66,7 @@ def loss_map_arrays():
     return np.ascontiguousarray(lut.tx), np.ascontiguousarray(lut.ty), np.ascontiguousarray(lut.coef)
 
 
-def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst=-1, lib=None, tmin=None, pit_lanes=0, init_mode=0):
+def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst=-1, lib=None, tmin=None, pit_lanes=0, init_mode=0, mu_init=0.1):
     """Solve instances (one NLP object per instance, equal structure flags) with the emulated device code."""
     lib = lib or build()
     n = len(nlps)
@@ -81,7 +81,7 @@ def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst
     c0 = np.concatenate([p[2] for p in packs])
     bmax = np.concatenate([p[3] for p in packs])
     pr = Problem(Nmax, int(ref.withPn), int(ref.withPower), int(ref.energy), {'none': 0, 'static': 1}.get(ref.lossKind, 2),
-                 int(ref.opts['numSteps']), int(ref.opts['numApproxSteps']), max_iter, tol, 0.1)
+                 int(ref.opts['numSteps']), int(ref.opts['numApproxSteps']), max_iter, tol, mu_init)
     stp = 3 + ref.nu
     z = np.zeros((n, Nmax * stp + 2))
     lam = np.zeros((n, Nmax * ref.rows_per))
