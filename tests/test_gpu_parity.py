@@ -618,3 +618,35 @@ def test_solve_tracks_matches_solve_instances(cabi):
     assert np.array_equal(a['status'], b['status']) and np.array_equal(a['iters'], b['iters'])
     ok = a['status'] == 0
     assert np.array_equal(a['z'][ok], b['z'][ok]) and np.array_equal(a['cost'][ok], b['cost'][ok])
+
+
+def test_energy_optimum_converges_to_the_gpops_energy_of_the_reference(cabi):
+    """The only energy-optimal numbers the reference repository holds are the GPOPS results of the figure-10 problem
+    (gpops/00_var_speed_limit_100_GPOPSI.csv / ...GPOPSII.csv: 440.1414723 / 440.1406149 kWh, simulations/figure10.py:14-36),
+    solutions of the CONTINUOUS problem.  The multiple-shooting optimum carries an O(1/N) discretisation error (0.2 % at N = 300);
+    solved on the device at N = 1200, 2400, 4800 and extrapolated to N -> infinity (Aitken) it must meet them to 1e-4."""
+    import csv
+    import os
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    here = os.path.dirname(os.path.abspath(__file__))
+    gpops = [float(list(csv.reader(open(os.path.join(here, 'golden', '00_var_speed_limit_100_GPOPS%s.csv' % v))))[1][6]) for v in ('I', 'II')]
+    assert abs(gpops[0] - 440.1414723) < 1e-6 and abs(gpops[1] - 440.1406149) < 1e-6
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})                    # figure10.py:14-22
+    train.forceMinPn = 0
+    train.forceMin = -train.forceMax
+    train.powerMax = 3129277
+    train.powerMin = -train.powerMax
+    train.etaTraction = train.etaRgBrake = 0.73
+    J = []
+    for N in (1200, 2400, 4800):
+        solver = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}),
+                              {'numIntervals': N, 'maxIterations': 1000, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}})
+        res = solver.solve_batch(1541.0, screen=False)
+        assert res['status'][0] == 0 and res['kkt'][0] <= 1e-8
+        J.append(float(res['cost'][0]))
+    assert J[0] > J[1] > J[2] > max(gpops)                                 # monotone from above
+    d1, d2 = J[1] - J[0], J[2] - J[1]
+    limit = J[2] - d2 * d2 / (d2 - d1)
+    assert abs(limit - gpops[1]) <= 1e-4 * gpops[1] and abs(limit - gpops[0]) <= 1e-4 * gpops[0], (J, limit)
