@@ -443,17 +443,19 @@ MS_HD double bar_finish(BarAcc& a) {
 // ------------------------------------------------------------------------------------------------
 // trial point                                                                 (IPOPT sec. 2.3, Alg. A step A-5)
 // ------------------------------------------------------------------------------------------------
-template <bool DYN>
-MS_HD void cell_trial(const Ctx& c, int k, int s) {
+// x + alpha dx of one cell (all primal, slack and multiplier planes, kappa_sigma safeguard of eq. 16) formed in registers
+// from the current iterate and the step; AO = the trial iterate of the cell, nb = what cell_eval needs of the neighbouring
+// cells at the trial point (t, b of node k+1; Fel of intervals k-1 and k+1).  The trial point is not a kernel of its own: it
+// is formed by the interval evaluation (cell_eval<DYN, true>), which evaluates the NLP there at once -- constraint violation,
+// objective and barrier sums for the filter test AND the stage QP of the next iteration -- because the first trial point is
+// accepted in ~95 % of the iterations; a rejected one costs one more evaluation at the halved step.
+struct TrialNeighbours {
+    double nT, nB, pFel, nFel;
+};
+MS_HD void form_trial_cell(const Ctx& c, int k, int s, int N, int cur, const Bnd& B, double* AO, TrialNeighbours& nb) {
     const Config& g = c.cfg;
-    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_TRIAL) return;
-    const int N = c.I(SI_N_INT, s);
-    if (k > N) return;
-    const int cur = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
-    const int alt = c.I(SI_PARITY, s) ? WS_IT0 : WS_IT1;
-    // ---- all loads first (independent, dozens in flight per thread), then arithmetic, then all stores
-    const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
-    double CI[IT_N], CS[ST_N], AO[IT_N];
+    const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0, kp = (k + 1 < N) ? k + 1 : k;
+    double CI[IT_N], CS[ST_N];
     {
         const double* ip = &c.W(cur, k, s);
         const double* sp = &c.W(WS_ST, k, s);
@@ -465,15 +467,10 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
     const double nT = c.W(cur + IT_T, kn, s), nB = c.W(cur + IT_B, kn, s);
     const double nDT = c.W(WS_ST + ST_T, kn, s), nDB = c.W(WS_ST + ST_B, kn, s);
     const double pFel = c.W(cur + IT_FEL, km, s), pDFel = c.W(WS_ST + ST_FEL, km, s);
-    const IntervalCoef q = load_coef(c, k, s);
-    const Bnd B = load_bounds(c, k, s);
+    const double nFel = c.W(cur + IT_FEL, kp, s), nDFel = c.W(WS_ST + ST_FEL, kp, s);
     const double al = c.D(SD_ALPHA, s), az = c.D(SD_ALPHA_Z, s), mu = c.D(SD_MU, s);
-    const double scale = c.P(P_SCALE, s);
 #pragma unroll
     for (int f = 0; f < IT_N; ++f) AO[f] = 0.0;
-    BarAcc bar{0.0, 0.0, true, 1.0, 0};
-    double th = 0.0, fo = 0.0;
-
     // multiplier update of one bound: z + az*dz, dz = mu/s - z -+ (z/s) dv, then the kappa_sigma safeguard (eq. 16)
     auto zstep = [&](int zi, double sOld, double sNew, double dvSigned) {
         const double z = CI[IT_Z + zi];
@@ -485,41 +482,26 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
         else if (pr < mu * (1.0 / MS_KAPPA_SIGMA)) zn = mu / (MS_KAPPA_SIGMA * sNew);
         AO[IT_Z + zi] = zn;
     };
-    auto var2 = [&](int itf, int stf, int zl, double L, double U, bool hasU, bool oneSided) -> double {
+    auto var2 = [&](int itf, int stf, int zl, double L, double U, bool hasU) {
         const double v = CI[itf], dv = CS[stf];
         const double vn = v + al * dv;
         AO[itf] = vn;
         zstep(zl, v - L, vn - L, dv);
-        bar_add(bar, vn - L, oneSided);
-        if (hasU) { zstep(zl + 1, U - v, U - vn, -dv); bar_add(bar, U - vn, false); }
-        return vn;
+        if (hasU) zstep(zl + 1, U - v, U - vn, -dv);
     };
-
-    double t, b;
     if (k == 0) {
-        t = CI[IT_T]; b = CI[IT_B];
-        AO[IT_T] = t; AO[IT_B] = b;
+        AO[IT_T] = CI[IT_T]; AO[IT_B] = CI[IT_B];
     } else {
-        t = var2(IT_T, ST_T, Z_T_L, B.tL, B.tU, true, false);
-        if (k < N) b = var2(IT_B, ST_B, Z_B_L, B.bL, B.bU, true, false);
-        else { b = CI[IT_B]; AO[IT_B] = b; }
+        var2(IT_T, ST_T, Z_T_L, B.tL, B.tU, true);
+        if (k < N) var2(IT_B, ST_B, Z_B_L, B.bL, B.bU, true);
+        else AO[IT_B] = CI[IT_B];
     }
     if (k < N) {
-        const double fel = var2(IT_FEL, ST_FEL, Z_FEL_L, B.felL, B.felU, true, false);
-        double fpb = 0.0;
-        if (g.withPn) fpb = var2(IT_FPB, ST_FPB, Z_FPB_L, B.fpbL, B.fpbU, true, false);
-        const double sl = var2(IT_SL, ST_SL, Z_SL_L, B.slL, 0.0, false, true);
-        // neighbours at the trial point
-        const double t1 = nT + al * nDT;
-        const double b1 = (k + 1 < N) ? nB + al * nDB : nB;
-        double tau, phib;
-        shoot<double>(b, fel + fpb, q, g.numSteps, g.numApprox, tau, phib);
-        const double ct = t1 - t - tau, cb = b1 - phib;
-        th += fabs(ct) + fabs(cb);
+        var2(IT_FEL, ST_FEL, Z_FEL_L, B.felL, B.felU, true);
+        if (g.withPn) var2(IT_FPB, ST_FPB, Z_FPB_L, B.fpbL, B.fpbU, true);
+        var2(IT_SL, ST_SL, Z_SL_L, B.slL, 0.0, false);
         AO[IT_YT] = CI[IT_YT] + al * CS[ST_YT];
         AO[IT_YB] = CI[IT_YB] + al * CS[ST_YB];
-        double d[NROW];
-        ineq_values<DYN>(c, s, fel, fpb, sl, b, b1, q, d);
 #pragma unroll
         for (int j = 0; j < NROW; ++j) {
             if (!row_on(g, j)) continue;
@@ -530,61 +512,22 @@ MS_HD void cell_trial(const Ctx& c, int k, int s) {
             const double wn = w + al * dw;
             AO[IT_W + j] = wn;
             zstep(zl, w - L, wn - L, dw);
-            bar_add(bar, wn - L, !hasU);
-            if (hasU) { zstep(zl + 1, U - w, U - wn, -dw); bar_add(bar, U - wn, false); }
+            if (hasU) zstep(zl + 1, U - w, U - wn, -dw);
             AO[IT_YD + j] = CI[IT_YD + j] + al * CS[ST_YD + j];
-            th += fabs(d[j] - wn);
         }
-        if (g.energy) {                                                            // ocp.py:223,243-245
-            fo += q.ds * (fel + sl) / scale;
-            if (k >= 1) {
-                const double fprev = pFel + al * pDFel;
-                fo += 1e-3 * (fel - fprev) * (fel - fprev) / scale;
-            }
-        } else {                                                                   // ocp.py:146-150
-            fo += 1e-4 * (fel * fel + fpb * fpb) / scale;
-        }
-    } else if (!g.energy) {
-        fo += t / scale;
     }
-    {
-        double* op = &c.W(alt, k, s);
-#pragma unroll
-        for (int f = 0; f < IT_N; ++f) op[f * 32] = AO[f];
-    }
-    c.W(WS_PART + PT_TH, k, s) = th;
-    c.W(WS_PART + PT_F, k, s) = fo;
-    c.W(WS_PART + PT_SLOG, k, s) = bar_finish(bar);
-    c.W(WS_PART + PT_SDAMP, k, s) = (k < N) ? bar.sdamp : 0.0;
+    nb.nT = nT + al * nDT;
+    nb.nB = (k + 1 < N) ? nB + al * nDB : nB;
+    nb.pFel = pFel + al * pDFel;
+    nb.nFel = nFel + al * nDFel;
 }
 
 // ------------------------------------------------------------------------------------------------
 // filter acceptance                                                         (IPOPT sec. 2.3, eqs. 18-20)
 // ------------------------------------------------------------------------------------------------
-// partial sums of the trial-point quantities over the intervals k = w, w+W, w+2W, ... (ascending)
 // The per-instance reductions read their partial planes MS_RED_U intervals at a time (all loads of a group in flight, then
 // summed in the original order: same bits as a one-by-one loop).
 #define MS_RED_U 4
-MS_HD void trial_partials(const Ctx& c, int s, int N, int w, int W, double* acc) {
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
-    for (int k0 = w; k0 <= N; k0 += MS_RED_U * W) {
-        double v[MS_RED_U][4];
-#pragma unroll
-        for (int u = 0; u < MS_RED_U; ++u) {
-            const int k = k0 + u * W;
-            if (k <= N) {
-                const double* q = &c.W(WS_PART + PT_TH, k, s);
-#pragma unroll
-                for (int f = 0; f < 4; ++f) v[u][f] = q[f * 32];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < MS_RED_U; ++u)
-            if (k0 + u * W <= N)
-                for (int f = 0; f < 4; ++f) acc[f] += v[u][f];
-    }
-}
-
 // IPOPT's second termination test with its default thresholds (acceptable_tol 1e-6, acceptable_constr_viol_tol 1e-2,
 // acceptable_compl_inf_tol 1e-2, acceptable_dual_inf_tol 1e10) on the errors of the current iterate (set by inst_kkt); CasADi
 // counts "Solved_To_Acceptable_Level" as success (reference ocp.py:364 reads stats()['success'])
@@ -652,25 +595,36 @@ enum { V_T = 0, V_B, V_F, V_FEL, V_FPB, V_SL, V_BN, NV7 };
 // ------------------------------------------------------------------------------------------------
 // interval evaluation: RK4 + sensitivities, Hessian of the Lagrangian, condensed stage QP, KKT partials
 // ------------------------------------------------------------------------------------------------
-template <bool DYN>
+// TRIAL = false: at the current iterate (first iteration).  TRIAL = true: at the trial point x + alpha dx, which is formed here
+// and written to the other iterate buffer (see form_trial_cell); inst_decide then reads theta, the objective and the barrier sums
+// from the same partial planes that inst_kkt uses when the point is accepted.
+template <bool DYN, bool TRIAL>
 MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
-    if (s >= g.nInst || c.I(SI_PHASE, s) != PH_EVAL) return;
+    if (s >= g.nInst || c.I(SI_PHASE, s) != (TRIAL ? PH_TRIAL : PH_EVAL)) return;
     const int N = c.I(SI_N_INT, s);
     if (k > N) return;
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
-    // ---- all loads first (independent, in flight together); the stores of this kernel are at the very end
+    // ---- all loads first (independent, in flight together); the stores of the stage QP are at the very end
     const int kn = (k < N) ? k + 1 : N, km = (k > 0) ? k - 1 : 0;
     double CI[IT_N];
-    {
+    Bnd B = load_bounds(c, k, s);
+    double nT, nB, pFel, nFel;
+    if (TRIAL) {
+        TrialNeighbours nb;
+        form_trial_cell(c, k, s, N, it, B, CI, nb);
+        nT = nb.nT; nB = nb.nB; pFel = nb.pFel; nFel = nb.nFel;
+        double* op = &c.W(c.I(SI_PARITY, s) ? WS_IT0 : WS_IT1, k, s);
+#pragma unroll
+        for (int f = 0; f < IT_N; ++f) op[f * 32] = CI[f];
+    } else {
         const double* ip = &c.W(it, k, s);
 #pragma unroll
         for (int f = 0; f < IT_N; ++f) CI[f] = ip[f * 32];
+        nT = c.W(it + IT_T, kn, s); nB = c.W(it + IT_B, kn, s);
+        pFel = c.W(it + IT_FEL, km, s); nFel = c.W(it + IT_FEL, (k + 1 < N) ? k + 1 : k, s);
     }
-    const double nT = c.W(it + IT_T, kn, s), nB = c.W(it + IT_B, kn, s);
-    const double pFel = c.W(it + IT_FEL, km, s), nFel = c.W(it + IT_FEL, (k + 1 < N) ? k + 1 : k, s);
     const double scale = c.P(P_SCALE, s);
-    Bnd B = load_bounds(c, k, s);
     double H[28], g0[NV7], g1[NV7];
     #pragma unroll
     for (int i = 0; i < 28; ++i) H[i] = 0.0;

@@ -44,7 +44,7 @@ thread_local std::string g_err;
         }                                                                       \
     }
 #ifndef MS_MINB_TRIAL
-#define MS_MINB_TRIAL 3
+#define MS_MINB_TRIAL 2
 #endif
 #ifndef MS_MINB_EVAL
 #define MS_MINB_EVAL 2
@@ -55,10 +55,12 @@ thread_local std::string g_err;
 MS_CELL_KERNEL(k_cell_setup, 4, cell_setup(c, io, k, s))
 MS_CELL_KERNEL(k_cell_init, 4, cell_init<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_init_dyn, 2, cell_init<true>(c, k, s))
-MS_CELL_KERNEL(k_cell_trial, MS_MINB_TRIAL, cell_trial<false>(c, k, s))
-MS_CELL_KERNEL(k_cell_trial_dyn, 2, cell_trial<true>(c, k, s))
-MS_CELL_KERNEL(k_cell_eval, MS_MINB_EVAL, cell_eval<false>(c, k, s))
-MS_CELL_KERNEL(k_cell_eval_dyn, 2, cell_eval<true>(c, k, s))
+// k_cell_trial_eval: the interval evaluation AT THE TRIAL POINT, which it forms on the way (one kernel per iteration instead of
+// trial + evaluation); k_cell_eval: the same at the current iterate, once per solve for the starting point
+MS_CELL_KERNEL(k_cell_trial_eval, MS_MINB_TRIAL, (cell_eval<false, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_trial_eval_dyn, 2, (cell_eval<true, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_eval, MS_MINB_EVAL, (cell_eval<false, false>(c, k, s)))
+MS_CELL_KERNEL(k_cell_eval_dyn, 2, (cell_eval<true, false>(c, k, s)))
 MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_step_dyn, MS_MINB_STEP, cell_step<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
@@ -84,22 +86,6 @@ __global__ void __launch_bounds__(128) k_inst_profile(Ctx c, int useSmem) {
 
 // ---- per-instance reductions: block = 32 instances x RED_W warps; warp w sums the intervals k = w, w+RED_W, ...
 // (coalesced rows), the partials are combined in fixed order by warp 0 -> bitwise reproducible, no atomics.
-__global__ void __launch_bounds__(32 * RED_W) k_inst_decide(Ctx c) {
-    __shared__ double sm[RED_W][4][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int s = blockIdx.x * 32 + lane;
-    const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_TRIAL;
-    double acc[4] = {0, 0, 0, 0};
-    if (on) trial_partials(c, s, c.I(SI_N_INT, s), w, RED_W, acc);
-    for (int f = 0; f < 4; ++f) sm[w][f][lane] = acc[f];
-    __syncthreads();
-    if (w == 0 && on) {
-        double tot[4] = {0, 0, 0, 0};
-        for (int ww = 0; ww < RED_W; ++ww) for (int f = 0; f < 4; ++f) tot[f] += sm[ww][f][lane];
-        inst_decide(c, s, tot);
-    }
-}
-
 // `mirror` (mapped pinned host memory): the completion counter as it stands when this kernel runs, for the host's polling --
 // a store from the kernel instead of a 4-byte cudaMemcpyAsync between two kernels of every tick (which cost ~10 us of stream time)
 __global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c, int* mirror) {
@@ -119,14 +105,18 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c, int* mirror) {
     }
 }
 
+// TRIAL = true: the sums belong to the trial point (in the other iterate buffer); the filter test (inst_decide) comes first and,
+// when the point is accepted, the convergence test and the barrier update (inst_kkt) follow at once on the same sums.
+// TRIAL = false: starting point, inst_kkt only.
+template <bool TRIAL>
 __global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
     __shared__ double sm[RED_W][10][32];      // field-major: conflict-free columns (one lane = one instance)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int s = blockIdx.x * 32 + lane;
-    const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_EVAL;
+    const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == (TRIAL ? PH_TRIAL : PH_EVAL);
     KktAcc acc;
     kkt_init(acc);
-    if (on) kkt_partials(c, s, c.I(SI_N_INT, s), c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0, w, RED_W, acc);
+    if (on) kkt_partials(c, s, c.I(SI_N_INT, s), ((c.I(SI_PARITY, s) != 0) != TRIAL) ? WS_IT1 : WS_IT0, w, RED_W, acc);
     sm[w][0][lane] = acc.th; sm[w][1][lane] = acc.fo; sm[w][2][lane] = acc.slog; sm[w][3][lane] = acc.sdamp;
     sm[w][4][lane] = acc.zsum; sm[w][5][lane] = acc.ysum; sm[w][6][lane] = acc.dinf; sm[w][7][lane] = acc.pinf;
     sm[w][8][lane] = acc.cmin; sm[w][9][lane] = acc.cmax;
@@ -141,7 +131,11 @@ __global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
             o.cmin = sm[ww][8][lane]; o.cmax = sm[ww][9][lane];
             kkt_combine(tot, o);
         }
-        inst_kkt(c, s, tot);
+        if (TRIAL) {
+            const double sums[4] = {tot.th, tot.fo, tot.slog, tot.sdamp};
+            inst_decide(c, s, sums);            // accepted: buffers swapped, phase -> evaluated
+        } else count_cells(c, 4, c.I(SI_N_INT, s) + 1);
+        inst_kkt(c, s, tot);                    // (nothing unless the point is the current iterate now)
     }
 }
 
@@ -331,8 +325,6 @@ struct mseetc_solver {
     std::vector<cudaEvent_t> ev;   // event pool (pairs), grown on demand, re-used across solves
     std::vector<int> ev_class;     // class of every event pair of the last solve (timeline)
     cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
-    cudaStream_t hp;               // experiment MSEETC_TWO_LEVEL: library-owned highest-priority stream for the small kernels
-    cudaEvent_t xev[16];           // hand-over events between the caller's stream and hp
     int sweep_lanes;               // 0: chosen per call; 1: sequential sweeps; 8 / 16 / 32: chunk lanes per instance of the parallel-in-time sweeps
     int last_lanes;                // what the last solve used
     long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
@@ -387,9 +379,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaHostAlloc"); }
     e = cudaHostGetDevicePointer((void**)&h->done_host_dev, h->done_host, 0);
     if (e != cudaSuccess) { cudaFreeHost(h->done_host); delete h; return cuda_fail(e, "cudaHostGetDevicePointer"); }
-    h->hp = nullptr;
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->poll_ev[i], cudaEventDisableTiming);
-    for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->xev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaFreeHost(h->done_host); delete h; return cuda_fail(e, "cudaEventCreateWithFlags"); }
     *out = h;
     return 0;
@@ -400,8 +390,6 @@ int mseetc_destroy(mseetc_handle h) {
     cudaFreeHost(h->done_host);
     if (h->lm_dev) cudaFree(h->lm_dev);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->poll_ev[i]);
-    for (int i = 0; i < 16; ++i) cudaEventDestroy(h->xev[i]);
-    if (h->hp) cudaStreamDestroy(h->hp);
     if (h->loop_exec) cudaGraphExecDestroy(h->loop_exec);
     if (h->loop_graph) cudaGraphDestroy(h->loop_graph);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
@@ -490,8 +478,10 @@ double mseetc_bytes_per_cell(mseetc_handle h, int cls) {
     const int step = prim + rows + 2 + rows;
     const bool dynMap = (p.loss_kind == 2 && p.energy_optimal);
     switch (cls) {
-        case CLS_TRIAL:  return 8.0 * ((iter + step + 6 + 3) + (iter + 4));
-        case CLS_DECIDE: return 8.0 * 4;
+        // evaluation at the trial point: reads iterate + step + 8 neighbour values + track 3, writes the trial iterate, the stage
+        // QP and the partial sums
+        case CLS_TRIAL:  return 8.0 * ((iter + step + 8 + 3) + iter + (QP_N - 2 * (NROW - rows) + 13)) - (dynMap ? 0.0 : 8.0 * 16);
+        case CLS_DECIDE: return 8.0 * 14;
         case CLS_EVAL:   return 8.0 * ((iter + 4 + 3) + (QP_N - 2 * (NROW - rows) + 13)) - (dynMap ? 0.0 : 8.0 * 16);     // row gradients / residuals not stored
         // factors written: K 6, kf 2, P 6, p 3; the parallel-in-time sweeps read the condensed stage QP twice (element pass and
         // in-chunk recursion) -- the second read is counted: it is issued and, beyond L2, served by HBM
@@ -624,37 +614,17 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     cudaError_t e;
     for (int i = 0; i < NCLS; ++i) { h->ms[i] = 0.0; h->launches[i] = 0; h->cells[i] = 0; }
     std::vector<int> evClass;   // class of each recorded event pair
-    static const bool twoLevel = []() { const char* e = getenv("MSEETC_TWO_LEVEL"); return e && atoi(e) != 0; }();
-    if (twoLevel && !h->hp) {
-        int least = 0, greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        cudaStreamCreateWithPriority(&h->hp, cudaStreamNonBlocking, greatest);
-    }
-    cudaStream_t cur = st;
-    int xev = 0;
-    // experiment: the small latency-critical kernels (reductions, sweeps) go to a highest-priority stream, the interval kernels
-    // stay on the caller's stream; hand-over by events
-    auto use = [&](bool high) -> cudaStream_t {
-        cudaStream_t want = (twoLevel && high) ? h->hp : st;
-        if (want != cur) {
-            cudaEvent_t ev = h->xev[xev++ % 16];
-            cudaEventRecord(ev, cur);
-            cudaStreamWaitEvent(want, ev, 0);
-            cur = want;
-        }
-        return want;
-    };
     auto begin = [&](int cls) {
         h->launches[cls] += 1;
         ++launches;
         if (!h->profiling) return;
         const size_t need = 2 * (evClass.size() + 1);
         while (h->ev.size() < need) { cudaEvent_t x; cudaEventCreate(&x); h->ev.push_back(x); }
-        cudaEventRecord(h->ev[2 * evClass.size()], cur);
+        cudaEventRecord(h->ev[2 * evClass.size()], st);
     };
     auto end = [&](int cls) {
         if (!h->profiling) return;
-        cudaEventRecord(h->ev[2 * evClass.size() + 1], cur);
+        cudaEventRecord(h->ev[2 * evClass.size() + 1], st);
         evClass.push_back(cls);
     };
     e = cudaMemsetAsync(c.done, 0, 256, st);
@@ -675,14 +645,38 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
-    // ---- the tick loop.  Small batches (latency: 7 small launches per tick): on the device -- a CUDA graph whose single node is a
-    // conditional WHILE node with one tick as its body; the last kernel of the body sets the condition from the completion counter,
-    // so the host neither launches the ticks nor polls (single solve 4.94 -> 4.46 ms).  Large batches keep the host loop below: it
-    // already runs two ticks ahead of the device, and next to the concurrent minimum-time presolve (a second while-graph on a
-    // high-priority stream) the device loop measured slower (30.2 against 23.8 ms per 4096-instance sweep).  MSEETC_GRAPH=1 / 0
-    // forces the device / host loop; per-kernel profiling needs the host loop.
+    // ---- starting point: evaluation, convergence test, barrier parameter
+    begin(CLS_EVAL);
+    if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
+    end(CLS_EVAL);
+    begin(CLS_KKT); k_inst_kkt<false><<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
+    // ---- the tick loop: direction (sweeps, interval-parallel rest, step-size limits), then the evaluation at the trial point with
+    // the filter test / convergence test / barrier update: five launches per tick.
+    // Small batches (latency): on the device -- a CUDA graph whose single node is a conditional WHILE node with one tick as its
+    // body; the last kernel of the body sets the condition from the completion counter, so the host neither launches the ticks nor
+    // polls.  Large batches keep the host loop below: it already runs two ticks ahead of the device, and next to the concurrent
+    // minimum-time presolve (a second while-graph on a high-priority stream) the device loop measured slower (30.2 against 23.8 ms
+    // per 4096-instance sweep).  MSEETC_GRAPH=1 / 0 forces the device / host loop; per-kernel profiling needs the host loop.
     static const int graphEnv = []() { const char* e = getenv("MSEETC_GRAPH"); return e ? atoi(e) : -1; }();
-    const bool useGraph = !h->profiling && !twoLevel && (graphEnv == 1 || (graphEnv != 0 && g.S <= 256 && !tmin));
+    const bool useGraph = !h->profiling && (graphEnv == 1 || (graphEnv != 0 && g.S <= 256 && !tmin));
+    auto tick_kernels = [&](cudaStream_t s0, int* mirror, bool prof) {
+        if (prof) begin(CLS_STEP);
+        if (pitKernel) pitKernel<<<(unsigned)(g.S / pitSL), pitThreads, pitBytes, s0>>>(c, c.done + 48);
+        else stepKernel<<<igrid, ib, ringBytes, s0>>>(c);
+        if (prof) end(CLS_STEP);
+        if (prof) begin(CLS_CSTEP);
+        if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, s0>>>(c, io); else k_cell_step<<<gridStep, 128, 0, s0>>>(c, io);
+        if (prof) end(CLS_CSTEP);
+        if (prof) begin(CLS_ALPHA);
+        k_inst_alpha<<<rgrid, 32 * RED_W, 0, s0>>>(c, mirror);
+        if (prof) end(CLS_ALPHA);
+        if (prof) begin(CLS_TRIAL);
+        if (dyn) k_cell_trial_eval_dyn<<<gridTrial, 128, 0, s0>>>(c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
+        if (prof) end(CLS_TRIAL);
+        if (prof) begin(CLS_DECIDE);
+        k_inst_kkt<true><<<rgrid, 32 * RED_W, 0, s0>>>(c);
+        if (prof) end(CLS_DECIDE);
+    };
     if (useGraph) {
         unsigned char key[sizeof h->loop_key];
         memset(key, 0, sizeof key);
@@ -696,13 +690,11 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             if (h->loop_exec) { cudaGraphExecDestroy(h->loop_exec); h->loop_exec = nullptr; }
             if (h->loop_graph) { cudaGraphDestroy(h->loop_graph); h->loop_graph = nullptr; }
             // the kernel nodes take the priority of the stream they are captured on: give the capture stream the priority of the
-            // caller's stream (the minimum-time presolve runs on a high-priority stream next to the batch it certifies)
-            int prio = 0;
-            cudaStreamGetPriority(st, &prio);
-            if (h->cap_stream && prio != h->cap_prio) { cudaStreamDestroy(h->cap_stream); h->cap_stream = nullptr; }
+            // caller's stream
+            if (h->cap_stream && stPrio != h->cap_prio) { cudaStreamDestroy(h->cap_stream); h->cap_stream = nullptr; }
             if (!h->cap_stream) {
-                if ((e = cudaStreamCreateWithPriority(&h->cap_stream, cudaStreamNonBlocking, prio)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
-                h->cap_prio = prio;
+                if ((e = cudaStreamCreateWithPriority(&h->cap_stream, cudaStreamNonBlocking, stPrio)) != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
+                h->cap_prio = stPrio;
             }
             if ((e = cudaGraphCreate(&h->loop_graph, 0)) != cudaSuccess) return cuda_fail(e, "cudaGraphCreate");
             cudaGraphConditionalHandle cond;
@@ -716,14 +708,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             cudaGraph_t bodyGraph = np.conditional.phGraph_out[0];
             cudaStream_t cs = h->cap_stream;
             if ((e = cudaStreamBeginCaptureToGraph(cs, bodyGraph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)) != cudaSuccess) return cuda_fail(e, "cudaStreamBeginCaptureToGraph");
-            if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, cs>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, cs>>>(c, io);
-            k_inst_kkt<<<rgrid, 32 * RED_W, 0, cs>>>(c);
-            if (pitKernel) pitKernel<<<(unsigned)(g.S / pitSL), pitThreads, pitBytes, cs>>>(c, c.done + 48);
-            else stepKernel<<<igrid, ib, ringBytes, cs>>>(c);
-            if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, cs>>>(c, io); else k_cell_step<<<gridStep, 128, 0, cs>>>(c, io);
-            k_inst_alpha<<<rgrid, 32 * RED_W, 0, cs>>>(c, nullptr);
-            if (dyn) k_cell_trial_dyn<<<gridTrial, 128, 0, cs>>>(c, io); else k_cell_trial<<<gridTrial, 128, 0, cs>>>(c, io);
-            k_inst_decide<<<rgrid, 32 * RED_W, 0, cs>>>(c);
+            tick_kernels(cs, nullptr, false);
             k_loop_cond<<<1, 1, 0, cs>>>(cond, c.done, n, maxTicks);
             cudaError_t le = cudaGetLastError();
             e = cudaStreamEndCapture(cs, nullptr);
@@ -733,46 +718,23 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
             memcpy(h->loop_key, key, sizeof key);
         }
         if ((e = cudaGraphLaunch(h->loop_exec, st)) != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
-        for (int cls : {CLS_EVAL, CLS_KKT, CLS_STEP, CLS_CSTEP, CLS_ALPHA, CLS_TRIAL, CLS_DECIDE}) h->launches[cls] = -1;      // counted after the run
-    } else
-    for (;;) {
-        begin(CLS_EVAL);
-        if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
-        end(CLS_EVAL);
-        use(true);
-        begin(CLS_KKT); k_inst_kkt<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_KKT);
-        begin(CLS_STEP);
-        if (pitKernel) pitKernel<<<(unsigned)(g.S / pitSL), pitThreads, pitBytes, cur>>>(c, c.done + 48);
-        else stepKernel<<<igrid, ib, ringBytes, cur>>>(c);
-        end(CLS_STEP);
-        use(false);
-        begin(CLS_CSTEP);
-        if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, st>>>(c, io); else k_cell_step<<<gridStep, 128, 0, st>>>(c, io);
-        end(CLS_CSTEP);
-        use(true);
-        begin(CLS_ALPHA); k_inst_alpha<<<rgrid, 32 * RED_W, 0, cur>>>(c, h->done_host_dev + 32 + tick % 4); end(CLS_ALPHA);
-        use(false);
-        if (tick >= maxTicks) break;
-        // completion polling without draining the queue: k_inst_alpha mirrors the counter every tick into a small mapped pinned
-        // ring and the mirror written two ticks ago is tested (its event has normally completed), so kernels of the next ticks
-        // are already queued
-        {
-            const int slot = tick % 4;
+    } else {
+        for (;;) {
+            // completion polling without draining the queue: k_inst_alpha mirrors the counter every tick into a small mapped
+            // pinned ring and the mirror written two ticks ago is tested (its event has normally completed), so the kernels of
+            // the next ticks are already queued
+            tick_kernels(st, h->done_host_dev + 32 + tick % 4, true);
+            ++tick;
+            if (tick >= maxTicks) break;
+            const int slot = (tick - 1) % 4;
             cudaEventRecord(h->poll_ev[slot], st);
-            if (tick >= 2) {
-                const int old = (tick - 2) % 4;
+            if (tick >= 3) {
+                const int old = (tick - 3) % 4;
                 e = cudaEventSynchronize(h->poll_ev[old]);
                 if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
                 if (h->done_host[32 + old] >= n) break;
             }
         }
-        begin(CLS_TRIAL);
-        if (dyn) k_cell_trial_dyn<<<gridTrial, 128, 0, st>>>(c, io); else k_cell_trial<<<gridTrial, 128, 0, st>>>(c, io);
-        end(CLS_TRIAL);
-        use(true);
-        begin(CLS_DECIDE); k_inst_decide<<<rgrid, 32 * RED_W, 0, cur>>>(c); end(CLS_DECIDE);
-        use(false);
-        ++tick;
     }
     begin(CLS_MISC); k_cell_extract<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
     e = cudaGetLastError();
@@ -783,13 +745,13 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
     {
         const unsigned long long* cnt = (const unsigned long long*)((const char*)h->done_host + 64);
-        h->cells[CLS_TRIAL] = (long long)cnt[0];
+        h->cells[CLS_TRIAL] = (long long)cnt[0];           // evaluations at trial points (accepted or not)
         h->cells[CLS_DECIDE] = (long long)cnt[0];
-        h->cells[CLS_EVAL] = (long long)cnt[1];
+        h->cells[CLS_EVAL] = (long long)cnt[4];            // evaluation of the starting point
         h->cells[CLS_STEP] = (long long)cnt[1];
         h->cells[CLS_CSTEP] = (long long)cnt[3] + (long long)(cnt[3] / (unsigned long long)(p.n_intervals_max));
         h->cells[CLS_ALPHA] = h->cells[CLS_CSTEP];
-        h->cells[CLS_KKT] = (long long)cnt[1];
+        h->cells[CLS_KKT] = (long long)cnt[4];
         h->cells[CLS_MISC] = 0;
         h->last_fallbacks = (long long)h->done_host[48];
         for (int i = 0; i < 3; ++i) h->fallback_why[i] = h->done_host[49 + i];
@@ -802,8 +764,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     h->ev_class = evClass;
     if (useGraph) {
         tick = h->done_host[53];                      // ticks the device loop ran
-        for (int cls : {CLS_EVAL, CLS_KKT, CLS_STEP, CLS_CSTEP, CLS_ALPHA, CLS_TRIAL, CLS_DECIDE}) h->launches[cls] = tick;
-        launches += 8 * tick;                         // seven solver kernels and the loop condition per tick
+        for (int cls : {CLS_STEP, CLS_CSTEP, CLS_ALPHA, CLS_TRIAL, CLS_DECIDE}) h->launches[cls] = tick;
+        launches += 6 * tick;                         // five solver kernels and the loop condition per tick
     }
     h->last_ticks = tick;
     h->last_launches = launches;

@@ -106,20 +106,22 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
                tick, c.I(SI_ITERS, s), c.I(SI_PHASE, s), c.D(SD_FOBJ, s), c.D(SD_THETA, s), c.D(SD_DINF, s), c.D(SD_PINF, s),
                c.D(SD_MU, s), c.D(SD_ALPHA, s), c.D(SD_ALPHA_Z, s), c.D(SD_KKT, s), c.I(SI_NLS, s), c.I(SI_NREG, s));
     };
-    for (;;) {
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_eval<true>(c, k, s); else cell_eval<false>(c, k, s); }
+    // the same lock-step sequence as mseetc_solve_batch: starting point, then per tick the direction and the evaluation at the trial point
+    auto reduce_kkt = [&](bool trial) {
         for (int s = 0; s < g.nInst; ++s) {
-            if (c.I(SI_PHASE, s) != PH_EVAL) continue;
-            const int N = c.I(SI_N_INT, s), it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+            if (c.I(SI_PHASE, s) != (trial ? PH_TRIAL : PH_EVAL)) continue;
+            const int N = c.I(SI_N_INT, s), it = ((c.I(SI_PARITY, s) != 0) != trial) ? WS_IT1 : WS_IT0;
             KktAcc tot, part;
             kkt_init(tot);
             for (int w = 0; w < RED_W; ++w) { kkt_partials(c, s, N, it, w, RED_W, part); kkt_combine(tot, part); }
+            if (trial) { const double sums[4] = {tot.th, tot.fo, tot.slog, tot.sdamp}; inst_decide(c, s, sums); }
             inst_kkt(c, s, tot);
-            if (diag >= 3 && s == verbose_inst) {
+            if (diag >= 3 && s == verbose_inst && c.I(SI_PHASE, s) != PH_TRIAL) {
+                const int itc = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
                 double best[3] = {0, 0, 0}; int at[3] = {-1, -1, -1};
                 for (int k = 0; k <= N; ++k) {
                     const double d0 = c.W(WS_PART + PC_DINF, k, s);
-                    const double d1 = (k >= 1) ? fabs(c.W(WS_PART + PC_OWN_T, k, s) + c.W(it + IT_YT, k - 1, s)) : 0.0;
+                    const double d1 = (k >= 1) ? fabs(c.W(WS_PART + PC_OWN_T, k, s) + c.W(itc + IT_YT, k - 1, s)) : 0.0;
                     const double d2 = (k >= 1 && k < N) ? fabs(c.W(WS_PART + PC_OWN_B, k, s) + c.W(WS_PART + PC_CN_B, k - 1, s)) : 0.0;
                     if (d0 > best[0]) { best[0] = d0; at[0] = k; }
                     if (d1 > best[1]) { best[1] = d1; at[1] = k; }
@@ -128,6 +130,10 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
                 printf("   dinf parts: controls %.2e at %d | t-node %.2e at %d | b-node %.2e at %d\n", best[0], at[0], best[1], at[1], best[2], at[2]);
             }
         }
+    };
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_eval<true, false>(c, k, s); else cell_eval<false, false>(c, k, s); }
+    reduce_kkt(false);
+    for (;;) {
         for (int s = 0; s < g.S; ++s) {
             DirectFetch<BwdFields> fb; DirectFetch<FwdFields> ff;
             if (pit_lanes > 1 && diag && s < g.nInst && c.I(SI_PHASE, s) == PH_FACTOR) {
@@ -184,14 +190,8 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         }
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_trial<true>(c, k, s); else cell_trial<false>(c, k, s); }
-        for (int s = 0; s < g.nInst; ++s) {
-            if (c.I(SI_PHASE, s) != PH_TRIAL) continue;
-            const int N = c.I(SI_N_INT, s);
-            double tot[4] = {0, 0, 0, 0}, part[4];
-            for (int w = 0; w < RED_W; ++w) { trial_partials(c, s, N, w, RED_W, part); for (int f = 0; f < 4; ++f) tot[f] += part[f]; }
-            inst_decide(c, s, tot);
-        }
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_eval<true, true>(c, k, s); else cell_eval<false, true>(c, k, s); }
+        reduce_kkt(true);
         ++tick;
         if (*c.done >= n) break;
     }
