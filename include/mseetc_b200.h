@@ -175,6 +175,10 @@ int mseetc_postprocess_batch(mseetc_handle h, int32_t n_instances, const double*
  * (what the Python layer sets): 16 lanes from 96 intervals, 32 from 1024, sequential sweeps beyond 4096 instances per call. */
 int mseetc_set_sweep_lanes(mseetc_handle h, int lanes);
 int mseetc_last_sweep_lanes(mseetc_handle h);          /* lanes the last mseetc_solve_batch on h ran with */
+/* compaction passes launched in the last solve (running instances moved into the slots of finished ones so that they fill whole
+ * warps; csrc/compact.cuh; results do not depend on it; MSEETC_COMPACT=0 switches it off) */
+int mseetc_last_compactions(mseetc_handle h);
+int mseetc_set_compaction(mseetc_handle h, int on);
 /* instances x iterations of the last solve that fell back to the sequential sweeps; reasons (out3): reference recursion of a
  * chunk not positive definite / chain step numerically singular / chain and recursion disagreed */
 long long mseetc_last_sweep_fallbacks(mseetc_handle h);

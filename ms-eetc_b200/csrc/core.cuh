@@ -205,7 +205,7 @@ MS_HD double speed_envelope(const Ctx& c, int s, int N, const TrainLimits& q, do
 MS_HD void inst_screen(const Ctx& c, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || !g.energy || !c.tmin || c.I(SI_PHASE, s) == PH_DONE) return;
-    if (c.tmin[s] < 0.0) return;        // the caller asserted that this instance is feasible: never screened
+    if (c.tmin[c.I(SI_ORIG, s)] < 0.0) return;        // the caller asserted that this instance is feasible: never screened
     const int N = c.I(SI_N_INT, s);
     const TrainLimits q = load_limits(c, s);
     // scratch plane: a step plane (zeroed by cell_init afterwards); inst_profile, which may run concurrently in another block,
@@ -418,6 +418,8 @@ MS_HD void inst_init(const Ctx& c, int s) {
     c.I(SI_LAST_GAIN, s) = 0;
     c.I(SI_FACT, s) = 0;
     c.I(SI_NACC, s) = 0;
+    c.I(SI_ORIG, s) = s;
+    c.I(SI_EXTRACTED, s) = 0;
 }
 
 // slack of a bound and the matching barrier pieces

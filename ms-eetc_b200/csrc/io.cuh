@@ -44,15 +44,18 @@ MS_HD void cell_setup(const Ctx& c, const BatchIO& io, int k, int s) {
     c.W(WS_TRK + TRK_BMAX, k, s) = io.bmax[off + trk + k];
 }
 
-MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s) {
+// finalPass = false: only the instances that have finished (their slots are about to be re-used, see compact.cuh)
+MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s, bool finalPass = true) {
     const Config& g = c.cfg;
-    if (s >= g.nInst) return;
+    if (s >= g.nInst || c.I(SI_EXTRACTED, s)) return;
+    if (!finalPass && c.I(SI_PHASE, s) != PH_DONE) return;
     const int N = c.I(SI_N_INT, s);
     if (k > N) return;
+    const int o = c.I(SI_ORIG, s);        // row of the caller's arrays
     const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
     const int nu = 1 + (g.withPn ? 1 : 0), stp = 3 + nu, Nmax = g.NK - 1;
     if (io.z_out) {
-        double* z = io.z_out + (size_t)s * ((size_t)Nmax * stp + 2) + (size_t)k * stp;
+        double* z = io.z_out + (size_t)o * ((size_t)Nmax * stp + 2) + (size_t)k * stp;
         if (k < N) {
             int o = 0;
             z[o++] = c.W(it + IT_FEL, k, s);
@@ -67,7 +70,7 @@ MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s) {
     }
     if (io.lam_out && k < N) {
         const int rows = (g.withPower ? 2 : 0) + 3 + (g.energy ? 2 : 0);
-        double* l = io.lam_out + (size_t)s * ((size_t)Nmax * rows) + (size_t)k * rows;
+        double* l = io.lam_out + (size_t)o * ((size_t)Nmax * rows) + (size_t)k * rows;
         int o = 0;
         if (g.withPower) { l[o++] = c.W(it + IT_YD + R_P0, k, s); l[o++] = c.W(it + IT_YD + R_P1, k, s); }
         l[o++] = c.W(it + IT_YD + R_ACC, k, s);
@@ -76,11 +79,11 @@ MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s) {
         if (g.energy) { l[o++] = c.W(it + IT_YD + R_LTR, k, s); l[o++] = c.W(it + IT_YD + R_LRG, k, s); }
     }
     if (k == 0) {
-        if (io.obj) io.obj[s] = c.D(SD_FOBJ, s);
-        if (io.kkt) io.kkt[s] = c.D(SD_KKT, s);
-        if (io.iters) io.iters[s] = c.I(SI_ITERS, s);
+        if (io.obj) io.obj[o] = c.D(SD_FOBJ, s);
+        if (io.kkt) io.kkt[o] = c.D(SD_KKT, s);
+        if (io.iters) io.iters[o] = c.I(SI_ITERS, s);
         int st = c.I(SI_STATUS, s);
-        io.status[s] = (st == ST_RUNNING) ? (int)ST_MAXITER : st;
+        io.status[o] = (st == ST_RUNNING) ? (int)ST_MAXITER : st;
     }
 }
 
@@ -120,7 +123,7 @@ MS_HD void eval_loss_rows_point(const LossMapDev& lm, int i, int n, const double
 
 // workspace carving (all sizes in bytes, 256-byte aligned sections)
 struct WsPlan {
-    size_t off_ws, off_par, off_sd, off_si, off_done, total;
+    size_t off_ws, off_par, off_sd, off_si, off_done, off_plan, total;
 };
 inline WsPlan plan_workspace(int S, int NK) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -131,6 +134,7 @@ inline WsPlan plan_workspace(int S, int NK) {
     p.off_sd = o; o = al(o + sizeof(double) * (size_t)SD_N * S);
     p.off_si = o; o = al(o + sizeof(int) * (size_t)SI_N * S);
     p.off_done = o; o = al(o + 256);   // int done; then 4 x uint64 cell counters at +64
+    p.off_plan = o; o = al(o + sizeof(int) * (size_t)(2 * S + 8));      // compaction plan (compact.cuh)
     p.total = o;
     return p;
 }

@@ -91,6 +91,8 @@ enum SdField {
 };
 enum SiField { SI_PHASE = 0, SI_PARITY, SI_ITERS, SI_STATUS, SI_NLS, SI_NFILT, SI_N_INT, SI_NREG, SI_TICKS, SI_LAST_GAIN,
                SI_NACC,     // consecutive iterations at IPOPT's "acceptable" level
+               SI_ORIG,     // index of the instance in the caller's arrays (slots are re-used when the batch is compacted)
+               SI_EXTRACTED,   // its results have been written to the caller's arrays
                SI_FACT,     // a factorisation has been stored (its chunk-end value functions are the references of pit.cuh)
                SI_N };
 
@@ -123,7 +125,8 @@ struct Ctx {
     int* done;     // number of finished instances (device counter polled by the host loop)
     unsigned long long* cnt;   // [4] processed cells: trial, eval, riccati backward, riccati forward
     LossMapDev lm;             // spline of the dynamic loss map (lossKind 2), device pointers
-    const double* tmin;        // [nInst] or null: minimum trip duration once known (0 = not known yet), see inst_kkt
+    const double* tmin;        // [nInst] or null: minimum trip duration once known (0 = not known yet), see inst_kkt; indexed by SI_ORIG
+    int* plan;                 // compaction plan (device only; null in the host emulation): [0] moves, [1] active, then sources, destinations
 
     MS_HD double& W(int field, int k, int slot) const {
         return ws[((size_t)(slot >> 5) * cfg.NK + k) * (WS_FIELDS * 32) + (slot & 31) + field * 32];

@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "../../include/mseetc_b200.h"
-#include "io.cuh"
+#include "compact.cuh"
 #include "table.cuh"
 
 using namespace mseetc;
@@ -327,6 +327,8 @@ struct mseetc_solver {
     cudaEvent_t poll_ev[4];        // completion polling (see mseetc_solve_batch)
     int sweep_lanes;               // 0: chosen per call; 1: sequential sweeps; 8 / 16 / 32: chunk lanes per instance of the parallel-in-time sweeps
     int last_lanes;                // what the last solve used
+    int last_compactions;          // compaction passes launched in the last solve
+    int compaction;                // 1: compact the running batch (default)
     long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
     int fallback_why[3];           // of those: reference recursion failed / chain step singular / chain and recursion disagreed
     // device-side tick loop: a graph with one conditional WHILE node whose body is one tick, kept while the call's arguments repeat
@@ -368,6 +370,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->profiling = 0;
     h->sweep_lanes = 1;
     h->last_lanes = 1;
+    h->last_compactions = 0;
     h->last_fallbacks = 0;
     h->fallback_why[0] = h->fallback_why[1] = h->fallback_why[2] = 0;
     h->lm_dev = nullptr;
@@ -444,6 +447,12 @@ int mseetc_set_sweep_lanes(mseetc_handle h, int lanes) {
 }
 long long mseetc_last_sweep_fallbacks(mseetc_handle h) { return h ? h->last_fallbacks : -1; }
 int mseetc_last_sweep_lanes(mseetc_handle h) { return h ? h->last_lanes : -1; }
+int mseetc_last_compactions(mseetc_handle h) { return h ? h->last_compactions : -1; }
+int mseetc_set_compaction(mseetc_handle h, int on) {
+    if (!h) return fail(-1, "mseetc_set_compaction: null handle");
+    h->compaction = on ? 1 : 0;
+    return 0;
+}
 int mseetc_last_sweep_fallback_reasons(mseetc_handle h, int32_t* out3) {
     if (!h || !out3) return fail(-1, "mseetc_last_sweep_fallback_reasons: null argument");
     for (int i = 0; i < 3; ++i) out3[i] = h->fallback_why[i];
@@ -527,6 +536,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.cnt = (unsigned long long*)(base + plan.off_done + 64);
     c.lm = h->lm;
     c.tmin = tmin;
+    c.plan = (int*)(base + plan.off_plan);
     const bool dyn = (p.loss_kind == 2 && p.energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
@@ -657,6 +667,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     // polls.  Large batches keep the host loop below: it already runs two ticks ahead of the device, and next to the concurrent
     // minimum-time presolve (a second while-graph on a high-priority stream) the device loop measured slower (30.2 against 23.8 ms
     // per 4096-instance sweep).  MSEETC_GRAPH=1 / 0 forces the device / host loop; per-kernel profiling needs the host loop.
+    static const bool compactOn = []() { const char* e = getenv("MSEETC_COMPACT"); return !e || atoi(e) != 0; }();
+    h->last_compactions = 0;
     static const int graphEnv = []() { const char* e = getenv("MSEETC_GRAPH"); return e ? atoi(e) : -1; }();
     const bool useGraph = !h->profiling && (graphEnv == 1 || (graphEnv != 0 && g.S <= 256 && !tmin));
     auto tick_kernels = [&](cudaStream_t s0, int* mirror, bool prof) {
@@ -732,7 +744,20 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
                 const int old = (tick - 3) % 4;
                 e = cudaEventSynchronize(h->poll_ev[old]);
                 if (e != cudaSuccess) return cuda_fail(e, "solver kernels");
-                if (h->done_host[32 + old] >= n) break;
+                const int doneLag = h->done_host[32 + old];
+                if (doneLag >= n) break;
+                // compaction (compact.cuh): every fourth tick once instances have finished; the plan kernel decides on the device
+                // whether the running instances are scattered enough to be worth moving, the other kernels return at once if not
+                if (compactOn && h->compaction && g.S >= 256 && doneLag > 0 && tick % 4 == 0) {
+                    const int activeUb = n - doneLag;
+                    k_compact_plan<<<1, 1024, 0, st>>>(c);
+                    k_compact_extract<<<cgrid, 128, 0, st>>>(c, io);
+                    k_compact_move<<<(unsigned)(((size_t)activeUb * g.NK + 127) / 128), 128, 0, st>>>(c);
+                    k_compact_finish<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(c);
+                    k_compact_state<<<(unsigned)((activeUb + 127) / 128), 128, 0, st>>>(c);
+                    launches += 5;
+                    ++h->last_compactions;
+                }
             }
         }
     }

@@ -593,7 +593,7 @@ MS_HD void inst_kkt(const Ctx& c, int s, const KktAcc& a) {
     // screening against a minimum trip duration that may arrive while the batch is running (computed concurrently by a
     // time-optimal solve on another stream): terminalTime is an upper bound on t_N (ocp.py:260-261)
     if (c.tmin) {
-        const double tm = c.tmin[s];
+        const double tm = c.tmin[c.I(SI_ORIG, s)];
         if (tm > 0.0 && (c.P(P_T, s) - c.P(P_T0, s)) < tm * (1.0 - MS_TMIN_MARGIN)) { finish(c, s, ST_INFEASIBLE); return; }
     }
     const double th = a.th, fo = a.fo, dinf = a.dinf, pinf = a.pinf, cmin = a.cmin, cmax = a.cmax, zsum = a.zsum, ysum = a.ysum;

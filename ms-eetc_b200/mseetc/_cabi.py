@@ -76,6 +76,8 @@ def lib():
     L.mseetc_last_sweep_fallbacks.argtypes = [vp]
     L.mseetc_last_sweep_fallbacks.restype = ctypes.c_longlong
     L.mseetc_last_sweep_lanes.argtypes = [vp]
+    L.mseetc_last_compactions.argtypes = [vp]
+    L.mseetc_set_compaction.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_sweep_fallback_reasons.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     L.mseetc_eval_loss_rows.argtypes = [vp, i32, vp, vp, vp, vp]
     _lib = L
@@ -128,6 +130,13 @@ class Handle:
         "lanes the last solve on this handle ran with (the setting, before the first solve)"
         n = int(lib().mseetc_last_sweep_lanes(self._h))
         return n if getattr(self, '_solved', False) else getattr(self, '_lanes', 1)
+
+    def set_compaction(self, on):
+        "Compaction of the running batch (csrc/compact.cuh); on by default, results do not depend on it."
+        _check(lib().mseetc_set_compaction(self._h, int(bool(on))), 'mseetc_set_compaction')
+
+    def last_compactions(self):
+        return int(lib().mseetc_last_compactions(self._h))
 
     def last_sweep_fallbacks(self):
         return int(lib().mseetc_last_sweep_fallbacks(self._h))

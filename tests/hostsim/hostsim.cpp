@@ -86,6 +86,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     c.done = (int*)(buf.data() + plan.off_done);
     c.cnt = (unsigned long long*)(buf.data() + plan.off_done + 64);
     c.tmin = tmin;
+    c.plan = nullptr;
     c.lm.tl = lm_tl; c.lm.tv = lm_tv; c.lm.coef = lm_coef; c.lm.nl = lm_nl; c.lm.nv = lm_nv;
     const bool dyn = (pr->loss_kind == 2 && pr->energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};

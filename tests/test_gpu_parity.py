@@ -650,3 +650,26 @@ def test_energy_optimum_converges_to_the_gpops_energy_of_the_reference(cabi):
     d1, d2 = J[1] - J[0], J[2] - J[1]
     limit = J[2] - d2 * d2 / (d2 - d1)
     assert abs(limit - gpops[1]) <= 1e-4 * gpops[1] and abs(limit - gpops[0]) <= 1e-4 * gpops[0], (J, limit)
+
+
+def test_compaction_of_the_running_batch_does_not_change_results(cabi):
+    """csrc/compact.cuh: running instances are moved into the slots of finished ones so that they fill whole warps.  An instance
+    computes the same numbers in any slot: every output is bitwise identical with and without compaction."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    opts = {'numIntervals': 300, 'maxIterations': 500, 'integrationMethod': 'RK', 'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}}
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    rng = np.random.default_rng(8)
+    T = rng.permutation(np.linspace(1037.0, 1400.0, 3000))               # iteration counts scattered over the slots
+    out = {}
+    for on in (True, False):
+        solver = casadiSolver(train, Track(config={'id': 'CH_StGallen_Wil'}), opts)
+        h = solver._ensure_handle()
+        h.set_compaction(on)
+        res = solver.solve_batch(T, screen=False, want_multipliers=True)
+        out[on] = {k: np.array(v) for k, v in res.items() if isinstance(v, np.ndarray)}
+        assert (h.last_compactions() > 0) == on                        # passes launched (the plan kernel decides whether anything moves)
+    assert np.all(out[True]['status'] == 0)
+    for key in ('z', 'lam', 'obj', 'kkt', 'iters', 'status'):
+        assert np.array_equal(out[True][key], out[False][key]), key
