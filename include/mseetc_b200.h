@@ -178,6 +178,7 @@ int mseetc_last_sweep_lanes(mseetc_handle h);          /* lanes the last mseetc_
 /* compaction passes launched in the last solve (running instances moved into the slots of finished ones so that they fill whole
  * warps; csrc/compact.cuh; results do not depend on it; MSEETC_COMPACT=0 switches it off) */
 int mseetc_last_compactions(mseetc_handle h);
+int mseetc_last_compaction_moves(mseetc_handle h);     /* instances moved by those passes */
 int mseetc_set_compaction(mseetc_handle h, int on);
 /* instances x iterations of the last solve that fell back to the sequential sweeps; reasons (out3): reference recursion of a
  * chunk not positive definite / chain step numerically singular / chain and recursion disagreed */

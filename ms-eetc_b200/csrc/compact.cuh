@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(128) k_compact_finish(Ctx c) {
 
 __global__ void __launch_bounds__(128) k_compact_state(Ctx c) {
     const int m = c.plan[PLAN_MOVES];
+    if (blockIdx.x == 0 && threadIdx.x == 0) c.done[54] += m;      // instances moved in this solve (statistics)
     for (int i = blockIdx.x * 128 + threadIdx.x; i < m; i += gridDim.x * 128) {
         const int src = c.plan[PLAN_HDR + i], dst = c.plan[PLAN_HDR + c.cfg.S + i];
         for (int f = 0; f < PAR_N; ++f) c.P(f, dst) = c.P(f, src);

@@ -329,6 +329,7 @@ struct mseetc_solver {
     int last_lanes;                // what the last solve used
     int last_compactions;          // compaction passes launched in the last solve
     int compaction;                // 1: compact the running batch (default)
+    int last_moves;                // instances moved by the compaction passes of the last solve
     long long last_fallbacks;      // instances x iterations that fell back to the sequential sweeps in the last solve
     int fallback_why[3];           // of those: reference recursion failed / chain step singular / chain and recursion disagreed
     // device-side tick loop: a graph with one conditional WHILE node whose body is one tick, kept while the call's arguments repeat
@@ -448,6 +449,7 @@ int mseetc_set_sweep_lanes(mseetc_handle h, int lanes) {
 long long mseetc_last_sweep_fallbacks(mseetc_handle h) { return h ? h->last_fallbacks : -1; }
 int mseetc_last_sweep_lanes(mseetc_handle h) { return h ? h->last_lanes : -1; }
 int mseetc_last_compactions(mseetc_handle h) { return h ? h->last_compactions : -1; }
+int mseetc_last_compaction_moves(mseetc_handle h) { return h ? h->last_moves : -1; }
 int mseetc_set_compaction(mseetc_handle h, int on) {
     if (!h) return fail(-1, "mseetc_set_compaction: null handle");
     h->compaction = on ? 1 : 0;
@@ -794,6 +796,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     }
     h->last_ticks = tick;
     h->last_launches = launches;
+    h->last_moves = h->done_host[54];
     return 0;
 }
 

@@ -78,6 +78,7 @@ def lib():
     L.mseetc_last_sweep_lanes.argtypes = [vp]
     L.mseetc_last_compactions.argtypes = [vp]
     L.mseetc_set_compaction.argtypes = [vp, ctypes.c_int]
+    L.mseetc_last_compaction_moves.argtypes = [vp]
     L.mseetc_last_sweep_fallback_reasons.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     L.mseetc_eval_loss_rows.argtypes = [vp, i32, vp, vp, vp, vp]
     _lib = L
@@ -136,7 +137,8 @@ class Handle:
         _check(lib().mseetc_set_compaction(self._h, int(bool(on))), 'mseetc_set_compaction')
 
     def last_compactions(self):
-        return int(lib().mseetc_last_compactions(self._h))
+        "(passes launched, instances moved) in the last solve"
+        return int(lib().mseetc_last_compactions(self._h)), int(lib().mseetc_last_compaction_moves(self._h))
 
     def last_sweep_fallbacks(self):
         return int(lib().mseetc_last_sweep_fallbacks(self._h))

@@ -26,8 +26,10 @@ def find(sub):
 
 
 out = {}
-for cls, sub in (('cell_trial', 'k_cell_trialE'), ('cell_eval', 'k_cell_evalE'), ('cell_step', 'k_cell_stepE'),
-                 ('cell_trial_dyn', 'k_cell_trial_dynE'), ('cell_eval_dyn', 'k_cell_eval_dynE')):
+# 'cell_trial' = evaluation at the trial point (k_cell_trial_eval: the kernel of every iteration), 'cell_eval' = the same at the
+# starting point (once per solve)
+for cls, sub in (('cell_trial', 'k_cell_trial_evalE'), ('cell_eval', 'k_cell_evalE'), ('cell_step', 'k_cell_stepE'),
+                 ('cell_trial_dyn', 'k_cell_trial_eval_dynE'), ('cell_eval_dyn', 'k_cell_eval_dynE')):
     f, n = flops(funcs[find(sub)[0]])
     out[cls] = {'flop_per_cell': f, 'instructions': n}
 ks = funcs[[k for k in find('k_stepILi32ELi8ELb0E')][0]]
@@ -50,6 +52,22 @@ fwd = min((l for l in loops if n_ldgsts(*l) == 14), key=lambda l: l[1] - l[0])
 f = n = 0
 for lo, hi in (bwd, fwd):
     a, b = flops(body(lo, hi)); f += a; n += b
-out['inst_step'] = {'flop_per_cell': f, 'instructions': n, 'note': 'backward (plain variant) + forward loop body per interval'}
+out['inst_step_sequential'] = {'flop_per_cell': f, 'instructions': n, 'note': 'k_step: backward (plain variant) + forward loop body per interval'}
+# parallel-in-time sweeps: element pass + in-chunk recursion + forward sweep per interval (loop bodies recognised the same way; the
+# kernel is inlined twice: lanes path and sequential fallback -- the three shortest loops with the right prefetch counts are taken)
+ks = funcs[find('k_step_pitILi16ELi16ELi1E')[0]]
+loops = []
+for a, t in ks:
+    m = re.search(r'BRA\s+(?:U?P\d,\s*)?(0x[0-9a-f]+)', t)
+    if m and int(m.group(1), 16) < a:
+        loops.append((int(m.group(1), 16), a))
+b23 = sorted((l for l in loops if n_ldgsts(*l) == 23), key=lambda l: l[1] - l[0])
+f14 = sorted((l for l in loops if n_ldgsts(*l) == 14), key=lambda l: l[1] - l[0])
+if len(b23) >= 2 and f14:
+    f = n = 0
+    # shortest 23-field loop = plain in-chunk recursion, the longest = element pass (recursion + Gramian + closed-loop product)
+    for lo, hi in (b23[0], b23[-1], f14[0]):
+        a, b = flops(body(lo, hi)); f += a; n += b
+    out['inst_step'] = {'flop_per_cell': f, 'instructions': n, 'note': 'k_step_pit<16,16>: element pass + in-chunk recursion + forward loop body per interval (chain steps not included)'}
 json.dump(out, open(os.path.join(ROOT, 'profiles', 'fp64_ops.json'), 'w'), indent=1)
 print(json.dumps(out, indent=1))

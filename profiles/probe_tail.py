@@ -27,6 +27,6 @@ for compaction in (False, True):
         n = names[int(cls)]
         rows.setdefault(n, []).append(1e3 * (b - a))
     running = [int((iters > t).sum()) for t in range(int(iters.max()) + 1)]
-    print(json.dumps(dict(compaction=compaction, compactions=h.last_compactions(), total_ms=float(tl[-1][2] - tl[0][1]), running_per_iteration=running,
+    print(json.dumps(dict(compaction=compaction, compactions=list(h.last_compactions()), total_ms=float(tl[-1][2] - tl[0][1]), running_per_iteration=running,
                           trial_eval_us=[round(x) for x in rows['cell_trial']], cell_step_us=[round(x) for x in rows['cell_step']],
                           sweep_us=[round(x) for x in rows['inst_step']])))

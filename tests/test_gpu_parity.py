@@ -669,7 +669,8 @@ def test_compaction_of_the_running_batch_does_not_change_results(cabi):
         h.set_compaction(on)
         res = solver.solve_batch(T, screen=False, want_multipliers=True)
         out[on] = {k: np.array(v) for k, v in res.items() if isinstance(v, np.ndarray)}
-        assert (h.last_compactions() > 0) == on                        # passes launched (the plan kernel decides whether anything moves)
+        passes, moved = h.last_compactions()
+        assert (passes > 0) == on and (moved > 100) == on               # a batch in random order does get compacted
     assert np.all(out[True]['status'] == 0)
     for key in ('z', 'lam', 'obj', 'kkt', 'iters', 'status'):
         assert np.array_equal(out[True][key], out[False][key]), key
