@@ -7,8 +7,8 @@
 // those that sit beyond the first A slots (A = number of running instances) are moved into the slots of finished instances among
 // the first A, after the results of those have been written out: the running instances fill whole warps again and the tiles
 // behind them exit at once.  (Measured, profiles/probe_tail.py: a SORTED sweep finishes tile by tile -- its kernels shrink with
-// the running set, 222 -> 113 -> 31 us -- and compacting it costs more than it saves, 20.5 against 20.0 ms: hence the threshold.)  Only the live planes move (track 3, current iterate 34, stage QP 52,
-// value functions 9 = references of the parallel-in-time sweeps) plus the per-instance state; an instance computes the same
+// the running set, 222 -> 113 -> 31 us -- and compacting it costs more than it saves, 20.5 against 20.0 ms: hence the threshold.)  Only the live planes move (track 3, current iterate 34, step 17, stage
+// QP 52, value functions 9 = references of the parallel-in-time sweeps) plus the per-instance state; an instance computes the same
 // numbers in any slot, so the results do not depend on when (or whether) the batch is compacted.
 //   k_compact_plan    one block: A, the holes among the first A slots, the running instances beyond; nothing to do unless the running
 //                     instances occupy noticeably more tiles than they need
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(128) k_compact_move(Ctx c) {
         for (int f = 0; f < TRK_N; ++f) b[(WS_TRK + f) * 32] = a[(WS_TRK + f) * 32];
 #pragma unroll 8
         for (int f = 0; f < IT_N; ++f) b[(it + f) * 32] = a[(it + f) * 32];
+#pragma unroll 8
+        for (int f = 0; f < ST_N; ++f) b[(WS_ST + f) * 32] = a[(WS_ST + f) * 32];        // an instance in its line search still needs its step
 #pragma unroll 8
         for (int f = 0; f < QP_N; ++f) b[(WS_QP + f) * 32] = a[(WS_QP + f) * 32];
 #pragma unroll

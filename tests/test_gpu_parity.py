@@ -674,3 +674,18 @@ def test_compaction_of_the_running_batch_does_not_change_results(cabi):
     assert np.all(out[True]['status'] == 0)
     for key in ('z', 'lam', 'obj', 'kkt', 'iters', 'status'):
         assert np.array_equal(out[True][key], out[False][key]), key
+    # a larger parameter Monte Carlo (sequential sweeps beyond 4096 instances): some instances are in the middle of their line
+    # search when they are moved -- their step planes have to travel with them
+    n = 16384
+    ov = dict(mass=391000 * rng.uniform(0.85, 1.15, n), r0=train.r0 * rng.uniform(0.8, 1.2, n), r1=train.r1 * rng.uniform(0.8, 1.2, n),
+              r2=train.r2 * rng.uniform(0.8, 1.2, n), etaTraction=rng.uniform(0.80, 0.92, n), etaRgBrake=rng.uniform(0.55, 0.85, n))
+    out = {}
+    for on in (True, False):
+        solver = casadiSolver(train, Track(config={'id': '00_var_speed_limit_100'}), opts)
+        solver._ensure_handle().set_compaction(on)
+        res = solver.solve_batch(1541.0, overrides=ov, screen=np.zeros(n, dtype=bool), restart=False)
+        out[on] = {k: np.array(v) for k, v in res.items() if isinstance(v, np.ndarray)}
+        assert (solver._ensure_handle().last_compactions()[1] > 500) == on
+    assert np.all(out[True]['status'] == 0)
+    for key in ('z', 'obj', 'kkt', 'iters', 'status'):
+        assert np.array_equal(out[True][key], out[False][key]), key
