@@ -332,9 +332,10 @@ template <bool DYN>
 MS_HD void ineq_values(const Ctx& c, int s, double fel, double fpb, double sl, double b0, double b1,
                        const IntervalCoef& q, double* d) {
     // every operation individually rounded (see mul_rn): cell_eval and cell_step both evaluate these rows
-    d[R_P0] = mul_rn(fel, sqrt(b0));
-    d[R_P1] = mul_rn(fel, sqrt(b1));
-    d[R_ACC] = sub_rn(sub_rn(add_rn(fel, fpb), fma(q.sr1, sqrt(b0), mul_rn(q.sr2, b0))), add_rn(q.sr0, q.c0));
+    const double r0 = fsqrt(b0);
+    d[R_P0] = mul_rn(fel, r0);
+    d[R_P1] = mul_rn(fel, fsqrt(b1));
+    d[R_ACC] = sub_rn(sub_rn(add_rn(fel, fpb), fma(q.sr1, r0, mul_rn(q.sr2, b0))), add_rn(q.sr0, q.c0));
     if (DYN) {
         LossRow tr, rg;
         loss_rows_dynamic(c.lm, load_losspar(c, s), fel, b0, b1, tr, rg);
@@ -422,23 +423,22 @@ MS_HD void inst_init(const Ctx& c, int s) {
     c.I(SI_EXTRACTED, s) = 0;
 }
 
-// slack of a bound and the matching barrier pieces
-// barrier sum of one interval: sum(log slack) is accumulated as the log of products of up to 6 slacks (one
-// log per group instead of one per bound); slacks lie in [1e-20, 1e4] so a group product cannot leave the range
+// barrier sum of one cell: sum(log slack) is accumulated as the log of ONE product -- mantissa and exponent kept apart (the
+// product of up to 6 slacks, each in [1e-20, 1e4], cannot leave the range; then it is renormalised), one log per cell
 struct BarAcc {
     double slog, sdamp;
     bool ok;
     double prod;
-    int nprod;
+    int nprod, expo;
 };
 MS_HD void bar_add(BarAcc& a, double slack, bool oneSided) {
     if (!(slack > 0.0)) a.ok = false;
     a.prod *= slack;
-    if (++a.nprod == 6) { a.slog += log(a.prod); a.prod = 1.0; a.nprod = 0; }
+    if (++a.nprod == 6) { int e; a.prod = frexp(a.prod, &e); a.expo += e; a.nprod = 0; }
     if (oneSided) a.sdamp += slack;
 }
 MS_HD double bar_finish(BarAcc& a) {
-    if (a.nprod > 0) { a.slog += log(a.prod); a.prod = 1.0; a.nprod = 0; }
+    a.slog = log(a.prod) + 0.6931471805599453 * a.expo;
     return a.ok ? a.slog : NAN;
 }
 
@@ -476,7 +476,7 @@ MS_HD void form_trial_cell(const Ctx& c, int k, int s, int N, int cur, const Bnd
     // multiplier update of one bound: z + az*dz, dz = mu/s - z -+ (z/s) dv, then the kappa_sigma safeguard (eq. 16)
     auto zstep = [&](int zi, double sOld, double sNew, double dvSigned) {
         const double z = CI[IT_Z + zi];
-        const double rOld = rcp(sOld);
+        const double rOld = rcp_slack(sOld);
         const double dz = mu * rOld - z - (z * rOld) * dvSigned;
         double zn = z + az * dz;
         const double pr = zn * sNew;                 // kappa_sigma safeguard: mu/kappa <= z*slack <= kappa*mu
@@ -632,13 +632,13 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     for (int i = 0; i < 28; ++i) H[i] = 0.0;
     #pragma unroll
     for (int i = 0; i < NV7; ++i) { g0[i] = 0.0; g1[i] = 0.0; }
-    BarAcc bar{0.0, 0.0, true, 1.0, 0};
+    BarAcc bar{0.0, 0.0, true, 1.0, 0, 0};
     double cmin = 1e300, cmax = 0.0, zsum = 0.0;
 
     auto bound = [&](int vi, int zi, double slack, double sign, bool oneSided) {
         // sign = +1 lower bound (slack = v-L), -1 upper bound (slack = U-v)
         const double z = CI[IT_Z + zi];
-        const double r = rcp(slack);
+        const double r = rcp_slack(slack);
         H[sidx(vi, vi)] += z * r;
         g1[vi] += -sign * r + (oneSided ? MS_KAPPA_D : 0.0);
         double pr = z * slack;
@@ -697,8 +697,10 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     Jet2 tau, phi;
     shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
     const double ct = t1 - t - tau.v, cb = b1 - phi.v;
-    const double v0 = sqrt(b), v1 = sqrt(b1);
-    const double iv0 = rcp(v0), iv1 = rcp(v1), ib0 = iv0 * iv0, ib1 = iv1 * iv1;
+    double v0, v1, iv0, iv1;
+    sqrt_inv(b, v0, iv0);
+    sqrt_inv(b1, v1, iv1);
+    const double ib0 = iv0 * iv0, ib1 = iv1 * iv1;
     const double a_b = -(0.5 * q.sr1 * iv0 + q.sr2), a_bb = 0.25 * q.sr1 * ib0 * iv0;
 
     // ---- Hessian of the Lagrangian: coupling rows (ct = t1 - t - tau, cb = b1 - phi)
@@ -788,7 +790,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
         const double w = CI[IT_W + j];
         const double vL = CI[IT_Z + zl], sL = w - L;
-        const double rL = rcp(sL);
+        const double rL = rcp_slack(sL);
         double sig = vL * rL, coef = -rL + (hasU ? 0.0 : MS_KAPPA_D);
         double rw = -ydv[j] - vL;
         double pr = vL * sL;
@@ -796,7 +798,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         bar_add(bar, sL, !hasU);
         if (hasU) {
             const double vU = CI[IT_Z + zl + 1], sU = U - w;
-            const double rU = rcp(sU);
+            const double rU = rcp_slack(sU);
             sig += vU * rU; coef += rU; rw += vU;
             pr = vU * sU;
             cmin = fmin(cmin, pr); cmax = fmax(cmax, pr); zsum += vU;

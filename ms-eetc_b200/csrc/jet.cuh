@@ -4,6 +4,9 @@
 #pragma once
 #include <math.h>
 
+#ifndef MS_FAST_RCP
+#define MS_FAST_RCP 1
+#endif
 #if defined(__CUDACC__)
 #define MS_HD __host__ __device__ __forceinline__
 #else
@@ -21,6 +24,40 @@ MS_HD double rcp(double x) {
     return 1.0 / x;
 #endif
 }
+
+// reciprocal of a slack (a positive, normal number): hardware approximation (2^-23) + two Newton steps, 1-2 ulp -- 5 instructions
+// against ~12 of the correctly rounded one; used where a last-bit difference is harmless (barrier terms z/s, mu/s: 38 of them
+// per cell and iteration)
+MS_HD double rcp_slack(double x) {
+#if defined(__CUDA_ARCH__) && MS_FAST_RCP
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return rcp(x);
+#endif
+}
+
+// square root and its reciprocal together: hardware rsqrt approximation + two Newton steps + one correction of the root, 1-2 ulp;
+// ~10 instructions against ~30 for the correctly rounded sqrt followed by the correctly rounded reciprocal.  Explicit fma / mul
+// only, so that every kernel that inlines it produces the same bits.
+MS_HD void sqrt_inv(double x, double& s, double& inv) {
+#if defined(__CUDA_ARCH__) && MS_FAST_RCP
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = __dmul_rn(0.5, x);
+    y = __dmul_rn(y, fma(__dmul_rn(-h, y), y, 1.5));
+    y = __dmul_rn(y, fma(__dmul_rn(-h, y), y, 1.5));
+    double r = __dmul_rn(x, y);
+    r = fma(fma(-r, r, x), __dmul_rn(0.5, y), r);
+    s = r; inv = y;
+#else
+    s = sqrt(x); inv = rcp(s);
+#endif
+}
+MS_HD double fsqrt(double x) { double s, i; sqrt_inv(x, s, i); return s; }
 
 // individually rounded operations that the compiler may not contract into an FMA: used where two kernels must reproduce the
 // same value bit for bit (the residual d(x) - w of an active row is a difference of nearly equal numbers that is later
@@ -90,13 +127,13 @@ MS_HD Jet2 jchain(const Jet2& a, double f0, double f1, double f2) {
     return r;
 }
 MS_HD Jet2 jsqrt(const Jet2& a) {
-    const double s = sqrt(a.v);
-    const double inv = rcp(s);
+    double s, inv;
+    sqrt_inv(a.v, s, inv);
     const double f1 = 0.5 * inv;
     return jchain(a, s, f1, -0.5 * f1 * inv * inv);
 }
 MS_HD Jet2 jrecip(const Jet2& a) {
-    const double r = rcp(a.v);
+    const double r = rcp_slack(a.v);
     return jchain(a, r, -r * r, 2.0 * r * r * r);
 }
 

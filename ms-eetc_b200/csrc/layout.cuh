@@ -56,8 +56,7 @@ enum QpField {
 enum RicField { RIC_K = 0, RIC_KF = 6, RIC_P = 8, RIC_PV = 14, RIC_N = 17 };
 // ---- per-interval partial sums (reduced sequentially per instance: deterministic)
 enum PartField {
-    PT_TH = 0, PT_F, PT_SLOG, PT_SDAMP,          // trial point: constraint violation, objective, barrier sums
-    PC_TH, PC_F, PC_SLOG, PC_SDAMP,              // current point
+    PC_TH = 0, PC_F, PC_SLOG, PC_SDAMP,          // evaluated point (the trial point, or the starting point): violation, objective, barrier sums
     PC_DINF, PC_PINF, PC_CMIN, PC_CMAX, PC_ZSUM, PC_YSUM, PC_OWN_B, PC_CN_B, PC_OWN_T,
     PS_AP, PS_AZ, PS_GPHID,                      // step: primal / dual fraction-to-boundary limits, barrier slope
     PART_N

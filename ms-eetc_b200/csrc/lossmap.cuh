@@ -185,9 +185,11 @@ struct LossRow {       // G(Fel, b0, b1) with gradient and Hessian; the row is  
 };
 
 MS_HD void loss_rows_dynamic(const LossMapDev& m, const LossPar& p, double fel, double b0, double b1, LossRow& tr, LossRow& rg) {
-    const double s0 = sqrt(b0), s1 = sqrt(b1);
+    double s0, s1, is0, is1;
+    sqrt_inv(b0, s0, is0);
+    sqrt_inv(b1, s1, is1);
     const double vm = 0.5 * (s0 + s1);
-    const double v_0 = 0.25 * rcp(s0), v_1 = 0.25 * rcp(s1);
+    const double v_0 = 0.25 * is0, v_1 = 0.25 * is1;
     const double v_00 = -0.5 * v_0 * rcp(b0), v_11 = -0.5 * v_1 * rcp(b1);
     const Jet2 v = jvar0(vm), fs = jvar1(fel);
     const bool pos = fel >= 0.0;

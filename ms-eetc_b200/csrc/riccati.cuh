@@ -710,7 +710,7 @@ struct Ftb {
 MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, double dvSigned, bool oneSided) {
     // dvSigned = change of the slack; primal fraction-to-boundary (eq. 15a), dual step (eq. 15b), barrier slope
     if (dvSigned < 0.0) f.aP = fmin(f.aP, -tau * slack / dvSigned);
-    const double r = rcp(slack);
+    const double r = rcp_slack(slack);
     const double dz = mu * r - z - (z * r) * dvSigned;
     if (dz < 0.0) f.aZ = fmin(f.aZ, -tau * z / dz);
     f.gphid += (-mu * r + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
@@ -798,8 +798,10 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
 #pragma unroll
             for (int j = 0; j < NROW; ++j) rres[j] = MS_QJ(QP_RES + j);
         } else {
-            const double bk = CI[IT_B], v0 = sqrt(bk), v1 = sqrt(bNext);
-            const double iv0 = rcp(v0), iv1 = rcp(v1);
+            const double bk = CI[IT_B];
+            double v0, v1, iv0, iv1;
+            sqrt_inv(bk, v0, iv0);
+            sqrt_inv(bNext, v1, iv1);
             double dval[NROW];
             ineq_values<false>(c, s, fel, fpb, sl, bk, bNext, q, dval);
             jP0b = 0.5 * fel * iv0; jP0f = v0; jP1f = v1; jP1n = 0.5 * fel * iv1;
@@ -856,12 +858,12 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
             const int zl = (j == R_P0) ? Z_P0_L : (j == R_P1) ? Z_P1_L : (j == R_ACC) ? Z_ACC_L : (j == R_LTR) ? Z_LTR_L : Z_LRG_L;
             const double w = CI[IT_W + j];
             const double vL = CI[IT_Z + zl], sL = w - L;
-            const double rL = rcp(sL);
+            const double rL = rcp_slack(sL);
             double sig = vL * rL, gw = -mu * rL + (hasU ? 0.0 : MS_KAPPA_D * mu);
             ftb_bound(f, tauF, mu, vL, sL, dw, !hasU);
             if (hasU) {
                 const double vU = CI[IT_Z + zl + 1], sU = U - w;
-                const double rU = rcp(sU);
+                const double rU = rcp_slack(sU);
                 sig += vU * rU; gw += mu * rU;
                 ftb_bound(f, tauF, mu, vU, sU, -dw, false);
             }
