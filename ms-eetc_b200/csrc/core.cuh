@@ -480,8 +480,8 @@ MS_HD void form_trial_cell(const Ctx& c, int k, int s, int N, int cur, const Bnd
         const double dz = mu * rOld - z - (z * rOld) * dvSigned;
         double zn = z + az * dz;
         const double pr = zn * sNew;                 // kappa_sigma safeguard: mu/kappa <= z*slack <= kappa*mu
-        if (pr > MS_KAPPA_SIGMA * mu) zn = MS_KAPPA_SIGMA * mu / sNew;
-        else if (pr < mu * (1.0 / MS_KAPPA_SIGMA)) zn = mu / (MS_KAPPA_SIGMA * sNew);
+        if (pr > MS_KAPPA_SIGMA * mu) zn = MS_KAPPA_SIGMA * mu * rcp_slack(sNew);
+        else if (pr < mu * (1.0 / MS_KAPPA_SIGMA)) zn = mu * (1.0 / MS_KAPPA_SIGMA) * rcp_slack(sNew);
         AO[IT_Z + zi] = zn;
     };
     auto var2 = [&](int itf, int stf, int zl, double L, double U, bool hasU) {
@@ -626,7 +626,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
         nT = c.W(it + IT_T, kn, s); nB = c.W(it + IT_B, kn, s);
         pFel = c.W(it + IT_FEL, km, s); nFel = c.W(it + IT_FEL, (k + 1 < N) ? k + 1 : k, s);
     }
-    const double scale = c.P(P_SCALE, s);
+    const double iscale = rcp_slack(c.P(P_SCALE, s));          // objective scaling: multiplications instead of divisions below
     double H[28], g0[NV7], g1[NV7];
     #pragma unroll
     for (int i = 0; i < 28; ++i) H[i] = 0.0;
@@ -661,7 +661,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     if (k == N) {
         // terminal node: only t_N carries a barrier; stored in the same QP planes for the Riccati start
         double fo = 0.0;
-        if (!g.energy) { own_t += 1.0 / scale; fo = t / scale; }
+        if (!g.energy) { own_t += iscale; fo = t * iscale; }
         c.W(WS_QP + QP_H_TT, k, s) = H[sidx(V_T, V_T)];
         c.W(WS_QP + QP_G1_T, k, s) = g1[V_T];
         c.W(WS_PART + PC_TH, k, s) = 0.0;
@@ -753,21 +753,21 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     // ---- objective                                                           (ocp.py:146-154,223,243-245)
     double fo = 0.0, gf_fel = 0.0, gf_fpb = 0.0, gf_sl = 0.0;
     if (g.energy) {
-        const double w2 = 2e-3 / scale;
-        fo = q.ds * (fel + sl) / scale;
-        gf_fel = q.ds / scale; gf_sl = q.ds / scale;
-        g0[V_FEL] += q.ds / scale; g0[V_SL] += q.ds / scale;
+        const double w2 = 2e-3 * iscale, dsc = q.ds * iscale;
+        fo = dsc * (fel + sl);
+        gf_fel = dsc; gf_sl = dsc;
+        g0[V_FEL] += dsc; g0[V_SL] += dsc;
         if (k >= 1) {
             double df = fel - pFel;
-            fo += 1e-3 * df * df / scale;
+            fo += 1e-3 * df * df * iscale;
             H[sidx(V_FEL, V_FEL)] += w2; H[sidx(V_F, V_F)] += w2; H[sidx(V_F, V_FEL)] -= w2;
             g0[V_FEL] += w2 * df; g0[V_F] -= w2 * df;
             gf_fel += w2 * df;
         }
         if (k + 1 < N) gf_fel -= w2 * (nFel - fel);
     } else {
-        const double w4 = 2e-4 / scale;
-        fo = 1e-4 * (fel * fel + fpb * fpb) / scale;
+        const double w4 = 2e-4 * iscale;
+        fo = 1e-4 * (fel * fel + fpb * fpb) * iscale;
         H[sidx(V_FEL, V_FEL)] += w4; g0[V_FEL] += w4 * fel; gf_fel = w4 * fel;
         if (g.withPn) { H[sidx(V_FPB, V_FPB)] += w4; g0[V_FPB] += w4 * fpb; gf_fpb = w4 * fpb; }
     }

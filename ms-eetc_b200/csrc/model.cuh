@@ -32,7 +32,7 @@ MS_HD T accel(const T& b, const T& F, const IntervalCoef& c) {
 // numSteps classic RK4 steps of db/dsigma = 2*ds*a(b,F) over sigma in [0,h]
 template <class T>
 MS_HD T rk4_b(const T& b0, const T& F, double h, int numSteps, const IntervalCoef& c) {
-    const double dt = h / numSteps;
+    const double dt = (numSteps == 1) ? h : h / numSteps;          // the usual single step costs no division
     const double w = 2.0 * c.ds * dt;
     T b = b0;
     for (int s = 0; s < numSteps; ++s) {
@@ -52,17 +52,18 @@ MS_HD void shoot(const T& b0, const T& F, const IntervalCoef& c, int numSteps, i
         T vprev = msqrt(b0);
         T acc_t = 0.0 * b0;
         T bf = b0;
+        const double wq = (numApprox == 1) ? 2.0 * c.ds : 2.0 * c.ds / numApprox;
         for (int i = 1; i <= numApprox; ++i) {
-            bf = rk4_b(b0, F, (double)i / numApprox, numSteps, c);
+            bf = rk4_b(b0, F, (i == numApprox) ? 1.0 : (double)i / numApprox, numSteps, c);
             T vnext = msqrt(bf);
-            acc_t = acc_t + (2.0 * c.ds / numApprox) * mrecip(vprev + vnext);
+            acc_t = acc_t + wq * mrecip(vprev + vnext);
             vprev = vnext;
         }
         tau = acc_t;
         phib = bf;
     } else {
         // RK4 on (t, b):  dt/dsigma = ds/sqrt(b),  db/dsigma = 2*ds*a          (train.py:255-259,298-299)
-        const double dt = 1.0 / numSteps;
+        const double dt = (numSteps == 1) ? 1.0 : 1.0 / numSteps;
         T b = b0;
         T t = 0.0 * b0;
         for (int s = 0; s < numSteps; ++s) {

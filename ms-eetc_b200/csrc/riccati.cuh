@@ -405,7 +405,7 @@ MS_HD void stage_store(const Ctx& c, int k, int s, const double K[3][3], const d
 MS_HD void terminal_value(const Ctx& c, int s, int N, double mu, double delta, double P[3][3], double p[3]) {
     for (int i = 0; i < 3; ++i) { p[i] = 0.0; for (int j = 0; j < 3; ++j) P[i][j] = 0.0; }
     P[0][0] = c.W(WS_QP + QP_H_TT, N, s) + delta;
-    p[0] = (c.cfg.energy ? 0.0 : 1.0 / c.P(P_SCALE, s)) + mu * c.W(WS_QP + QP_G1_T, N, s);
+    p[0] = (c.cfg.energy ? 0.0 : rcp_slack(c.P(P_SCALE, s))) + mu * c.W(WS_QP + QP_G1_T, N, s);
     for (int i = 0; i < 6; ++i) c.W(WS_RIC + RIC_P + i, N, s) = 0.0;
     c.W(WS_RIC + RIC_P + 0, N, s) = P[0][0];
     c.W(WS_RIC + RIC_PV + 0, N, s) = p[0];
@@ -704,15 +704,18 @@ __device__ void inst_step_warp(const Ctx& c, int s, unsigned mask, FetchB& fb, F
 #endif
 
 // ---- interval-parallel part of the step --------------------------------------------------------------------
+// fraction-to-boundary limits of one cell, kept as fractions: the smallest ratio slack / (-d slack) (and z / (-d z)) of the bounds
+// seen so far is nP / dP (nZ / dZ), compared by cross-multiplication -- one division per cell instead of one per bound
 struct Ftb {
-    double aP, aZ, gphid;
+    double nP, dP, nZ, dZ, gphid;
 };
 MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, double dvSigned, bool oneSided) {
     // dvSigned = change of the slack; primal fraction-to-boundary (eq. 15a), dual step (eq. 15b), barrier slope
-    if (dvSigned < 0.0) f.aP = fmin(f.aP, -tau * slack / dvSigned);
+    (void)tau;
+    if (dvSigned < 0.0 && slack * f.dP < f.nP * (-dvSigned)) { f.nP = slack; f.dP = -dvSigned; }
     const double r = rcp_slack(slack);
     const double dz = mu * r - z - (z * r) * dvSigned;
-    if (dz < 0.0) f.aZ = fmin(f.aZ, -tau * z / dz);
+    if (dz < 0.0 && z * f.dZ < f.nZ * (-dz)) { f.nZ = z; f.dZ = -dz; }
     f.gphid += (-mu * r + (oneSided ? MS_KAPPA_D * mu : 0.0)) * dvSigned;
 }
 
@@ -760,9 +763,9 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
     const double pFel = c.W(it + IT_FEL, km, s), pDFel = c.W(WS_ST + ST_FEL, km, s);
     const double dsk = c.W(WS_TRK + TRK_DS, k, s);
     const Bnd B = load_bounds(c, k, s);
-    const double mu = c.D(SD_MU, s), tauF = c.D(SD_TAU, s), scale = c.P(P_SCALE, s);
+    const double mu = c.D(SD_MU, s), tauF = c.D(SD_TAU, s), iscale = rcp_slack(c.P(P_SCALE, s));
 #define MS_QJ(F) QJ[(F) - QP_H_BSL]
-    Ftb f{1.0, 1.0, 0.0};
+    Ftb f{1.0, tauF, 1.0, tauF, 0.0};          // ratio 1 / tau: alpha = tau * ratio = 1 unless a bound is closer
     double OW[NROW], OYD[NROW], oyt = 0.0, oyb = 0.0, ods = 0.0;
 #pragma unroll
     for (int j = 0; j < NROW; ++j) { OW[j] = 0.0; OYD[j] = 0.0; }
@@ -837,10 +840,10 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
         ftb_bound(f, tauF, mu, CI[IT_Z + Z_SL_L], sl - B.slL, du2, true);
         // objective part of the barrier directional derivative
         if (g.energy) {
-            f.gphid += dsk * (du0 + du2) / scale;
-            if (k >= 1) f.gphid += (2e-3 / scale) * (fel - pFel) * (du0 - pDFel);
+            f.gphid += dsk * (du0 + du2) * iscale;
+            if (k >= 1) f.gphid += (2e-3 * iscale) * (fel - pFel) * (du0 - pDFel);
         } else {
-            f.gphid += (2e-4 / scale) * (fel * du0 + fpb * du1);
+            f.gphid += (2e-4 * iscale) * (fel * du0 + fpb * du1);
         }
         // inequality rows: slack step d w = J d + (d(x) - w), multiplier step from the condensed equations
 #pragma unroll
@@ -871,7 +874,7 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
             OYD[j] = sig * dw + gw - CI[IT_YD + j];
         }
     } else if (!g.energy) {
-        f.gphid += dt / scale;
+        f.gphid += dt * iscale;
     }
 #undef MS_QJ
     if (k < N) {
@@ -881,8 +884,8 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
 #pragma unroll
         for (int j = 0; j < NROW; ++j) { c.W(WS_ST + ST_W + j, k, s) = OW[j]; c.W(WS_ST + ST_YD + j, k, s) = OYD[j]; }
     }
-    c.W(WS_PART + PS_AP, k, s) = f.aP;
-    c.W(WS_PART + PS_AZ, k, s) = f.aZ;
+    c.W(WS_PART + PS_AP, k, s) = fmin(1.0, tauF * f.nP / f.dP);
+    c.W(WS_PART + PS_AZ, k, s) = fmin(1.0, tauF * f.nZ / f.dZ);
     c.W(WS_PART + PS_GPHID, k, s) = f.gphid;
 }
 
