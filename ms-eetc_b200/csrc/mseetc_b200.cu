@@ -5,6 +5,7 @@
 //   k_insts<OP>  one thread per instance: sequential sweeps over k (Riccati), loads coalesced across the warp
 // No tensor cores: the per-interval blocks are 3x3 / 6x6 FP64 and there is no dense contraction.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -84,53 +85,88 @@ __global__ void __launch_bounds__(128) k_inst_profile(Ctx c, int useSmem) {
     else inst_profile(c, s);
 }
 
-// ---- per-instance reductions: block = 32 instances x RED_W warps; warp w sums the intervals k = w, w+RED_W, ...
-// (coalesced rows), the partials are combined in fixed order by warp 0 -> bitwise reproducible, no atomics.
+// ---- per-instance reductions: one thread-block CLUSTER of RED_CL blocks per tile of 32 instances, RED_W warps in all; warp w sums
+// the intervals k = w, w+RED_W, ... (coalesced rows) and the partials are combined in fixed order by warp 0 of the first block,
+// which reads the other blocks' partials through distributed shared memory -> bitwise reproducible, no atomics.  A sweep of 2048
+// running instances has only 64 tiles: one block per tile left 84 of the 148 SMs idle in these latency-bound kernels.
 // `mirror` (mapped pinned host memory): the completion counter as it stands when this kernel runs, for the host's polling --
 // a store from the kernel instead of a 4-byte cudaMemcpyAsync between two kernels of every tick (which cost ~10 us of stream time)
-__global__ void __launch_bounds__(32 * RED_W) k_inst_alpha(Ctx c, int* mirror) {
+#ifndef MS_RED_CL
+#define MS_RED_CL 4
+#endif
+enum { RED_CL = MS_RED_CL, RED_WB = RED_W / RED_CL };      // blocks per cluster, warps per block
+static_assert(RED_W % RED_CL == 0, "cluster size must divide the interleave factor");
+__device__ __forceinline__ const double* cluster_peer(const double* p, unsigned rank) {
+    return cooperative_groups::this_cluster().map_shared_rank(p, rank);
+}
+// The warp that runs the per-instance logic after the sums (filter test, convergence test, barrier update: a chain of dependent
+// loads of the instance state) asks for that state just before the barrier (after its own share of the sums, which would flush it from L1), so that the chain finds it in L1 instead of paying
+// one L2 round trip per link.
+__device__ __forceinline__ void prefetch_instance_state(const Ctx& c, int s) {
+    for (int f = 0; f < SD_N; ++f) asm volatile("prefetch.global.L1 [%0];" ::"l"(&c.D(f, s)));
+    for (int f = 0; f < SI_N; ++f) asm volatile("prefetch.global.L1 [%0];" ::"l"(&c.I(f, s)));
+}
+
+__global__ void __cluster_dims__(RED_CL, 1, 1) __launch_bounds__(32 * RED_WB) k_inst_alpha(Ctx c, int* mirror) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
     if (mirror && blockIdx.x == 0 && threadIdx.x == 0) *mirror = *(volatile int*)c.done;
-    __shared__ double sm[RED_W][3][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int s = blockIdx.x * 32 + lane;
+    __shared__ double sm[RED_WB][3][32];
+    const unsigned rank = cl.block_rank();
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, w = (int)rank * RED_WB + wl;
+    const int s = (blockIdx.x / RED_CL) * 32 + lane;
     const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == PH_STEPPED;
     double acc[3] = {1.0, 1.0, 0.0};
     if (on) alpha_partials(c, s, c.I(SI_N_INT, s), w, RED_W, acc);
-    for (int f = 0; f < 3; ++f) sm[w][f][lane] = acc[f];
-    __syncthreads();
-    if (w == 0 && on) {
-        double tot[3] = {1.0, 1.0, 0.0};
-        for (int ww = 0; ww < RED_W; ++ww) { tot[0] = fmin(tot[0], sm[ww][0][lane]); tot[1] = fmin(tot[1], sm[ww][1][lane]); tot[2] += sm[ww][2][lane]; }
-        inst_alpha(c, s, tot);
+    if (on && rank == 0 && wl == 0) prefetch_instance_state(c, s);
+    for (int f = 0; f < 3; ++f) sm[wl][f][lane] = acc[f];
+    cl.sync();
+    double tot[3] = {1.0, 1.0, 0.0};
+    if (rank == 0 && wl == 0 && on) {
+        for (int ww = 0; ww < RED_W; ++ww) {
+            const double* q = cluster_peer(&sm[ww % RED_WB][0][lane], ww / RED_WB);
+            tot[0] = fmin(tot[0], q[0]); tot[1] = fmin(tot[1], q[32]); tot[2] += q[64];
+        }
     }
+    cl.sync();                                   // the peers' shared memory has been read: they may exit
+    if (rank == 0 && wl == 0 && on) inst_alpha(c, s, tot);
 }
 
 // TRIAL = true: the sums belong to the trial point (in the other iterate buffer); the filter test (inst_decide) comes first and,
 // when the point is accepted, the convergence test and the barrier update (inst_kkt) follow at once on the same sums.
 // TRIAL = false: starting point, inst_kkt only.
 template <bool TRIAL>
-__global__ void __launch_bounds__(32 * RED_W) k_inst_kkt(Ctx c) {
-    __shared__ double sm[RED_W][10][32];      // field-major: conflict-free columns (one lane = one instance)
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int s = blockIdx.x * 32 + lane;
+__global__ void __cluster_dims__(RED_CL, 1, 1) __launch_bounds__(32 * RED_WB) k_inst_kkt(Ctx c) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    __shared__ double sm[RED_WB][10][32];      // field-major: conflict-free columns (one lane = one instance)
+    const unsigned rank = cl.block_rank();
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5, w = (int)rank * RED_WB + wl;
+    const int s = (blockIdx.x / RED_CL) * 32 + lane;
     const bool on = s < c.cfg.nInst && c.I(SI_PHASE, s) == (TRIAL ? PH_TRIAL : PH_EVAL);
     KktAcc acc;
     kkt_init(acc);
     if (on) kkt_partials(c, s, c.I(SI_N_INT, s), ((c.I(SI_PARITY, s) != 0) != TRIAL) ? WS_IT1 : WS_IT0, w, RED_W, acc);
-    sm[w][0][lane] = acc.th; sm[w][1][lane] = acc.fo; sm[w][2][lane] = acc.slog; sm[w][3][lane] = acc.sdamp;
-    sm[w][4][lane] = acc.zsum; sm[w][5][lane] = acc.ysum; sm[w][6][lane] = acc.dinf; sm[w][7][lane] = acc.pinf;
-    sm[w][8][lane] = acc.cmin; sm[w][9][lane] = acc.cmax;
-    __syncthreads();
-    if (w == 0 && on) {
-        KktAcc tot;
-        kkt_init(tot);
+    if (on && rank == 0 && wl == 0) prefetch_instance_state(c, s);
+    sm[wl][0][lane] = acc.th; sm[wl][1][lane] = acc.fo; sm[wl][2][lane] = acc.slog; sm[wl][3][lane] = acc.sdamp;
+    sm[wl][4][lane] = acc.zsum; sm[wl][5][lane] = acc.ysum; sm[wl][6][lane] = acc.dinf; sm[wl][7][lane] = acc.pinf;
+    sm[wl][8][lane] = acc.cmin; sm[wl][9][lane] = acc.cmax;
+    cl.sync();
+    KktAcc tot;
+    kkt_init(tot);
+    const bool lead = rank == 0 && wl == 0 && on;
+    if (lead) {
         for (int ww = 0; ww < RED_W; ++ww) {
+            const double* q = cluster_peer(&sm[ww % RED_WB][0][lane], ww / RED_WB);
             KktAcc o;
-            o.th = sm[ww][0][lane]; o.fo = sm[ww][1][lane]; o.slog = sm[ww][2][lane]; o.sdamp = sm[ww][3][lane];
-            o.zsum = sm[ww][4][lane]; o.ysum = sm[ww][5][lane]; o.dinf = sm[ww][6][lane]; o.pinf = sm[ww][7][lane];
-            o.cmin = sm[ww][8][lane]; o.cmax = sm[ww][9][lane];
+            o.th = q[0]; o.fo = q[32]; o.slog = q[64]; o.sdamp = q[96];
+            o.zsum = q[128]; o.ysum = q[160]; o.dinf = q[192]; o.pinf = q[224];
+            o.cmin = q[256]; o.cmax = q[288];
             kkt_combine(tot, o);
         }
+    }
+    cl.sync();                                   // the peers' shared memory has been read: they may exit
+    if (lead) {
         if (TRIAL) {
             const double sums[4] = {tot.th, tot.fo, tot.slog, tot.sdamp};
             inst_decide(c, s, sums);            // accepted: buffers swapped, phase -> evaluated
@@ -661,7 +697,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     begin(CLS_EVAL);
     if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
     end(CLS_EVAL);
-    begin(CLS_KKT); k_inst_kkt<false><<<rgrid, 32 * RED_W, 0, st>>>(c); end(CLS_KKT);
+    begin(CLS_KKT); k_inst_kkt<false><<<rgrid * RED_CL, 32 * RED_WB, 0, st>>>(c); end(CLS_KKT);
     // ---- the tick loop: direction (sweeps, interval-parallel rest, step-size limits), then the evaluation at the trial point with
     // the filter test / convergence test / barrier update: five launches per tick.
     // Small batches (latency): on the device -- a CUDA graph whose single node is a conditional WHILE node with one tick as its
@@ -682,13 +718,13 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, s0>>>(c, io); else k_cell_step<<<gridStep, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_CSTEP);
         if (prof) begin(CLS_ALPHA);
-        k_inst_alpha<<<rgrid, 32 * RED_W, 0, s0>>>(c, mirror);
+        k_inst_alpha<<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c, mirror);
         if (prof) end(CLS_ALPHA);
         if (prof) begin(CLS_TRIAL);
         if (dyn) k_cell_trial_eval_dyn<<<gridTrial, 128, 0, s0>>>(c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_TRIAL);
         if (prof) begin(CLS_DECIDE);
-        k_inst_kkt<true><<<rgrid, 32 * RED_W, 0, s0>>>(c);
+        k_inst_kkt<true><<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c);
         if (prof) end(CLS_DECIDE);
     };
     if (useGraph) {

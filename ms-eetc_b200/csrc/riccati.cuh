@@ -541,9 +541,11 @@ MS_HD void kkt_init(KktAcc& a) {
     a.th = a.fo = a.slog = a.sdamp = a.zsum = a.ysum = 0.0;
     a.dinf = a.pinf = a.cmax = 0.0; a.cmin = 1e300;
 }
-// 14 planes per interval: two intervals per group keep the loaded values in registers (four spill under the 128-register
-// limit of a 512-thread block, and a spilled load is waited for at once)
-#define MS_KKT_U 2
+// 14 planes per interval: MS_KKT_U intervals per group, all loads of a group in flight together (the blocks of the reduction
+// clusters have 128 threads, so the 56 values of four intervals stay in registers)
+#ifndef MS_KKT_U
+#define MS_KKT_U 4
+#endif
 MS_HD void kkt_partials(const Ctx& c, int s, int N, int it, int w, int W, KktAcc& a) {
     kkt_init(a);
     for (int k0 = w; k0 <= N; k0 += MS_KKT_U * W) {
