@@ -215,6 +215,19 @@ int mseetc_measure_fp64_peak(double* gflops_out, void* cuda_stream);
 int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx_steps,
                          const double* in_dev, double* out_dev, void* cuda_stream);
 
+/* Shooting integrator of the handle (TrainIntegrator, mseetc/train.py:282-322).  The default is the explicit branch
+ * (ca.simpleRK, train.py:294-301).  stages >= 1 selects collocation steps (ca.simpleIRK, train.py:303-310): `A` [stages*stages,
+ * row-major] and `w` [stages] are HOST arrays with the Runge-Kutta coefficients of the collocation method on the chosen points
+ * (A_ij = int_0^{c_i} l_j, w_j = int_0^1 l_j), `max_newton` the iteration limit of the stage solve (OptionsIRK.maxIter,
+ * train.py:494).  The number of steps and the time approximation stay the num_steps and num_approx_steps of the problem structure.
+ * The 'CVODES' branch (train.py:312-322) is served by the same entry point with a high-order Gauss tableau, see DESIGN.md.
+ * stages = 0 returns to the explicit steps. */
+int mseetc_set_integrator(mseetc_handle h, int32_t stages, const double* A, const double* w, int32_t max_newton);
+
+/* mseetc_eval_interval with collocation steps (same planes in and out; A, w: host arrays as above). */
+int mseetc_eval_interval_irk(int32_t n, int32_t num_steps, int32_t num_approx_steps, int32_t stages, const double* A,
+                             const double* w, int32_t max_newton, const double* in_dev, double* out_dev, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -600,7 +600,7 @@ enum { V_T = 0, V_B, V_F, V_FEL, V_FPB, V_SL, V_BN, NV7 };
 // TRIAL = false: at the current iterate (first iteration).  TRIAL = true: at the trial point x + alpha dx, which is formed here
 // and written to the other iterate buffer (see form_trial_cell); inst_decide then reads theta, the objective and the barrier sums
 // from the same partial planes that inst_kkt uses when the point is accepted.
-template <bool DYN, bool TRIAL>
+template <bool DYN, bool TRIAL, bool IRK = false>
 MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != (TRIAL ? PH_TRIAL : PH_EVAL)) return;
@@ -695,7 +695,8 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     // ---- shooting: values + exact first/second sensitivities w.r.t. (b_k, F)
     IntervalCoef q = load_coef(c, k, s);
     Jet2 tau, phi;
-    shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
+    if (IRK) shoot_irk(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, *c.irk, tau, phi);
+    else shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
     const double ct = t1 - t - tau.v, cb = b1 - phi.v;
     double v0, v1, iv0, iv1;
     sqrt_inv(b, v0, iv0);

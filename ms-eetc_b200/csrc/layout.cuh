@@ -115,6 +115,8 @@ struct Config {
     int initMode;     // 0: initial guess of the reference (ocp.py:325-339); 1: dynamically consistent speed-envelope guess
 };
 
+struct IrkTab;     // model.cuh: Butcher tableau of the collocation integrator
+
 struct Ctx {
     Config cfg;
     double* ws;    // WS_FIELDS planes of NK*S
@@ -125,6 +127,7 @@ struct Ctx {
     unsigned long long* cnt;   // [4] processed cells: trial, eval, riccati backward, riccati forward
     LossMapDev lm;             // spline of the dynamic loss map (lossKind 2), device pointers
     const double* tmin;        // [nInst] or null: minimum trip duration once known (0 = not known yet), see inst_kkt; indexed by SI_ORIG
+    const IrkTab* irk;         // null: explicit RK4 (integrationMethod 'RK'); else collocation steps ('IRK', and 'CVODES' by a high-order tableau)
     int* plan;                 // compaction plan (device only; null in the host emulation): [0] moves, [1] active, then sources, destinations
 
     MS_HD double& W(int field, int k, int slot) const {

@@ -62,6 +62,12 @@ MS_CELL_KERNEL(k_cell_trial_eval, MS_MINB_TRIAL, (cell_eval<false, true>(c, k, s
 MS_CELL_KERNEL(k_cell_trial_eval_dyn, 2, (cell_eval<true, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_eval, MS_MINB_EVAL, (cell_eval<false, false>(c, k, s)))
 MS_CELL_KERNEL(k_cell_eval_dyn, 2, (cell_eval<true, false>(c, k, s)))
+// the same with the collocation integrator (integrationMethod 'IRK' / 'CVODES'): separate instantiations, so that the Newton
+// iterations and their local arrays stay out of the explicit-RK kernels
+MS_CELL_KERNEL(k_cell_trial_eval_irk, 1, (cell_eval<false, true, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_trial_eval_dyn_irk, 1, (cell_eval<true, true, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_eval_irk, 1, (cell_eval<false, false, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_eval_dyn_irk, 1, (cell_eval<true, false, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_step_dyn, MS_MINB_STEP, cell_step<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
@@ -339,9 +345,9 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, doub
     if (acc == 12345.678) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;      // never true: keeps the chains alive
 }
 
-__global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out) {
+__global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out, const IrkTab* irk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    eval_interval_point(i, n, numSteps, numApprox, in, out);
+    eval_interval_point(i, n, numSteps, numApprox, in, out, irk);
 }
 
 }  // namespace
@@ -376,6 +382,7 @@ struct mseetc_solver {
     unsigned char loop_key[sizeof(Ctx) + sizeof(BatchIO) + 16];
     double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
     LossMapDev lm;
+    IrkTab* irk_dev;               // Butcher tableau of the collocation integrator in device memory; null: explicit RK4
 };
 
 extern "C" {
@@ -411,6 +418,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->last_fallbacks = 0;
     h->fallback_why[0] = h->fallback_why[1] = h->fallback_why[2] = 0;
     h->lm_dev = nullptr;
+    h->irk_dev = nullptr;
     h->loop_graph = nullptr; h->loop_exec = nullptr; h->cap_stream = nullptr; h->cap_prio = 0;
     memset(h->loop_key, 0, sizeof h->loop_key);
     memset(&h->lm, 0, sizeof h->lm);
@@ -429,6 +437,7 @@ int mseetc_destroy(mseetc_handle h) {
     if (!h) return 0;
     cudaFreeHost(h->done_host);
     if (h->lm_dev) cudaFree(h->lm_dev);
+    if (h->irk_dev) cudaFree(h->irk_dev);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(h->poll_ev[i]);
     if (h->loop_exec) cudaGraphExecDestroy(h->loop_exec);
     if (h->loop_graph) cudaGraphDestroy(h->loop_graph);
@@ -494,6 +503,27 @@ int mseetc_set_compaction(mseetc_handle h, int on) {
 int mseetc_last_sweep_fallback_reasons(mseetc_handle h, int32_t* out3) {
     if (!h || !out3) return fail(-1, "mseetc_last_sweep_fallback_reasons: null argument");
     for (int i = 0; i < 3; ++i) out3[i] = h->fallback_why[i];
+    return 0;
+}
+
+int mseetc_set_integrator(mseetc_handle h, int32_t stages, const double* A, const double* w, int32_t max_newton) {
+    if (!h) return fail(-1, "mseetc_set_integrator: null handle");
+    if (stages == 0) {                      // back to the explicit RK4 steps
+        if (h->irk_dev) { cudaFree(h->irk_dev); h->irk_dev = nullptr; }
+        memset(h->loop_key, 0, sizeof h->loop_key);
+        return 0;
+    }
+    if (stages < 1 || stages > MS_IRK_MAXD || !A || !w || max_newton < 1) return fail(-2, "mseetc_set_integrator: 1 <= stages <= 9, tableau and max_newton >= 1 required");
+    IrkTab t;
+    memset(&t, 0, sizeof t);
+    t.d = stages; t.maxNewton = max_newton;
+    for (int i = 0; i < stages * stages; ++i) t.A[i] = A[i];
+    for (int i = 0; i < stages; ++i) t.w[i] = w[i];
+    cudaError_t e = cudaSuccess;
+    if (!h->irk_dev) e = cudaMalloc((void**)&h->irk_dev, sizeof(IrkTab));
+    if (e != cudaSuccess) { h->irk_dev = nullptr; return cuda_fail(e, "mseetc_set_integrator: cudaMalloc"); }
+    e = cudaMemcpy(h->irk_dev, &t, sizeof t, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "mseetc_set_integrator: cudaMemcpy");
     return 0;
 }
 
@@ -575,6 +605,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.lm = h->lm;
     c.tmin = tmin;
     c.plan = (int*)(base + plan.off_plan);
+    c.irk = h->irk_dev;
     const bool dyn = (p.loss_kind == 2 && p.energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
@@ -596,7 +627,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         const unsigned want = (unsigned)(nsm * minb * cellWaves) | 1u;
         return want < cgridFull ? want : cgridFull;
     };
-    const unsigned cgrid = pgrid(4), gridTrial = pgrid(dyn ? 2 : MS_MINB_TRIAL), gridEval = pgrid(dyn ? 2 : MS_MINB_EVAL), gridStep = pgrid(MS_MINB_STEP);
+    const unsigned cgrid = pgrid(4), gridTrial = pgrid(dyn ? 2 : MS_MINB_TRIAL), gridEval = pgrid(dyn ? 2 : MS_MINB_EVAL), gridStep = pgrid(MS_MINB_STEP), gridIrk = pgrid(1);
     const int blocksPerSm = (int)((igrid + nsm - 1) / nsm);
     const size_t slotBytes = sizeof(double) * RING_NF_MAX * ib;
     int depth = (int)((size_t)200 * 1024 / ((size_t)(blocksPerSm < 1 ? 1 : blocksPerSm) * slotBytes)) - 1;
@@ -695,7 +726,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     int tick = 0;
     // ---- starting point: evaluation, convergence test, barrier parameter
     begin(CLS_EVAL);
-    if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
+    if (c.irk) { if (dyn) k_cell_eval_dyn_irk<<<gridIrk, 128, 0, st>>>(c, io); else k_cell_eval_irk<<<gridIrk, 128, 0, st>>>(c, io); }
+    else if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
     end(CLS_EVAL);
     begin(CLS_KKT); k_inst_kkt<false><<<rgrid * RED_CL, 32 * RED_WB, 0, st>>>(c); end(CLS_KKT);
     // ---- the tick loop: direction (sweeps, interval-parallel rest, step-size limits), then the evaluation at the trial point with
@@ -721,7 +753,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         k_inst_alpha<<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c, mirror);
         if (prof) end(CLS_ALPHA);
         if (prof) begin(CLS_TRIAL);
-        if (dyn) k_cell_trial_eval_dyn<<<gridTrial, 128, 0, s0>>>(c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
+        if (c.irk) { if (dyn) k_cell_trial_eval_dyn_irk<<<gridIrk, 128, 0, s0>>>(c, io); else k_cell_trial_eval_irk<<<gridIrk, 128, 0, s0>>>(c, io); }
+        else if (dyn) k_cell_trial_eval_dyn<<<gridTrial, 128, 0, s0>>>(c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_TRIAL);
         if (prof) begin(CLS_DECIDE);
         k_inst_kkt<true><<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c);
@@ -957,11 +990,36 @@ int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const
     if (n < 1 || !in || !out) return fail(-1, "mseetc_eval_interval: bad argument");
     if (num_steps < 1 || num_approx < 0) return fail(-2, "mseetc_eval_interval: bad RK options");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out);
+    k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_eval_interval launch");
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "k_eval_interval");
+    return 0;
+}
+
+int mseetc_eval_interval_irk(int32_t n, int32_t num_steps, int32_t num_approx, int32_t stages, const double* A, const double* w,
+                             int32_t max_newton, const double* in, double* out, void* cuda_stream) {
+    if (n < 1 || !in || !out) return fail(-1, "mseetc_eval_interval_irk: bad argument");
+    if (num_steps < 1 || num_approx < 0) return fail(-2, "mseetc_eval_interval_irk: bad step options");
+    if (stages < 1 || stages > MS_IRK_MAXD || !A || !w || max_newton < 1) return fail(-3, "mseetc_eval_interval_irk: 1 <= stages <= 9, tableau and max_newton >= 1 required");
+    IrkTab t;
+    memset(&t, 0, sizeof t);
+    t.d = stages; t.maxNewton = max_newton;
+    for (int i = 0; i < stages * stages; ++i) t.A[i] = A[i];
+    for (int i = 0; i < stages; ++i) t.w[i] = w[i];
+    IrkTab* dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev, sizeof t);
+    if (e != cudaSuccess) return cuda_fail(e, "mseetc_eval_interval_irk: cudaMalloc");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    e = cudaMemcpyAsync(dev, &t, sizeof t, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out, dev);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "k_eval_interval (irk)");
     return 0;
 }
 

@@ -71,6 +71,8 @@ def lib():
         L.mseetc_measure_fp64_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
     L.mseetc_bytes_per_cell.restype = ctypes.c_double
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
+    L.mseetc_eval_interval_irk.argtypes = [i32, i32, i32, i32, vp, vp, i32, vp, vp, vp]
+    L.mseetc_set_integrator.argtypes = [vp, i32, vp, vp, i32]
     L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
     L.mseetc_set_sweep_lanes.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_sweep_fallbacks.argtypes = [vp]
@@ -121,6 +123,15 @@ class Handle:
                 self._h = ctypes.c_void_p(0)
         except Exception:
             pass
+
+    def set_integrator(self, A, w, max_newton=10):
+        "Collocation steps with the Runge-Kutta coefficients (A, w) instead of explicit RK4 (A = None: back to RK4)."
+        if A is None:
+            _check(lib().mseetc_set_integrator(self._h, 0, None, None, 1), 'mseetc_set_integrator')
+            return
+        A = np.ascontiguousarray(A, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64)
+        _check(lib().mseetc_set_integrator(self._h, int(len(w)), A.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p),
+                                           int(max_newton)), 'mseetc_set_integrator')
 
     def set_sweep_lanes(self, lanes):
         "0 = chosen per call; 1 = sequential Riccati sweeps; 8 / 16 / 32 = parallel-in-time sweeps with that many chunk lanes per instance."
@@ -374,14 +385,21 @@ def last_timeline(handle, origin=None, max_entries=4096):
     return buf[:n]
 
 
-def eval_interval(inp, num_steps, num_approx):
-    """inp: numpy [7, n] planes (b0, F, ds, c0, sr0, sr1, sr2) -> numpy [12, n] (tau jets, b1 jets)."""
+def eval_interval(inp, num_steps, num_approx, tableau=None):
+    """inp: numpy [7, n] planes (b0, F, ds, c0, sr0, sr1, sr2) -> numpy [12, n] (tau jets, b1 jets).
+    tableau: None = explicit RK4 steps; dict(A, w, maxIter) = collocation steps (mseetc.train.collocationTableau)."""
     torch = _torch_cuda()
     inp = np.ascontiguousarray(inp, dtype=np.float64)
     n = inp.shape[1]
     d_in = torch.from_numpy(inp).cuda()
     d_out = torch.empty((12, n), dtype=torch.float64, device=d_in.device)
     stream = torch.cuda.current_stream().cuda_stream
-    _check(lib().mseetc_eval_interval(n, int(num_steps), int(num_approx), _ptr(d_in), _ptr(d_out), ctypes.c_void_p(stream)),
-           'mseetc_eval_interval')
+    if tableau is None:
+        _check(lib().mseetc_eval_interval(n, int(num_steps), int(num_approx), _ptr(d_in), _ptr(d_out), ctypes.c_void_p(stream)),
+               'mseetc_eval_interval')
+    else:
+        A = np.ascontiguousarray(tableau['A'], dtype=np.float64); w = np.ascontiguousarray(tableau['w'], dtype=np.float64)
+        _check(lib().mseetc_eval_interval_irk(n, int(num_steps), int(num_approx), int(len(w)), A.ctypes.data_as(ctypes.c_void_p),
+                                              w.ctypes.data_as(ctypes.c_void_p), int(tableau.get('maxIter', 10)), _ptr(d_in), _ptr(d_out),
+                                              ctypes.c_void_p(stream)), 'mseetc_eval_interval_irk')
     return d_out.cpu().numpy()

@@ -186,8 +186,6 @@ class casadiSolver():
         track.checkFields()
         train.checkFields()
         opts = OptionsCasadiSolver(optsDict)
-        if opts.integrationMethod != 'RK':
-            raise NotImplementedError("integrationMethod '{}' is not implemented on the device (only 'RK')".format(opts.integrationMethod))
         if opts.integrateLosses:
             raise NotImplementedError("integrateLosses=True is not implemented on the device")
 
@@ -290,16 +288,27 @@ class casadiSolver():
         bmax[1:N] = np.minimum(np.minimum(lim[1:N], vmax), lim[0:N - 1]) ** 2    # reference ocp.py:266-269
         return np.asarray(self.steps, dtype=float), c0, bmax
 
+    def _integrator(self):
+        "(numSteps, numApproxSteps, collocation tableau or None) of this solver's integrationMethod / integrationOptions"
+        from mseetc.train import integratorSetup
+        return integratorSetup(self.opts.integrationMethod, self.opts.integrationOptions)
+
+    def _integrator_key(self):
+        ns, na, tab = self._integrator()
+        return (self.opts.integrationMethod, ns, na) + (() if tab is None else (tab['A'].tobytes(), tab['maxIter']))
+
     def _make_handle(self):
-        io = self.opts.integrationOptions
+        numSteps, numApprox, tableau = self._integrator()
         h = _cabi.Handle(self.numIntervals, self.withPnBrake, self.withPower, self.energyOptimal,
-                         {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], io.numSteps, io.numApproxSteps,
+                         {'none': 0, 'static': 1, 'dynamic': 2}[self._lossKind], numSteps, numApprox,
                          int(self.opts.maxIterations), mu_init=float(self.muInit),
                          initial_guess={'reference': 0, 'profile': 1}[self.initialGuess], stall_iterations=int(self.stallIterations))
         if self._lossKind == 'dynamic' and self.energyOptimal:
             dp = self.train.powerLosses.device_params
             h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
         h.set_sweep_lanes(0 if self.sweepLanes == 'auto' else int(self.sweepLanes))      # 0: the library picks per call
+        if tableau is not None:            # 'IRK' / 'CVODES' (reference train.py:303-322): collocation steps instead of explicit RK4
+            h.set_integrator(tableau['A'], tableau['w'], tableau['maxIter'])
         return h
 
     def _ensure_pool(self, dev):
@@ -718,8 +727,7 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
         raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     n = len(solvers)
     ref = solvers[0]
-    sig = lambda s: (s.withPnBrake, s.withRgBrake, s.withPower, s.energyOptimal, s._lossKind, int(s.opts.integrationOptions.numSteps),
-                     int(s.opts.integrationOptions.numApproxSteps))
+    sig = lambda s: (s.withPnBrake, s.withRgBrake, s.withPower, s.energyOptimal, s._lossKind) + s._integrator_key()
     if any(sig(s) != sig(ref) for s in solvers):
         raise ValueError("solve_instances needs solvers with identical problem structure")
     bc = [np.broadcast_to(np.atleast_1d(np.asarray(a, dtype=float)), (n,)) for a in (terminalTime, initialTime, terminalVelocity, initialVelocity)]
@@ -740,14 +748,16 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
     nint = np.array([s.numIntervals for s in solvers], dtype=np.int32)
     trk_off = np.concatenate([[0], np.cumsum(nint)]).astype(np.int32)
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
-    io = ref.opts.integrationOptions
+    numSteps, numApprox, tableau = ref._integrator()
     guess = ref.initialGuess if restart is not None else 'reference'       # restart=None: this IS the second attempt
 
     def mk(energy, loss):
-        hd = _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, io.numSteps, io.numApproxSteps,
+        hd = _cabi.Handle(Nmax, ref.withPnBrake, ref.withPower, energy, loss, numSteps, numApprox,
                           int(ref.opts.maxIterations), initial_guess={'reference': 0, 'profile': 1}[guess],
                           stall_iterations=int(ref.stallIterations))
         hd.set_sweep_lanes(0 if ref.sweepLanes == 'auto' else int(ref.sweepLanes))
+        if tableau is not None:
+            hd.set_integrator(tableau['A'], tableau['w'], tableau['maxIter'])
         return hd
     dev_tabs = dict(nint=up(nint, torch.int32), trk_of=up(np.arange(n, dtype=np.int32), torch.int32), trk_off=up(trk_off, torch.int32),
                     ds=up(np.concatenate([t[0] for t in tabs]), torch.float64), c0=up(np.concatenate([t[1] for t in tabs]), torch.float64),

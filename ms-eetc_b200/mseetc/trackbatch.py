@@ -159,14 +159,16 @@ def solve_tracks(train, batch, numIntervals, optsDict=None, terminalTime=None, t
     t_build = _time.perf_counter() - t_begin
 
     def handle(solver, guess):
-        io = solver.opts.integrationOptions
+        numSteps, numApprox, tableau = solver._integrator()
         h = _cabi.Handle(Nmax, solver.withPnBrake, solver.withPower, solver.energyOptimal, {'none': 0, 'static': 1, 'dynamic': 2}[solver._lossKind],
-                         io.numSteps, io.numApproxSteps, int(solver.opts.maxIterations), mu_init=float(solver.muInit),
+                         numSteps, numApprox, int(solver.opts.maxIterations), mu_init=float(solver.muInit),
                          initial_guess={'reference': 0, 'profile': 1}[guess], stall_iterations=int(solver.stallIterations))
         if solver._lossKind == 'dynamic' and solver.energyOptimal:
             dp = solver.train.powerLosses.device_params
             h.set_loss_map(dp['knots_load'], dp['knots_speed'], dp['coef'])
         h.set_sweep_lanes(0 if solver.sweepLanes == 'auto' else int(solver.sweepLanes))
+        if tableau is not None:
+            h.set_integrator(tableau['A'], tableau['w'], tableau['maxIter'])
         return h
 
     def run(solver, T, tmin_dev=None):

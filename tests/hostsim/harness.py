@@ -66,6 +66,16 @@ def loss_map_arrays():
     return np.ascontiguousarray(lut.tx), np.ascontiguousarray(lut.ty), np.ascontiguousarray(lut.coef)
 
 
+def product_tableau(order, scheme):
+    import sys
+    pkg = os.path.join(HERE, '..', '..', 'ms-eetc_b200')
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    from mseetc.train import collocationTableau
+    A, w, _ = collocationTableau(order, scheme)
+    return np.ascontiguousarray(A), np.ascontiguousarray(w)
+
+
 def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst=-1, lib=None, tmin=None, pit_lanes=0, init_mode=0, mu_init=0.1):
     """Solve instances (one NLP object per instance, equal structure flags) with the emulated device code."""
     lib = lib or build()
@@ -94,6 +104,11 @@ def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst
         lm = (cf.shape[0], cf.shape[1], P(tl), P(tv), P(cf))
     else:
         lm = (0, 0, ctypes.c_void_p(0), ctypes.c_void_p(0), ctypes.c_void_p(0))
+    if ref.opts.get('irk'):                 # collocation integrator: the tableau the product would hand to mseetc_set_integrator
+        A, w = product_tableau(*ref.opts['irk'])
+        lib.hostsim_set_integrator(len(w), P(A), P(w), 10)
+    else:
+        lib.hostsim_set_integrator(0, ctypes.c_void_p(0), ctypes.c_void_p(0), 1)
     lib.hostsim_solve_batch(ctypes.byref(pr), n, P(params), P(nint), P(trk_of), P(trk_off), P(ds), P(c0), P(bmax),
                             P(np.ascontiguousarray(tmin, dtype=float)) if tmin is not None else ctypes.c_void_p(0), P(z), P(lam),
                             P(obj), P(kkt), P(iters), P(status), verbose_inst, ctypes.byref(ticks), int(pit_lanes), *lm, int(init_mode))

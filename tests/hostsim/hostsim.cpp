@@ -50,6 +50,9 @@ static void lin_residual(const Ctx& c, int s, int N, const char* tag) {
     printf("   lin-res %s: controls %.2e at %d | costate %.2e at %d | dynamics %.2e at %d\n", tag, worstU, kU, worstX, kX, worstD, kD);
 }
 
+static IrkTab g_irk;
+static bool g_irk_on = false;
+
 extern "C" {
 
 struct hostsim_problem {
@@ -87,6 +90,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     c.cnt = (unsigned long long*)(buf.data() + plan.off_done + 64);
     c.tmin = tmin;
     c.plan = nullptr;
+    c.irk = g_irk_on ? &g_irk : nullptr;
     c.lm.tl = lm_tl; c.lm.tv = lm_tv; c.lm.coef = lm_coef; c.lm.nl = lm_nl; c.lm.nv = lm_nv;
     const bool dyn = (pr->loss_kind == 2 && pr->energy_optimal);
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
@@ -132,7 +136,10 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
             }
         }
     };
-    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_eval<true, false>(c, k, s); else cell_eval<false, false>(c, k, s); }
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) {
+        if (c.irk) { if (dyn) cell_eval<true, false, true>(c, k, s); else cell_eval<false, false, true>(c, k, s); }
+        else if (dyn) cell_eval<true, false>(c, k, s); else cell_eval<false, false>(c, k, s);
+    }
     reduce_kkt(false);
     for (;;) {
         for (int s = 0; s < g.S; ++s) {
@@ -191,7 +198,10 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         }
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_eval<true, true>(c, k, s); else cell_eval<false, true>(c, k, s); }
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) {
+            if (c.irk) { if (dyn) cell_eval<true, true, true>(c, k, s); else cell_eval<false, true, true>(c, k, s); }
+            else if (dyn) cell_eval<true, true>(c, k, s); else cell_eval<false, true>(c, k, s);
+        }
         reduce_kkt(true);
         ++tick;
         if (*c.done >= n) break;
@@ -211,6 +221,20 @@ int hostsim_eval_loss_rows(int32_t n, int32_t nl, int32_t nv, const double* tl, 
 
 int hostsim_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out) {
     for (int i = 0; i < n; ++i) eval_interval_point(i, n, num_steps, num_approx, in, out);
+    return 0;
+}
+
+// collocation integrator (mseetc_set_integrator): stages = 0 switches it off again
+int hostsim_set_integrator(int32_t stages, const double* A, const double* w, int32_t max_newton) {
+    g_irk_on = stages > 0;
+    if (!g_irk_on) return 0;
+    g_irk.d = stages; g_irk.maxNewton = max_newton;
+    for (int i = 0; i < stages * stages; ++i) g_irk.A[i] = A[i];
+    for (int i = 0; i < stages; ++i) g_irk.w[i] = w[i];
+    return 0;
+}
+int hostsim_eval_interval_irk(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out) {
+    for (int i = 0; i < n; ++i) eval_interval_point(i, n, num_steps, num_approx, in, out, &g_irk);
     return 0;
 }
 

@@ -33,6 +33,8 @@ def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True, in
     h = cabi.Handle(Nmax, ref.withPn, ref.withPower, ref.energy, {'none': 0, 'static': 1}[ref.lossKind],
                     ref.opts['numSteps'], ref.opts['numApproxSteps'], max_iter, initial_guess=initial_guess)
     h.set_sweep_lanes(lanes)
+    if ref.opts.get('irk'):                      # collocation integrator: the tableau the product computes
+        h.set_integrator(*harness.product_tableau(*ref.opts['irk']), 10)
     out = h.solve_device(cu(params, torch.float64), cu(nint, torch.int32), cu(np.arange(n, dtype=np.int32), torch.int32),
                          cu(trk_off, torch.int32), cu(np.concatenate([p[1] for p in packs]), torch.float64),
                          cu(np.concatenate([p[2] for p in packs]), torch.float64),
@@ -60,6 +62,60 @@ def test_interval_kernel_matches_sympy(cabi):
                 assert np.max(np.abs(out[6 * a + i] - ref) / np.maximum(1e-12, np.abs(ref))) < 1e-9
 
 
+def test_collocation_interval_kernel_matches_oracle(cabi):
+    "mseetc_eval_interval_irk (TrainIntegrator 'IRK', train.py:303-310, 347-364) vs the oracle's collocation restatement."
+    import harness
+    from oracle import irk
+    rng = np.random.default_rng(5)
+    n = 256
+    b0 = rng.uniform(4.0, 1600.0, n); F = rng.uniform(-0.6, 0.5, n); ds = rng.uniform(0.05, 400.0, n)
+    F = np.maximum(F, (6.0 - b0) / (2 * ds) + 0.3)
+    c0 = rng.uniform(-0.2, 0.2, n)
+    sr = (1.41244e-2, 1.78932e-4, 3.12696e-5)
+    inp = np.stack([b0, F, ds, c0, np.full(n, sr[0]), np.full(n, sr[1]), np.full(n, sr[2])])
+    for order, scheme, numSteps, numApprox in ((2, 'radau', 1, 0), (3, 'legendre', 1, 1), (4, 'legendre', 4, 0), (9, 'radau', 1, 2)):
+        A, w = harness.product_tableau(order, scheme)
+        out = cabi.eval_interval(inp, numSteps, numApprox, dict(A=A, w=w, maxIter=12))
+        (tau, gt, ht), (phi, gp, hp) = irk.shoot(b0, F, ds, c0, sr, numSteps, numApprox, order, scheme)
+        ref = [tau] + gt + ht + [phi] + gp + hp
+        for i in range(12):
+            assert np.max(np.abs(out[i] - ref[i]) / np.maximum(1e-10, np.abs(ref[i]))) < 2e-8, (order, scheme, numSteps, numApprox, i)
+
+
+def test_public_api_integration_methods(cabi):
+    """casadiSolver with integrationMethod 'IRK' and 'CVODES' (reference ocp.py:116, train.py:303-322): optimum against the oracle
+    with the same collocation scheme; ERK4+ with the average-speed rule for time and the CVODES-equivalent scheme agree on the
+    energy (a two-point Radau step on (t, b) does not: its quadrature of dt = ds/v over the first interval, where the train starts
+    at 1 m/s, is coarse -- the reference's IRK branch has the same property, so that case is only compared with the oracle)."""
+    import pandas as pd      # noqa: F401
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train, TrainIntegrator, CVODES_EQUIVALENT as Q
+    from mseetc.track import Track
+    from oracle.problem import load_track
+    train = Train(config={'id': 'NL_Intercity_VIRM6'})
+    track = Track(config={'id': '00_var_speed_limit_100'})
+    costs = {}
+    for method, io, irk_key, ns, na in (('RK', {'numApproxSteps': 1}, None, 1, 1),
+                                       ('IRK', {'order': 2, 'collMethod': 'radau', 'numApproxSteps': 0}, (2, 'radau'), 1, 0),
+                                       ('CVODES', {}, (Q['order'], Q['collMethod']), Q['numSteps'], Q['numApproxSteps'])):
+        solver = casadiSolver(train, track, {'numIntervals': 200, 'integrationMethod': method, 'integrationOptions': io})
+        df, stats = solver.solve(1541.0)
+        assert df is not None and stats['Cost'] > 0, (method, stats)
+        costs[method] = stats['Cost']
+        if irk_key:
+            nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), 200, energy=True, numSteps=ns, numApproxSteps=na, irk=irk_key)
+            ref = oracle_solve(nlp, 1541.0)
+            assert ref.success
+            assert abs(stats['Cost'] - nlp.cost(ref.f)) <= 1e-6 * nlp.cost(ref.f), method
+            assert np.max(np.abs(df['Velocity [m/s]'].values ** 2 - ref.x[nlp.iB])) <= 1e-4 * nlp.limit.max() ** 2
+    assert abs(costs['RK'] - costs['CVODES']) < 5e-3 * costs['CVODES'], costs
+    # TrainIntegrator.solve (train.py:347-364) with the three methods on one interval
+    model = train.exportModel()
+    ends = [TrainIntegrator(model, m, o).solve(0.0, 400.0, 250.0, traction=0.3) for m, o in (('RK', {'numSteps': 4}), ('IRK', {'order': 3}), ('CVODES', {}))]
+    for e in ends[:2]:
+        assert abs(e['time'] - ends[2]['time']) < 1e-5 * ends[2]['time'] and abs(e['velSquared'] - ends[2]['velSquared']) < 1e-5 * ends[2]['velSquared']
+
+
 def test_interval_kernel_bitwise_equals_host_compilation(cabi):
     "Same source compiled by nvcc (device) and g++ (tests/hostsim): values agree to the last few ulps (FMA contraction differs)."
     import harness
@@ -85,6 +141,10 @@ CASES = [
      300, 200.0, True, 1.0, 1.0, dict()),
     ('rk4 on both states', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict(numApproxSteps=0)),
     ('two time sub-points', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numSteps=1, numApproxSteps=2)),
+    # integrationMethod 'IRK' (reference train.py:303-310)
+    ('irk radau 2 on both states', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numApproxSteps=0, irk=(2, 'radau'))),
+    ('irk legendre 3, two steps, time approximation', lambda: virm6(), SWISS_JSON, None, 300, 1242.0, True, 1.0, 1.0,
+     dict(numSteps=2, numApproxSteps=1, irk=(3, 'legendre'))),
 ]
 
 
@@ -134,7 +194,9 @@ def test_cuda_solver_matches_oracle(cabi, case, guess, lanes):
     sl, su = (z - lbz)[free], (ubz - z)[free]
     with np.errstate(invalid='ignore'):
         comp = np.where(r > 0, r * sl, -r * np.where(np.isfinite(su), su, 1.0))
-    assert np.max(comp) < 1e-7
+    # (collocation cases: the oracle's Jacobian comes from autograd through unrolled Newton iterations and agrees with the device's
+    # to ~1e-8 relative only, which shows here through the multipliers)
+    assert np.max(comp) < (1e-6 if rk.get('irk') else 1e-7)
     g = nlp.g(z)
     assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7
     a0, amb0 = active_set(nlp, z, T, 0.0, v0, vN)

@@ -330,3 +330,29 @@ def test_random_track_batch_has_the_recipe_statistics(built_lib):
     assert set(np.round(lv * 3.6).astype(int)) <= {80, 100, 120, 140} and np.abs(gv).max() <= 25.0 and np.abs(cv).max() <= 1 / 300 + 1e-12
     assert np.all(lp[lo[:-1]] == 0) and np.all(gp[go[:-1]] == 0)
     assert 0.6 < (cv == 0).mean() < 0.8 and (grid['error'] == 0).mean() > 0.9
+
+
+def test_collocation_tableau_is_the_known_radau_and_gauss_scheme():
+    "mseetc.train.collocationTableau (host side of integrationMethod 'IRK', reference train.py:310) against the textbook coefficients."
+    from mseetc.train import collocationTableau, integratorSetup, OptionsIRK, OptionsCVODES, OptionsRK
+    A, w, c = collocationTableau(2, 'radau')                      # Radau IIA, order 3
+    assert np.allclose(c, [1 / 3, 1]) and np.allclose(w, [3 / 4, 1 / 4]) and np.allclose(A, [[5 / 12, -1 / 12], [3 / 4, 1 / 4]], atol=1e-14)
+    A, w, c = collocationTableau(2, 'legendre')                   # Gauss, order 4
+    r = np.sqrt(3) / 6
+    assert np.allclose(c, [0.5 - r, 0.5 + r]) and np.allclose(w, [0.5, 0.5]) and np.allclose(A, [[0.25, 0.25 - r], [0.25 + r, 0.25]], atol=1e-14)
+    A, w, c = collocationTableau(1, 'radau')                      # implicit Euler
+    assert np.allclose(A, [[1.0]]) and np.allclose(w, [1.0]) and np.allclose(c, [1.0])
+    for d in range(1, 10):
+        for m in ('radau', 'legendre'):
+            A, w, c = collocationTableau(d, m)
+            assert abs(w.sum() - 1) < 1e-12 and np.allclose(A.sum(axis=1), c, atol=1e-11)          # consistency conditions
+            order = 2 * d - 1 if m == 'radau' else 2 * d                                          # quadrature order of the points
+            for q in range(1, order):
+                assert abs(w @ c ** q - 1 / (q + 1)) < 1e-10, (d, m, q)
+    with pytest.raises(ValueError, match='Unknown collocation method'):
+        collocationTableau(2, 'lobatto')
+    assert integratorSetup('RK', OptionsRK({'numSteps': 3, 'numApproxSteps': 2})) == (3, 2, None)
+    ns, na, tab = integratorSetup('IRK', OptionsIRK({'order': 3, 'maxIter': 7}))
+    assert (ns, na, tab['maxIter'], tab['A'].shape) == (1, 0, 7, (3, 3))
+    ns, na, tab = integratorSetup('CVODES', OptionsCVODES({}))
+    assert na == 0 and tab['A'].shape == (4, 4)                   # reference train.py:315: numApproxSteps = 0 with CVODES

@@ -42,6 +42,45 @@ def test_interval_sensitivities_match_sympy(lib):
             assert np.max(np.abs(out[6 + i] - ref_phi[i]) / scale) < 1e-9, (numSteps, numApprox, 'phi', i)
 
 
+def test_collocation_interval_sensitivities_match_oracle(lib):
+    """Collocation steps (integrationMethod 'IRK'): Newton passes in jet arithmetic on the Runge-Kutta form (device code) vs autograd
+    through the unrolled Newton iterations on CasADi's collocation form (oracle), values and both derivative orders."""
+    from oracle import irk
+    rng = np.random.default_rng(5)
+    n = 64
+    b0 = rng.uniform(4.0, 1600.0, n); F = rng.uniform(-0.6, 0.5, n); ds = rng.uniform(0.05, 400.0, n)
+    F = np.maximum(F, (6.0 - b0) / (2 * ds) + 0.3)
+    c0 = rng.uniform(-0.2, 0.2, n)
+    sr = (1.41244e-2, 1.78932e-4, 3.12696e-5)
+    inp = np.ascontiguousarray(np.stack([b0, F, ds, c0, np.full(n, sr[0]), np.full(n, sr[1]), np.full(n, sr[2])]))
+    for order, scheme, numSteps, numApprox in ((2, 'radau', 1, 0), (1, 'radau', 2, 0), (3, 'legendre', 1, 1), (4, 'legendre', 2, 0), (9, 'radau', 1, 2)):
+        A, w = harness.product_tableau(order, scheme)
+        lib.hostsim_set_integrator(order, A.ctypes.data, w.ctypes.data, 12)
+        out = np.zeros((12, n))
+        lib.hostsim_eval_interval_irk(n, numSteps, numApprox, inp.ctypes.data, out.ctypes.data)
+        (tau, gt, ht), (phi, gp, hp) = irk.shoot(b0, F, ds, c0, sr, numSteps, numApprox, order, scheme)
+        ref = [tau] + gt + ht + [phi] + gp + hp
+        for i in range(12):
+            scale = np.maximum(1e-10, np.abs(ref[i]))
+            assert np.max(np.abs(out[i] - ref[i]) / scale) < 2e-8, (order, scheme, numSteps, numApprox, i)
+    lib.hostsim_set_integrator(0, None, None, 1)
+    # a high-order tableau reproduces the exact flow (what the 'CVODES' method is served by): against DOP853 at 1e-13
+    from scipy.integrate import solve_ivp
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'ms-eetc_b200'))
+    from mseetc.train import CVODES_EQUIVALENT as Q
+    A, w = harness.product_tableau(Q['order'], Q['collMethod'])
+    lib.hostsim_set_integrator(Q['order'], A.ctypes.data, w.ctypes.data, Q['maxIter'])
+    out = np.zeros((12, n))
+    lib.hostsim_eval_interval_irk(n, Q['numSteps'], Q['numApproxSteps'], inp.ctypes.data, out.ctypes.data)
+    lib.hostsim_set_integrator(0, None, None, 1)
+    for i in range(0, n, 4):
+        rhs = lambda s_, x: [ds[i] / np.sqrt(x[1]), 2 * ds[i] * (F[i] - (sr[0] + sr[1] * np.sqrt(x[1]) + sr[2] * x[1]) - c0[i])]
+        sol = solve_ivp(rhs, [0, 1], [0.0, b0[i]], rtol=1e-13, atol=1e-13, method='DOP853')
+        assert abs(out[0, i] - sol.y[0, -1]) <= 1e-8 * abs(sol.y[0, -1]), i          # two orders inside CVODES's default relTol 1e-6
+        assert abs(out[6, i] - sol.y[1, -1]) <= 1e-8 * abs(sol.y[1, -1]), i
+
+
 CASES = [
     ('config1 flat energy', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict()),
     ('swiss energy', lambda: virm6(), SWISS_JSON, None, 300, 1242.0, True, 1.0, 1.0, dict()),
@@ -54,6 +93,11 @@ CASES = [
     ('rk4 on both states', lambda: virm6(), FLAT_JSON, None, 300, 1541.0, True, 1.0, 1.0, dict(numApproxSteps=0)),
     ('two rk steps on both states', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numSteps=2, numApproxSteps=0)),
     ('two time sub-points', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numSteps=1, numApproxSteps=2)),
+    # integrationMethod 'IRK' (train.py:303-310): Radau IIA with two points on (t, b) -- the defaults of OptionsIRK -- and three
+    # Gauss-Legendre points, two steps, time from the average-speed rule
+    ('irk radau 2 on both states', lambda: virm6(), FLAT_JSON, None, 200, 1541.0, True, 1.0, 1.0, dict(numApproxSteps=0, irk=(2, 'radau'))),
+    ('irk legendre 3, two steps, time approximation', lambda: virm6(), SWISS_JSON, None, 300, 1242.0, True, 1.0, 1.0,
+     dict(numSteps=2, numApproxSteps=1, irk=(3, 'legendre'))),
 ]
 
 
