@@ -118,7 +118,9 @@ MS_HD double init_t(const Ctx& c, int j, int s, int N) {
 #define MS_TMIN_MARGIN 1e-6
 // Both per-instance set-up routines below walk the track sequentially (one thread per instance).  Their loops work on chunks
 // of MS_PCH intervals -- all loads of a chunk are issued before the first dependent operation and the results are stored after
-// the last one -- so a pass costs one memory latency per chunk instead of one per interval.
+// the last one -- so a pass costs one memory latency per chunk instead of one per interval.  Square roots and reciprocals are the
+// short hardware-approximation + Newton sequences of jet.cuh (1-2 ulp): these are dependent chains, one link per interval, and the
+// values only shape the starting point and the 1 % screening test.
 #define MS_PCH 8
 struct TrainLimits {
     double sr0, sr1, sr2, felU, felL, fpbL, pUp, pLo, aLo, aUp, b0, bN, bmin;
@@ -153,9 +155,9 @@ MS_HD double speed_envelope(const Ctx& c, int s, int N, const TrainLimits& q, do
 #pragma unroll
         for (int i = 0; i < MS_PCH; ++i) {
             if (k0 + i < N) {
-                const double v = sqrt(b);
+                const double v = fsqrt(b);
                 const double r = q.sr0 + q.sr1 * v + q.sr2 * b + c0[i];
-                const double a = fmin(frac * (fmin(q.felU, q.pUp * rcp(fmax(v, vfloor))) - r), frac * q.aUp);
+                const double a = fmin(frac * (fmin(q.felU, q.pUp * rcp_slack(fmax(v, vfloor))) - r), frac * q.aUp);
                 b = fmax(q.bmin, fmin(lim[i], b + 2.0 * ds[i] * a));
                 out[i] = b;
             }
@@ -165,7 +167,7 @@ MS_HD double speed_envelope(const Ctx& c, int s, int N, const TrainLimits& q, do
     }
     b = q.bN;
     c.W(dst, N, s) = q.bN;
-    double vn = sqrt(q.bN), tt = 0.0, bmx = 0.0;
+    double vn = fsqrt(q.bN), tt = 0.0, bmx = 0.0;
     for (int k1 = N - 1; k1 >= 0; k1 -= MS_PCH) {
         double ds[MS_PCH], c0[MS_PCH], fw[MS_PCH], out[MS_PCH];
 #pragma unroll
@@ -181,16 +183,16 @@ MS_HD double speed_envelope(const Ctx& c, int s, int N, const TrainLimits& q, do
                 if (k >= 1) {
                     bk = b;
                     for (int it = 0; it < brakeIters; ++it) {   // the braking deceleration depends on the speed at the start of the interval
-                        const double v = sqrt(bk);
+                        const double v = fsqrt(bk);
                         const double r = q.sr0 + q.sr1 * v + q.sr2 * bk + c0[i];
-                        const double a = fmax(frac * (fmax(q.felL, q.pLo * rcp(fmax(v, vfloor))) + q.fpbL - r), frac * q.aLo);      // negative
+                        const double a = fmax(frac * (fmax(q.felL, q.pLo * rcp_slack(fmax(v, vfloor))) + q.fpbL - r), frac * q.aLo);      // negative
                         bk = b - 2.0 * ds[i] * a;
                     }
                     bk = fmin(fw[i], bk);
                     bmx = fmax(bmx, bk);
                 }
-                const double vk = sqrt(bk);
-                tt += 2.0 * ds[i] * rcp(vk + vn);
+                const double vk = fsqrt(bk);
+                tt += 2.0 * ds[i] * rcp_slack(vk + vn);
                 b = bk; vn = vk;
                 out[i] = bk;
             }
@@ -244,7 +246,7 @@ MS_HD void inst_profile(const Ctx& c, int s, double* smv = nullptr, double* smd 
                 if (k0 + i <= N) { bb[i] = c.W(P + IT_B, k0 + i, s); dd[i] = (copyDs && k0 + i < N) ? c.W(WS_TRK + TRK_DS, k0 + i, s) : 0.0; }
 #pragma unroll
             for (int i = 0; i < MS_PCH; ++i)
-                if (k0 + i <= N) { smv[(size_t)(k0 + i) * sms] = sqrt(bb[i]); if (copyDs && k0 + i < N) smd[(size_t)(k0 + i) * sms] = dd[i]; }
+                if (k0 + i <= N) { smv[(size_t)(k0 + i) * sms] = fsqrt(bb[i]); if (copyDs && k0 + i < N) smd[(size_t)(k0 + i) * sms] = dd[i]; }
         }
         auto trip = [&](double vcap) {            // interior nodes capped, boundary speeds kept
             double tt = 0.0, vp = smv[0];
@@ -252,12 +254,12 @@ MS_HD void inst_profile(const Ctx& c, int s, double* smv = nullptr, double* smd 
             for (int k = 0; k < N; ++k) {
                 const double vk = smv[(size_t)(k + 1) * sms];
                 const double vn = (k + 1 < N) ? fmin(vk, vcap) : vk;
-                tt += 2.0 * smd[(size_t)k * sms] * rcp(vp + vn);
+                tt += 2.0 * smd[(size_t)k * sms] * rcp_slack(vp + vn);
                 vp = vn;
             }
             return tt;
         };
-        double lo = sqrt(q.bmin), hi = sqrt(bmaxAll);
+        double lo = fsqrt(q.bmin), hi = fsqrt(bmaxAll);
         double fhi = tFast - target;              // fastest profile: negative, there is slack in the timetable
         if (hi > lo) {
             double flo = trip(lo) - target;       // slowest cap: positive unless even crawling is too fast
@@ -279,7 +281,7 @@ MS_HD void inst_profile(const Ctx& c, int s, double* smv = nullptr, double* smd 
     // ---- times, forces and epigraph variable of the profile
     double t = c.P(P_T0, s);
     c.W(P + IT_T, 0, s) = t;
-    double b = q.b0, vb = sqrt(q.b0);
+    double b = q.b0, vb = fsqrt(q.b0);
     for (int k0 = 0; k0 < N; k0 += MS_PCH) {
         double bnx[MS_PCH], ds[MS_PCH], c0[MS_PCH], ot[MS_PCH], of[MS_PCH], op[MS_PCH];
 #pragma unroll
@@ -293,12 +295,12 @@ MS_HD void inst_profile(const Ctx& c, int s, double* smv = nullptr, double* smd 
             if (k < N) {
                 const double bn = (k + 1 < N) ? fmin(bnx[i], cap) : bnx[i];
                 bnx[i] = bn;
-                const double vbn = sqrt(bn);
-                t += 2.0 * ds[i] * rcp(vb + vbn);
+                const double vbn = fsqrt(bn);
+                t += 2.0 * ds[i] * rcp_slack(vb + vbn);
                 ot[i] = t;
                 const double bm = 0.5 * (b + bn);
-                const double F = (bn - b) * rcp(2.0 * ds[i]) + q.sr0 + q.sr1 * sqrt(bm) + q.sr2 * bm + c0[i];
-                const double ivmx = 0.97 * rcp(fmax(fmax(vb, vbn), 1.0));
+                const double F = (bn - b) * rcp_slack(2.0 * ds[i]) + q.sr0 + q.sr1 * fsqrt(bm) + q.sr2 * bm + c0[i];
+                const double ivmx = 0.97 * rcp_slack(fmax(fmax(vb, vbn), 1.0));
                 const double fel = fmin(fmax(F, fmax(0.97 * q.felL, q.pLo * ivmx)), fmin(0.97 * q.felU, q.pUp * ivmx));
                 of[i] = fel;
                 op[i] = g.withPn ? fmin(0.0, fmax(0.97 * q.fpbL, F - fel)) : 0.0;
