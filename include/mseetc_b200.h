@@ -224,6 +224,12 @@ int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx_steps,
  * stages = 0 returns to the explicit steps. */
 int mseetc_set_integrator(mseetc_handle h, int32_t stages, const double* A, const double* w, int32_t max_newton);
 
+/* integrateLosses = True of the reference (OptionsCasadiSolver, mseetc/ocp.py:28,118-120,231-241): the two epigraph rows of every
+ * interval bound s_k from below by the traction / regenerative-braking loss ENERGY of the interval, integrated in the time domain
+ * (TrainIntegrator.calcLosses, train.py:367-413), and the objective becomes sum(ds_k Fel_k + s_k).  Energy-optimal mode with the
+ * constant-efficiency or the spline loss model, explicit RK integrator.  See DESIGN.md section 2 for the formulation. */
+int mseetc_set_integrate_losses(mseetc_handle h, int on);
+
 /* mseetc_eval_interval with collocation steps (same planes in and out; A, w: host arrays as above). */
 int mseetc_eval_interval_irk(int32_t n, int32_t num_steps, int32_t num_approx_steps, int32_t stages, const double* A,
                              const double* w, int32_t max_newton, const double* in_dev, double* out_dev, void* cuda_stream);

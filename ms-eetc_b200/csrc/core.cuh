@@ -330,7 +330,7 @@ MS_HD LossPar load_losspar(const Ctx& c, int s) {
 }
 
 // values of the inequality rows at a point                                  (ocp.py:189,199,225-226)
-template <bool DYN>
+template <bool DYN, bool INTL = false>
 MS_HD void ineq_values(const Ctx& c, int s, double fel, double fpb, double sl, double b0, double b1,
                        const IntervalCoef& q, double* d) {
     // every operation individually rounded (see mul_rn): cell_eval and cell_step both evaluate these rows
@@ -338,7 +338,9 @@ MS_HD void ineq_values(const Ctx& c, int s, double fel, double fpb, double sl, d
     d[R_P0] = mul_rn(fel, r0);
     d[R_P1] = mul_rn(fel, fsqrt(b1));
     d[R_ACC] = sub_rn(sub_rn(add_rn(fel, fpb), fma(q.sr1, r0, mul_rn(q.sr2, b0))), add_rn(q.sr0, q.c0));
-    if (DYN) {
+    if (INTL) {
+        d[R_LTR] = 0.0; d[R_LRG] = 0.0;      // integrated losses: filled in by the caller (loss_energy_rows)
+    } else if (DYN) {
         LossRow tr, rg;
         loss_rows_dynamic(c.lm, load_losspar(c, s), fel, b0, b1, tr, rg);
         d[R_LTR] = sl - tr.v;
@@ -346,6 +348,75 @@ MS_HD void ineq_values(const Ctx& c, int s, double fel, double fpb, double sl, d
     } else {
         d[R_LTR] = fma(-c.P(P_CT, s), fel, sl);
         d[R_LRG] = fma(c.P(P_CR, s), fel, sl);
+    }
+}
+
+// ---- integrateLosses = True                                            (ocp.py:231-241, train.py:367-413)
+// The reference's rows are  s_k - E(sqrt(b_k), t_{k+1} - t_k, Fel_k, Fpb_k) >= 0  with E = (eTr, eBr) at the end of the time-domain
+// integration of  dv/dt = a(v^2, F),  d eTr/dt = PLtr(Fel, v),  d eBr/dt = PLrgb(Fel, v)  over the interval's duration from v =
+// sqrt(b_k), eTr = eBr = 0 (specific quantities; CVODES with relTol 1e-6 in the reference).  Here the duration is taken from the
+// shooting function of the same interval, t_{k+1} - t_k = tau(b_k, Fel_k + Fpb_k): the shooting row t_{k+1} - t_k - tau = 0 is an
+// equality constraint of the NLP, so feasible set, objective and minimisers are those of the reference's formulation, while the
+// rows stay functions of (b_k, Fel_k, Fpb_k, s_k) -- the variables the stage QP of the sweeps carries.
+// The integration runs over the normalised time theta in [0,1] with MS_INTL_STEPS classic RK4 steps and second-order jets in
+// (b_k, Fel_k, Fpb_k); MS_INTL_STEPS_KINK steps in an interval in which the speed crosses a kink of the spline loss map (the ends of
+// its speed range and the turning speed Pmax/Fmax, efficiency.py:10-12,40): the integrand is only continuous there, and the error of
+// 4 steps (6e-5 of the total losses on a 60-interval grid) would exceed the tolerance of the reference's CVODES integration.
+#define MS_INTL_STEPS 4
+#ifndef MS_INTL_CLAMP
+#define MS_INTL_CLAMP true
+#endif
+#ifndef MS_INTL_STEPS_KINK
+#define MS_INTL_STEPS_KINK 32
+#endif
+MS_HD void power_loss_jets(const Ctx& c, int s, const LossPar& lp, bool pos, const Jet3& FEL, const Jet3& v, Jet3& ptr, Jet3& prg) {
+    if (c.cfg.lossKind == 2) {
+        const Jet2 vv = jvar0(v.v), ff = jvar1(FEL.v);       // the map returns PL/v with partials w.r.t. (v, specific force)
+        // The motor map is zero outside its grid (efficiency.py:40-51,137); its upper load edge is the power hyperbola F v = Pmax, where
+        // the power rows are active at the nodes.  The last stage of the integration reproduces the node speed only to the integration
+        // error and may land 1e-6 beyond the edge: the load is clamped to the edge there (an adaptive integrator like the reference's
+        // CVODES loses a vanishing sliver at that point, a fixed-step stage would lose a sixth of a step).
+        const Jet2 qt = pos ? loss_full(c.lm, lp, vv, ff, true, MS_INTL_CLAMP) : loss_tangent(c.lm, lp, vv, ff, true);
+        const Jet2 qr = pos ? loss_tangent(c.lm, lp, vv, ff, false) : loss_full(c.lm, lp, vv, ff, false, MS_INTL_CLAMP);
+        ptr = j3compose(qt * vv, v, FEL);
+        prg = j3compose(qr * vv, v, FEL);
+    } else if (c.cfg.lossKind == 1) {                        // constant efficiencies: PLtr = cT f v, PLrgb = -cR f v
+        const Jet3 fv = FEL * v;
+        ptr = c.P(P_CT, s) * fv;
+        prg = (-c.P(P_CR, s)) * fv;
+    } else { ptr = j3const(0.0); prg = j3const(0.0); }
+}
+MS_HD void loss_energy_rows(const Ctx& c, int s, const IntervalCoef& q, double b0, double b1, double fel, double fpb, const Jet2& tau, Jet3& etr, Jet3& erg) {
+    const Jet3 B = j3var(b0, 0), FEL = j3var(fel, 1);
+    const Jet3 F = c.cfg.withPn ? FEL + j3var(fpb, 2) : FEL;
+    const Jet3 e = j3compose(tau, B, F);                      // duration of the interval as a function of (b_k, Fel_k, Fpb_k)
+    LossPar lp;
+    if (c.cfg.lossKind == 2) lp = load_losspar(c, s);
+    const bool pos = fel >= 0.0;
+    Jet3 v = j3sqrt(B);
+    etr = j3const(0.0); erg = j3const(0.0);
+    int nsteps = MS_INTL_STEPS;
+    if (c.cfg.lossKind == 2) {        // does the speed cross a kink of the map between the nodes (with a 3 % margin)?  (v is monotone in t)
+        const double va = fmin(v.v, sqrt(b1)) * 0.97, vb = fmax(v.v, sqrt(b1)) * 1.03;
+        const double kinks[3] = {c.lm.tv[0], lp.pMax / lp.fMax, c.lm.tv[c.lm.nv + 3]};
+        for (int i = 0; i < 3; ++i) if (va < kinks[i] && kinks[i] < vb) nsteps = MS_INTL_STEPS_KINK;
+    }
+    const double h = 1.0 / nsteps, r0 = q.sr0 + q.c0;
+    auto rhs = [&](const Jet3& vv, Jet3& dv, Jet3& dtr, Jet3& drg) {
+        dv = e * (F - (q.sr1 * vv + q.sr2 * (vv * vv)) + (-r0));      // train.py:377: acceleration with b -> v^2
+        Jet3 pt, pr;
+        power_loss_jets(c, s, lp, pos, FEL, vv, pt, pr);
+        dtr = e * pt; drg = e * pr;
+    };
+    for (int st = 0; st < nsteps; ++st) {
+        Jet3 k1v, k1t, k1r, k2v, k2t, k2r, k3v, k3t, k3r, k4v, k4t, k4r;
+        rhs(v, k1v, k1t, k1r);
+        rhs(v + (0.5 * h) * k1v, k2v, k2t, k2r);
+        rhs(v + (0.5 * h) * k2v, k3v, k3t, k3r);
+        rhs(v + h * k3v, k4v, k4t, k4r);
+        v = v + (h / 6.0) * (k1v + 2.0 * k2v + 2.0 * k3v + k4v);
+        etr = etr + (h / 6.0) * (k1t + 2.0 * k2t + 2.0 * k3t + k4t);
+        erg = erg + (h / 6.0) * (k1r + 2.0 * k2r + 2.0 * k3r + k4r);
     }
 }
 
@@ -364,7 +435,7 @@ MS_HD void row_bounds(const Bnd& B, int j, double& L, double& U, bool& hasU) {
 // ------------------------------------------------------------------------------------------------
 // initialisation: x0 pushed inside the bounds, slacks from d(x0), multipliers 1 / 0   (IPOPT sec. 3.6)
 // ------------------------------------------------------------------------------------------------
-template <bool DYN>
+template <bool DYN, bool INTL = false>
 MS_HD void cell_init(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     const int N = c.I(SI_N_INT, s);
@@ -381,7 +452,9 @@ MS_HD void cell_init(const Ctx& c, int k, int s) {
     if (k == N) return;
     double fel = push2(g.initMode ? c.W(WS_IT1 + IT_FEL, k, s) : 0.5, B.felL, B.felU);
     double fpb = g.withPn ? push2(g.initMode ? c.W(WS_IT1 + IT_FPB, k, s) : -0.1, B.fpbL, B.fpbU) : 0.0;
-    double sl = push1(g.initMode ? c.W(WS_IT1 + IT_SL, k, s) : 1.0, B.slL);
+    IntervalCoef q = load_coef(c, k, s);
+    // (integrateLosses: s_k is the loss energy of the interval, not a force -- the profile's guess is scaled by the interval length)
+    double sl = push1(g.initMode ? c.W(WS_IT1 + IT_SL, k, s) * (INTL ? q.ds : 1.0) : 1.0, B.slL);
     c.W(it + IT_FEL, k, s) = fel;
     c.W(it + IT_FPB, k, s) = fpb;
     c.W(it + IT_SL, k, s) = sl;
@@ -389,9 +462,15 @@ MS_HD void cell_init(const Ctx& c, int k, int s) {
     c.W(it + IT_Z + Z_FEL_U, k, s) = 1.0;
     if (g.withPn) { c.W(it + IT_Z + Z_FPB_L, k, s) = 1.0; c.W(it + IT_Z + Z_FPB_U, k, s) = 1.0; }
     c.W(it + IT_Z + Z_SL_L, k, s) = 1.0;
-    IntervalCoef q = load_coef(c, k, s);
     double d[NROW];
-    ineq_values<DYN>(c, s, fel, fpb, sl, b, init_b(c, k + 1, s, N), q, d);
+    ineq_values<DYN, INTL>(c, s, fel, fpb, sl, b, init_b(c, k + 1, s, N), q, d);
+    if (INTL && g.energy) {
+        Jet2 tau, phi;
+        shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
+        Jet3 etr, erg;
+        loss_energy_rows(c, s, q, b, init_b(c, k + 1, s, N), fel, fpb, tau, etr, erg);
+        d[R_LTR] = sl - etr.v; d[R_LRG] = sl - erg.v;
+    }
     for (int j = 0; j < NROW; ++j) {
         if (!row_on(g, j)) continue;
         double L, U; bool hasU;
@@ -602,7 +681,7 @@ enum { V_T = 0, V_B, V_F, V_FEL, V_FPB, V_SL, V_BN, NV7 };
 // TRIAL = false: at the current iterate (first iteration).  TRIAL = true: at the trial point x + alpha dx, which is formed here
 // and written to the other iterate buffer (see form_trial_cell); inst_decide then reads theta, the objective and the barrier sums
 // from the same partial planes that inst_kkt uses when the point is accepted.
-template <bool DYN, bool TRIAL, bool IRK = false>
+template <bool DYN, bool TRIAL, bool IRK = false, bool INTL = false>
 MS_HD void cell_eval(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != (TRIAL ? PH_TRIAL : PH_EVAL)) return;
@@ -718,7 +797,7 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     double d[NROW], J[NROW][NV7];
     #pragma unroll
     for (int j = 0; j < NROW; ++j) for (int i = 0; i < NV7; ++i) J[j][i] = 0.0;
-    ineq_values<false>(c, s, fel, fpb, sl, b, b1, q, d);
+    ineq_values<false, INTL>(c, s, fel, fpb, sl, b, b1, q, d);
     double ydv[NROW];
     #pragma unroll
     for (int j = 0; j < NROW; ++j) ydv[j] = CI[IT_YD + j];
@@ -727,7 +806,22 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     J[R_ACC][V_B] = a_b; J[R_ACC][V_FEL] = 1.0; J[R_ACC][V_FPB] = g.withPn ? 1.0 : 0.0;
     J[R_LTR][V_FEL] = -c.P(P_CT, s); J[R_LTR][V_SL] = 1.0;
     J[R_LRG][V_FEL] = c.P(P_CR, s); J[R_LRG][V_SL] = 1.0;
-    if (DYN && g.energy) {
+    if (INTL && g.energy) {
+        // integrateLosses: rows s - E(b_k, Fel_k, Fpb_k) with E the loss energies integrated over the interval in the time domain
+        Jet3 en[2];
+        loss_energy_rows(c, s, q, b, b1, fel, fpb, tau, en[0], en[1]);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int row = (a == 0) ? R_LTR : R_LRG;
+            d[row] = sl - en[a].v;
+            J[row][V_B] = -en[a].g[0]; J[row][V_FEL] = -en[a].g[1]; J[row][V_FPB] = g.withPn ? -en[a].g[2] : 0.0; J[row][V_BN] = 0.0;
+            const double y = ydv[row];
+            H[sidx(V_B, V_B)] -= y * en[a].h[0];
+            H[sidx(V_B, V_FEL)] -= y * en[a].h[1];
+            H[sidx(V_FEL, V_FEL)] -= y * en[a].h[3];
+            if (g.withPn) { H[sidx(V_B, V_FPB)] -= y * en[a].h[2]; H[sidx(V_FEL, V_FPB)] -= y * en[a].h[4]; H[sidx(V_FPB, V_FPB)] -= y * en[a].h[5]; }
+        }
+    } else if (DYN && g.energy) {
         // loss map of efficiency.py: rows s - G(Fel, b_k, b_{k+1}) with full first and second derivatives
         LossRow lr[2];
         loss_rows_dynamic(c.lm, load_losspar(c, s), fel, b, b1, lr[0], lr[1]);
@@ -756,10 +850,10 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     // ---- objective                                                           (ocp.py:146-154,223,243-245)
     double fo = 0.0, gf_fel = 0.0, gf_fpb = 0.0, gf_sl = 0.0;
     if (g.energy) {
-        const double w2 = 2e-3 * iscale, dsc = q.ds * iscale;
-        fo = dsc * (fel + sl);
-        gf_fel = dsc; gf_sl = dsc;
-        g0[V_FEL] += dsc; g0[V_SL] += dsc;
+        const double w2 = 2e-3 * iscale, dsc = q.ds * iscale, ssc = INTL ? iscale : dsc;      // ocp.py:223 / :235
+        fo = dsc * fel + ssc * sl;
+        gf_fel = dsc; gf_sl = ssc;
+        g0[V_FEL] += dsc; g0[V_SL] += ssc;
         if (k >= 1) {
             double df = fel - pFel;
             fo += 1e-3 * df * df * iscale;
@@ -900,10 +994,10 @@ MS_HD void cell_eval(const Ctx& c, int k, int s) {
     c.W(WS_QP + QP_J_ACC_B, k, s) = J[R_ACC][V_B];
     c.W(WS_QP + QP_J_LTR_FEL, k, s) = J[R_LTR][V_FEL];
     c.W(WS_QP + QP_J_LTR_B, k, s) = J[R_LTR][V_B];
-    c.W(WS_QP + QP_J_LTR_BN, k, s) = J[R_LTR][V_BN];
+    c.W(WS_QP + QP_J_LTR_BN, k, s) = INTL ? J[R_LTR][V_FPB] : J[R_LTR][V_BN];      // integrated losses: the rows depend on Fpb_k, not on b_{k+1}
     c.W(WS_QP + QP_J_LRG_FEL, k, s) = J[R_LRG][V_FEL];
     c.W(WS_QP + QP_J_LRG_B, k, s) = J[R_LRG][V_B];
-    c.W(WS_QP + QP_J_LRG_BN, k, s) = J[R_LRG][V_BN];
+    c.W(WS_QP + QP_J_LRG_BN, k, s) = INTL ? J[R_LRG][V_FPB] : J[R_LRG][V_BN];
     }
     c.W(WS_PART + PC_TH, k, s) = th;
     c.W(WS_PART + PC_F, k, s) = fo;

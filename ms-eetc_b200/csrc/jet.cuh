@@ -137,4 +137,67 @@ MS_HD Jet2 jrecip(const Jet2& a) {
     return jchain(a, r, -r * r, 2.0 * r * r * r);
 }
 
+// ---- second-order jets in three variables (value, gradient, symmetric Hessian 00 01 02 11 12 22): used by the time-domain loss
+// integration of integrateLosses=True, whose rows depend on (b_k, Fel_k, Fpb_k)
+struct Jet3 {
+    double v, g[3], h[6];
+};
+MS_HD int j3idx(int i, int j) { return (i <= j) ? (i == 0 ? j : (i == 1 ? 2 + j : 5)) : j3idx(j, i); }
+MS_HD Jet3 j3const(double c) { return Jet3{c, {0, 0, 0}, {0, 0, 0, 0, 0, 0}}; }
+MS_HD Jet3 j3var(double x, int i) { Jet3 r = j3const(x); r.g[i] = 1.0; return r; }
+MS_HD Jet3 operator+(const Jet3& a, const Jet3& b) {
+    Jet3 r; r.v = a.v + b.v;
+    for (int i = 0; i < 3; ++i) r.g[i] = a.g[i] + b.g[i];
+    for (int i = 0; i < 6; ++i) r.h[i] = a.h[i] + b.h[i];
+    return r;
+}
+MS_HD Jet3 operator-(const Jet3& a, const Jet3& b) {
+    Jet3 r; r.v = a.v - b.v;
+    for (int i = 0; i < 3; ++i) r.g[i] = a.g[i] - b.g[i];
+    for (int i = 0; i < 6; ++i) r.h[i] = a.h[i] - b.h[i];
+    return r;
+}
+MS_HD Jet3 operator*(double c, const Jet3& a) {
+    Jet3 r; r.v = c * a.v;
+    for (int i = 0; i < 3; ++i) r.g[i] = c * a.g[i];
+    for (int i = 0; i < 6; ++i) r.h[i] = c * a.h[i];
+    return r;
+}
+MS_HD Jet3 operator+(const Jet3& a, double c) { Jet3 r = a; r.v += c; return r; }
+MS_HD Jet3 operator*(const Jet3& a, const Jet3& b) {
+    Jet3 r; r.v = a.v * b.v;
+    for (int i = 0; i < 3; ++i) r.g[i] = a.g[i] * b.v + a.v * b.g[i];
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            const int q = j3idx(i, j);
+            r.h[q] = a.h[q] * b.v + a.g[i] * b.g[j] + a.g[j] * b.g[i] + a.v * b.h[q];
+        }
+    return r;
+}
+// f(a) for scalar f with derivatives f1, f2 at a.v
+MS_HD Jet3 j3chain(const Jet3& a, double f0, double f1, double f2) {
+    Jet3 r; r.v = f0;
+    for (int i = 0; i < 3; ++i) r.g[i] = f1 * a.g[i];
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) { const int q = j3idx(i, j); r.h[q] = f1 * a.h[q] + f2 * a.g[i] * a.g[j]; }
+    return r;
+}
+MS_HD Jet3 j3sqrt(const Jet3& a) {
+    double s, inv;
+    sqrt_inv(a.v, s, inv);
+    const double f1 = 0.5 * inv;
+    return j3chain(a, s, f1, -0.5 * f1 * inv * inv);
+}
+// S(u, w): composition of a two-variable jet S (value and partials up to second order w.r.t. its arguments) with jets u, w
+MS_HD Jet3 j3compose(const Jet2& S, const Jet3& u, const Jet3& w) {
+    Jet3 r; r.v = S.v;
+    for (int i = 0; i < 3; ++i) r.g[i] = S.g0 * u.g[i] + S.g1 * w.g[i];
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            const int q = j3idx(i, j);
+            r.h[q] = S.g0 * u.h[q] + S.g1 * w.h[q] + S.h00 * u.g[i] * u.g[j] + S.h01 * (u.g[i] * w.g[j] + u.g[j] * w.g[i]) + S.h11 * w.g[i] * w.g[j];
+        }
+    return r;
+}
+
 }  // namespace mseetc

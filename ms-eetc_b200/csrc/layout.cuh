@@ -113,6 +113,7 @@ struct Config {
     double tol, muInit;
     int stallIters;   // > 0: give up (status MAXITER) after that many iterations without a 10 % gain of the best KKT error
     int initMode;     // 0: initial guess of the reference (ocp.py:325-339); 1: dynamically consistent speed-envelope guess
+    int intLosses;    // 1: integrateLosses = True (ocp.py:231-241): epigraph rows on the loss energy integrated over the interval
 };
 
 struct IrkTab;     // model.cuh: Butcher tableau of the collocation integrator

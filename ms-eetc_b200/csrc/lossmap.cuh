@@ -107,7 +107,7 @@ struct LossPar {       // per-instance numbers of the map
 };
 
 // total losses / v as jets in (v, fs) on the side given by `traction`; full map (no tangent extension)
-MS_HD Jet2 loss_full(const LossMapDev& m, const LossPar& p, const Jet2& v, const Jet2& fs, bool traction) {
+MS_HD Jet2 loss_full(const LossMapDev& m, const LossPar& p, const Jet2& v, const Jet2& fs, bool traction, bool clampLoad = false) {
     const double vMin = m.tv[0], vMax = m.tv[m.nv + 3];
     Jet2 vc = v;
     if (v.v < vMin) vc = jconst(vMin);
@@ -115,7 +115,11 @@ MS_HD Jet2 loss_full(const LossMapDev& m, const LossPar& p, const Jet2& v, const
     const Jet2 fa = p.M * fs;                               // absolute force
     const Jet2 absf = traction ? fa : (-1.0) * fa;
     const double tp = p.pMax / p.fMax;
-    const Jet2 load = (vc.v <= tp) ? (100.0 / p.fMax) * absf : (100.0 / p.pMax) * (absf * vc);
+    Jet2 load = (vc.v <= tp) ? (100.0 / p.fMax) * absf : (100.0 / p.pMax) * (absf * vc);
+    // clampLoad (time-domain loss integration, see power_loss_jets in core.cuh): a stage point that overshoots the upper load edge
+    // of the grid -- the power hyperbola, where the NLP's power rows are active -- by the integration error is evaluated at the edge
+    // (overshoots up to 0.1 % only: further out the map is zero as in the reference)
+    if (clampLoad && load.v > m.tl[m.nl + 3] && load.v <= 1.001 * m.tl[m.nl + 3]) load = jconst(m.tl[m.nl + 3]);
     double D[3][3];
     const bool inside = spline_eval(m, load.v, vc.v, D);
     if (!inside || !(p.scale * D[0][0] > 0.0)) return jconst(0.0);      // efficiency.py:137

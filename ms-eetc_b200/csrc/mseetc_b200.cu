@@ -68,6 +68,11 @@ MS_CELL_KERNEL(k_cell_trial_eval_irk, 1, (cell_eval<false, true, true>(c, k, s))
 MS_CELL_KERNEL(k_cell_trial_eval_dyn_irk, 1, (cell_eval<true, true, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_eval_irk, 1, (cell_eval<false, false, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_eval_dyn_irk, 1, (cell_eval<true, false, true>(c, k, s)))
+// integrateLosses = True (ocp.py:231-241): loss energies integrated in the time domain inside the interval evaluation
+MS_CELL_KERNEL(k_cell_init_intl, 1, (cell_init<true, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_trial_eval_intl, 1, (cell_eval<true, true, false, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_eval_intl, 1, (cell_eval<true, false, false, true>(c, k, s)))
+MS_CELL_KERNEL(k_cell_step_intl, 2, (cell_step<true, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step<false>(c, k, s))
 MS_CELL_KERNEL(k_cell_step_dyn, MS_MINB_STEP, cell_step<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
@@ -383,6 +388,7 @@ struct mseetc_solver {
     double* lm_dev;                // knots + coefficients of the dynamic loss map (loss_kind 2)
     LossMapDev lm;
     IrkTab* irk_dev;               // Butcher tableau of the collocation integrator in device memory; null: explicit RK4
+    int int_losses;                // 1: integrateLosses = True (loss rows on integrated energies)
 };
 
 extern "C" {
@@ -419,6 +425,7 @@ int mseetc_create(const mseetc_problem* p, mseetc_handle* out) {
     h->fallback_why[0] = h->fallback_why[1] = h->fallback_why[2] = 0;
     h->lm_dev = nullptr;
     h->irk_dev = nullptr;
+    h->int_losses = 0;
     h->loop_graph = nullptr; h->loop_exec = nullptr; h->cap_stream = nullptr; h->cap_prio = 0;
     memset(h->loop_key, 0, sizeof h->loop_key);
     memset(&h->lm, 0, sizeof h->lm);
@@ -506,6 +513,13 @@ int mseetc_last_sweep_fallback_reasons(mseetc_handle h, int32_t* out3) {
     return 0;
 }
 
+int mseetc_set_integrate_losses(mseetc_handle h, int on) {
+    if (!h) return fail(-1, "mseetc_set_integrate_losses: null handle");
+    h->int_losses = on ? 1 : 0;
+    memset(h->loop_key, 0, sizeof h->loop_key);
+    return 0;
+}
+
 int mseetc_set_integrator(mseetc_handle h, int32_t stages, const double* A, const double* w, int32_t max_newton) {
     if (!h) return fail(-1, "mseetc_set_integrator: null handle");
     if (stages == 0) {                      // back to the explicit RK4 steps
@@ -589,6 +603,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     g.withPn = p.with_pn_brake; g.withPower = p.with_power_rows; g.energy = p.energy_optimal; g.lossKind = p.loss_kind;
     g.numSteps = p.num_steps; g.numApprox = p.num_approx_steps; g.maxIter = p.max_iterations;
     g.tol = p.tol; g.muInit = p.mu_init; g.initMode = p.initial_guess; g.stallIters = p.stall_iterations;
+    g.intLosses = (h->int_losses && p.energy_optimal) ? 1 : 0;
     WsPlan plan = plan_workspace(g.S, g.NK);
     if (ws_bytes < plan.total) return fail(-4, "mseetc_solve_batch: workspace too small (see mseetc_workspace_bytes)");
     if (((uintptr_t)workspace & 255) != 0) return fail(-5, "mseetc_solve_batch: workspace must be 256-byte aligned");
@@ -607,6 +622,8 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.plan = (int*)(base + plan.off_plan);
     c.irk = h->irk_dev;
     const bool dyn = (p.loss_kind == 2 && p.energy_optimal);
+    const bool intl = g.intLosses != 0;
+    if (intl && c.irk) return fail(-9, "mseetc_solve_batch: integrated losses are available with the explicit RK integrator only");
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
     const size_t cellThreads = (size_t)g.NK * g.S;
@@ -720,13 +737,15 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_MISC); k_inst_profile<<<igrid, 2 * ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
     }
     begin(CLS_MISC);
-    if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
+    if (intl) k_cell_init_intl<<<cgrid, 128, 0, st>>>(c, io);
+    else if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
     end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
     // ---- starting point: evaluation, convergence test, barrier parameter
     begin(CLS_EVAL);
-    if (c.irk) { if (dyn) k_cell_eval_dyn_irk<<<gridIrk, 128, 0, st>>>(c, io); else k_cell_eval_irk<<<gridIrk, 128, 0, st>>>(c, io); }
+    if (intl) k_cell_eval_intl<<<gridIrk, 128, 0, st>>>(c, io);
+    else if (c.irk) { if (dyn) k_cell_eval_dyn_irk<<<gridIrk, 128, 0, st>>>(c, io); else k_cell_eval_irk<<<gridIrk, 128, 0, st>>>(c, io); }
     else if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
     end(CLS_EVAL);
     begin(CLS_KKT); k_inst_kkt<false><<<rgrid * RED_CL, 32 * RED_WB, 0, st>>>(c); end(CLS_KKT);
@@ -747,13 +766,15 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         else stepKernel<<<igrid, ib, ringBytes, s0>>>(c);
         if (prof) end(CLS_STEP);
         if (prof) begin(CLS_CSTEP);
-        if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, s0>>>(c, io); else k_cell_step<<<gridStep, 128, 0, s0>>>(c, io);
+        if (intl) k_cell_step_intl<<<pgrid(2), 128, 0, s0>>>(c, io);
+        else if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, s0>>>(c, io); else k_cell_step<<<gridStep, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_CSTEP);
         if (prof) begin(CLS_ALPHA);
         k_inst_alpha<<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c, mirror);
         if (prof) end(CLS_ALPHA);
         if (prof) begin(CLS_TRIAL);
-        if (c.irk) { if (dyn) k_cell_trial_eval_dyn_irk<<<gridIrk, 128, 0, s0>>>(c, io); else k_cell_trial_eval_irk<<<gridIrk, 128, 0, s0>>>(c, io); }
+        if (intl) k_cell_trial_eval_intl<<<gridIrk, 128, 0, s0>>>(c, io);
+        else if (c.irk) { if (dyn) k_cell_trial_eval_dyn_irk<<<gridIrk, 128, 0, s0>>>(c, io); else k_cell_trial_eval_irk<<<gridIrk, 128, 0, s0>>>(c, io); }
         else if (dyn) k_cell_trial_eval_dyn<<<gridTrial, 128, 0, s0>>>(c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_TRIAL);
         if (prof) begin(CLS_DECIDE);

@@ -725,7 +725,7 @@ MS_HD void ftb_bound(Ftb& f, double tau, double mu, double z, double slack, doub
 // of the iterate this kernel loads anyway, so they are recomputed here -- bit for bit, see mul_rn -- instead of being stored
 // by cell_eval and read back (16 planes less traffic in each of the two kernels); with the spline loss map they come from
 // the stage-QP record.
-template <bool DYN>
+template <bool DYN, bool INTL = false>
 MS_HD void cell_step(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || c.I(SI_PHASE, s) != PH_STEPPED) return;
@@ -842,7 +842,7 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
         ftb_bound(f, tauF, mu, CI[IT_Z + Z_SL_L], sl - B.slL, du2, true);
         // objective part of the barrier directional derivative
         if (g.energy) {
-            f.gphid += dsk * (du0 + du2) * iscale;
+            f.gphid += (dsk * du0 + (INTL ? 1.0 : dsk) * du2) * iscale;
             if (k >= 1) f.gphid += (2e-3 * iscale) * (fel - pFel) * (du0 - pDFel);
         } else {
             f.gphid += (2e-4 * iscale) * (fel * du0 + fpb * du1);
@@ -855,8 +855,8 @@ MS_HD void cell_step(const Ctx& c, int k, int s) {
             if (j == R_P0) jd = jP0b * db + jP0f * du0;
             else if (j == R_P1) jd = jP1f * du0 + jP1n * dbn;
             else if (j == R_ACC) jd = jAccb * db + du0 + du1;
-            else if (j == R_LTR) jd = du2 + jLtrF * du0 + jLtrB * db + jLtrN * dbn;
-            else jd = du2 + jLrgF * du0 + jLrgB * db + jLrgN * dbn;
+            else if (j == R_LTR) jd = du2 + jLtrF * du0 + jLtrB * db + jLtrN * (INTL ? du1 : dbn);      // INTL: coefficient of Fpb_k
+            else jd = du2 + jLrgF * du0 + jLrgB * db + jLrgN * (INTL ? du1 : dbn);
             const double dw = jd + rres[j];
             double L, U; bool hasU;
             row_bounds(B, j, L, U, hasU);

@@ -73,6 +73,7 @@ def lib():
     L.mseetc_eval_interval.argtypes = [i32, i32, i32, vp, vp, vp]
     L.mseetc_eval_interval_irk.argtypes = [i32, i32, i32, i32, vp, vp, i32, vp, vp, vp]
     L.mseetc_set_integrator.argtypes = [vp, i32, vp, vp, i32]
+    L.mseetc_set_integrate_losses.argtypes = [vp, ctypes.c_int]
     L.mseetc_set_loss_map.argtypes = [vp, i32, i32, vp, vp, vp]
     L.mseetc_set_sweep_lanes.argtypes = [vp, ctypes.c_int]
     L.mseetc_last_sweep_fallbacks.argtypes = [vp]
@@ -132,6 +133,10 @@ class Handle:
         A = np.ascontiguousarray(A, dtype=np.float64); w = np.ascontiguousarray(w, dtype=np.float64)
         _check(lib().mseetc_set_integrator(self._h, int(len(w)), A.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p),
                                            int(max_newton)), 'mseetc_set_integrator')
+
+    def set_integrate_losses(self, on):
+        "integrateLosses = True of the reference (ocp.py:231-241): epigraph rows on the loss energies integrated over each interval"
+        _check(lib().mseetc_set_integrate_losses(self._h, 1 if on else 0), 'mseetc_set_integrate_losses')
 
     def set_sweep_lanes(self, lanes):
         "0 = chosen per call; 1 = sequential Riccati sweeps; 8 / 16 / 32 = parallel-in-time sweeps with that many chunk lanes per instance."

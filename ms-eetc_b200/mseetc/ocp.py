@@ -186,8 +186,8 @@ class casadiSolver():
         track.checkFields()
         train.checkFields()
         opts = OptionsCasadiSolver(optsDict)
-        if opts.integrateLosses:
-            raise NotImplementedError("integrateLosses=True is not implemented on the device")
+        if opts.integrateLosses and opts.energyOptimal and opts.integrationMethod != 'RK':
+            raise NotImplementedError("integrateLosses=True is available with integrationMethod 'RK' only in this build of the device library")
 
         self.train = train
         self.opts = opts
@@ -309,6 +309,8 @@ class casadiSolver():
         h.set_sweep_lanes(0 if self.sweepLanes == 'auto' else int(self.sweepLanes))      # 0: the library picks per call
         if tableau is not None:            # 'IRK' / 'CVODES' (reference train.py:303-322): collocation steps instead of explicit RK4
             h.set_integrator(tableau['A'], tableau['w'], tableau['maxIter'])
+        if self.opts.integrateLosses and self.energyOptimal:      # reference ocp.py:118-120,231-241
+            h.set_integrate_losses(True)
         return h
 
     def _ensure_pool(self, dev):
@@ -727,7 +729,7 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
         raise RuntimeError("mseetc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     n = len(solvers)
     ref = solvers[0]
-    sig = lambda s: (s.withPnBrake, s.withRgBrake, s.withPower, s.energyOptimal, s._lossKind) + s._integrator_key()
+    sig = lambda s: (s.withPnBrake, s.withRgBrake, s.withPower, s.energyOptimal, s._lossKind, bool(s.opts.integrateLosses)) + s._integrator_key()
     if any(sig(s) != sig(ref) for s in solvers):
         raise ValueError("solve_instances needs solvers with identical problem structure")
     bc = [np.broadcast_to(np.atleast_1d(np.asarray(a, dtype=float)), (n,)) for a in (terminalTime, initialTime, terminalVelocity, initialVelocity)]
@@ -758,6 +760,8 @@ def solve_instances(solvers, terminalTime, initialTime=0, terminalVelocity=1, in
         hd.set_sweep_lanes(0 if ref.sweepLanes == 'auto' else int(ref.sweepLanes))
         if tableau is not None:
             hd.set_integrator(tableau['A'], tableau['w'], tableau['maxIter'])
+        if ref.opts.integrateLosses and energy:
+            hd.set_integrate_losses(True)
         return hd
     dev_tabs = dict(nint=up(nint, torch.int32), trk_of=up(np.arange(n, dtype=np.int32), torch.int32), trk_off=up(trk_off, torch.int32),
                     ds=up(np.concatenate([t[0] for t in tabs]), torch.float64), c0=up(np.concatenate([t[1] for t in tabs]), torch.float64),

@@ -169,6 +169,8 @@ def solve_tracks(train, batch, numIntervals, optsDict=None, terminalTime=None, t
         h.set_sweep_lanes(0 if solver.sweepLanes == 'auto' else int(solver.sweepLanes))
         if tableau is not None:
             h.set_integrator(tableau['A'], tableau['w'], tableau['maxIter'])
+        if solver.opts.integrateLosses and solver.energyOptimal:
+            h.set_integrate_losses(True)
         return h
 
     def run(solver, T, tmin_dev=None):

@@ -70,20 +70,22 @@ class DynamicLossMap:
                 val = val + self.coef[i - 3 + a, j - 3 + b] * Nx[a] * Ny[b]
         return torch.where(inside, val, torch.zeros_like(val))
 
-    def motor(self, f, v):
+    def motor(self, f, v, clamp_load=False):
         vMin, vMax = self.box[2], self.box[3]
         vc = torch.clamp(v, vMin, vMax)                                         # efficiency.py:40 (zero slope outside)
         absf = torch.where(f >= 0, f, -f)                                       # efficiency.py:42 (slope +1 at f = 0, as CasADi)
         tp = self.powerMax / self.forceMax
         load = torch.where(vc <= tp, 100 * absf / self.forceMax, 100 * absf * vc / self.powerMax)   # efficiency.py:10-12
+        if clamp_load:      # see oracle/intlosses.py: stage points of a time integration that overshoot the power hyperbola by rounding
+            load = torch.where((load > self.box[1]) & (load <= 1.001 * self.box[1]), torch.full_like(load, self.box[1]), load)
         return self.spline(load, vc)
 
-    def total(self, f, v):
+    def total(self, f, v, clamp_load=False):
         "efficiency.py:103-139, absolute units: force [N], losses [W]"
         tr = f >= 0
         pw_t, pw_b = f * v, -f * v
         gear = torch.where(tr, ((1 - self.etaGear) / self.etaGear) * pw_t, (1 - self.etaGear) * pw_b)
-        mot = self.motor(f, v)
+        mot = self.motor(f, v, clamp_load)
         pm_t = pw_t + gear + mot + self.aux
         pm_b = pw_b - gear - mot - self.aux
         arg = torch.where(tr, V_CAT ** 2 - 4 * R_TRAFO * pm_t, V_CAT ** 2 + 4 * R_TRAFO * pm_b)
@@ -91,17 +93,17 @@ class DynamicLossMap:
         tot = gear + mot + self.aux + trafo
         return torch.where(mot > 0, tot, torch.zeros_like(tot))
 
-    def specific(self, fs, v, M):
-        return self.total(fs * M, v) / M                                        # train.py:216
+    def specific(self, fs, v, M, clamp_load=False):
+        return self.total(fs * M, v, clamp_load) / M                            # train.py:216
 
-    def split(self, fs, v, M):
+    def split(self, fs, v, M, clamp_load=False):
         "utils.py:197-220: (funTr, funRgb) of specific force fs and speed v"
         def slope(sign):
             ft = torch.full_like(v, sign * TOL, requires_grad=True)
             (g,) = torch.autograd.grad(self.specific(ft, v, M).sum(), ft, create_graph=True)
             return g
         beta = self.specific(torch.zeros_like(v), v, M)
-        full = self.specific(fs, v, M)
+        full = self.specific(fs, v, M, clamp_load)
         fun_tr = torch.where(fs >= 0, full, slope(+1.0) * fs + beta)
         fun_rg = torch.where(fs < 0, full, slope(-1.0) * fs + beta)
         return fun_tr, fun_rg

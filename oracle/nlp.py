@@ -87,7 +87,7 @@ HESS_PAIRS = [(i, j) for i in range(4) for j in range(i, 4)]  # over (b0, Fel, F
 class ReferenceNLP:
     """min f(z) s.t. lbg<=g(z)<=ubg, lbz<=z<=ubz exactly as assembled in ocp.py:166-284."""
 
-    def __init__(self, train, pos, grad_permil, limit, curv, track_length, opts=None, loss_rows=None, interval_fn=None):
+    def __init__(self, train, pos, grad_permil, limit, curv, track_length, opts=None, loss_rows=None, interval_fn=None, energy_fn=None):
         o = dict(numIntervals=len(pos) - 1, energyOptimal=True, minimumVelocity=1.0, numSteps=1, numApproxSteps=0)
         o.update(opts or {})
         self.opts = o
@@ -122,6 +122,8 @@ class ReferenceNLP:
         if self.lossKind == 'static':
             self.cT = (1 - losses[1]) / losses[1]
             self.cR = (1 - losses[2])
+        # integrateLosses = True (ocp.py:231-241): energy_fn = oracle.intlosses.energy_fn(...); rows s_i - E(b_i, Fel_i, Fpb_i, t_{i+1} - t_i)
+        self.energy_fn = energy_fn
         self.interval_fn = interval_fn  # None: explicit RK4 (sympy, below); else oracle.irk.interval_rows(...) for the 'IRK' integrator
         self.loss_rows = loss_rows  # callable (Fel, b0, b1) -> ((val,grad3,hess6) x2) for non-symbolic maps
         if self.energy:
@@ -216,6 +218,9 @@ class ReferenceNLP:
         for r, name in enumerate(self.names):
             blk = [np.broadcast_to(np.asarray(x, float), (self.N,)) for x in out[r * per:(r + 1) * per]]
             res[name] = (blk[0], blk[1:5], blk[5:])
+        if self.energy_fn is not None and self.energy:      # the rows are assembled separately (they involve t_i, t_{i+1})
+            zero = np.zeros(self.N)
+            res['ltr'] = res['lrg'] = (zero, [zero] * 4, [zero] * 10)
         if self.interval_fn is not None:     # train.py:303-310: the shooting rows from the collocation integrator
             res.update(self.interval_fn(b[:-1], Fel, Fpb, b[1:], self.ds, self.c0, self.sr, self.withPn))
         if self.loss_rows is not None and self.energy:
@@ -232,7 +237,10 @@ class ReferenceNLP:
     def f(self, z):
         Fel = z[self.iFel]
         if self.energy:   # ocp.py:223,243-245
-            obj = np.sum(self.ds * (Fel + z[self.iS])) + 1e-3 * np.sum(np.diff(Fel) ** 2)
+            if self.energy_fn is not None:   # ocp.py:235
+                obj = np.sum(self.ds * Fel + z[self.iS]) + 1e-3 * np.sum(np.diff(Fel) ** 2)
+            else:
+                obj = np.sum(self.ds * (Fel + z[self.iS])) + 1e-3 * np.sum(np.diff(Fel) ** 2)
         else:             # ocp.py:146-150
             obj = z[self.iT[-1]] + 1e-4 * (Fel @ Fel + (z[self.iFpb] @ z[self.iFpb] if self.withPn else 0.0))
         return obj / self.scale
@@ -242,7 +250,7 @@ class ReferenceNLP:
         Fel = z[self.iFel]
         if self.energy:
             gr[self.iFel] = self.ds
-            gr[self.iS] = self.ds
+            gr[self.iS] = self.ds if self.energy_fn is None else 1.0
             d = np.diff(Fel)
             gr[self.iFel[1:]] += 2e-3 * d
             gr[self.iFel[:-1]] -= 2e-3 * d
@@ -266,7 +274,21 @@ class ReferenceNLP:
         if self.energy:
             g[self.rLtr] = z[self.iS] + s['ltr'][0]
             g[self.rLrg] = z[self.iS] + s['lrg'][0]
+            if self.energy_fn is not None:
+                (etr, _, _), (erg, _, _) = self._energies(z)
+                g[self.rLtr] -= etr
+                g[self.rLrg] -= erg
         return g
+
+    def _energies(self, z):
+        b, t = z[self.iB], z[self.iT]
+        Fpb = z[self.iFpb] if self.withPn else np.zeros(self.N)
+        return self.energy_fn(b[:-1], z[self.iFel], Fpb, t[1:] - t[:-1], self.c0, b[1:])
+
+    def _energy_cols(self):
+        "columns and signs of the arguments (b0, Fel, Fpb, dt = t1 - t0) of the energy rows: dt contributes through t1 (+) and t0 (-)"
+        return [(self.iB[:-1], 0, 1.0), (self.iFel, 1, 1.0)] + ([(self.iFpb, 2, 1.0)] if self.withPn else []) + \
+               [(self.iT[1:], 3, 1.0), (self.iT[:-1], 3, -1.0)]
 
     def _rowspec(self):
         spec = []
@@ -301,6 +323,10 @@ class ReferenceNLP:
             R += [self.rLtr, self.rLrg]
             C += [self.iS, self.iS]
             V += [ones, ones]
+        if self.energy and self.energy_fn is not None:
+            for rows, (_, gr, _) in zip((self.rLtr, self.rLrg), self._energies(z)):
+                for cols_, a, sg in self._energy_cols():
+                    R.append(rows); C.append(cols_); V.append(-sg * gr[a])
         J = sp.coo_matrix((np.concatenate(V), (np.concatenate(R), np.concatenate(C))), shape=(self.ng, self.nz))
         return J.tocsr()
 
@@ -318,6 +344,15 @@ class ReferenceNLP:
                 R.append(cols[i]); C.append(cols[j]); V.append(lr * h)
                 if i != j:
                     R.append(cols[j]); C.append(cols[i]); V.append(lr * h)
+        if self.energy and self.energy_fn is not None:
+            pair = {(i, j): q for q, (i, j) in enumerate(HESS_PAIRS)}
+            for rows, (_, _, hs) in zip((self.rLtr, self.rLrg), self._energies(z)):
+                lr = lam[rows]
+                ec = self._energy_cols()
+                for c1, a1, s1 in ec:
+                    for c2, a2, s2 in ec:
+                        h = hs[pair[(min(a1, a2), max(a1, a2))]]
+                        R.append(c1); C.append(c2); V.append(-lr * s1 * s2 * h)
         w = sigma / self.scale
         if self.energy:
             a, b = self.iFel[1:], self.iFel[:-1]

@@ -20,7 +20,22 @@ def oracle_nlp(train, track, N, energy=True, vmin=1.0, **rk):
     if o.get('irk'):                       # (order, collMethod): the reference's 'IRK' integrator (train.py:303-310)
         from oracle.irk import interval_rows
         interval_fn = interval_rows(o['irk'][0], o['irk'][1], o['numSteps'], o['numApproxSteps'])
-    return ReferenceNLP(train, pos, g, v, c, track.length, o, interval_fn=interval_fn)
+    energy_fn = None
+    if o.get('integrateLosses') and energy:    # ocp.py:231-241 with the constant-efficiency model of the train
+        from oracle.intlosses import energy_fn as mk, static_power_fns
+        M = train.mass * train.rho
+        losses = train.losses if train.losses is not None else ('none',)
+        sr = (train.r0 / M, train.r1 / M, train.r2 / M)
+        if losses[0] == 'dynamic':             # efficiency.totalLossesFunction(train, auxiliaries, etaGear)
+            from oracle.intlosses import dynamic_power_fns
+            from oracle.lossmap import DynamicLossMap
+            lm = DynamicLossMap(train.forceMax, losses[1], losses[2], losses[3])
+            energy_fn = mk(sr, None, dynamic_power_fns(lm, M), train.forceMinPn != 0, steps=o.get('oracleLossSteps', 8),
+                           kinks=(lm.box[2], lm.powerMax / lm.forceMax, lm.box[3]))
+        else:
+            cT, cR = ((1 - losses[1]) / losses[1], 1 - losses[2]) if losses[0] == 'static' else (0.0, 0.0)
+            energy_fn = mk(sr, None, static_power_fns(cT, cR), train.forceMinPn != 0)
+    return ReferenceNLP(train, pos, g, v, c, track.length, o, interval_fn=interval_fn, energy_fn=energy_fn)
 
 
 def oracle_solve(nlp, T, t0=0.0, v0=1.0, vN=1.0, **kw):

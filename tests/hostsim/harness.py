@@ -109,6 +109,7 @@ def solve(nlps, Ts, t0=0.0, v0=1.0, vN=1.0, max_iter=500, tol=1e-8, verbose_inst
         lib.hostsim_set_integrator(len(w), P(A), P(w), 10)
     else:
         lib.hostsim_set_integrator(0, ctypes.c_void_p(0), ctypes.c_void_p(0), 1)
+    lib.hostsim_set_integrate_losses(1 if ref.opts.get('integrateLosses') else 0)
     lib.hostsim_solve_batch(ctypes.byref(pr), n, P(params), P(nint), P(trk_of), P(trk_off), P(ds), P(c0), P(bmax),
                             P(np.ascontiguousarray(tmin, dtype=float)) if tmin is not None else ctypes.c_void_p(0), P(z), P(lam),
                             P(obj), P(kkt), P(iters), P(status), verbose_inst, ctypes.byref(ticks), int(pit_lanes), *lm, int(init_mode))

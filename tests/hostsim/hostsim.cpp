@@ -52,6 +52,7 @@ static void lin_residual(const Ctx& c, int s, int N, const char* tag) {
 
 static IrkTab g_irk;
 static bool g_irk_on = false;
+static int g_int_losses = 0;
 
 extern "C" {
 
@@ -73,7 +74,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     g.nInst = n;
     g.withPn = pr->with_pn_brake; g.withPower = pr->with_power_rows; g.energy = pr->energy_optimal;
     g.lossKind = pr->loss_kind; g.numSteps = pr->num_steps; g.numApprox = pr->num_approx_steps;
-    g.maxIter = pr->max_iterations; g.tol = pr->tol; g.muInit = pr->mu_init; g.initMode = init_mode;
+    g.maxIter = pr->max_iterations; g.tol = pr->tol; g.muInit = pr->mu_init; g.initMode = init_mode; g.intLosses = (g_int_losses && pr->energy_optimal) ? 1 : 0;
     WsPlan plan = plan_workspace(g.S, g.NK);
     // the device workspace is uninitialised memory: poison it here (0xFF bytes = NaN doubles, -1 ints) so that a read of a plane
     // nobody has written shows up in the emulation too; the library clears the integer state and the counters itself
@@ -97,7 +98,8 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     for (int s = 0; s < g.S; ++s) inst_setup(c, io, s);
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
     for (int s = 0; s < g.S; ++s) { inst_screen(c, s); inst_profile(c, s); }
-    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
+    const bool intl = g.intLosses != 0;
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (intl) cell_init<true, true>(c, k, s); else if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
     int tick = 0;
     long fallbacks = 0;
     const int diag = getenv("HOSTSIM_PIT_DIAG") ? atoi(getenv("HOSTSIM_PIT_DIAG")) : 0;
@@ -137,7 +139,8 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         }
     };
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) {
-        if (c.irk) { if (dyn) cell_eval<true, false, true>(c, k, s); else cell_eval<false, false, true>(c, k, s); }
+        if (intl) cell_eval<true, false, false, true>(c, k, s);
+        else if (c.irk) { if (dyn) cell_eval<true, false, true>(c, k, s); else cell_eval<false, false, true>(c, k, s); }
         else if (dyn) cell_eval<true, false>(c, k, s); else cell_eval<false, false>(c, k, s);
     }
     reduce_kkt(false);
@@ -188,7 +191,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
             if (pit_lanes > 1 && (s >= g.nInst || c.I(SI_ITERS, s) < pit_until)) inst_step_pit_emulated(c, s, pit_lanes, fb, ff, &fallbacks);   // chunked parallel-in-time variant
             else inst_step(c, s, fb, ff);
         }
-        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (dyn) cell_step<true>(c, k, s); else cell_step<false>(c, k, s); }
+        for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (intl) cell_step<true, true>(c, k, s); else if (dyn) cell_step<true>(c, k, s); else cell_step<false>(c, k, s); }
         for (int s = 0; s < g.nInst; ++s) {
             if (c.I(SI_PHASE, s) != PH_STEPPED) continue;
             const int N = c.I(SI_N_INT, s);
@@ -199,7 +202,8 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) {
-            if (c.irk) { if (dyn) cell_eval<true, true, true>(c, k, s); else cell_eval<false, true, true>(c, k, s); }
+            if (intl) cell_eval<true, true, false, true>(c, k, s);
+            else if (c.irk) { if (dyn) cell_eval<true, true, true>(c, k, s); else cell_eval<false, true, true>(c, k, s); }
             else if (dyn) cell_eval<true, true>(c, k, s); else cell_eval<false, true>(c, k, s);
         }
         reduce_kkt(true);
@@ -223,6 +227,8 @@ int hostsim_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, cons
     for (int i = 0; i < n; ++i) eval_interval_point(i, n, num_steps, num_approx, in, out);
     return 0;
 }
+
+int hostsim_set_integrate_losses(int on) { g_int_losses = on; return 0; }
 
 // collocation integrator (mseetc_set_integrator): stages = 0 switches it off again
 int hostsim_set_integrator(int32_t stages, const double* A, const double* w, int32_t max_newton) {

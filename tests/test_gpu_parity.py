@@ -35,6 +35,8 @@ def device_solve(cabi, nlps, Ts, v0=1.0, vN=1.0, max_iter=500, want_lam=True, in
     h.set_sweep_lanes(lanes)
     if ref.opts.get('irk'):                      # collocation integrator: the tableau the product computes
         h.set_integrator(*harness.product_tableau(*ref.opts['irk']), 10)
+    if ref.opts.get('integrateLosses'):
+        h.set_integrate_losses(True)
     out = h.solve_device(cu(params, torch.float64), cu(nint, torch.int32), cu(np.arange(n, dtype=np.int32), torch.int32),
                          cu(trk_off, torch.int32), cu(np.concatenate([p[1] for p in packs]), torch.float64),
                          cu(np.concatenate([p[2] for p in packs]), torch.float64),
@@ -114,6 +116,61 @@ def test_public_api_integration_methods(cabi):
     ends = [TrainIntegrator(model, m, o).solve(0.0, 400.0, 250.0, traction=0.3) for m, o in (('RK', {'numSteps': 4}), ('IRK', {'order': 3}), ('CVODES', {}))]
     for e in ends[:2]:
         assert abs(e['time'] - ends[2]['time']) < 1e-5 * ends[2]['time'] and abs(e['velSquared'] - ends[2]['velSquared']) < 1e-5 * ends[2]['velSquared']
+
+
+@pytest.mark.parametrize('lanes', [1, 16], ids=['seq', 'pit16'])
+def test_integrated_losses_match_oracle_reference_formulation(cabi, lanes):
+    """integrateLosses = True (reference ocp.py:231-241, train.py:367-413) through the C ABI: the oracle keeps the reference's rows
+    s_i - E(sqrt(b_i), t_{i+1} - t_i, Fel_i, Fpb_i); the kernels take the duration from the shooting function of the interval.  Same
+    optimum: objective 1e-6, trajectories 1e-4, the oracle's rows satisfied by the device's solution."""
+    from oracle.problem import load_track
+    T = 1541.0
+    nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True, integrateLosses=True)
+    ref = oracle_solve(nlp, T)
+    assert ref.success
+    for guess in (0, 1):
+        out = device_solve(cabi, [nlp], [T], initial_guess=guess, lanes=lanes)
+        assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8
+        assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
+        z = out['z'][0]
+        for idx, scale in ((nlp.iB, nlp.limit.max() ** 2), (nlp.iT, T), (nlp.iFel, nlp.forceMax), (nlp.iS, np.max(ref.x[nlp.iS]))):
+            assert np.max(np.abs(z[idx] - ref.x[idx])) <= 1e-4 * scale
+        lbz, ubz, lbg, ubg = nlp.bounds(T)
+        g = nlp.g(z)
+        assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7 * max(1.0, np.max(ref.x[nlp.iS]))      # energies up to ~100 J/kg; 4 vs 8 RK4 steps
+
+
+def test_public_api_integrate_losses(cabi):
+    """casadiSolver(..., {'integrateLosses': True}) with constant efficiencies (against the oracle) and with the spline loss map of
+    simulations/table3.py (against the oracle fixture); a batch of trip times gives the same optima as single solves."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from mseetc.efficiency import totalLossesFunction
+    from oracle.problem import load_track
+    track = Track(config={'id': '00_var_speed_limit_100'})
+    opts = {'numIntervals': 100, 'integrateLosses': True, 'integrationMethod': 'RK', 'integrationOptions': {'numApproxSteps': 1}}
+    solver = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), track, opts)
+    df, stats = solver.solve(1541.0)
+    nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True, integrateLosses=True)
+    ref = oracle_solve(nlp, 1541.0)
+    assert df is not None and abs(stats['Cost'] - nlp.cost(ref.f)) <= 1e-6 * nlp.cost(ref.f)
+    assert np.max(np.abs(df['Velocity [m/s]'].values ** 2 - ref.x[nlp.iB])) <= 1e-4 * nlp.limit.max() ** 2
+    plain = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), track, dict(opts, integrateLosses=False)).solve(1541.0)[1]['Cost']
+    assert 1e-5 < abs(plain - stats['Cost']) / plain < 1e-3            # another formulation, not the mid-point rows
+    res = solver.solve_batch(np.array([1541.0, 1600.0, 1700.0]), screen=False)
+    assert np.all(res['status'] == 0) and abs(res['cost'][0] - stats['Cost']) <= 1e-9 * stats['Cost'] and np.all(np.diff(res['cost']) < 0)
+    # spline loss map
+    gold = _golden('intlosses_dynamic_flat_N60.json')
+    train = Train(config={'id': 'NL_Intercity_VIRM6'}); train.forceMinPn = 0
+    train.powerLosses = totalLossesFunction(train, auxiliaries=gold['auxiliaries'], etaGear=gold['etaGear'])
+    dyn = casadiSolver(train, track, dict(opts, numIntervals=gold['N']))
+    df, stats = dyn.solve(gold['T'])
+    assert df is not None and abs(stats['Cost'] - gold['cost_kwh']) <= 1e-6 * gold['cost_kwh']
+    assert np.max(np.abs(df['Velocity [m/s]'].values ** 2 - np.array(gold['b']))) <= 1e-4 * 1975.0
+    assert np.max(np.abs(df.index.values - np.array(gold['t']))) <= 1e-4 * gold['T']
+    with pytest.raises(NotImplementedError):
+        casadiSolver(train, track, dict(opts, integrationMethod='IRK', integrationOptions={}))
 
 
 def test_interval_kernel_bitwise_equals_host_compilation(cabi):

@@ -275,3 +275,52 @@ def test_profile_starting_point_reaches_the_same_optimum_in_fewer_iterations(lib
         assert np.all(np.abs(a['obj'] - b['obj']) <= 1e-9 * np.abs(a['obj']))
         assert np.max(np.abs(a['z'] - b['z'])) < 1e-4
         assert np.all(b['iters'] < 0.8 * a['iters'])
+
+
+def _check_against(z, nlp, ref_t, ref_b, ref_fel, T):
+    assert np.max(np.abs(z[nlp.iB] - ref_b)) <= 1e-4 * nlp.limit.max() ** 2
+    assert np.max(np.abs(z[nlp.iT] - ref_t)) <= 1e-4 * T
+    assert np.max(np.abs(z[nlp.iFel] - ref_fel)) <= 1e-4 * nlp.forceMax
+
+
+def test_integrated_losses_match_oracle_reference_formulation(lib):
+    """integrateLosses = True (ocp.py:231-241).  The oracle keeps the reference's rows s_i - E(sqrt(b_i), t_{i+1} - t_i, Fel_i, Fpb_i)
+    (loss energies by 8 RK4 steps in time, autograd); the device code takes the duration from the shooting function and 4 RK4 steps
+    with jets: same optimum -- objective 1e-6, trajectories 1e-4, the oracle's rows satisfied by the device's solution."""
+    from oracle.problem import load_track
+    T = 1541.0
+    nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True, integrateLosses=True)          # constant efficiencies
+    ref = oracle_solve(nlp, T)
+    assert ref.success
+    out = harness.solve([nlp], [T], lib=lib)
+    assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8
+    assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
+    z = out['z'][0]
+    _check_against(z, nlp, ref.x[nlp.iT], ref.x[nlp.iB], ref.x[nlp.iFel], T)
+    assert np.max(np.abs(z[nlp.iS] - ref.x[nlp.iS])) <= 1e-4 * np.max(ref.x[nlp.iS])
+    lbz, ubz, lbg, ubg = nlp.bounds(T)
+    g = nlp.g(z)
+    # incl. the rows on the integrated energies, in the reference's form (energies up to ~100 J/kg; 4 vs 8 RK4 steps)
+    assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7 * max(1.0, np.max(ref.x[nlp.iS]))
+    # not the mid-point formulation in disguise: that optimum differs in the fifth digit
+    mid = oracle_solve(oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True), T)
+    assert 1e-5 < abs(mid.f - ref.f) / ref.f < 1e-3
+    # profile starting point: same optimum
+    out1 = harness.solve([nlp], [T], lib=lib, init_mode=1)
+    assert out1['status'][0] == 0 and abs(out1['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
+
+
+def test_integrated_losses_with_the_spline_loss_map_match_golden(lib):
+    "the same with efficiency.totalLossesFunction (oracle fixture: tests/golden/make_golden_intlosses.py)"
+    import json, os
+    from oracle.problem import load_track
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'intlosses_dynamic_flat_N60.json')))
+    tr = fig5_train()
+    tr.losses = ('dynamic', gold['auxiliaries'], gold['etaGear'], 1.0)
+    nlp = oracle_nlp(tr, load_track(FLAT_JSON), gold['N'])     # packing only (the oracle's optimum comes from the fixture)
+    nlp.lossKind = 'dynamic'
+    nlp.opts['integrateLosses'] = True
+    out = harness.solve([nlp], [gold['T']], lib=lib)
+    assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8
+    assert abs(out['obj'][0] - gold['objective']) <= 1e-6 * gold['objective']
+    _check_against(out['z'][0], nlp, np.array(gold['t']), np.array(gold['b']), np.array(gold['Fel']), gold['T'])
