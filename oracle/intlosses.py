@@ -14,7 +14,7 @@ import torch
 def energy_fn(sr, c0_of, power_fns, withPn, steps=8, kinks=(), steps_kink=32):
     """Returns fn(b0, Fel, Fpb, dt, c0) -> [(E, grad4, hess10)] for E in (eTr, eBr); grad over (b0, Fel, Fpb, dt), hess pairs
     00 01 02 03 11 12 13 22 23 33.  power_fns(fs, v) -> (PLtr, PLrgb) specific power losses [W/kg] as torch expressions."""
-    def fn(b0, Fel, Fpb, dt, c0, b1=None):
+    def fn(b0, Fel, Fpb, dt, c0, b1=None, derivs=True):
         # intervals in which the speed crosses a kink of the loss map (`kinks`: speeds) are integrated with steps_kink steps: the
         # integrand is only continuous there (an adaptive integrator like the reference's CVODES refines there by itself)
         if len(kinks) and b1 is not None:
@@ -23,8 +23,8 @@ def energy_fn(sr, c0_of, power_fns, withPn, steps=8, kinks=(), steps_kink=32):
             for kv in kinks:
                 hard |= (va < kv) & (kv < vb)
             if hard.any():
-                out = run(b0, Fel, Fpb, dt, c0, steps)
-                sub = run(b0[hard], Fel[hard], Fpb[hard], dt[hard], np.asarray(c0)[hard], steps_kink)
+                out = run(b0, Fel, Fpb, dt, c0, steps, derivs)
+                sub = run(b0[hard], Fel[hard], Fpb[hard], dt[hard], np.asarray(c0)[hard], steps_kink, derivs)
                 for (E, g, H), (Es, gs, Hs) in zip(out, sub):
                     E[hard] = Es
                     for a, b_ in zip(g, gs):
@@ -32,9 +32,9 @@ def energy_fn(sr, c0_of, power_fns, withPn, steps=8, kinks=(), steps_kink=32):
                     for a, b_ in zip(H, Hs):
                         a[hard] = b_
                 return out
-        return run(b0, Fel, Fpb, dt, c0, steps)
+        return run(b0, Fel, Fpb, dt, c0, steps, derivs)
 
-    def run(b0, Fel, Fpb, dt, c0, steps):
+    def run(b0, Fel, Fpb, dt, c0, steps, derivs=True):
         x = [torch.tensor(np.asarray(a, float), dtype=torch.float64, requires_grad=True) for a in (b0, Fel, Fpb, dt)]
         tc0 = torch.tensor(np.asarray(c0, float), dtype=torch.float64)
         F = x[1] + (x[2] if withPn else 0.0 * x[2])
@@ -52,6 +52,8 @@ def energy_fn(sr, c0_of, power_fns, withPn, steps=8, kinks=(), steps_kink=32):
         out = []
         n = lambda t: t.detach().numpy().copy()
         zero = torch.zeros_like(x[0])
+        if not derivs:      # values only (line search)
+            return [(n(etr), [], []), (n(erg), [], [])]
         for E in (etr, erg):
             g = torch.autograd.grad(E.sum(), x, create_graph=True, allow_unused=True)
             g = [gi if gi is not None else zero for gi in g]

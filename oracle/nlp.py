@@ -275,15 +275,24 @@ class ReferenceNLP:
             g[self.rLtr] = z[self.iS] + s['ltr'][0]
             g[self.rLrg] = z[self.iS] + s['lrg'][0]
             if self.energy_fn is not None:
-                (etr, _, _), (erg, _, _) = self._energies(z)
+                (etr, _, _), (erg, _, _) = self._energies(z, derivs=False)
                 g[self.rLtr] -= etr
                 g[self.rLrg] -= erg
         return g
 
-    def _energies(self, z):
-        b, t = z[self.iB], z[self.iT]
-        Fpb = z[self.iFpb] if self.withPn else np.zeros(self.N)
-        return self.energy_fn(b[:-1], z[self.iFel], Fpb, t[1:] - t[:-1], self.c0, b[1:])
+    def _energies(self, z, derivs=True):
+        "loss energies of all intervals at z (memoised per point: g, jac and hess of one iterate share one evaluation)"
+        key = (z.tobytes(), derivs)
+        memo = self.__dict__.setdefault('_energy_memo', {})
+        if key not in memo:
+            if derivs is False and (z.tobytes(), True) in memo:
+                return memo[(z.tobytes(), True)]
+            if len(memo) > 8:
+                memo.clear()
+            b, t = z[self.iB], z[self.iT]
+            Fpb = z[self.iFpb] if self.withPn else np.zeros(self.N)
+            memo[key] = self.energy_fn(b[:-1], z[self.iFel], Fpb, t[1:] - t[:-1], self.c0, b[1:], derivs)
+        return memo[key]
 
     def _energy_cols(self):
         "columns and signs of the arguments (b0, Fel, Fpb, dt = t1 - t0) of the energy rows: dt contributes through t1 (+) and t0 (-)"
