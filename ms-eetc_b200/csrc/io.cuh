@@ -88,13 +88,14 @@ MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s, bool fina
 }
 
 // kernel-level parity hook: one shooting interval with sensitivities (train.py:347-364)
-MS_HD void eval_interval_point(int i, int n, int numSteps, int numApprox, const double* in, double* out, const IrkTab* irk = nullptr) {
+template <bool IRK>
+MS_HD void eval_interval_point(int i, int n, int numSteps, int numApprox, const double* in, double* out, const IrkTab* irk) {
     if (i >= n) return;
     IntervalCoef q;
     const double b0 = in[i], F = in[n + i];
     q.ds = in[2 * n + i]; q.c0 = in[3 * n + i]; q.sr0 = in[4 * n + i]; q.sr1 = in[5 * n + i]; q.sr2 = in[6 * n + i];
     Jet2 tau, phi;
-    if (irk) shoot_irk(jvar0(b0), jvar1(F), q, numSteps, numApprox, *irk, tau, phi);
+    if (IRK) shoot_irk(jvar0(b0), jvar1(F), q, numSteps, numApprox, *irk, tau, phi);
     else shoot<Jet2>(jvar0(b0), jvar1(F), q, numSteps, numApprox, tau, phi);
     const Jet2* js[2] = {&tau, &phi};
     for (int a = 0; a < 2; ++a) {

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/mseetc_b200.h"
+#include "variants.h"
 #include "compact.cuh"
 #include "table.cuh"
 
@@ -34,16 +35,7 @@ thread_local std::string g_err;
 // the cells, so any grid works; the default is one block per 128 cells (measured faster than a persistent grid of a few blocks
 // per SM, MSEETC_CELL_WAVES=w selects the latter for experiments: 110.9k / 115.5k / 118.6k / 122.0k solves/s at w = 1/2/4/8
 // against 122.6k with the full grid on the bench workload).
-#define MS_CELL_KERNEL(NAME, MINB, CALL)                                        \
-    __global__ void __launch_bounds__(128, MINB) NAME(Ctx c, BatchIO io) {      \
-        const size_t total = (size_t)c.cfg.NK * c.cfg.S;                        \
-        const size_t stride = (size_t)gridDim.x * 128;                          \
-        for (size_t idx = (size_t)blockIdx.x * 128 + threadIdx.x; idx < total; idx += stride) { \
-            const int s = (int)(idx % c.cfg.S);                                 \
-            const int k = (int)(idx / c.cfg.S);                                 \
-            CALL;                                                               \
-        }                                                                       \
-    }
+// (MS_CELL_KERNEL: variants.h)
 #ifndef MS_MINB_TRIAL
 #define MS_MINB_TRIAL 2
 #endif
@@ -55,26 +47,13 @@ thread_local std::string g_err;
 #endif
 MS_CELL_KERNEL(k_cell_setup, 4, cell_setup(c, io, k, s))
 MS_CELL_KERNEL(k_cell_init, 4, cell_init<false>(c, k, s))
-MS_CELL_KERNEL(k_cell_init_dyn, 2, cell_init<true>(c, k, s))
 // k_cell_trial_eval: the interval evaluation AT THE TRIAL POINT, which it forms on the way (one kernel per iteration instead of
 // trial + evaluation); k_cell_eval: the same at the current iterate, once per solve for the starting point
 MS_CELL_KERNEL(k_cell_trial_eval, MS_MINB_TRIAL, (cell_eval<false, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_trial_eval_dyn, 2, (cell_eval<true, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_eval, MS_MINB_EVAL, (cell_eval<false, false>(c, k, s)))
-MS_CELL_KERNEL(k_cell_eval_dyn, 2, (cell_eval<true, false>(c, k, s)))
-// the same with the collocation integrator (integrationMethod 'IRK' / 'CVODES'): separate instantiations, so that the Newton
-// iterations and their local arrays stay out of the explicit-RK kernels
-MS_CELL_KERNEL(k_cell_trial_eval_irk, 1, (cell_eval<false, true, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_trial_eval_dyn_irk, 1, (cell_eval<true, true, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_eval_irk, 1, (cell_eval<false, false, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_eval_dyn_irk, 1, (cell_eval<true, false, true>(c, k, s)))
-// integrateLosses = True (ocp.py:231-241): loss energies integrated in the time domain inside the interval evaluation
-MS_CELL_KERNEL(k_cell_init_intl, 1, (cell_init<true, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_trial_eval_intl, 1, (cell_eval<true, true, false, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_eval_intl, 1, (cell_eval<true, false, false, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_step_intl, 2, (cell_step<true, true>(c, k, s)))
+// (the variants with the spline loss map, the collocation integrator and integrated losses live in variants_*.cu: further translation units that
+// compile next to this one, launched through mseetc::launch_variant)
 MS_CELL_KERNEL(k_cell_step, MS_MINB_STEP, cell_step<false>(c, k, s))
-MS_CELL_KERNEL(k_cell_step_dyn, MS_MINB_STEP, cell_step<true>(c, k, s))
 MS_CELL_KERNEL(k_cell_extract, 4, cell_extract(c, io, k, s))
 
 __global__ void __launch_bounds__(64) k_inst_setup(Ctx c, BatchIO io) {
@@ -350,9 +329,9 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters, doub
     if (acc == 12345.678) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;      // never true: keeps the chains alive
 }
 
-__global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out, const IrkTab* irk) {
+__global__ void k_eval_interval(int n, int numSteps, int numApprox, const double* in, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    eval_interval_point(i, n, numSteps, numApprox, in, out, irk);
+    eval_interval_point<false>(i, n, numSteps, numApprox, in, out, nullptr);
 }
 
 }  // namespace
@@ -737,16 +716,16 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_MISC); k_inst_profile<<<igrid, 2 * ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
     }
     begin(CLS_MISC);
-    if (intl) k_cell_init_intl<<<cgrid, 128, 0, st>>>(c, io);
-    else if (dyn) k_cell_init_dyn<<<cgrid, 128, 0, st>>>(c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
+    if (intl) launch_variant(VK_INIT_INTL, cgrid, st, c, io);
+    else if (dyn) launch_variant(VK_INIT_DYN, cgrid, st, c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
     end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
     // ---- starting point: evaluation, convergence test, barrier parameter
     begin(CLS_EVAL);
-    if (intl) k_cell_eval_intl<<<gridIrk, 128, 0, st>>>(c, io);
-    else if (c.irk) { if (dyn) k_cell_eval_dyn_irk<<<gridIrk, 128, 0, st>>>(c, io); else k_cell_eval_irk<<<gridIrk, 128, 0, st>>>(c, io); }
-    else if (dyn) k_cell_eval_dyn<<<gridEval, 128, 0, st>>>(c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
+    if (intl) launch_variant(VK_EVAL_INTL, gridIrk, st, c, io);
+    else if (c.irk) launch_variant(dyn ? VK_EVAL_DYN_IRK : VK_EVAL_IRK, gridIrk, st, c, io);
+    else if (dyn) launch_variant(VK_EVAL_DYN, gridEval, st, c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
     end(CLS_EVAL);
     begin(CLS_KKT); k_inst_kkt<false><<<rgrid * RED_CL, 32 * RED_WB, 0, st>>>(c); end(CLS_KKT);
     // ---- the tick loop: direction (sweeps, interval-parallel rest, step-size limits), then the evaluation at the trial point with
@@ -766,16 +745,16 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         else stepKernel<<<igrid, ib, ringBytes, s0>>>(c);
         if (prof) end(CLS_STEP);
         if (prof) begin(CLS_CSTEP);
-        if (intl) k_cell_step_intl<<<pgrid(2), 128, 0, s0>>>(c, io);
-        else if (dyn) k_cell_step_dyn<<<gridStep, 128, 0, s0>>>(c, io); else k_cell_step<<<gridStep, 128, 0, s0>>>(c, io);
+        if (intl) launch_variant(VK_STEP_INTL, pgrid(2), s0, c, io);
+        else if (dyn) launch_variant(VK_STEP_DYN, gridStep, s0, c, io); else k_cell_step<<<gridStep, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_CSTEP);
         if (prof) begin(CLS_ALPHA);
         k_inst_alpha<<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c, mirror);
         if (prof) end(CLS_ALPHA);
         if (prof) begin(CLS_TRIAL);
-        if (intl) k_cell_trial_eval_intl<<<gridIrk, 128, 0, s0>>>(c, io);
-        else if (c.irk) { if (dyn) k_cell_trial_eval_dyn_irk<<<gridIrk, 128, 0, s0>>>(c, io); else k_cell_trial_eval_irk<<<gridIrk, 128, 0, s0>>>(c, io); }
-        else if (dyn) k_cell_trial_eval_dyn<<<gridTrial, 128, 0, s0>>>(c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
+        if (intl) launch_variant(VK_TRIAL_INTL, gridIrk, s0, c, io);
+        else if (c.irk) launch_variant(dyn ? VK_TRIAL_DYN_IRK : VK_TRIAL_IRK, gridIrk, s0, c, io);
+        else if (dyn) launch_variant(VK_TRIAL_DYN, gridTrial, s0, c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_TRIAL);
         if (prof) begin(CLS_DECIDE);
         k_inst_kkt<true><<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c);
@@ -1011,7 +990,7 @@ int mseetc_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const
     if (n < 1 || !in || !out) return fail(-1, "mseetc_eval_interval: bad argument");
     if (num_steps < 1 || num_approx < 0) return fail(-2, "mseetc_eval_interval: bad RK options");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out, nullptr);
+    k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "k_eval_interval launch");
     e = cudaStreamSynchronize(st);
@@ -1035,7 +1014,7 @@ int mseetc_eval_interval_irk(int32_t n, int32_t num_steps, int32_t num_approx, i
     cudaStream_t st = (cudaStream_t)cuda_stream;
     e = cudaMemcpyAsync(dev, &t, sizeof t, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        k_eval_interval<<<(n + 127) / 128, 128, 0, st>>>(n, num_steps, num_approx, in, out, dev);
+        launch_eval_interval_irk(n, num_steps, num_approx, in, out, dev, st);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -224,7 +224,7 @@ int hostsim_eval_loss_rows(int32_t n, int32_t nl, int32_t nv, const double* tl, 
 }
 
 int hostsim_eval_interval(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out) {
-    for (int i = 0; i < n; ++i) eval_interval_point(i, n, num_steps, num_approx, in, out);
+    for (int i = 0; i < n; ++i) eval_interval_point<false>(i, n, num_steps, num_approx, in, out, nullptr);
     return 0;
 }
 
@@ -240,7 +240,7 @@ int hostsim_set_integrator(int32_t stages, const double* A, const double* w, int
     return 0;
 }
 int hostsim_eval_interval_irk(int32_t n, int32_t num_steps, int32_t num_approx, const double* in, double* out) {
-    for (int i = 0; i < n; ++i) eval_interval_point(i, n, num_steps, num_approx, in, out, &g_irk);
+    for (int i = 0; i < n; ++i) eval_interval_point<true>(i, n, num_steps, num_approx, in, out, &g_irk);
     return 0;
 }
 
