@@ -118,6 +118,25 @@ def test_public_api_integration_methods(cabi):
         assert abs(e['time'] - ends[2]['time']) < 1e-5 * ends[2]['time'] and abs(e['velSquared'] - ends[2]['velSquared']) < 1e-5 * ends[2]['velSquared']
 
 
+def test_spline_loss_map_with_the_other_integrators(cabi):
+    "efficiency.py loss map + integrationMethod 'IRK' / 'CVODES' through the public API (kernels k_cell_*_dyn_irk)"
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    from mseetc.efficiency import totalLossesFunction
+    train = Train(config={'id': 'NL_Intercity_VIRM6'}); train.forceMinPn = 0
+    train.powerLosses = totalLossesFunction(train, auxiliaries=27000, etaGear=0.96)
+    track = Track(config={'id': 'CH_StGallen_Wil'})
+    cost = {}
+    for method, io in (('RK', {'numApproxSteps': 1}), ('CVODES', {}), ('IRK', {'order': 2, 'collMethod': 'radau'})):
+        df, stats = casadiSolver(train, track, {'numIntervals': 300, 'integrationMethod': method, 'integrationOptions': io}).solve(1242.0)
+        assert df is not None, (method, stats)
+        cost[method] = stats['Cost']
+    assert abs(cost['RK'] - cost['CVODES']) < 2e-4 * cost['CVODES']
+    assert 2e-4 * cost['CVODES'] < abs(cost['IRK'] - cost['CVODES']) < 5e-3 * cost['CVODES']
+    assert abs(cost['RK'] - 47.3401426) < 1e-5 and abs(cost['CVODES'] - 47.3379331) < 1e-5      # the CPU emulation's optima
+
+
 @pytest.mark.parametrize('lanes', [1, 16], ids=['seq', 'pit16'])
 def test_integrated_losses_match_oracle_reference_formulation(cabi, lanes):
     """integrateLosses = True (reference ocp.py:231-241, train.py:367-413) through the C ABI: the oracle keeps the reference's rows

@@ -324,3 +324,20 @@ def test_integrated_losses_with_the_spline_loss_map_match_golden(lib):
     assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8
     assert abs(out['obj'][0] - gold['objective']) <= 1e-6 * gold['objective']
     _check_against(out['z'][0], nlp, np.array(gold['t']), np.array(gold['b']), np.array(gold['Fel']), gold['T'])
+
+
+def test_spline_loss_map_with_collocation_integrator(lib):
+    """efficiency.py loss rows together with integrationMethod 'IRK' / 'CVODES' (cell_eval<DYN, ., IRK>): the near-exact Gauss scheme
+    and ERK4+ with one step agree to the integration error of the latter; the two-point Radau scheme is coarser (as in the reference)."""
+    from oracle.problem import load_track
+    tr = fig5_train()
+    tr.losses = ('dynamic', 27000.0, 0.96, 1.0)
+    cost = {}
+    for name, rk in (('rk', dict()), ('gauss', dict(numSteps=4, numApproxSteps=0, irk=(4, 'legendre'))), ('radau', dict(numApproxSteps=0, irk=(2, 'radau')))):
+        nlp = oracle_nlp(tr, load_track(SWISS_JSON), 300, **rk)       # packing only
+        nlp.lossKind = 'dynamic'
+        out = harness.solve([nlp], [1242.0], lib=lib, init_mode=1)
+        assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8, name
+        cost[name] = nlp.cost(out['obj'][0])
+    assert abs(cost['rk'] - cost['gauss']) < 2e-4 * cost['gauss']
+    assert 2e-4 * cost['gauss'] < abs(cost['radau'] - cost['gauss']) < 5e-3 * cost['gauss']
