@@ -154,3 +154,41 @@ def test_loss_map_pins_figure3():
     LL, SS = np.meshgrid(loads, speeds, indexing='ij')
     assert np.max(np.abs(lut(LL, SS) - best)) < 1e-8
     assert lut(150.0, 20.0) == 0.0 and fun(3e5, 20.0) == 0.0                      # zero outside the measured box
+
+
+def test_integrated_loss_energies_match_an_adaptive_integrator():
+    """oracle/intlosses.py (TrainIntegrator.calcLosses, reference train.py:367-413, integrated there by CVODES with relTol 1e-6):
+    the fixed-step RK4 restatement against scipy's DOP853 at 1e-12 on the same right-hand side -- constant efficiencies (smooth) and
+    the spline loss map incl. intervals whose speed crosses its kinks (32 steps there)."""
+    import torch
+    from scipy.integrate import solve_ivp
+    from oracle.intlosses import energy_fn, static_power_fns, dynamic_power_fns
+    from oracle.lossmap import DynamicLossMap
+    tr = fig5_train()
+    M = tr.mass * tr.rho
+    sr = (tr.r0 / M, tr.r1 / M, tr.r2 / M)
+    lm = DynamicLossMap(tr.forceMax, 27000.0, 0.96, 1.0)
+    kinks = (lm.box[2], lm.powerMax / lm.forceMax, lm.box[3])
+    # (b0, Fel, dt, c0): acceleration from 1 m/s through both kinks, cruising, braking, a gradient
+    pts = np.array([[1.0, 0.25, 60.0, 0.0], [400.0, 0.05, 20.0, 0.002], [900.0, -0.2, 15.0, -0.01], [150.0, 0.2, 12.0, 0.0], [36.0, 0.28, 10.0, 0.0]])
+    b0, Fel, dt, c0 = pts.T
+    zero = np.zeros(len(b0))
+
+    def reference(power_fns):
+        out = []
+        for i in range(len(b0)):
+            def rhs(t, x):
+                v = torch.tensor([x[0]], dtype=torch.float64)
+                ptr, prg = power_fns(torch.tensor([Fel[i]], dtype=torch.float64), v)
+                return [Fel[i] - (sr[0] + sr[1] * x[0] + sr[2] * x[0] ** 2) - c0[i], float(ptr.detach()[0]), float(prg.detach()[0])]
+            sol = solve_ivp(rhs, [0.0, dt[i]], [np.sqrt(b0[i]), 0.0, 0.0], method='DOP853', rtol=1e-12, atol=1e-12, max_step=dt[i] / 60)
+            out.append(sol.y[:, -1])
+        return np.array(out)
+    for power_fns, kk, tol in ((static_power_fns(0.12, 0.15), (), 1e-8), (dynamic_power_fns(lm, M), kinks, 1e-5)):      # 6e-6 on the start from 1 m/s through both kinks
+        ref = reference(power_fns)
+        fn = energy_fn(sr, None, power_fns, False, steps=8, kinks=kk)
+        v_end = ref[:, 0]
+        (etr, _, _), (erg, _, _) = fn(b0, Fel, zero, dt, c0, v_end ** 2, derivs=False)
+        scale = np.maximum(np.abs(ref[:, 1]), np.abs(ref[:, 2]))
+        assert np.max(np.abs(etr - ref[:, 1]) / scale) < tol, (np.abs(etr - ref[:, 1]) / scale)
+        assert np.max(np.abs(erg - ref[:, 2]) / scale) < tol, (np.abs(erg - ref[:, 2]) / scale)
