@@ -386,10 +386,14 @@ MS_HD void power_loss_jets(const Ctx& c, int s, const LossPar& lp, bool pos, con
         prg = (-c.P(P_CR, s)) * fv;
     } else { ptr = j3const(0.0); prg = j3const(0.0); }
 }
-MS_HD void loss_energy_rows(const Ctx& c, int s, const IntervalCoef& q, double b0, double b1, double fel, double fpb, const Jet2& tau, Jet3& etr, Jet3& erg) {
-    const Jet3 B = j3var(b0, 0), FEL = j3var(fel, 1);
-    const Jet3 F = c.cfg.withPn ? FEL + j3var(fpb, 2) : FEL;
-    const Jet3 e = j3compose(tau, B, F);                      // duration of the interval as a function of (b_k, Fel_k, Fpb_k)
+// wrtDuration = false: jets w.r.t. (b_k, Fel_k, Fpb_k), the duration being tau(b_k, Fel_k + Fpb_k) -- the rows of the NLP.
+// wrtDuration = true: (b_k, Fel_k, Fpb_k) held fixed, component 0 of the jets = derivative w.r.t. the duration (of this discrete
+// map, not of the continuous integral) -- for the multipliers of the time rows in the reference's formulation (io.cuh).
+MS_HD void loss_energy_rows(const Ctx& c, int s, const IntervalCoef& q, double b0, double b1, double fel, double fpb, const Jet2& tau, Jet3& etr, Jet3& erg,
+                            bool wrtDuration = false) {
+    const Jet3 B = wrtDuration ? j3const(b0) : j3var(b0, 0), FEL = wrtDuration ? j3const(fel) : j3var(fel, 1);
+    const Jet3 F = c.cfg.withPn ? FEL + (wrtDuration ? j3const(fpb) : j3var(fpb, 2)) : FEL;
+    const Jet3 e = wrtDuration ? j3var(tau.v, 0) : j3compose(tau, B, F);      // duration of the interval
     LossPar lp;
     if (c.cfg.lossKind == 2) lp = load_losspar(c, s);
     const bool pos = fel >= 0.0;

@@ -87,6 +87,30 @@ MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s, bool fina
     }
 }
 
+// integrateLosses = True: the multipliers of the shooting-time rows in the reference's formulation.  The device takes the duration in
+// the loss rows from the shooting function (core.cuh, loss_energy_rows), the reference from t_{k+1} - t_k; the two Lagrangians have
+// the same stationary points with  y_t(reference) = y_t(device) + y_ltr dE_tr/d(duration) + y_lrg dE_rgb/d(duration),  and
+// dE/d(duration) is the loss power at the end of the interval.  Applied to lam_out after cell_extract (final pass only).
+MS_HD void cell_fix_time_multiplier_intl(const Ctx& c, const BatchIO& io, int k, int s) {
+    const Config& g = c.cfg;
+    if (s >= g.nInst || !io.lam_out || !g.energy) return;
+    const int N = c.I(SI_N_INT, s);
+    if (k >= N) return;
+    const int o = c.I(SI_ORIG, s);
+    const int it = c.I(SI_PARITY, s) ? WS_IT1 : WS_IT0;
+    const int rows = (g.withPower ? 2 : 0) + 3 + 2, Nmax = g.NK - 1;
+    const double b = c.W(it + IT_B, k, s), b1 = c.W(it + IT_B, k + 1, s), fel = c.W(it + IT_FEL, k, s), fpb = g.withPn ? c.W(it + IT_FPB, k, s) : 0.0;
+    const IntervalCoef q = load_coef(c, k, s);
+    Jet2 tau, phi;
+    shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
+    Jet3 etr, erg;
+    loss_energy_rows(c, s, q, b, b1, fel, fpb, tau, etr, erg, true);
+    const double pl[2] = {etr.g[0], erg.g[0]};
+    double* l = io.lam_out + (size_t)o * ((size_t)Nmax * rows) + (size_t)k * rows;
+    const int iyt = (g.withPower ? 2 : 0) + 1;
+    l[iyt] += c.W(it + IT_YD + R_LTR, k, s) * pl[0] + c.W(it + IT_YD + R_LRG, k, s) * pl[1];
+}
+
 // kernel-level parity hook: one shooting interval with sensitivities (train.py:347-364)
 template <bool IRK>
 MS_HD void eval_interval_point(int i, int n, int numSteps, int numApprox, const double* in, double* out, const IrkTab* irk) {

@@ -819,7 +819,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
                 if (doneLag >= n) break;
                 // compaction (compact.cuh): every fourth tick once instances have finished; the plan kernel decides on the device
                 // whether the running instances are scattered enough to be worth moving, the other kernels return at once if not
-                if (compactOn && h->compaction && g.S >= 256 && doneLag > 0 && tick % 4 == 0) {
+                if (compactOn && h->compaction && !intl && g.S >= 256 && doneLag > 0 && tick % 4 == 0) {
                     const int activeUb = n - doneLag;
                     k_compact_plan<<<1, 1024, 0, st>>>(c);
                     k_compact_extract<<<cgrid, 128, 0, st>>>(c, io);
@@ -833,6 +833,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         }
     }
     begin(CLS_MISC); k_cell_extract<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
+    if (intl && lam_out) launch_variant(VK_LAM_INTL, cgrid, st, c, io);      // multipliers of the time rows in the reference's formulation
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     e = cudaMemcpyAsync(h->done_host, c.done, 256, cudaMemcpyDeviceToHost, st);

@@ -10,7 +10,7 @@ namespace mseetc {
 enum VariantKernel {
     VK_INIT_DYN, VK_EVAL_DYN, VK_TRIAL_DYN, VK_STEP_DYN,                // spline loss map (efficiency.py)
     VK_EVAL_IRK, VK_EVAL_DYN_IRK, VK_TRIAL_IRK, VK_TRIAL_DYN_IRK,      // cell_eval with collocation steps
-    VK_INIT_INTL, VK_EVAL_INTL, VK_TRIAL_INTL, VK_STEP_INTL            // integrateLosses = True
+    VK_INIT_INTL, VK_EVAL_INTL, VK_TRIAL_INTL, VK_STEP_INTL, VK_LAM_INTL      // integrateLosses = True
 };
 // one launch of 128-thread blocks on `st` (same grid-stride cell loop as the kernels of mseetc_b200.cu)
 void launch_variant_dyn(int which, unsigned grid, cudaStream_t st, const Ctx& c, const BatchIO& io);

@@ -34,7 +34,7 @@ def oracle_nlp(train, track, N, energy=True, vmin=1.0, **rk):
                            kinks=(lm.box[2], lm.powerMax / lm.forceMax, lm.box[3]))
         else:
             cT, cR = ((1 - losses[1]) / losses[1], 1 - losses[2]) if losses[0] == 'static' else (0.0, 0.0)
-            energy_fn = mk(sr, None, static_power_fns(cT, cR), train.forceMinPn != 0)
+            energy_fn = mk(sr, None, static_power_fns(cT, cR), train.forceMinPn != 0, steps=o.get('oracleLossSteps', 8))
     return ReferenceNLP(train, pos, g, v, c, track.length, o, interval_fn=interval_fn, energy_fn=energy_fn)
 
 

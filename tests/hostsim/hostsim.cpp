@@ -211,6 +211,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         if (*c.done >= n) break;
     }
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_extract(c, io, k, s);
+    if (intl) for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_fix_time_multiplier_intl(c, io, k, s);
     if (ticks_out) *ticks_out = tick;
     if (pit_lanes > 1 && getenv("HOSTSIM_PIT_DIAG")) printf("pit: fallbacks %ld  worst relative step deviation %.2e\n", fallbacks, diag_worst);
     return 0;

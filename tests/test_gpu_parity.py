@@ -157,6 +157,16 @@ def test_integrated_losses_match_oracle_reference_formulation(cabi, lanes):
         lbz, ubz, lbg, ubg = nlp.bounds(T)
         g = nlp.g(z)
         assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7 * max(1.0, np.max(ref.x[nlp.iS]))      # energies up to ~100 J/kg; 4 vs 8 RK4 steps
+        # full KKT conditions of the REFERENCE formulation (rows on t_{i+1} - t_i; oracle with the device's 4 RK4 steps) at the device's
+        # solution with the device's multipliers, the time-row multipliers mapped (io.cuh: cell_fix_time_multiplier_intl)
+        same = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True, integrateLosses=True, oracleLossSteps=4)
+        lam = out['lam'][0]
+        free = lbz != ubz
+        r = (same.grad_f(z) + same.jac(z).T @ lam)[free]
+        sl, su = (z - lbz)[free], (ubz - z)[free]
+        with np.errstate(invalid='ignore'):
+            comp = np.where(r > 0, r * sl, -r * np.where(np.isfinite(su), su, 1.0))
+        assert np.max(comp) < 1e-7
 
 
 def test_public_api_integrate_losses(cabi):

@@ -302,6 +302,20 @@ def test_integrated_losses_match_oracle_reference_formulation(lib):
     g = nlp.g(z)
     # incl. the rows on the integrated energies, in the reference's form (energies up to ~100 J/kg; 4 vs 8 RK4 steps)
     assert np.max(np.maximum(lbg - g, g - ubg)) < 1e-7 * max(1.0, np.max(ref.x[nlp.iS]))
+    # full KKT conditions of the REFERENCE formulation (rows on t_{i+1} - t_i), evaluated by the oracle with the same 4 RK4 steps,
+    # at the device's solution with the device's multipliers (time-row multipliers mapped, io.cuh): stationarity + complementarity
+    same = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True, integrateLosses=True, oracleLossSteps=4)
+    lam = out['lam'][0]
+    free = lbz != ubz
+    r = (same.grad_f(z) + same.jac(z).T @ lam)[free]
+    sl, su = (z - lbz)[free], (ubz - z)[free]
+    with np.errstate(invalid='ignore'):
+        comp = np.where(r > 0, r * sl, -r * np.where(np.isfinite(su), su, 1.0))
+    assert np.max(comp) < 1e-7
+    gs = same.g(z)
+    with np.errstate(invalid='ignore'):
+        compg = np.where(lam < 0, -lam * (gs - lbg), lam * np.where(np.isfinite(ubg), ubg - gs, 1.0))
+    assert np.max(compg[lbg != ubg]) < 1e-7
     # not the mid-point formulation in disguise: that optimum differs in the fifth digit
     mid = oracle_solve(oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True), T)
     assert 1e-5 < abs(mid.f - ref.f) / ref.f < 1e-3
