@@ -170,7 +170,7 @@ def test_integrated_loss_energies_match_an_adaptive_integrator():
     lm = DynamicLossMap(tr.forceMax, 27000.0, 0.96, 1.0)
     kinks = (lm.box[2], lm.powerMax / lm.forceMax, lm.box[3])
     # (b0, Fel, dt, c0): acceleration from 1 m/s through both kinks, cruising, braking, a gradient
-    pts = np.array([[1.0, 0.25, 60.0, 0.0], [400.0, 0.05, 20.0, 0.002], [900.0, -0.2, 15.0, -0.01], [150.0, 0.2, 12.0, 0.0], [36.0, 0.28, 10.0, 0.0]])
+    pts = np.array([[1.0, 0.25, 60.0, 0.0], [400.0, 0.05, 20.0, 0.002], [900.0, -0.2, 15.0, -0.01], [36.0, 0.28, 10.0, 0.0]])
     b0, Fel, dt, c0 = pts.T
     zero = np.zeros(len(b0))
 
