@@ -227,7 +227,7 @@ int mseetc_set_integrator(mseetc_handle h, int32_t stages, const double* A, cons
 /* integrateLosses = True of the reference (OptionsCasadiSolver, mseetc/ocp.py:28,118-120,231-241): the two epigraph rows of every
  * interval bound s_k from below by the traction / regenerative-braking loss ENERGY of the interval, integrated in the time domain
  * (TrainIntegrator.calcLosses, train.py:367-413), and the objective becomes sum(ds_k Fel_k + s_k).  Energy-optimal mode with the
- * constant-efficiency or the spline loss model, explicit RK integrator.  lam_out holds the multipliers of the reference's
+ * constant-efficiency or the spline loss model, any integrator of mseetc_set_integrator.  lam_out holds the multipliers of the reference's
  * formulation (rows on t_{k+1} - t_k).  See DESIGN.md section 2 for the formulation solved on the device. */
 int mseetc_set_integrate_losses(mseetc_handle h, int on);
 

@@ -439,7 +439,7 @@ MS_HD void row_bounds(const Bnd& B, int j, double& L, double& U, bool& hasU) {
 // ------------------------------------------------------------------------------------------------
 // initialisation: x0 pushed inside the bounds, slacks from d(x0), multipliers 1 / 0   (IPOPT sec. 3.6)
 // ------------------------------------------------------------------------------------------------
-template <bool DYN, bool INTL = false>
+template <bool DYN, bool INTL = false, bool IRK = false>
 MS_HD void cell_init(const Ctx& c, int k, int s) {
     const Config& g = c.cfg;
     const int N = c.I(SI_N_INT, s);
@@ -470,7 +470,8 @@ MS_HD void cell_init(const Ctx& c, int k, int s) {
     ineq_values<DYN, INTL>(c, s, fel, fpb, sl, b, init_b(c, k + 1, s, N), q, d);
     if (INTL && g.energy) {
         Jet2 tau, phi;
-        shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
+        if (IRK) shoot_irk(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, *c.irk, tau, phi);
+        else shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
         Jet3 etr, erg;
         loss_energy_rows(c, s, q, b, init_b(c, k + 1, s, N), fel, fpb, tau, etr, erg);
         d[R_LTR] = sl - etr.v; d[R_LRG] = sl - erg.v;

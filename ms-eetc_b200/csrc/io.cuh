@@ -91,6 +91,7 @@ MS_HD void cell_extract(const Ctx& c, const BatchIO& io, int k, int s, bool fina
 // the loss rows from the shooting function (core.cuh, loss_energy_rows), the reference from t_{k+1} - t_k; the two Lagrangians have
 // the same stationary points with  y_t(reference) = y_t(device) + y_ltr dE_tr/d(duration) + y_lrg dE_rgb/d(duration),  and
 // dE/d(duration) is the loss power at the end of the interval.  Applied to lam_out after cell_extract (final pass only).
+template <bool IRK>
 MS_HD void cell_fix_time_multiplier_intl(const Ctx& c, const BatchIO& io, int k, int s) {
     const Config& g = c.cfg;
     if (s >= g.nInst || !io.lam_out || !g.energy) return;
@@ -102,7 +103,8 @@ MS_HD void cell_fix_time_multiplier_intl(const Ctx& c, const BatchIO& io, int k,
     const double b = c.W(it + IT_B, k, s), b1 = c.W(it + IT_B, k + 1, s), fel = c.W(it + IT_FEL, k, s), fpb = g.withPn ? c.W(it + IT_FPB, k, s) : 0.0;
     const IntervalCoef q = load_coef(c, k, s);
     Jet2 tau, phi;
-    shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
+    if (IRK) shoot_irk(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, *c.irk, tau, phi);
+    else shoot<Jet2>(jvar0(b), jvar1(fel + fpb), q, g.numSteps, g.numApprox, tau, phi);
     Jet3 etr, erg;
     loss_energy_rows(c, s, q, b, b1, fel, fpb, tau, etr, erg, true);
     const double pl[2] = {etr.g[0], erg.g[0]};

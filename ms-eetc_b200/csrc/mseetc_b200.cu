@@ -602,7 +602,6 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
     c.irk = h->irk_dev;
     const bool dyn = (p.loss_kind == 2 && p.energy_optimal);
     const bool intl = g.intLosses != 0;
-    if (intl && c.irk) return fail(-9, "mseetc_solve_batch: integrated losses are available with the explicit RK integrator only");
     BatchIO io{params, nint, trk_of, trk_off, ds, c0, bmax, tmin, z_out, lam_out, obj, kkt, iters, status};
 
     const size_t cellThreads = (size_t)g.NK * g.S;
@@ -716,14 +715,14 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         begin(CLS_MISC); k_inst_profile<<<igrid, 2 * ib, profBytes, st>>>(c, profBytes ? 1 : 0); end(CLS_MISC);
     }
     begin(CLS_MISC);
-    if (intl) launch_variant(VK_INIT_INTL, cgrid, st, c, io);
+    if (intl) launch_variant(c.irk ? VK_INIT_INTL_IRK : VK_INIT_INTL, cgrid, st, c, io);
     else if (dyn) launch_variant(VK_INIT_DYN, cgrid, st, c, io); else k_cell_init<<<cgrid, 128, 0, st>>>(c, io);
     end(CLS_MISC);
     const int maxTicks = 3 * p.max_iterations + 100;
     int tick = 0;
     // ---- starting point: evaluation, convergence test, barrier parameter
     begin(CLS_EVAL);
-    if (intl) launch_variant(VK_EVAL_INTL, gridIrk, st, c, io);
+    if (intl) launch_variant(c.irk ? VK_EVAL_INTL_IRK : VK_EVAL_INTL, gridIrk, st, c, io);
     else if (c.irk) launch_variant(dyn ? VK_EVAL_DYN_IRK : VK_EVAL_IRK, gridIrk, st, c, io);
     else if (dyn) launch_variant(VK_EVAL_DYN, gridEval, st, c, io); else k_cell_eval<<<gridEval, 128, 0, st>>>(c, io);
     end(CLS_EVAL);
@@ -752,7 +751,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         k_inst_alpha<<<rgrid * RED_CL, 32 * RED_WB, 0, s0>>>(c, mirror);
         if (prof) end(CLS_ALPHA);
         if (prof) begin(CLS_TRIAL);
-        if (intl) launch_variant(VK_TRIAL_INTL, gridIrk, s0, c, io);
+        if (intl) launch_variant(c.irk ? VK_TRIAL_INTL_IRK : VK_TRIAL_INTL, gridIrk, s0, c, io);
         else if (c.irk) launch_variant(dyn ? VK_TRIAL_DYN_IRK : VK_TRIAL_IRK, gridIrk, s0, c, io);
         else if (dyn) launch_variant(VK_TRIAL_DYN, gridTrial, s0, c, io); else k_cell_trial_eval<<<gridTrial, 128, 0, s0>>>(c, io);
         if (prof) end(CLS_TRIAL);
@@ -833,7 +832,7 @@ int mseetc_solve_batch(mseetc_handle h, int32_t n, const double* params, const i
         }
     }
     begin(CLS_MISC); k_cell_extract<<<cgrid, 128, 0, st>>>(c, io); end(CLS_MISC);
-    if (intl && lam_out) launch_variant(VK_LAM_INTL, cgrid, st, c, io);      // multipliers of the time rows in the reference's formulation
+    if (intl && lam_out) launch_variant(c.irk ? VK_LAM_INTL_IRK : VK_LAM_INTL, cgrid, st, c, io);      // multipliers of the time rows in the reference's formulation
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     e = cudaMemcpyAsync(h->done_host, c.done, 256, cudaMemcpyDeviceToHost, st);

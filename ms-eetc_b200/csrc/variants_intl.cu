@@ -8,7 +8,7 @@ MS_CELL_KERNEL(k_cell_init_intl, 1, (cell_init<true, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_trial_eval_intl, 1, (cell_eval<true, true, false, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_eval_intl, 1, (cell_eval<true, false, false, true>(c, k, s)))
 MS_CELL_KERNEL(k_cell_step_intl, 2, (cell_step<true, true>(c, k, s)))
-MS_CELL_KERNEL(k_cell_lam_intl, 1, cell_fix_time_multiplier_intl(c, io, k, s))
+MS_CELL_KERNEL(k_cell_lam_intl, 1, cell_fix_time_multiplier_intl<false>(c, io, k, s))
 }  // namespace
 
 void launch_variant_intl(int which, unsigned grid, cudaStream_t st, const Ctx& c, const BatchIO& io) {

@@ -186,8 +186,6 @@ class casadiSolver():
         track.checkFields()
         train.checkFields()
         opts = OptionsCasadiSolver(optsDict)
-        if opts.integrateLosses and opts.energyOptimal and opts.integrationMethod != 'RK':
-            raise NotImplementedError("integrateLosses=True is available with integrationMethod 'RK' only in this build of the device library")
 
         self.train = train
         self.opts = opts

@@ -99,7 +99,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_setup(c, io, k, s);
     for (int s = 0; s < g.S; ++s) { inst_screen(c, s); inst_profile(c, s); }
     const bool intl = g.intLosses != 0;
-    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (intl) cell_init<true, true>(c, k, s); else if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
+    for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (intl) { if (c.irk) cell_init<true, true, true>(c, k, s); else cell_init<true, true>(c, k, s); } else if (dyn) cell_init<true>(c, k, s); else cell_init<false>(c, k, s); }
     int tick = 0;
     long fallbacks = 0;
     const int diag = getenv("HOSTSIM_PIT_DIAG") ? atoi(getenv("HOSTSIM_PIT_DIAG")) : 0;
@@ -139,7 +139,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         }
     };
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) {
-        if (intl) cell_eval<true, false, false, true>(c, k, s);
+        if (intl) { if (c.irk) cell_eval<true, false, true, true>(c, k, s); else cell_eval<true, false, false, true>(c, k, s); }
         else if (c.irk) { if (dyn) cell_eval<true, false, true>(c, k, s); else cell_eval<false, false, true>(c, k, s); }
         else if (dyn) cell_eval<true, false>(c, k, s); else cell_eval<false, false>(c, k, s);
     }
@@ -202,7 +202,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         report("step ");
         if (*c.done >= n || tick >= maxTicks) break;
         for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) {
-            if (intl) cell_eval<true, true, false, true>(c, k, s);
+            if (intl) { if (c.irk) cell_eval<true, true, true, true>(c, k, s); else cell_eval<true, true, false, true>(c, k, s); }
             else if (c.irk) { if (dyn) cell_eval<true, true, true>(c, k, s); else cell_eval<false, true, true>(c, k, s); }
             else if (dyn) cell_eval<true, true>(c, k, s); else cell_eval<false, true>(c, k, s);
         }
@@ -211,7 +211,7 @@ int hostsim_solve_batch(const hostsim_problem* pr, int32_t n, const double* para
         if (*c.done >= n) break;
     }
     for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_extract(c, io, k, s);
-    if (intl) for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) cell_fix_time_multiplier_intl(c, io, k, s);
+    if (intl) for (int k = 0; k < g.NK; ++k) for (int s = 0; s < g.S; ++s) { if (c.irk) cell_fix_time_multiplier_intl<true>(c, io, k, s); else cell_fix_time_multiplier_intl<false>(c, io, k, s); }
     if (ticks_out) *ticks_out = tick;
     if (pit_lanes > 1 && getenv("HOSTSIM_PIT_DIAG")) printf("pit: fallbacks %ld  worst relative step deviation %.2e\n", fallbacks, diag_worst);
     return 0;

@@ -198,8 +198,14 @@ def test_public_api_integrate_losses(cabi):
     assert df is not None and abs(stats['Cost'] - gold['cost_kwh']) <= 1e-6 * gold['cost_kwh']
     assert np.max(np.abs(df['Velocity [m/s]'].values ** 2 - np.array(gold['b']))) <= 1e-4 * 1975.0
     assert np.max(np.abs(df.index.values - np.array(gold['t']))) <= 1e-4 * gold['T']
-    with pytest.raises(NotImplementedError):
-        casadiSolver(train, track, dict(opts, integrationMethod='IRK', integrationOptions={}))
+    # together with the collocation integrator (three Gauss points, time from the average-speed rule): against the oracle
+    irk = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), track, dict(opts, integrationMethod='IRK',
+                       integrationOptions={'order': 3, 'collMethod': 'legendre', 'numApproxSteps': 1}))
+    df, stats = irk.solve(1541.0)
+    nlp3 = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, energy=True, integrateLosses=True, numSteps=1, numApproxSteps=1, irk=(3, 'legendre'))
+    ref3 = oracle_solve(nlp3, 1541.0)
+    assert df is not None and ref3.success and abs(stats['Cost'] - nlp3.cost(ref3.f)) <= 1e-6 * nlp3.cost(ref3.f)
+    assert np.max(np.abs(df['Velocity [m/s]'].values ** 2 - ref3.x[nlp3.iB])) <= 1e-4 * nlp3.limit.max() ** 2
 
 
 def test_interval_kernel_bitwise_equals_host_compilation(cabi):

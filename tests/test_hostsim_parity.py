@@ -355,3 +355,26 @@ def test_spline_loss_map_with_collocation_integrator(lib):
         cost[name] = nlp.cost(out['obj'][0])
     assert abs(cost['rk'] - cost['gauss']) < 2e-4 * cost['gauss']
     assert 2e-4 * cost['gauss'] < abs(cost['radau'] - cost['gauss']) < 5e-3 * cost['gauss']
+
+
+def test_integrated_losses_with_collocation_integrator(lib):
+    "integrateLosses = True together with integrationMethod 'IRK' (three Gauss points, time from the average-speed rule) vs the oracle"
+    from oracle.problem import load_track
+    T = 1541.0
+    kw = dict(energy=True, integrateLosses=True, numSteps=1, numApproxSteps=1, irk=(3, 'legendre'))
+    nlp = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, **kw)
+    ref = oracle_solve(nlp, T)
+    assert ref.success
+    out = harness.solve([nlp], [T], lib=lib)
+    assert out['status'][0] == 0 and out['kkt'][0] <= 1e-8
+    assert abs(out['obj'][0] - ref.f) <= 1e-6 * abs(ref.f)
+    z = out['z'][0]
+    _check_against(z, nlp, ref.x[nlp.iT], ref.x[nlp.iB], ref.x[nlp.iFel], T)
+    same = oracle_nlp(virm6(), load_track(FLAT_JSON), 100, oracleLossSteps=4, **kw)       # reference formulation, the device's 4 RK4 steps
+    lbz, ubz, lbg, ubg = nlp.bounds(T)
+    lam, free = out['lam'][0], lbz != ubz
+    r = (same.grad_f(z) + same.jac(z).T @ lam)[free]
+    sl, su = (z - lbz)[free], (ubz - z)[free]
+    with np.errstate(invalid='ignore'):
+        comp = np.where(r > 0, r * sl, -r * np.where(np.isfinite(su), su, 1.0))
+    assert np.max(comp) < 1e-6
