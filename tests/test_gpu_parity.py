@@ -169,6 +169,24 @@ def test_integrated_losses_match_oracle_reference_formulation(cabi, lanes):
         assert np.max(comp) < 1e-7
 
 
+def test_integrated_losses_trip_time_sweep_converges(cabi):
+    """A sweep of 1024 trip times with integrateLosses = True on the bench problem: every instance reaches the full tolerance and
+    the energy decreases with the trip time (a build whose loss-integration routine was not inlined passed the single-instance
+    parity cases and stalled on 8 % of such a sweep)."""
+    from mseetc.ocp import casadiSolver
+    from mseetc.train import Train
+    from mseetc.track import Track
+    solver = casadiSolver(Train(config={'id': 'NL_Intercity_VIRM6'}), Track(config={'id': 'CH_StGallen_Wil'}),
+                          {'numIntervals': 300, 'maxIterations': 500, 'integrateLosses': True, 'integrationMethod': 'RK',
+                           'integrationOptions': {'order': 4, 'numSteps': 1, 'numApproxSteps': 1}})
+    tmin = float(np.atleast_1d(solver.minimum_time()[0])[0])
+    T = tmin * np.linspace(1.001, 1.2, 1024)
+    res = solver.solve_batch(T, screen=False)
+    assert np.all(np.asarray(res['status']) == 0), np.unique(np.asarray(res['status']), return_counts=True)
+    assert np.all(np.asarray(res['kkt']) <= 1e-8) and int(np.max(res['iters'])) < 80
+    assert np.all(np.diff(np.asarray(res['cost'])) < 0)
+
+
 def test_public_api_integrate_losses(cabi):
     """casadiSolver(..., {'integrateLosses': True}) with constant efficiencies (against the oracle) and with the spline loss map of
     simulations/table3.py (against the oracle fixture); a batch of trip times gives the same optima as single solves."""
