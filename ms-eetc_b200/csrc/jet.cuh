@@ -9,12 +9,8 @@
 #endif
 #if defined(__CUDACC__)
 #define MS_HD __host__ __device__ __forceinline__
-// large routines of the less common variants (collocation steps, time-domain loss integration): one copy per translation unit
-// instead of one per call site -- they dominate the compile time otherwise
-#define MS_HD_NI inline __host__ __device__ __noinline__
 #else
 #define MS_HD inline
-#define MS_HD_NI inline
 #endif
 
 namespace mseetc {

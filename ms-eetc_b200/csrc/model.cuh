@@ -132,7 +132,7 @@ MS_HD void irk_lu_solve(const double* J, const int* piv, int d, double* x) {
 
 // numSteps collocation steps of db/dsigma = 2*ds*a(b,F) over sigma in [0,h]; tq (optional) += int ds/sqrt(b) dsigma by the
 // quadrature of the same method
-MS_HD_NI Jet2 irk_b(const Jet2& b0, const Jet2& F, double h, int numSteps, const IntervalCoef& c, const IrkTab& K, Jet2* tq) {
+MS_HD Jet2 irk_b(const Jet2& b0, const Jet2& F, double h, int numSteps, const IntervalCoef& c, const IrkTab& K, Jet2* tq) {
     const int d = K.d;
     const double dt = h / numSteps, wb = 2.0 * c.ds * dt, wt = c.ds * dt;
     Jet2 b = b0;
